@@ -1,0 +1,155 @@
+/*
+ * daisy_b200.h -- C ABI of libdaisy_b200.so: the B200 (sm_100a) implementation of Daisy's
+ * BPR-MF / funk-SVD training hot path and its top-K evaluation.
+ *
+ * The reference (NotFoundGG/recommend-lib) has no FFI of its own: the hot path sits behind Python
+ * object protocols.  Each entry point below names the reference code it
+ * replaces (file:line relative to the reference root); INTEGRATION.md shows the ctypes binding a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative DAISY_E* code; daisy_last_error() returns a
+ *    thread-local message for the last failing call on this thread;
+ *  - device buffers (tables, index arrays, outputs) are OWNED BY THE CALLER (e.g. torch.Tensor.data_ptr());
+ *    the handle owns only its workspace;
+ *  - every call is asynchronous on the CUDA stream passed in (a cudaStream_t cast to void*; NULL = the
+ *    legacy default stream);  a handle is bound to one device and is not thread-safe;
+ *  - row ids are validated on the device: an out-of-range id never faults, it raises a sticky flag that
+ *    daisy_check() reports as DAISY_EINDEX (mirrors nn.Embedding's IndexError / predict's ValueError);
+ *  - tables are row-major contiguous fp32 [rows, dim], dim % 4 == 0, dim <= 512, base 16-byte aligned.
+ */
+#ifndef DAISY_B200_H
+#define DAISY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAISY_OK 0
+#define DAISY_EINVAL (-1)       /* bad argument */
+#define DAISY_ECUDA (-2)        /* CUDA runtime error (message has the cudaError string) */
+#define DAISY_EINDEX (-3)       /* a user / item id was out of range (sticky until daisy_check) */
+#define DAISY_EUNSUPPORTED (-4) /* shape not supported by this build */
+#define DAISY_ENOMEM (-5)
+
+#define DAISY_ABI_VERSION 1
+
+typedef struct daisy_ctx *daisy_handle_t;
+typedef void *daisy_stream_t; /* cudaStream_t */
+
+/* create flags */
+#define DAISY_FLAG_DEFAULT 0u
+#define DAISY_FLAG_EAGER_DECAY 1u /* apply the dense L2 shrink to every row every step (reference-literal,
+                                     BPRMFRecommender.py:154,176) instead of the exact lazy scale */
+
+int daisy_abi_version(void);
+const char *daisy_last_error(void);
+
+/* Workspace for one model: tables of user_num x dim and item_num x dim, batches of at most max_batch.
+ * Replaces: BPR.__init__ allocation side (BPRMFRecommender.py:29-40) + optim.SGD construction (:154). */
+int daisy_create(daisy_handle_t *out, int device, int64_t user_num, int64_t item_num, int dim,
+                 int64_t max_batch, unsigned flags);
+int daisy_destroy(daisy_handle_t h);
+
+/* Synchronise `stream` and report (then clear) the sticky device-side index error.  On DAISY_EINDEX the
+ * message names the first offending position.  Mirrors IndexError of nn.Embedding (BPRMFRecommender.py:43-45). */
+int daisy_check(daisy_handle_t h, daisy_stream_t stream);
+
+/* ---- lazy L2 decay ------------------------------------------------------------------------------
+ * optim.SGD(weight_decay) shrinks EVERY row by (1 - lr*wd) each step (BPRMFRecommender.py:154,176).
+ * The library stores W_hat = W / c and keeps the scalar c per handle; scores use c^2.  The true tables
+ * are W = c * W_hat; daisy_materialize() multiplies both tables by c and resets c = 1 (one pass over the
+ * tables) -- call it before anything outside the library reads the weights (eval by foreign code,
+ * torch.save, predict).  daisy_get_scale() returns c. */
+int daisy_get_scale(daisy_handle_t h, double *c);
+int daisy_set_scale(daisy_handle_t h, double c);
+int daisy_materialize(daisy_handle_t h, float *P, float *Q, daisy_stream_t stream);
+
+/* BPR.forward (BPRMFRecommender.py:42-50): pred_i[t] = <P[u_t],Q[i_t]>, pred_j[t] = <P[u_t],Q[j_t]>.
+ * triples: device int32 [B,3] packed (u,i,j).  Honours the handle's lazy scale. */
+int daisy_bpr_forward(daisy_handle_t h, const float *P, const float *Q, const int32_t *triples, int64_t B,
+                      float *pred_i, float *pred_j, daisy_stream_t stream);
+
+/* One training step = model.zero_grad(); forward; loss = -(pi-pj).sigmoid().log().sum(); loss.backward();
+ * optimizer.step()  (BPRMFRecommender.py:172-176) fused: gradients at the pre-step tables, repeated rows
+ * accumulate deterministically (sort-by-row segmented reduction, no float atomics), SGD + L2.
+ * loss_accum (device double, may be NULL): the batch-sum loss is ADDED to it.
+ * triples: device int32 [B,3], B <= max_batch. */
+int daisy_bpr_step(daisy_handle_t h, float *P, float *Q, const int32_t *triples, int64_t B, float lr, float wd,
+                   double *loss_accum, daisy_stream_t stream);
+
+/* Same step fed from HOST memory (the reference's `user.cuda(); item_i.cuda(); item_j.cuda()`,
+ * BPRMFRecommender.py:163-166): triples_host is int32 [B,3] in host memory (pinned for a truly async
+ * copy); the library copies it into its own device buffer on `stream` and runs the step. */
+int daisy_bpr_step_host(daisy_handle_t h, float *P, float *Q, const int32_t *triples_host, int64_t B, float lr,
+                        float wd, double *loss_accum, daisy_stream_t stream);
+
+/* Lazy sparse Adam variant of the step (no Daisy counterpart -- BPR-MF uses SGD only; semantics =
+ * torch.optim.SparseAdam: only rows present in the batch change, weights and moments alike).
+ * mP,vP [user_num,dim], mQ,vQ [item_num,dim] fp32 moments owned by the caller; step_no is 1-based. */
+int daisy_bpr_adam_step(daisy_handle_t h, float *P, float *Q, float *mP, float *vP, float *mQ, float *vQ,
+                        const int32_t *triples, int64_t B, float lr, float beta1, float beta2, float eps,
+                        int64_t step_no, double *loss_accum, daisy_stream_t stream);
+
+/* metric_eval / _bpr_topk (util/metrics.py:46-66,88-94), all groups in one launch:
+ * for n < N: score[c] = <P[users[n]], Q[cand[n,c]]>, c < C; the K best in (score desc, position asc) order.
+ * out_pos [N,K] int32 = candidate positions (the `indices` of torch.topk), out_item [N,K] = cand ids
+ * (`torch.take`), out_score [N,K].  C <= 8192, K <= 128, K <= C. */
+int daisy_topk_candidates(daisy_handle_t h, const float *P, const float *Q, const int32_t *users,
+                          const int32_t *cand, int64_t N, int C, int K, int32_t *out_pos, int32_t *out_item,
+                          float *out_score, daisy_stream_t stream);
+
+/* Full-catalogue score + top-K (replaces the per-candidate scalar loop BPRMFRecommender.py:196-207):
+ * for n < N the K best items of score[i] = <P[users[n]], Q[i]>, i < item_num, order (score desc, item asc).
+ * Optional exclusion lists in CSR form (excl_ptr [N+1] int64, excl_idx int32: the user's training positives).
+ * K <= 128. */
+int daisy_topk_full(daisy_handle_t h, const float *P, const float *Q, const int32_t *users, int64_t N, int K,
+                    const int64_t *excl_ptr, const int32_t *excl_idx, int32_t *out_item, float *out_score,
+                    daisy_stream_t stream);
+
+/* ---- funk-SVD / RSVD (util/matrix_factorization.pyx) ---------------------------------------------
+ * variant: 0 = SVD (:132-151), 1 = RSVD version 1, 2 = RSVD version 2 (:41-61).
+ * One call runs `n_epochs` passes over the n ratings IN THE GIVEN ORDER with the reference's strictly
+ * sequential semantics (update t+1 sees update t): the kernel is a dataflow over per-row version
+ * counters, so independent ratings run in parallel and dependent ones in sequence order.
+ * Tables are float64 like the reference's (pu [U,dim], qi [I,dim], bu [U], bi [I]); users/items int32,
+ * ratings float64, all on the device.  sse_out (device double[n_epochs], may be NULL) receives the sum
+ * of squared errors of each epoch. */
+typedef struct {
+    int variant;
+    int biased; /* SVD only */
+    double lr_bu, lr_bi, lr_pu, lr_qi;
+    double reg_bu, reg_bi, reg_pu, reg_qi;
+    double reg2;        /* RSVD2 */
+    double global_mean; /* SVD: mu if biased else 0;  RSVD2: mu in the bias coupling */
+} daisy_mf_params;
+
+int daisy_mf_fit(daisy_handle_t h, double *pu, double *qi, double *bu, double *bi, const int32_t *users,
+                 const int32_t *items, const double *ratings, int64_t n, int n_epochs,
+                 const daisy_mf_params *prm, double *sse_out, daisy_stream_t stream);
+
+/* SVD.predict / RSVD.predict (util/matrix_factorization.pyx:157-167, 68-78), batched:
+ * est[n] = (with_bias ? mu + bu[u] + bi[i] : 0) + <pu[u], qi[i]>.  Out-of-range codes raise DAISY_EINDEX
+ * at daisy_check (ValueError('Invalid user code' / 'Invalid item code') in the reference). */
+int daisy_mf_predict(daisy_handle_t h, const double *pu, const double *qi, const double *bu, const double *bi,
+                     const int32_t *users, const int32_t *items, int64_t n, int with_bias, double mu,
+                     double *est, daisy_stream_t stream);
+
+/* ---- introspection for tests / bench ------------------------------------------------------------- */
+/* Number of kernels launched by this handle since creation (the bench's gpu_launches claim). */
+int daisy_launch_count(daisy_handle_t h, int64_t *n);
+/* Device time (ms) of the dominant kernel of the last daisy_bpr_step, measured with CUDA events on the
+ * launching stream when timing was enabled with daisy_set_timing(h, 1).  Synchronises. */
+int daisy_set_timing(daisy_handle_t h, int on);
+int daisy_last_step_timing(daisy_handle_t h, float *ms_main_kernel, float *ms_total);
+/* Pin rows [0, n_rows) of the item table in L2 through a stream access-policy window
+ * (hot items first when the catalogue is popularity-ordered).  n_rows = 0 clears the window. */
+int daisy_set_l2_window(daisy_handle_t h, const float *Q, int64_t n_rows, float hit_ratio,
+                        daisy_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAISY_B200_H */

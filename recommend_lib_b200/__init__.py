@@ -1,0 +1,33 @@
+"""daisy-b200: B200-native (sm_100a) BPR-MF / funk-SVD training hot path behind Daisy's surface.
+
+Public surface (mirrors the reference):
+
+* ``BPR(user_num, item_num, factor_num)``            -- BPRMFRecommender.py:28-50
+* ``BPRMFRecommender(...).fit()/predict()``           -- the epoch loop BPRMFRecommender.py:157-181
+* ``metric_eval(model, test_loader, top_k)``          -- util/metrics.py:88-94
+* ``SVD`` / ``RSVD`` (ctor kwargs, ``fit``, ``predict``)  -- util/matrix_factorization.pyx:5-167
+
+All compute goes through the C-ABI library ``libdaisy_b200.so`` (``include/daisy_b200.h``);
+there is no CPU fallback: using any of the above without the built library or without
+a CUDA device raises.
+"""
+from importlib import import_module
+
+__all__ = ["BPR", "BPRMFRecommender", "metric_eval", "SVD", "RSVD", "MFRecommender",
+           "TripleSampler", "lib"]
+
+_LAZY = {
+    "BPR": ".bpr", "BPRMFRecommender": ".bpr", "BPRSGD": ".bpr", "BPRAdam": ".bpr",
+    "metric_eval": ".metrics", "topk_candidates": ".metrics", "topk_full": ".metrics",
+    "SVD": ".mf", "RSVD": ".mf", "MFRecommender": ".mf",
+    "TripleSampler": ".sampler",
+    "ShardedBPR": ".sharded",
+    "lib": "._lib",
+}
+
+
+def __getattr__(name):
+    if name in _LAZY:
+        mod = import_module(_LAZY[name], __name__)
+        return mod if name == "lib" else getattr(mod, name)
+    raise AttributeError(name)

@@ -1,0 +1,116 @@
+"""Deterministic host-side triple sampler (replaces ``BPRData.ng_sample`` + DataLoader shuffle).
+
+The reference draws, for every training positive ``(u, i)``, ``num_ng`` negatives
+``j ~ U[0, item_num)`` re-drawn while ``(u, j)`` is a training positive
+(util/data_loader.py:680-690), then lets ``DataLoader(shuffle=True)`` permute the
+``num_ng * |train|`` triples into batches (BPRMFRecommender.py:141-142).  Both use
+global, unseeded RNG state.  This sampler produces triples with the same
+distribution from a counter-based Philox stream keyed by ``(seed, epoch)``, fully
+vectorised, and hands out packed ``int32 [N, 3]`` batches that are fed
+*identically* to the CUDA path and to the CPU oracle.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _rng(seed, *stream):
+    """Philox generator keyed by (seed, stream...) -- independent streams per epoch / purpose."""
+    key = np.random.SeedSequence([int(seed), *[int(s) for s in stream]]).generate_state(2, dtype=np.uint64)
+    return np.random.Generator(np.random.Philox(key=key))
+
+
+class TripleSampler:
+    """``(u, i, j)`` triples for BPR training.
+
+    Parameters mirror ``BPRData(features, num_item, train_mat, num_ng, is_training=True)``
+    (util/data_loader.py:668): ``train_pairs`` are the ``features`` (``[N, 2]`` ints), the
+    rejection set is the pair set itself (the role of ``train_mat``).
+    """
+
+    def __init__(self, train_pairs, item_num, num_ng=4, seed=2019, reject=True):
+        p = np.ascontiguousarray(np.asarray(train_pairs)[:, :2], dtype=np.int64)
+        self.users = p[:, 0].copy()
+        self.items = p[:, 1].copy()
+        self.item_num = int(item_num)
+        self.num_ng = int(num_ng)
+        self.seed = int(seed)
+        self.reject = bool(reject)
+        # sorted 64-bit keys u * item_num + i: membership test == "(u, j) in train_mat"
+        self._keys = np.unique(self.users * self.item_num + self.items)
+
+    def __len__(self):
+        return self.num_ng * len(self.users)
+
+    def _is_positive(self, u, j):
+        k = u * self.item_num + j
+        pos = np.searchsorted(self._keys, k)
+        pos[pos == len(self._keys)] = 0
+        return self._keys[pos] == k
+
+    def sample_epoch(self, epoch, shuffle=True):
+        """All triples of one epoch, ``int32 [num_ng * |train|, 3]``.
+
+        Un-shuffled order is the reference's ``features_fill`` order (positive-major,
+        ``num_ng`` consecutive negatives each, util/data_loader.py:684-690); ``shuffle``
+        applies one epoch-keyed permutation (DataLoader ``shuffle=True``).
+        """
+        g = _rng(self.seed, 1, epoch)
+        u = np.repeat(self.users, self.num_ng)
+        i = np.repeat(self.items, self.num_ng)
+        j = g.integers(0, self.item_num, size=u.shape[0], dtype=np.int64)
+        if self.reject:
+            bad = np.nonzero(self._is_positive(u, j))[0]
+            while bad.size:                       # re-draw only the rejected ones, in index order
+                j[bad] = g.integers(0, self.item_num, size=bad.size, dtype=np.int64)
+                bad = bad[self._is_positive(u[bad], j[bad])]
+        out = np.empty((u.shape[0], 3), dtype=np.int32)
+        out[:, 0], out[:, 1], out[:, 2] = u, i, j
+        if shuffle:
+            out = out[_rng(self.seed, 2, epoch).permutation(out.shape[0])]
+        return np.ascontiguousarray(out)
+
+    def batches(self, epoch, batch_size, shuffle=True):
+        """Yield consecutive ``int32 [<=batch_size, 3]`` batches; the last one may be short (drop_last=False)."""
+        t = self.sample_epoch(epoch, shuffle)
+        for s in range(0, t.shape[0], batch_size):
+            yield t[s:s + batch_size]
+
+
+# --------------------------------------------------------------------------
+# synthetic workloads of BASELINE.json configs 2-5
+# --------------------------------------------------------------------------
+def zipf_items(g, n, item_num, exponent=1.0, perm_seed=None):
+    """``n`` item ids with P(rank r) ~ 1/r^exponent over a seeded permutation of the catalogue.
+
+    Inverse-CDF on the exact cumulative weights for catalogues up to 2^25 items.
+    """
+    w = 1.0 / np.power(np.arange(1, item_num + 1, dtype=np.float64), exponent)
+    cdf = np.cumsum(w)
+    cdf /= cdf[-1]
+    ranks = np.searchsorted(cdf, g.random(n), side="right").astype(np.int64)
+    np.minimum(ranks, item_num - 1, out=ranks)
+    if perm_seed is None:
+        return ranks
+    perm = _rng(perm_seed, 3).permutation(item_num)
+    return perm[ranks]
+
+
+def synthetic_triples(n, user_num, item_num, seed=2019, stream=0, zipf=1.0, permute_items=True):
+    """Config 3/4/5 triples: users uniform, positives Zipf(zipf) over a permuted catalogue, negatives uniform
+    without rejection (collision probability ~1e-6 at these sizes; both implementations get the same triples)."""
+    g = _rng(seed, 10, stream)
+    out = np.empty((n, 3), dtype=np.int32)
+    out[:, 0] = g.integers(0, user_num, size=n, dtype=np.int64)
+    out[:, 1] = zipf_items(g, n, item_num, zipf, perm_seed=seed if permute_items else None)
+    out[:, 2] = g.integers(0, item_num, size=n, dtype=np.int64)
+    return out
+
+
+def synthetic_ratings(n, user_num, item_num, seed=2019, zipf=1.0):
+    """Config 2 ratings: users uniform, items Zipf over a permutation, ratings 1..5 with the ml-100k histogram."""
+    g = _rng(seed, 11)
+    users = g.integers(0, user_num, size=n, dtype=np.int64).astype(np.int32)
+    items = zipf_items(g, n, item_num, zipf, perm_seed=seed).astype(np.int32)
+    ratings = g.choice(np.arange(1, 6, dtype=np.float64), size=n, p=[0.061, 0.114, 0.271, 0.342, 0.212])
+    return users, items, ratings

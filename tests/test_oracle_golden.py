@@ -1,0 +1,150 @@
+"""Pin the CPU oracle against fixtures produced by the UNMODIFIED reference (tests/golden/make_golden.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, rel_err
+from oracle import bpr_oracle, mf_oracle
+
+
+# ---------------------------------------------------------------- BPR step
+def test_closed_form_matches_reference_small(golden):
+    g = golden("bpr_small.npz")
+    P, Q = g["P0"], g["Q0"]
+    for k, batch in enumerate(g["batches"]):
+        P, Q, loss = bpr_oracle.bpr_step_closed_form(P, Q, batch, float(g["lr"]), float(g["wd"]), np.float64)
+        assert rel_err(P, g["P"][k]) < 2e-6, k
+        assert rel_err(Q, g["Q"][k]) < 2e-6, k
+        assert abs(loss - g["losses"][k]) / g["losses"][k] < 1e-5
+
+
+def test_closed_form_fp32_matches_reference_small(golden):
+    g = golden("bpr_small.npz")
+    P, Q = g["P0"], g["Q0"]
+    for k, batch in enumerate(g["batches"]):
+        P, Q, _ = bpr_oracle.bpr_step_closed_form(P, Q, batch, float(g["lr"]), float(g["wd"]), np.float32)
+        assert rel_err(P, g["P"][k]) < 1e-5 and rel_err(Q, g["Q"][k]) < 1e-5
+
+
+def test_torch_port_is_bit_identical_to_reference_small(golden):
+    g = golden("bpr_small.npz")
+    port = bpr_oracle.TorchPort(g["P0"], g["Q0"], float(g["lr"]), float(g["wd"]))
+    for k, batch in enumerate(g["batches"]):
+        loss = port.step(batch)
+        P, Q = port.tables()
+        assert np.array_equal(P, g["P"][k]) and np.array_equal(Q, g["Q"][k])
+        assert loss == pytest.approx(float(g["losses"][k]), rel=1e-6)
+
+
+def test_forward_matches_reference(golden):
+    g = golden("bpr_small.npz")
+    b = g["batches"][0]
+    pi, pj = bpr_oracle.bpr_scores(g["P"][-1], g["Q"][-1], b[:, 0], b[:, 1], b[:, 2])
+    assert np.allclose(pi, g["fwd_pred_i"], rtol=1e-5, atol=1e-7)
+    assert np.allclose(pj, g["fwd_pred_j"], rtol=1e-5, atol=1e-7)
+
+
+def test_config1_first_step(golden):
+    g = golden("bpr_config1_step.npz")
+    P1, Q1, loss = bpr_oracle.bpr_step_closed_form(g["P0"], g["Q0"], g["batch"], 0.01, 0.001, np.float64)
+    assert rel_err(P1, g["P1"]) < 1e-6 and rel_err(Q1, g["Q1"]) < 1e-6
+    assert abs(loss - float(g["loss"])) / float(g["loss"]) < 1e-6
+    # untouched rows shrink by exactly 1 - lr*wd (dense decay)
+    untouched = np.setdiff1d(np.arange(g["P0"].shape[0]), g["batch"][:, 0])
+    if untouched.size:
+        assert np.allclose(g["P1"][untouched], g["P0"][untouched] * (1 - 1e-5), rtol=2e-7, atol=0)
+    port = bpr_oracle.TorchPort(g["P0"], g["Q0"], 0.01, 0.001)
+    port.step(g["batch"])
+    P, Q = port.tables()
+    assert np.array_equal(P, g["P1"]) and np.array_equal(Q, g["Q1"])
+
+
+def test_sampler_reproduces_golden_batch(golden):
+    """The fixture's batch came from TripleSampler(seed 2019): the sampler must be reproducible."""
+    from recommend_lib_b200.sampler import TripleSampler
+    g = golden("bpr_config1_step.npz")
+    s = golden("ml100k_split.npz")
+    sampler = TripleSampler(s["train_pairs"].astype(np.int64), int(s["item_num"]), num_ng=4, seed=2019)
+    batch = next(iter(sampler.batches(0, 4096)))
+    assert np.array_equal(batch, g["batch"])
+
+
+# ---------------------------------------------------------------- eval
+def test_eval_matches_reference_metric_eval(golden):
+    g = golden("bpr_eval_small.npz")
+    hr, ndcg, top = bpr_oracle.bpr_topk_eval(g["P"], g["Q"], g["users"], g["cands"], int(g["top_k"]))
+    assert hr == pytest.approx(float(g["hr"]), abs=1e-12)
+    assert ndcg == pytest.approx(float(g["ndcg"]), abs=1e-9)
+    assert 0.0 < hr < 1.0
+
+
+def test_topk_order_ties():
+    assert list(bpr_oracle.topk_order(np.array([1., 3., 3., 2., 3., 0.]), 3)) == [1, 2, 4]
+
+
+def test_trajectory_fixture_is_sane():
+    path = os.path.join(GOLDEN, "bpr_ml100k_traj.json")
+    if not os.path.exists(path):
+        pytest.skip("trajectory fixture not generated")
+    t = json.load(open(path))
+    ep = t["epochs"]
+    assert len(ep) == 20 and ep[0]["loss"] > ep[-1]["loss"]
+    assert abs(ep[0]["loss"] - 396228 * np.log(2)) / ep[0]["loss"] < 0.01     # epoch 1 ~ N ln 2
+    assert 0.15 < ep[-1]["hr"] < 0.25                                         # HR@10 ~ 0.204
+
+
+# ---------------------------------------------------------------- funk-SVD / RSVD
+@pytest.mark.parametrize("name,biased,kw", [("svd_b", True, {}), ("svd_u", False, dict(lr_all=0.01, reg_all=0.05))])
+def test_svd_c_oracle_bit_identical_to_cython_reference(golden, name, biased, kw):
+    g = golden("mf_small.npz")
+    o = mf_oracle.svd_fit(g["users"], g["items"], g["ratings"], g[f"{name}_pu0"], g[f"{name}_qi0"],
+                          n_epochs=int(g["E"]), biased=biased, **kw)
+    for k in ("pu", "qi", "bu", "bi"):
+        assert np.array_equal(o[k], g[f"{name}_{k}"]), k
+    assert o["global_mean"] == float(g[f"{name}_mu"])
+    for n in range(20):
+        est = mf_oracle.predict(g["users"][n], g["items"][n], o["pu"], o["qi"], o["bu"], o["bi"], biased, o["global_mean"])
+        assert est == pytest.approx(g[f"{name}_pred"][n], rel=1e-12, abs=1e-14)
+
+
+@pytest.mark.parametrize("name,version", [("rsvd_1", 1), ("rsvd_2", 2)])
+def test_rsvd_c_oracle_bit_identical_to_cython_reference(golden, name, version):
+    g = golden("mf_small.npz")
+    o = mf_oracle.rsvd_fit(g["users"], g["items"], g["ratings"], g[f"{name}_ui0"], g[f"{name}_vj0"],
+                           n_epochs=int(g["E"]), version=version, lr=0.005)
+    for k in ("ui", "vj", "ci", "dj"):
+        assert np.array_equal(o[k], g[f"{name}_{k}"]), k
+    for n in range(20):
+        est = mf_oracle.predict(g["users"][n], g["items"][n], o["ui"], o["vj"], o["ci"], o["dj"], version == 2)
+        assert est == pytest.approx(g[f"{name}_pred"][n], rel=1e-12, abs=1e-14)
+
+
+def test_predict_rejects_invalid_codes(golden):
+    g = golden("mf_small.npz")
+    z = np.zeros(1)
+    with pytest.raises(ValueError, match="Invalid user code"):
+        mf_oracle.predict(int(g["U"]), 0, g["svd_b_pu"], g["svd_b_qi"], g["svd_b_bu"], g["svd_b_bi"], True)
+    with pytest.raises(ValueError, match="Invalid item code"):
+        mf_oracle.predict(0, int(g["I"]), g["svd_b_pu"], g["svd_b_qi"], g["svd_b_bu"], g["svd_b_bi"], True)
+
+
+def test_live_reference_extension_when_present():
+    """When oracle/_ref is built (build container, or shipped to the GPU box) re-check on fresh data."""
+    from oracle.build_ref import load_ref
+    m = load_ref()
+    if m is None:
+        pytest.skip("oracle/_ref not available")
+    import pandas as pd
+    rng = np.random.default_rng(5)
+    U, I, D, N = 30, 20, 6, 300
+    users, items = rng.integers(0, U, N), rng.integers(0, I, N)
+    ratings = rng.integers(1, 6, N).astype(float)
+    np.random.seed(1)
+    a = m.SVD(U, I, n_factors=D, n_epochs=2, verbose=False)
+    a.fit(pd.DataFrame({"user": users, "item": items, "rating": ratings}))
+    np.random.seed(1)
+    pu0, qi0 = mf_oracle.draw_init(U, I, D)
+    o = mf_oracle.svd_fit(users, items, ratings, pu0, qi0, n_epochs=2)
+    assert np.array_equal(o["pu"], a.pu) and np.array_equal(o["qi"], a.qi)
