@@ -36,6 +36,12 @@ extern "C" {
 
 #define DAISY_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define DAISY_API __attribute__((visibility("default")))
+#else
+#define DAISY_API
+#endif
+
 typedef struct daisy_ctx *daisy_handle_t;
 typedef void *daisy_stream_t; /* cudaStream_t */
 
@@ -44,18 +50,18 @@ typedef void *daisy_stream_t; /* cudaStream_t */
 #define DAISY_FLAG_EAGER_DECAY 1u /* apply the dense L2 shrink to every row every step (reference-literal,
                                      BPRMFRecommender.py:154,176) instead of the exact lazy scale */
 
-int daisy_abi_version(void);
-const char *daisy_last_error(void);
+DAISY_API int daisy_abi_version(void);
+DAISY_API const char *daisy_last_error(void);
 
 /* Workspace for one model: tables of user_num x dim and item_num x dim, batches of at most max_batch.
  * Replaces: BPR.__init__ allocation side (BPRMFRecommender.py:29-40) + optim.SGD construction (:154). */
-int daisy_create(daisy_handle_t *out, int device, int64_t user_num, int64_t item_num, int dim,
+DAISY_API int daisy_create(daisy_handle_t *out, int device, int64_t user_num, int64_t item_num, int dim,
                  int64_t max_batch, unsigned flags);
-int daisy_destroy(daisy_handle_t h);
+DAISY_API int daisy_destroy(daisy_handle_t h);
 
 /* Synchronise `stream` and report (then clear) the sticky device-side index error.  On DAISY_EINDEX the
  * message names the first offending position.  Mirrors IndexError of nn.Embedding (BPRMFRecommender.py:43-45). */
-int daisy_check(daisy_handle_t h, daisy_stream_t stream);
+DAISY_API int daisy_check(daisy_handle_t h, daisy_stream_t stream);
 
 /* ---- lazy L2 decay ------------------------------------------------------------------------------
  * optim.SGD(weight_decay) shrinks EVERY row by (1 - lr*wd) each step (BPRMFRecommender.py:154,176).
@@ -63,13 +69,13 @@ int daisy_check(daisy_handle_t h, daisy_stream_t stream);
  * are W = c * W_hat; daisy_materialize() multiplies both tables by c and resets c = 1 (one pass over the
  * tables) -- call it before anything outside the library reads the weights (eval by foreign code,
  * torch.save, predict).  daisy_get_scale() returns c. */
-int daisy_get_scale(daisy_handle_t h, double *c);
-int daisy_set_scale(daisy_handle_t h, double c);
-int daisy_materialize(daisy_handle_t h, float *P, float *Q, daisy_stream_t stream);
+DAISY_API int daisy_get_scale(daisy_handle_t h, double *c);
+DAISY_API int daisy_set_scale(daisy_handle_t h, double c);
+DAISY_API int daisy_materialize(daisy_handle_t h, float *P, float *Q, daisy_stream_t stream);
 
 /* BPR.forward (BPRMFRecommender.py:42-50): pred_i[t] = <P[u_t],Q[i_t]>, pred_j[t] = <P[u_t],Q[j_t]>.
  * triples: device int32 [B,3] packed (u,i,j).  Honours the handle's lazy scale. */
-int daisy_bpr_forward(daisy_handle_t h, const float *P, const float *Q, const int32_t *triples, int64_t B,
+DAISY_API int daisy_bpr_forward(daisy_handle_t h, const float *P, const float *Q, const int32_t *triples, int64_t B,
                       float *pred_i, float *pred_j, daisy_stream_t stream);
 
 /* One training step = model.zero_grad(); forward; loss = -(pi-pj).sigmoid().log().sum(); loss.backward();
@@ -77,19 +83,19 @@ int daisy_bpr_forward(daisy_handle_t h, const float *P, const float *Q, const in
  * accumulate deterministically (sort-by-row segmented reduction, no float atomics), SGD + L2.
  * loss_accum (device double, may be NULL): the batch-sum loss is ADDED to it.
  * triples: device int32 [B,3], B <= max_batch. */
-int daisy_bpr_step(daisy_handle_t h, float *P, float *Q, const int32_t *triples, int64_t B, float lr, float wd,
+DAISY_API int daisy_bpr_step(daisy_handle_t h, float *P, float *Q, const int32_t *triples, int64_t B, float lr, float wd,
                    double *loss_accum, daisy_stream_t stream);
 
 /* Same step fed from HOST memory (the reference's `user.cuda(); item_i.cuda(); item_j.cuda()`,
  * BPRMFRecommender.py:163-166): triples_host is int32 [B,3] in host memory (pinned for a truly async
  * copy); the library copies it into its own device buffer on `stream` and runs the step. */
-int daisy_bpr_step_host(daisy_handle_t h, float *P, float *Q, const int32_t *triples_host, int64_t B, float lr,
+DAISY_API int daisy_bpr_step_host(daisy_handle_t h, float *P, float *Q, const int32_t *triples_host, int64_t B, float lr,
                         float wd, double *loss_accum, daisy_stream_t stream);
 
 /* Lazy sparse Adam variant of the step (no Daisy counterpart -- BPR-MF uses SGD only; semantics =
  * torch.optim.SparseAdam: only rows present in the batch change, weights and moments alike).
  * mP,vP [user_num,dim], mQ,vQ [item_num,dim] fp32 moments owned by the caller; step_no is 1-based. */
-int daisy_bpr_adam_step(daisy_handle_t h, float *P, float *Q, float *mP, float *vP, float *mQ, float *vQ,
+DAISY_API int daisy_bpr_adam_step(daisy_handle_t h, float *P, float *Q, float *mP, float *vP, float *mQ, float *vQ,
                         const int32_t *triples, int64_t B, float lr, float beta1, float beta2, float eps,
                         int64_t step_no, double *loss_accum, daisy_stream_t stream);
 
@@ -97,7 +103,7 @@ int daisy_bpr_adam_step(daisy_handle_t h, float *P, float *Q, float *mP, float *
  * for n < N: score[c] = <P[users[n]], Q[cand[n,c]]>, c < C; the K best in (score desc, position asc) order.
  * out_pos [N,K] int32 = candidate positions (the `indices` of torch.topk), out_item [N,K] = cand ids
  * (`torch.take`), out_score [N,K].  C <= 8192, K <= 128, K <= C. */
-int daisy_topk_candidates(daisy_handle_t h, const float *P, const float *Q, const int32_t *users,
+DAISY_API int daisy_topk_candidates(daisy_handle_t h, const float *P, const float *Q, const int32_t *users,
                           const int32_t *cand, int64_t N, int C, int K, int32_t *out_pos, int32_t *out_item,
                           float *out_score, daisy_stream_t stream);
 
@@ -105,7 +111,7 @@ int daisy_topk_candidates(daisy_handle_t h, const float *P, const float *Q, cons
  * for n < N the K best items of score[i] = <P[users[n]], Q[i]>, i < item_num, order (score desc, item asc).
  * Optional exclusion lists in CSR form (excl_ptr [N+1] int64, excl_idx int32: the user's training positives).
  * K <= 128. */
-int daisy_topk_full(daisy_handle_t h, const float *P, const float *Q, const int32_t *users, int64_t N, int K,
+DAISY_API int daisy_topk_full(daisy_handle_t h, const float *P, const float *Q, const int32_t *users, int64_t N, int K,
                     const int64_t *excl_ptr, const int32_t *excl_idx, int32_t *out_item, float *out_score,
                     daisy_stream_t stream);
 
@@ -126,27 +132,34 @@ typedef struct {
     double global_mean; /* SVD: mu if biased else 0;  RSVD2: mu in the bias coupling */
 } daisy_mf_params;
 
-int daisy_mf_fit(daisy_handle_t h, double *pu, double *qi, double *bu, double *bi, const int32_t *users,
+DAISY_API int daisy_mf_fit(daisy_handle_t h, double *pu, double *qi, double *bu, double *bi, const int32_t *users,
                  const int32_t *items, const double *ratings, int64_t n, int n_epochs,
                  const daisy_mf_params *prm, double *sse_out, daisy_stream_t stream);
 
 /* SVD.predict / RSVD.predict (util/matrix_factorization.pyx:157-167, 68-78), batched:
  * est[n] = (with_bias ? mu + bu[u] + bi[i] : 0) + <pu[u], qi[i]>.  Out-of-range codes raise DAISY_EINDEX
  * at daisy_check (ValueError('Invalid user code' / 'Invalid item code') in the reference). */
-int daisy_mf_predict(daisy_handle_t h, const double *pu, const double *qi, const double *bu, const double *bi,
+DAISY_API int daisy_mf_predict(daisy_handle_t h, const double *pu, const double *qi, const double *bu, const double *bi,
                      const int32_t *users, const int32_t *items, int64_t n, int with_bias, double mu,
                      double *est, daisy_stream_t stream);
 
 /* ---- introspection for tests / bench ------------------------------------------------------------- */
 /* Number of kernels launched by this handle since creation (the bench's gpu_launches claim). */
-int daisy_launch_count(daisy_handle_t h, int64_t *n);
+DAISY_API int daisy_launch_count(daisy_handle_t h, int64_t *n);
 /* Device time (ms) of the dominant kernel of the last daisy_bpr_step, measured with CUDA events on the
  * launching stream when timing was enabled with daisy_set_timing(h, 1).  Synchronises. */
-int daisy_set_timing(daisy_handle_t h, int on);
-int daisy_last_step_timing(daisy_handle_t h, float *ms_main_kernel, float *ms_total);
+DAISY_API int daisy_set_timing(daisy_handle_t h, int on);
+DAISY_API int daisy_last_step_timing(daisy_handle_t h, float *ms_main_kernel, float *ms_total);
+/* Timing mode 1 (asynchronous, main fused kernel only): average device time of that kernel over the steps
+ * issued since daisy_set_timing(h, 1), and how many launches were measured.  Synchronises on the events. */
+DAISY_API int daisy_main_kernel_ms(daisy_handle_t h, double *avg_ms, int64_t *count);
+/* Timing mode 2 (synchronises once per step): average device time of each phase of the step, in launch order:
+ * prep, sort_i, refs, sort_u, sort_q, slots, main, seg_u, seg_q, heavy, loss (11 values). */
+#define DAISY_NUM_PHASES 11
+DAISY_API int daisy_phase_ms(daisy_handle_t h, double *avg_ms, int n, int64_t *steps);
 /* Pin rows [0, n_rows) of the item table in L2 through a stream access-policy window
  * (hot items first when the catalogue is popularity-ordered).  n_rows = 0 clears the window. */
-int daisy_set_l2_window(daisy_handle_t h, const float *Q, int64_t n_rows, float hit_ratio,
+DAISY_API int daisy_set_l2_window(daisy_handle_t h, const float *Q, int64_t n_rows, float hit_ratio,
                         daisy_stream_t stream);
 
 #ifdef __cplusplus

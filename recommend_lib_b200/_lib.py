@@ -1,0 +1,188 @@
+"""ctypes binding of libdaisy_b200.so (include/daisy_b200.h).  No fallback: a missing library raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdaisy_b200.so")
+
+OK, EINVAL, ECUDA, EINDEX, EUNSUPPORTED, ENOMEM = 0, -1, -2, -3, -4, -5
+FLAG_EAGER_DECAY = 1
+NUM_PHASES = 11
+PHASES = ("prep", "sort_i", "refs", "sort_u", "sort_q", "slots", "main", "seg_u", "seg_q", "heavy", "loss")
+
+c_i32, c_i64, c_f32, c_f64, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
+
+
+class MFParams(ctypes.Structure):
+    """daisy_mf_params"""
+    _fields_ = [("variant", c_i32), ("biased", c_i32),
+                ("lr_bu", c_f64), ("lr_bi", c_f64), ("lr_pu", c_f64), ("lr_qi", c_f64),
+                ("reg_bu", c_f64), ("reg_bi", c_f64), ("reg_pu", c_f64), ("reg_qi", c_f64),
+                ("reg2", c_f64), ("global_mean", c_f64)]
+
+
+# name -> argtypes; every entry returns int except daisy_last_error.  Kept in one table so that the CPU test
+# can check it against the prototypes of include/daisy_b200.h.
+SIGNATURES = {
+    "daisy_abi_version": [],
+    "daisy_create": [ctypes.POINTER(c_vp), c_i32, c_i64, c_i64, c_i32, c_i64, ctypes.c_uint],
+    "daisy_destroy": [c_vp],
+    "daisy_check": [c_vp, c_vp],
+    "daisy_get_scale": [c_vp, ctypes.POINTER(c_f64)],
+    "daisy_set_scale": [c_vp, c_f64],
+    "daisy_materialize": [c_vp, c_vp, c_vp, c_vp],
+    "daisy_bpr_forward": [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
+    "daisy_bpr_step": [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp],
+    "daisy_bpr_step_host": [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp],
+    "daisy_bpr_adam_step": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32,
+                            c_i64, c_vp, c_vp],
+    "daisy_topk_candidates": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp],
+    "daisy_topk_full": [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "daisy_mf_fit": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, ctypes.POINTER(MFParams),
+                     c_vp, c_vp],
+    "daisy_mf_predict": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_f64, c_vp, c_vp],
+    "daisy_launch_count": [c_vp, ctypes.POINTER(c_i64)],
+    "daisy_set_timing": [c_vp, c_i32],
+    "daisy_last_step_timing": [c_vp, ctypes.POINTER(c_f32), ctypes.POINTER(c_f32)],
+    "daisy_main_kernel_ms": [c_vp, ctypes.POINTER(c_f64), ctypes.POINTER(c_i64)],
+    "daisy_phase_ms": [c_vp, ctypes.POINTER(c_f64), c_i32, ctypes.POINTER(c_i64)],
+    "daisy_set_l2_window": [c_vp, c_vp, c_i64, c_f32, c_vp],
+}
+
+_lib = None
+
+
+class DaisyError(RuntimeError):
+    pass
+
+
+def dlopen():
+    """dlopen libdaisy_b200.so.  It links the shared CUDA runtime (libcudart.so.12): importing torch first makes
+    the dynamic loader bind it to the runtime torch already mapped; otherwise the usual locations are tried."""
+    if not os.path.exists(LIB_PATH):
+        raise DaisyError(
+            f"{LIB_PATH} is missing: build it with `python -m recommend_lib_b200.build` "
+            "(or __graft_entry__.build()).  There is no CPU fallback.")
+    try:
+        import torch  # noqa: F401  (maps libcudart.so.12 from the nvidia-cuda-runtime wheel)
+    except Exception:
+        pass
+    try:
+        return ctypes.CDLL(LIB_PATH)
+    except OSError:
+        import glob
+        import site
+        cands = []
+        for sp in site.getsitepackages():
+            cands += glob.glob(os.path.join(sp, "nvidia", "cuda_runtime", "lib", "libcudart.so.12*"))
+        cands += glob.glob("/usr/local/cuda/lib64/libcudart.so.12*")
+        for c in cands:
+            try:
+                ctypes.CDLL(c, mode=ctypes.RTLD_GLOBAL)
+                return ctypes.CDLL(LIB_PATH)
+            except OSError:
+                continue
+        raise
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built -- there is no CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    L = dlopen()
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(L, name)          # AttributeError if the library does not export a declared symbol
+        fn.argtypes = argtypes
+        fn.restype = c_i32
+    L.daisy_last_error.argtypes = []
+    L.daisy_last_error.restype = ctypes.c_char_p
+    if L.daisy_abi_version() != 1:
+        raise DaisyError("libdaisy_b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def last_error():
+    return load().daisy_last_error().decode("utf-8", "replace")
+
+
+def check(rc):
+    """Map a DAISY_E* return code to the exception the reference surface would raise."""
+    if rc == OK:
+        return
+    msg = last_error()
+    if rc == EINDEX:
+        raise IndexError(msg)
+    if rc in (EINVAL, EUNSUPPORTED):
+        raise ValueError(msg)
+    if rc == ENOMEM:
+        raise MemoryError(msg)
+    raise DaisyError(msg)
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise DaisyError("recommend_lib_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def stream_ptr(torch, device):
+    return c_vp(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Handle:
+    """RAII wrapper of daisy_handle_t bound to (device, user_num, item_num, dim, max_batch)."""
+
+    def __init__(self, device_index, user_num, item_num, dim, max_batch, flags=0):
+        self.L = load()
+        self.ptr = c_vp()
+        check(self.L.daisy_create(ctypes.byref(self.ptr), int(device_index), int(user_num), int(item_num), int(dim),
+                                  int(max_batch), int(flags)))
+        self.device_index = int(device_index)
+        self.user_num, self.item_num, self.dim, self.max_batch = int(user_num), int(item_num), int(dim), int(max_batch)
+
+    def close(self):
+        if getattr(self, "ptr", None) is not None and self.ptr.value:
+            self.L.daisy_destroy(self.ptr)
+            self.ptr = c_vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- small conveniences ------------------------------------------------------------------
+    @property
+    def scale(self):
+        c = c_f64()
+        check(self.L.daisy_get_scale(self.ptr, ctypes.byref(c)))
+        return c.value
+
+    @scale.setter
+    def scale(self, v):
+        check(self.L.daisy_set_scale(self.ptr, float(v)))
+
+    @property
+    def launches(self):
+        n = c_i64()
+        check(self.L.daisy_launch_count(self.ptr, ctypes.byref(n)))
+        return n.value
+
+    def set_timing(self, mode):
+        check(self.L.daisy_set_timing(self.ptr, int(mode)))
+
+    def main_kernel_ms(self):
+        avg, cnt = c_f64(), c_i64()
+        check(self.L.daisy_main_kernel_ms(self.ptr, ctypes.byref(avg), ctypes.byref(cnt)))
+        return avg.value, cnt.value
+
+    def phase_ms(self):
+        arr = (c_f64 * NUM_PHASES)()
+        steps = c_i64()
+        check(self.L.daisy_phase_ms(self.ptr, arr, NUM_PHASES, ctypes.byref(steps)))
+        return dict(zip(PHASES, list(arr))), steps.value

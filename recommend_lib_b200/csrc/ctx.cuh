@@ -1,0 +1,169 @@
+// Shared context, error plumbing and device helpers for libdaisy_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/daisy_b200.h"
+
+#define DAISY_DIRECT 0xFFFFFFFFu  // slot value: "this row has a single contribution -> update it in place"
+#define DAISY_EVPOOL 2048  // main-kernel event pairs kept between two daisy_main_kernel_ms() calls
+
+// Phases of one BPR step, in launch order (daisy_last_step_phases).
+enum {
+    PH_PREP = 0,   // validate ids, emit (pos-item key, triple id)
+    PH_SORT_I,     // radix sort triples by positive item
+    PH_REFS,       // gather triples into sorted order, emit user refs and item refs (negatives + run heads)
+    PH_SORT_U,     // radix sort user refs by row
+    PH_SORT_Q,     // radix sort item refs by row
+    PH_SLOTS,      // singleton / staged classification, slot scatter
+    PH_MAIN,       // fused gather + score + sigmoid coefficient + in-place update / staging   (dominant)
+    PH_SEG_U,      // segmented reduce + update of repeated user rows
+    PH_SEG_Q,      // segmented reduce + update of repeated item rows
+    PH_HEAVY,      // block-per-row reduce of very hot rows
+    PH_LOSS,       // deterministic loss reduction
+    PH_COUNT
+};
+
+struct daisy_ctx {
+    int device;
+    int num_sms;
+    int64_t U, I, maxB;
+    int D;
+    unsigned flags;
+    double scale;  // lazy L2 decay factor c: true tables = c * stored tables
+
+    // --- workspace (device) ---
+    int32_t *triples;       // [2][maxB,3]  double-buffered H2D landing zone of daisy_bpr_step_host
+    cudaStream_t copy_stream;
+    cudaEvent_t ev_copied[2], ev_consumed[2];
+    int h2d_idx;
+    int32_t *st;            // [maxB,3]  triples in positive-item order
+    uint32_t *key_in, *key_out, *val_in, *val_out;      // [2*maxB] item refs (negatives + run heads), unsorted / sorted
+    uint32_t *ukey_in, *ukey_out, *uval_in, *uval_out;  // [maxB]   user refs, unsorted / sorted
+    uint32_t *ikey_in, *ikey_out, *ival_in, *ival_out;  // [maxB]   (positive item, triple id), unsorted / sorted
+    uint32_t *uslot, *jslot, *islot;                    // [maxB]   per sorted triple: DIRECT or staging slot
+    float *stageU;          // [maxB, D]   staged user-row gradient contributions (by sorted user-ref position)
+    float *stageQ;          // [2*maxB, D] staged item-row contributions (by sorted item-ref position)
+    float *loss_part;       // [maxB] per-warp loss partials
+    uint32_t *heavy;        // [0] = count, [1..] = (table, first sorted position) of very hot rows
+    int *err;               // [2]: flag, first bad position
+    int *err_host;          // pinned mirror
+    void *cub_tmp;
+    size_t cub_tmp_bytes;
+    int heavy_cap;
+
+    // tuning (env overridable, see api.cu)
+    int chunk;       // max positive-item run length handled by one warp in the main kernel (0 = auto)
+    int heavy_len;   // segments longer than this go to the block-per-row kernel
+
+    // --- instrumentation ---
+    int64_t launches;
+    int timing;                       // 0 off, 1 main kernel only (asynchronous event pool), 2 every phase (syncs per step)
+    cudaEvent_t ev[PH_COUNT + 1];     // timing == 2
+    double phase_ms_sum[PH_COUNT];
+    int64_t timed_steps;
+    int ev_pending;
+    cudaStream_t ev_stream;
+    cudaEvent_t evpool[2 * DAISY_EVPOOL];  // timing == 1
+    int pool_used;
+    double main_ms_sum;
+    int64_t main_count;
+};
+
+void daisy_set_error(const char *fmt, ...);
+
+#define DAISY_CUDA(call)                                                                     \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            daisy_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return DAISY_ECUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+
+#define DAISY_REQUIRE(cond, code, ...)      \
+    do {                                    \
+        if (!(cond)) {                      \
+            daisy_set_error(__VA_ARGS__);   \
+            return (code);                  \
+        }                                   \
+    } while (0)
+
+#define DAISY_LAUNCH_CHECK(h)                                                                \
+    do {                                                                                     \
+        (h)->launches++;                                                                     \
+        cudaError_t e__ = cudaGetLastError();                                                \
+        if (e__ != cudaSuccess) {                                                            \
+            daisy_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return DAISY_ECUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+
+static inline int daisy_ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// RAII-less device guard: the handle is bound to one device.
+struct DeviceGuard {
+    int prev;
+    bool ok;
+    explicit DeviceGuard(int dev) : prev(-1), ok(true) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// 128-bit row-slice accessors.  Table rows are re-used across triples (hot items) so they take the normal
+// cached path; staging rows are written once and read once much later, so they stream past L1.
+__device__ __forceinline__ float4 ld_row(const float *base, size_t f4_index) {
+    return reinterpret_cast<const float4 *>(base)[f4_index];
+}
+__device__ __forceinline__ void st_row(float *base, size_t f4_index, float4 v) {
+    reinterpret_cast<float4 *>(base)[f4_index] = v;
+}
+__device__ __forceinline__ float4 ld_stream(const float *base, size_t f4_index) {
+    float4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(reinterpret_cast<const float4 *>(base) + f4_index));
+    return r;
+}
+__device__ __forceinline__ void st_stream(float *base, size_t f4_index, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(
+                     reinterpret_cast<float4 *>(base) + f4_index),
+                 "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 f4_sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+// a + s * b with separately rounded multiply and add (no FMA contraction): keeps "row + alpha*grad"
+// the same number whether grad was applied directly or staged and re-read.
+__device__ __forceinline__ float4 f4_axpy(float4 a, float s, float4 b) {
+    return make_float4(__fadd_rn(a.x, __fmul_rn(s, b.x)), __fadd_rn(a.y, __fmul_rn(s, b.y)),
+                       __fadd_rn(a.z, __fmul_rn(s, b.z)), __fadd_rn(a.w, __fmul_rn(s, b.w)));
+}
+__device__ __forceinline__ float f4_dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+#endif

@@ -85,15 +85,32 @@ def zipf_items(g, n, item_num, exponent=1.0, perm_seed=None):
 
     Inverse-CDF on the exact cumulative weights for catalogues up to 2^25 items.
     """
-    w = 1.0 / np.power(np.arange(1, item_num + 1, dtype=np.float64), exponent)
-    cdf = np.cumsum(w)
-    cdf /= cdf[-1]
+    cdf = _zipf_cdf(int(item_num), float(exponent))
     ranks = np.searchsorted(cdf, g.random(n), side="right").astype(np.int64)
     np.minimum(ranks, item_num - 1, out=ranks)
     if perm_seed is None:
         return ranks
-    perm = _rng(perm_seed, 3).permutation(item_num)
-    return perm[ranks]
+    return _item_perm(int(perm_seed), int(item_num))[ranks]
+
+
+_CACHE = {}
+
+
+def _zipf_cdf(item_num, exponent):
+    key = ("cdf", item_num, exponent)
+    if key not in _CACHE:
+        w = 1.0 / np.power(np.arange(1, item_num + 1, dtype=np.float64), exponent)
+        cdf = np.cumsum(w)
+        cdf /= cdf[-1]
+        _CACHE[key] = cdf
+    return _CACHE[key]
+
+
+def _item_perm(seed, item_num):
+    key = ("perm", seed, item_num)
+    if key not in _CACHE:
+        _CACHE[key] = _rng(seed, 3).permutation(item_num)
+    return _CACHE[key]
 
 
 def synthetic_triples(n, user_num, item_num, seed=2019, stream=0, zipf=1.0, permute_items=True):

@@ -1,0 +1,138 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares (no compute calls),
+the ctypes table matches the header, and the host-side sampler / data prep behave like the reference's."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "daisy_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = re.findall(r"DAISY_API\s+[\w\s\*]+?\b(daisy_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S)
+    return {name: [a.strip() for a in args.split(",")] if args.strip() != "void" else [] for name, args in protos}
+
+
+def test_library_exports_every_declared_symbol():
+    from recommend_lib_b200 import _lib, build
+    build.build()
+    L = _lib.dlopen()
+    decl = _header_functions()
+    assert len(decl) >= 20
+    for name in decl:
+        assert hasattr(L, name), f"{name} declared in include/daisy_b200.h but not exported"
+
+
+def test_ctypes_table_matches_header():
+    from recommend_lib_b200 import _lib
+    decl = _header_functions()
+    table = dict(_lib.SIGNATURES)
+    table["daisy_last_error"] = []
+    assert set(table) == set(decl)
+    for name, args in decl.items():
+        assert len(table[name]) == len(args), f"{name}: header has {len(args)} args, ctypes table {len(table[name])}"
+
+
+def test_loader_fails_loudly_without_library(monkeypatch, tmp_path):
+    from recommend_lib_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.DaisyError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "recommend_lib_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "mf_oracle" not in text and "bpr_oracle" not in text, f
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from recommend_lib_b200 import _lib
+    from recommend_lib_b200.bpr import BPR, BPRSGD
+    m = BPR(10, 10, 8)
+    with pytest.raises(_lib.DaisyError):
+        m(torch.tensor([1]), torch.tensor([2]), torch.tensor([3]))
+    with pytest.raises(_lib.DaisyError):
+        BPRSGD(m, 0.1, 0.0).step(torch.tensor([1]), torch.tensor([2]), torch.tensor([3]))
+
+
+# ---------------------------------------------------------------- sampler (util/data_loader.py:680-700)
+def test_sampler_semantics(golden):
+    from recommend_lib_b200.sampler import TripleSampler
+    s = golden("ml100k_split.npz")
+    pairs = s["train_pairs"].astype(np.int64)
+    I = int(s["item_num"])
+    sm = TripleSampler(pairs, I, num_ng=4, seed=2019)
+    t = sm.sample_epoch(0, shuffle=False)
+    assert t.shape == (4 * len(pairs), 3) and t.dtype == np.int32 and len(sm) == t.shape[0]
+    # features_fill order: positive-major, num_ng consecutive negatives
+    assert np.array_equal(t[::4, :2], pairs) and np.array_equal(t[3::4, :2], pairs)
+    # rejection: no sampled (u, j) is a training positive
+    pos = set(map(tuple, pairs.tolist()))
+    assert not any((u, j) in pos for u, _, j in t[:20000].tolist())
+    keys = np.unique(pairs[:, 0] * I + pairs[:, 1])
+    assert not np.isin(t[:, 0].astype(np.int64) * I + t[:, 2], keys).any()
+    assert t[:, 2].min() >= 0 and t[:, 2].max() < I
+    # deterministic per (seed, epoch), different across epochs, shuffle is a permutation of the same multiset
+    assert np.array_equal(t, sm.sample_epoch(0, shuffle=False))
+    assert not np.array_equal(t, sm.sample_epoch(1, shuffle=False))
+    sh = sm.sample_epoch(0, shuffle=True)
+    key = lambda a: np.sort(a[:, 0].astype(np.int64) * I * I + a[:, 1].astype(np.int64) * I + a[:, 2])
+    assert np.array_equal(key(sh), key(t))
+    sizes = [b.shape[0] for b in sm.batches(0, 4096)]
+    assert len(sizes) == 97 and sizes[-1] == t.shape[0] - 96 * 4096          # 97 steps
+
+
+def test_negatives_are_uniform_over_non_positives():
+    from recommend_lib_b200.sampler import TripleSampler
+    pairs = np.array([[0, i] for i in range(0, 50, 2)])          # user 0 likes the even items
+    sm = TripleSampler(pairs, 50, num_ng=400, seed=1)
+    j = sm.sample_epoch(0)[:, 2]
+    assert (j % 2 == 1).all()
+    cnt = np.bincount(j, minlength=50)[1::2]
+    assert cnt.min() > 0.8 * cnt.mean() and cnt.max() < 1.2 * cnt.mean()
+
+
+def test_synthetic_generators():
+    from recommend_lib_b200.sampler import synthetic_triples, synthetic_ratings
+    t = synthetic_triples(200000, 1000, 500, seed=3)
+    assert t.dtype == np.int32 and t[:, 0].max() < 1000 and t[:, 1:].max() < 500 and t.min() >= 0
+    cnt = np.sort(np.bincount(t[:, 1], minlength=500))[::-1]
+    assert cnt[0] > 20 * cnt[100]                                # Zipf(1): rank 1 >> rank 100
+    assert np.array_equal(t, synthetic_triples(200000, 1000, 500, seed=3))
+    u, i, r = synthetic_ratings(10000, 100, 50, seed=3)
+    assert set(np.unique(r)) <= {1.0, 2.0, 3.0, 4.0, 5.0} and u.max() < 100 and i.max() < 50
+
+
+def test_eval_candidates(golden):
+    from recommend_lib_b200 import data
+    s = golden("ml100k_split.npz")
+    tr, te = s["train_pairs"].astype(np.int64), s["test_pairs"].astype(np.int64)
+    allp = np.concatenate([tr, te])
+    I = int(s["item_num"])
+    eu, ec = data.eval_candidates(allp[:, 0], allp[:, 1], te[:, 0], te[:, 1], I, 999, 2019)
+    assert ec.shape == (941, 1000) and len(eu) == 941            # users 405 and 655 dropped
+    seen = {}
+    for u, i in allp.tolist():
+        seen.setdefault(u, set()).add(i)
+    for u, row in list(zip(eu.tolist(), ec.tolist()))[:50]:
+        assert len(set(row)) == 1000 and not (set(row[1:]) & seen[u]) and row[0] in seen[u]
+
+
+def test_split_loo_ties_and_order():
+    from recommend_lib_b200 import data
+    users = np.array([0, 0, 0, 1, 1])
+    ts = np.array([5, 9, 9, 3, 1])
+    tr, te = data.split_loo_by_time(users, np.arange(5), ts)
+    assert list(te) == [1, 3] and list(tr) == [0, 2, 4]          # tie at ts=9: first row wins (rank method='first')
