@@ -206,7 +206,7 @@ def run_single(args):
 
     def device_resident_pass(first, count):
         for s in range(first, first + count):
-            opt.step(devtri[s], loss_out=loss_dev[s:s + 1])
+            opt.step(devtri[s], loss_out=loss_dev[s:s + 1], ready=True)   # uploaded + synchronised before timing
             if mat_every and (s + 1) % mat_every == 0:
                 model.materialize()
 

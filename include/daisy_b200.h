@@ -86,6 +86,14 @@ DAISY_API int daisy_bpr_forward(daisy_handle_t h, const float *P, const float *Q
 DAISY_API int daisy_bpr_step(daisy_handle_t h, float *P, float *Q, const int32_t *triples, int64_t B, float lr, float wd,
                    double *loss_accum, daisy_stream_t stream);
 
+/* The integer bookkeeping of a step (sorting the batch by row) depends on the triples only, so the library runs
+ * it on a private stream where, for step n+1, it overlaps the table kernels of step n.  By default
+ * daisy_bpr_step assumes `triples` may still be being produced by earlier work on `stream` and orders its
+ * bookkeeping after that work (which also orders it after step n: no overlap).  Declare with on = 1 that device
+ * triples passed to daisy_bpr_step are complete at call time (e.g. batches uploaded and synchronised up front)
+ * to get the overlap.  daisy_bpr_step_host always overlaps (host memory is complete at call time). */
+DAISY_API int daisy_set_inputs_ready(daisy_handle_t h, int on);
+
 /* Same step fed from HOST memory (the reference's `user.cuda(); item_i.cuda(); item_j.cuda()`,
  * BPRMFRecommender.py:163-166): triples_host is int32 [B,3] in host memory (pinned for a truly async
  * copy); the library copies it into its own device buffer on `stream` and runs the step. */

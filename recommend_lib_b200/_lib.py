@@ -34,6 +34,7 @@ SIGNATURES = {
     "daisy_set_scale": [c_vp, c_f64],
     "daisy_materialize": [c_vp, c_vp, c_vp, c_vp],
     "daisy_bpr_forward": [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
+    "daisy_set_inputs_ready": [c_vp, c_i32],
     "daisy_bpr_step": [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp],
     "daisy_bpr_step_host": [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp],
     "daisy_bpr_adam_step": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32,
@@ -172,6 +173,9 @@ class Handle:
         n = c_i64()
         check(self.L.daisy_launch_count(self.ptr, ctypes.byref(n)))
         return n.value
+
+    def set_inputs_ready(self, on):
+        check(self.L.daisy_set_inputs_ready(self.ptr, int(bool(on))))
 
     def set_timing(self, mode):
         check(self.L.daisy_set_timing(self.ptr, int(mode)))

@@ -151,9 +151,12 @@ class BPRSGD:
             self._loss = torch.zeros(1, dtype=torch.float64, device=device)
         return self._loss
 
-    def step(self, user, item_i=None, item_j=None, loss_out=None):
+    def step(self, user, item_i=None, item_j=None, loss_out=None, ready=False):
         """One fused step.  ``user`` may also be a packed int32 [B,3] tensor: on the device it is used in place;
-        on the host (pinned for an asynchronous copy) it goes through ``daisy_bpr_step_host``."""
+        on the host (pinned for an asynchronous copy) it goes through ``daisy_bpr_step_host``.
+        ``ready=True`` declares that a packed DEVICE tensor is complete at call time (uploaded and synchronised
+        earlier), which lets the library overlap this step's bookkeeping with the previous step's kernels
+        (``daisy_set_inputs_ready``); host tensors always overlap."""
         m = self.model
         P, Q = m._tables()
         packed = item_i is None
@@ -162,6 +165,10 @@ class BPRSGD:
             raise ValueError("packed triples must be a contiguous int32 [B, 3] tensor")
         B = tri.shape[0]
         h = m.handle(B)
+        ready = bool(ready and packed and tri.is_cuda)
+        if getattr(h, "_ready", False) != ready:
+            h.set_inputs_ready(ready)
+            h._ready = ready
         loss = self._loss_buf(P.device) if loss_out is None else loss_out
         fn = h.L.daisy_bpr_step if tri.is_cuda else h.L.daisy_bpr_step_host
         _lib.check(fn(h.ptr, c_vp(P.data_ptr()), c_vp(Q.data_ptr()), c_vp(tri.data_ptr()), B, self.lr,

@@ -59,9 +59,13 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
     *out = nullptr;
     DAISY_REQUIRE(user_num > 0 && item_num > 0, DAISY_EINVAL, "user_num and item_num must be positive");
     DAISY_REQUIRE(user_num < 0x7fffffffLL && item_num < 0x7ffffffeLL, DAISY_EUNSUPPORTED, "row ids must fit int32");
-    DAISY_REQUIRE(dim > 0 && dim % 4 == 0 && dim <= 512, DAISY_EUNSUPPORTED,
-                  "dim %d unsupported: need dim %% 4 == 0 and dim <= 512", dim);
-    DAISY_REQUIRE(max_batch > 0 && max_batch <= (1LL << 28), DAISY_EUNSUPPORTED, "max_batch must be in [1, 2^28]");
+    DAISY_REQUIRE(dim > 0 && dim <= 4096, DAISY_EUNSUPPORTED, "dim %d unsupported", dim);
+    DAISY_REQUIRE(max_batch >= 0 && max_batch <= (1LL << 28), DAISY_EUNSUPPORTED, "max_batch must be in [0, 2^28]");
+    // BPR kernels move rows as 128-bit vectors: they need dim % 4 == 0 and dim <= 512 (checked per call); a handle
+    // created with max_batch == 0 carries no BPR workspace and serves the funk-SVD / eval entry points only.
+    if (max_batch > 0)
+        DAISY_REQUIRE(dim % 4 == 0 && dim <= 512, DAISY_EUNSUPPORTED,
+                      "dim %d unsupported by the BPR step: need dim %% 4 == 0 and dim <= 512", dim);
     int ndev = 0;
     DAISY_CUDA(cudaGetDeviceCount(&ndev));
     DAISY_REQUIRE(device >= 0 && device < ndev, DAISY_EINVAL, "device %d not present (%d visible)", device, ndev);
@@ -87,24 +91,34 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
     if (h->chunk < 0) h->chunk = 0;
     h->heavy_len = env_int("DAISY_HEAVY_LEN", 128);
     if (h->heavy_len < 8) h->heavy_len = 8;
-    h->heavy_cap = (int)(2 * max_batch / h->heavy_len) + 4;
+    // a row is "very hot" above heavy_len contributions; at most 3B contributions exist per step
+    h->heavy_cap = (int)(3 * max_batch / h->heavy_len) + 4;
+    h->slice_cap = (int)(3 * max_batch / DAISY_SLICE) + h->heavy_cap + 4;
+    h->pipeline = env_int("DAISY_PIPELINE", 1) ? 1 : 0;
+    h->inputs_ready = 0;
 
     const size_t B = (size_t)max_batch;
     int rc = DAISY_OK;
 #define A(ptr, n) if (!rc) rc = dalloc(&h->ptr, (n))
-    A(triples, 2 * 3 * B);
-    A(st, 3 * B);
-    A(key_in, 2 * B); A(key_out, 2 * B); A(val_in, 2 * B); A(val_out, 2 * B);
-    A(ukey_in, B); A(ukey_out, B); A(uval_in, B); A(uval_out, B);
-    A(ikey_in, B); A(ikey_out, B); A(ival_in, B); A(ival_out, B);
-    A(uslot, B); A(jslot, B); A(islot, B);
-    A(stageU, B * dim);
-    A(stageQ, 2 * B * dim);
-    A(loss_part, B);
-    A(heavy, 1 + 2 * (size_t)h->heavy_cap);
     A(err, 2);
+    if (B > 0) {
+        A(triples, 2 * 3 * B);
+        for (int i = 0; i < 2; ++i) {
+            A(book[i].st, 3 * B);
+            A(book[i].ukey_s, B); A(book[i].qkey_s, 2 * B);
+            A(book[i].uslot, B); A(book[i].jslot, B); A(book[i].islot, B);
+        }
+        A(key_in, 2 * B); A(val_in, 2 * B); A(val_out, 2 * B);
+        A(ukey_in, B); A(uval_in, B); A(uval_out, B);
+        A(ikey_in, B); A(ikey_out, B); A(ival_in, B); A(ival_out, B);
+        A(stageU, B * dim);
+        A(stageQ, 2 * B * dim);
+        A(stage2, (size_t)h->slice_cap * dim);
+        A(loss_part, B);
+        A(heavy, 2 + 5 * (size_t)h->heavy_cap);
+    }
 #undef A
-    if (!rc) {
+    if (!rc && B > 0) {
         size_t need = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, need, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
                                         (uint32_t *)nullptr, (int)(2 * B), 0, 32, (cudaStream_t)0);
@@ -116,14 +130,17 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
         rc = DAISY_ENOMEM;
     }
     if (!rc) {
-        cudaMemset(h->islot, 0xFF, B * sizeof(uint32_t));
-        cudaMemset(h->heavy, 0, sizeof(uint32_t));
+        if (B > 0) {
+            for (int i = 0; i < 2; ++i) cudaMemset(h->book[i].islot, 0xFF, B * sizeof(uint32_t));
+            cudaMemset(h->heavy, 0, 2 * sizeof(uint32_t));
+        }
         k_err_reset<<<1, 1>>>(h->err);
         for (int i = 0; i <= PH_COUNT; ++i) cudaEventCreate(&h->ev[i]);
-        cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&h->ev_call, cudaEventDisableTiming);
         for (int i = 0; i < 2; ++i) {
-            cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming);
-            cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&h->book[i].ready, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&h->book[i].freed, cudaEventDisableTiming);
         }
         if (cudaDeviceSynchronize() != cudaSuccess) {
             daisy_set_error("workspace initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -142,17 +159,22 @@ extern "C" int daisy_destroy(daisy_handle_t h) {
     if (!h) return DAISY_OK;
     DeviceGuard g(h->device);
     cudaDeviceSynchronize();
-    void *ptrs[] = {h->triples, h->st, h->key_in, h->key_out, h->val_in, h->val_out, h->ukey_in, h->ukey_out,
-                    h->uval_in, h->uval_out, h->ikey_in, h->ikey_out, h->ival_in, h->ival_out, h->uslot, h->jslot,
-                    h->islot, h->stageU, h->stageQ, h->loss_part, h->heavy, h->err, h->cub_tmp};
+    void *ptrs[] = {h->triples, h->key_in, h->val_in, h->val_out, h->ukey_in, h->uval_in, h->uval_out, h->ikey_in,
+                    h->ikey_out, h->ival_in, h->ival_out, h->stageU, h->stageQ, h->stage2, h->loss_part, h->heavy,
+                    h->err, h->cub_tmp, h->scores, h->sel_hist};
     for (void *p : ptrs)
         if (p) cudaFree(p);
-    if (h->err_host) cudaFreeHost(h->err_host);
-    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (int i = 0; i < 2; ++i) {
-        if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
-        if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
+        void *bp[] = {h->book[i].st, h->book[i].ukey_s, h->book[i].qkey_s, h->book[i].uslot, h->book[i].jslot,
+                      h->book[i].islot};
+        for (void *p : bp)
+            if (p) cudaFree(p);
+        if (h->book[i].ready) cudaEventDestroy(h->book[i].ready);
+        if (h->book[i].freed) cudaEventDestroy(h->book[i].freed);
     }
+    if (h->err_host) cudaFreeHost(h->err_host);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_call) cudaEventDestroy(h->ev_call);
     for (int i = 0; i <= PH_COUNT; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 2 * DAISY_EVPOOL; ++i)
@@ -204,6 +226,12 @@ extern "C" int daisy_materialize(daisy_handle_t h, float *P, float *Q, daisy_str
     return DAISY_OK;
 }
 
+extern "C" int daisy_set_inputs_ready(daisy_handle_t h, int on) {
+    DAISY_REQUIRE(h != nullptr, DAISY_EINVAL, "null handle");
+    h->inputs_ready = on ? 1 : 0;
+    return DAISY_OK;
+}
+
 extern "C" int daisy_launch_count(daisy_handle_t h, int64_t *n) {
     DAISY_REQUIRE(h && n, DAISY_EINVAL, "null argument");
     *n = h->launches;
@@ -214,6 +242,7 @@ extern "C" int daisy_set_timing(daisy_handle_t h, int mode) {
     DAISY_REQUIRE(h != nullptr, DAISY_EINVAL, "null handle");
     DAISY_REQUIRE(mode >= 0 && mode <= 2, DAISY_EINVAL, "timing mode must be 0, 1 or 2");
     DeviceGuard g(h->device);
+    DAISY_CUDA(cudaDeviceSynchronize());  // mode 2 moves the bookkeeping onto the caller's stream: drain first
     if (mode == 1 && !h->evpool[0])
         for (int i = 0; i < 2 * DAISY_EVPOOL; ++i) DAISY_CUDA(cudaEventCreate(&h->evpool[i]));
     h->timing = mode;

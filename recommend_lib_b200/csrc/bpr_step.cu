@@ -20,7 +20,8 @@
 //            write their contribution to the staging slot
 //   seg_u / seg_q   one warp per window of 32 sorted refs: for every multi-contribution row, sum the staged
 //            contributions in sorted order (contiguous, streaming reads) and update the row once
-//   heavy    rows with more contributions than `heavy_len` are reduced by a whole block
+//   heavy    rows with more contributions than `heavy_len` are reduced in two levels: one warp per slice of 64
+//            contributions, then one block per row over the slice partials
 //   loss     fixed-order reduction of the per-warp loss partials into *loss_accum
 //
 // No float atomics anywhere: the result is bit-reproducible run to run.
@@ -367,12 +368,32 @@ __global__ void __launch_bounds__(256) k_seg_reduce(int tbl, const float *__rest
             }
         }
         const size_t q0 = (size_t)(base + b);
-        if (len > heavy_len) {  // very hot row: a whole block reduces it (k_heavy)
+        if (len > heavy_len) {  // very hot row: reduced in two levels by k_heavy_slices / k_heavy_final
+            // exact length by a 32-ary search over the sorted keys: keys[q] == row for q in [q0, q0 + len)
+            long long lo = (long long)q0 + len, hi = n;
+            while (lo < hi) {
+                const long long step = (hi - lo + 31) / 32;
+                const long long probe = lo + lane * step;
+                const bool ok = (probe < hi) && (keys[probe] == row);
+                const unsigned m = __ballot_sync(FULL, ok);
+                const int c = (m == FULL) ? 32 : (__ffs(~m) - 1);
+                if (c == 0) break;
+                const long long nhi = lo + c * step;
+                lo = lo + (c - 1) * step + 1;
+                hi = nhi < hi ? nhi : hi;
+            }
+            const uint32_t full = (uint32_t)(lo - (long long)q0);
             if (lane == 0) {
+                const uint32_t nsl = (full + DAISY_SLICE - 1) / DAISY_SLICE;
                 const uint32_t idx = atomicAdd(&heavy[0], 1u);
+                const uint32_t sl0 = atomicAdd(&heavy[1], nsl);
                 if ((int)idx < heavy_cap) {
-                    heavy[1 + 2 * idx] = (uint32_t)tbl;
-                    heavy[2 + 2 * idx] = (uint32_t)q0;
+                    uint32_t *rec = heavy + 2 + 5 * (size_t)idx;
+                    rec[0] = (uint32_t)tbl;
+                    rec[1] = row;
+                    rec[2] = (uint32_t)q0;
+                    rec[3] = full;
+                    rec[4] = sl0;
                 }
             }
             continue;
@@ -390,43 +411,65 @@ __global__ void __launch_bounds__(256) k_seg_reduce(int tbl, const float *__rest
     }
 }
 
+// Level 1: every slice of DAISY_SLICE consecutive staged contributions of a hot row is summed by one warp into
+// stage2[first_slice + j].  SPLIT blocks share one hot row so that even the hottest row is spread over
+// SPLIT * 8 warps.
+template <int V>
+__global__ void __launch_bounds__(256) k_heavy_slices(const float *__restrict__ stageU, const float *__restrict__ stageQ,
+                                                       float *__restrict__ stage2, int D4,
+                                                       const uint32_t *__restrict__ heavy, int heavy_cap, int split) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int count = min((int)heavy[0], heavy_cap);
+    bool act[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
+    for (int w = blockIdx.x; w < count * split; w += gridDim.x) {
+        const uint32_t *rec = heavy + 2 + 5 * (size_t)(w / split);
+        const int part = w % split;
+        const float *stage = rec[0] ? stageQ : stageU;
+        const size_t q0 = rec[2];
+        const int len = (int)rec[3];
+        const size_t sl0 = rec[4];
+        const int nsl = (len + DAISY_SLICE - 1) / DAISY_SLICE;
+        for (int j = part + split * wid; j < nsl; j += split * 8) {
+            const int c0 = j * DAISY_SLICE;
+            const int cn = min(DAISY_SLICE, len - c0);
+            float4 acc[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] = f4_zero();
+            sum_staged<V>(stage, q0 + c0, cn, D4, lane, act, acc);
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if (act[v]) st_stream(stage2, (sl0 + j) * D4 + lane + 32 * v, acc[v]);
+        }
+    }
+}
+
+// Level 2: one block per hot row sums the row's slice partials (fixed split over 8 warps, fixed combine order)
+// and applies the update.
 template <int V, class Opt>
-__global__ void __launch_bounds__(256) k_heavy(const float *__restrict__ P, const float *__restrict__ Q,
-                                                const uint32_t *__restrict__ ukeys, int nu,
-                                                const uint32_t *__restrict__ qkeys, int nq,
-                                                const float *__restrict__ stageU, const float *__restrict__ stageQ,
-                                                int D4, Opt opt, const uint32_t *__restrict__ heavy, int heavy_cap) {
+__global__ void __launch_bounds__(256) k_heavy_final(const float *__restrict__ P, const float *__restrict__ Q,
+                                                      const float *__restrict__ stage2, int D4, Opt opt,
+                                                      const uint32_t *__restrict__ heavy, int heavy_cap) {
     __shared__ float4 part[8][32 * V];
-    __shared__ int s_len;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int count = min((int)heavy[0], heavy_cap);
     bool act[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
     for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
-        const int tbl = (int)heavy[1 + 2 * idx];
-        const size_t q0 = heavy[2 + 2 * idx];
-        const uint32_t *keys = tbl ? qkeys : ukeys;
-        const int n = tbl ? nq : nu;
-        const float *stage = tbl ? stageQ : stageU;
+        const uint32_t *rec = heavy + 2 + 5 * (size_t)idx;
+        const int tbl = (int)rec[0];
+        const uint32_t row = rec[1];
+        const int nsl = ((int)rec[3] + DAISY_SLICE - 1) / DAISY_SLICE;
+        const size_t sl0 = rec[4];
         const float *table = tbl ? Q : P;
-        const uint32_t row = keys[q0];
-        if (threadIdx.x == 0) {  // keys are sorted ascending: first position after q0 whose key differs
-            size_t lo = q0 + 1, hi = (size_t)n;
-            while (lo < hi) {
-                const size_t mid = (lo + hi) >> 1;
-                if (keys[mid] == row) lo = mid + 1; else hi = mid;
-            }
-            s_len = (int)(lo - q0);
-        }
-        __syncthreads();
-        const int len = s_len;
-        const int per = (len + 7) / 8;
-        const int c0 = min(len, wid * per), c1 = min(len, c0 + per);
+        const int per = (nsl + 7) / 8;
+        const int c0 = min(nsl, wid * per), c1 = min(nsl, c0 + per);
         float4 acc[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) acc[v] = f4_zero();
-        sum_staged<V>(stage, q0 + c0, c1 - c0, D4, lane, act, acc);
+        sum_staged<V>(stage2, sl0 + c0, c1 - c0, D4, lane, act, acc);
 #pragma unroll
         for (int v = 0; v < V; ++v) part[wid][lane + 32 * v] = acc[v];
         __syncthreads();
@@ -485,12 +528,20 @@ static inline void phase_mark(daisy_ctx *h, int ph, cudaStream_t s) {
 
 template <int V, class Opt>
 static int run_step_v(daisy_ctx *h, const float *P, const float *Q, const int32_t *triples, int64_t B64, const Opt &opt,
-                      float c2, double *loss_accum, cudaStream_t s) {
+                      float c2, double *loss_accum, cudaStream_t s, const int32_t *host_src, bool inputs_ready) {
     const int B = (int)B64;
     const int D4 = h->D / 4;
     const int C = auto_chunk(h, B);
     const uint32_t U = (uint32_t)h->U, I = (uint32_t)h->I;
     const int T = 256;
+    // The integer bookkeeping of a step (prep .. slots) depends on the triples only, never on the tables.  It
+    // runs on the handle's side stream into one of two bookkeeping sets, so that for step n+1 it overlaps the
+    // bandwidth-bound kernels of step n on the caller's stream.  Per-phase timing (mode 2) serialises everything
+    // on the caller's stream so that phase times do not overlap.
+    const bool piped = h->pipeline && h->timing != 2;
+    cudaStream_t bs = piped ? h->side_stream : s;
+    BookSet &k = h->book[h->book_idx];
+    h->book_idx ^= 1;
     if (h->timing == 2) {
         if (h->ev_pending) {  // fold the previous step's phase times in
             cudaEventSynchronize(h->ev[PH_COUNT]);
@@ -504,41 +555,55 @@ static int run_step_v(daisy_ctx *h, const float *P, const float *Q, const int32_
         }
         cudaEventRecord(h->ev[0], s);
     }
+    if (piped) {
+        if (!inputs_ready) {  // the triples may have been produced by earlier work on the caller's stream
+            DAISY_CUDA(cudaEventRecord(h->ev_call, s));
+            DAISY_CUDA(cudaStreamWaitEvent(bs, h->ev_call, 0));
+        }
+        DAISY_CUDA(cudaStreamWaitEvent(bs, k.freed, 0));  // the step that last used this set has finished
+    }
+    if (host_src) {  // daisy_bpr_step_host: the H2D copy is the first node of the bookkeeping chain
+        DAISY_CUDA(cudaMemcpyAsync((void *)triples, host_src, (size_t)B * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, bs));
+    }
     // prep
-    k_prep<<<daisy_ceil_div(B, T), T, 0, s>>>(triples, B, U, I, h->ikey_in, h->ival_in, h->err);
+    k_prep<<<daisy_ceil_div(B, T), T, 0, bs>>>(triples, B, U, I, h->ikey_in, h->ival_in, h->err);
     DAISY_LAUNCH_CHECK(h);
     phase_mark(h, PH_PREP, s);
     // sort by positive item
     size_t tmp = h->cub_tmp_bytes;
     DAISY_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->ikey_in, h->ikey_out, h->ival_in, h->ival_out, B, 0,
-                                               bits_for(I - 1), s));
+                                               bits_for(I - 1), bs));
     h->launches += 4;
     phase_mark(h, PH_SORT_I, s);
     // refs
-    k_refs<<<daisy_ceil_div(B, T), T, 0, s>>>(triples, h->ival_out, h->ikey_out, B, U, I, C, h->st, h->ukey_in,
-                                              h->uval_in, h->key_in, h->val_in);
+    k_refs<<<daisy_ceil_div(B, T), T, 0, bs>>>(triples, h->ival_out, h->ikey_out, B, U, I, C, k.st, h->ukey_in,
+                                               h->uval_in, h->key_in, h->val_in);
     DAISY_LAUNCH_CHECK(h);
     phase_mark(h, PH_REFS, s);
     tmp = h->cub_tmp_bytes;
-    DAISY_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->ukey_in, h->ukey_out, h->uval_in, h->uval_out, B, 0,
-                                               bits_for(U - 1), s));
+    DAISY_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->ukey_in, k.ukey_s, h->uval_in, h->uval_out, B, 0,
+                                               bits_for(U - 1), bs));
     h->launches += 4;
     phase_mark(h, PH_SORT_U, s);
     tmp = h->cub_tmp_bytes;
-    DAISY_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->key_in, h->key_out, h->val_in, h->val_out, 2 * B, 0,
-                                               bits_for(I), s));
+    DAISY_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->key_in, k.qkey_s, h->val_in, h->val_out, 2 * B, 0,
+                                               bits_for(I), bs));
     h->launches += 4;
     phase_mark(h, PH_SORT_Q, s);
     // slots
-    k_slots_user<<<daisy_ceil_div(B, T), T, 0, s>>>(h->ukey_out, h->uval_out, B, h->uslot);
+    k_slots_user<<<daisy_ceil_div(B, T), T, 0, bs>>>(k.ukey_s, h->uval_out, B, k.uslot);
     DAISY_LAUNCH_CHECK(h);
-    k_slots_item<<<daisy_ceil_div(2 * (int64_t)B, T), T, 0, s>>>(h->key_out, h->val_out, 2 * B, B, I, h->jslot, h->islot);
+    k_slots_item<<<daisy_ceil_div(2 * (int64_t)B, T), T, 0, bs>>>(k.qkey_s, h->val_out, 2 * B, B, I, k.jslot, k.islot);
     DAISY_LAUNCH_CHECK(h);
-    DAISY_CUDA(cudaMemsetAsync(h->heavy, 0, sizeof(uint32_t), s));
     phase_mark(h, PH_SLOTS, s);
+    if (piped) {
+        DAISY_CUDA(cudaEventRecord(k.ready, bs));
+        DAISY_CUDA(cudaStreamWaitEvent(s, k.ready, 0));
+    }
     // main
+    DAISY_CUDA(cudaMemsetAsync(h->heavy, 0, 2 * sizeof(uint32_t), s));
     MainArgs a;
-    a.P = P; a.Q = Q; a.st = h->st; a.uslot = h->uslot; a.jslot = h->jslot; a.islot = h->islot;
+    a.P = P; a.Q = Q; a.st = k.st; a.uslot = k.uslot; a.jslot = k.jslot; a.islot = k.islot;
     a.stageU = h->stageU; a.stageQ = h->stageQ; a.loss_part = h->loss_part;
     a.B = B; a.D4 = D4; a.C = C; a.c2 = c2;
     const int warps = daisy_ceil_div(B, C);
@@ -553,15 +618,17 @@ static int run_step_v(daisy_ctx *h, const float *P, const float *Q, const int32_
     phase_mark(h, PH_MAIN, s);
     // segmented reduces
     k_seg_reduce<V, Opt><<<daisy_ceil_div(daisy_ceil_div(B, 32), 8), 256, 0, s>>>(
-        0, P, h->ukey_out, B, 0xFFFFFFFFu, h->stageU, D4, opt, h->heavy_len, h->heavy, h->heavy_cap);
+        0, P, k.ukey_s, B, 0xFFFFFFFFu, h->stageU, D4, opt, h->heavy_len, h->heavy, h->heavy_cap);
     DAISY_LAUNCH_CHECK(h);
     phase_mark(h, PH_SEG_U, s);
     k_seg_reduce<V, Opt><<<daisy_ceil_div(daisy_ceil_div(2 * (int64_t)B, 32), 8), 256, 0, s>>>(
-        1, Q, h->key_out, 2 * B, I, h->stageQ, D4, opt, h->heavy_len, h->heavy, h->heavy_cap);
+        1, Q, k.qkey_s, 2 * B, I, h->stageQ, D4, opt, h->heavy_len, h->heavy, h->heavy_cap);
     DAISY_LAUNCH_CHECK(h);
     phase_mark(h, PH_SEG_Q, s);
-    k_heavy<V, Opt><<<h->num_sms * 2, 256, 0, s>>>(P, Q, h->ukey_out, B, h->key_out, 2 * B, h->stageU, h->stageQ, D4, opt,
-                                                    h->heavy, h->heavy_cap);
+    const int split = 8;
+    k_heavy_slices<V><<<h->num_sms * 4, 256, 0, s>>>(h->stageU, h->stageQ, h->stage2, D4, h->heavy, h->heavy_cap, split);
+    DAISY_LAUNCH_CHECK(h);
+    k_heavy_final<V, Opt><<<h->num_sms, 256, 0, s>>>(P, Q, h->stage2, D4, opt, h->heavy, h->heavy_cap);
     DAISY_LAUNCH_CHECK(h);
     phase_mark(h, PH_HEAVY, s);
     if (loss_accum) {
@@ -569,6 +636,7 @@ static int run_step_v(daisy_ctx *h, const float *P, const float *Q, const int32_
         DAISY_LAUNCH_CHECK(h);
     }
     phase_mark(h, PH_LOSS, s);
+    if (piped) DAISY_CUDA(cudaEventRecord(k.freed, s));
     if (h->timing == 2) {
         h->ev_pending = 1;
         h->ev_stream = s;
@@ -578,32 +646,28 @@ static int run_step_v(daisy_ctx *h, const float *P, const float *Q, const int32_
 
 template <class Opt>
 static int run_step(daisy_ctx *h, const float *P, const float *Q, const int32_t *triples, int64_t B, const Opt &opt,
-                    float c2, double *loss_accum, cudaStream_t s) {
+                    float c2, double *loss_accum, cudaStream_t s, const int32_t *host_src, bool inputs_ready) {
     const int D4 = h->D / 4;
-    if (D4 <= 32) return run_step_v<1, Opt>(h, P, Q, triples, B, opt, c2, loss_accum, s);
-    if (D4 <= 64) return run_step_v<2, Opt>(h, P, Q, triples, B, opt, c2, loss_accum, s);
-    if (D4 <= 96) return run_step_v<3, Opt>(h, P, Q, triples, B, opt, c2, loss_accum, s);
-    return run_step_v<4, Opt>(h, P, Q, triples, B, opt, c2, loss_accum, s);
+    if (D4 <= 32) return run_step_v<1, Opt>(h, P, Q, triples, B, opt, c2, loss_accum, s, host_src, inputs_ready);
+    if (D4 <= 64) return run_step_v<2, Opt>(h, P, Q, triples, B, opt, c2, loss_accum, s, host_src, inputs_ready);
+    if (D4 <= 96) return run_step_v<3, Opt>(h, P, Q, triples, B, opt, c2, loss_accum, s, host_src, inputs_ready);
+    return run_step_v<4, Opt>(h, P, Q, triples, B, opt, c2, loss_accum, s, host_src, inputs_ready);
 }
 
 static int check_step_args(daisy_ctx *h, const void *P, const void *Q, const void *triples, int64_t B) {
     DAISY_REQUIRE(h != nullptr, DAISY_EINVAL, "null handle");
     DAISY_REQUIRE(P && Q && (triples || B == 0), DAISY_EINVAL, "null table or triples pointer");
+    DAISY_REQUIRE(h->maxB > 0 && h->D % 4 == 0 && h->D <= 512, DAISY_EUNSUPPORTED,
+                  "BPR step needs a handle created with max_batch > 0 and dim %% 4 == 0, dim <= 512 (dim is %d)", h->D);
     DAISY_REQUIRE(B >= 0 && B <= h->maxB, DAISY_EINVAL, "batch of %lld triples exceeds max_batch %lld", (long long)B,
                   (long long)h->maxB);
     DAISY_REQUIRE(((uintptr_t)P % 16 == 0) && ((uintptr_t)Q % 16 == 0), DAISY_EINVAL, "tables must be 16-byte aligned");
     return DAISY_OK;
 }
 
-}  // namespace
-
-// ------------------------------------------------------------------------------------------------
-// C ABI
-// ------------------------------------------------------------------------------------------------
-extern "C" int daisy_bpr_step(daisy_handle_t h, float *P, float *Q, const int32_t *triples, int64_t B, float lr,
-                              float wd, double *loss_accum, daisy_stream_t stream) {
-    int rc = check_step_args(h, P, Q, triples, B);
-    if (rc) return rc;
+// shared body of daisy_bpr_step / daisy_bpr_step_host
+static int sgd_step(daisy_ctx *h, float *P, float *Q, const int32_t *triples_dev, const int32_t *host_src, int64_t B,
+                    float lr, float wd, double *loss_accum, daisy_stream_t stream) {
     const double shrink = 1.0 - (double)lr * (double)wd;
     DAISY_REQUIRE(shrink > 0.0, DAISY_EINVAL, "lr*wd = %g >= 1: the L2 shrink factor is not positive", (double)lr * wd);
     if (B == 0) {  // an empty batch still decays every row (optim.SGD.step with zero gradients)
@@ -617,35 +681,34 @@ extern "C" int daisy_bpr_step(daisy_handle_t h, float *P, float *Q, const int32_
     opt.Q = Q;
     opt.alpha = (float)((double)lr / shrink);
     const float c2 = (float)(h->scale * h->scale);
-    rc = run_step<SgdOpt>(h, P, Q, triples, B, opt, c2, loss_accum, (cudaStream_t)stream);
+    int rc = run_step<SgdOpt>(h, P, Q, triples_dev, B, opt, c2, loss_accum, (cudaStream_t)stream, host_src,
+                              host_src != nullptr || h->inputs_ready);
     if (rc) return rc;
     h->scale *= shrink;
     if ((h->flags & DAISY_FLAG_EAGER_DECAY) || h->scale < 1e-4) return daisy_materialize(h, P, Q, stream);
     return DAISY_OK;
 }
 
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int daisy_bpr_step(daisy_handle_t h, float *P, float *Q, const int32_t *triples, int64_t B, float lr,
+                              float wd, double *loss_accum, daisy_stream_t stream) {
+    int rc = check_step_args(h, P, Q, triples, B);
+    if (rc) return rc;
+    return sgd_step(h, P, Q, triples, nullptr, B, lr, wd, loss_accum, stream);
+}
+
 extern "C" int daisy_bpr_step_host(daisy_handle_t h, float *P, float *Q, const int32_t *triples_host, int64_t B,
                                    float lr, float wd, double *loss_accum, daisy_stream_t stream) {
     int rc = check_step_args(h, P, Q, triples_host, B);
     if (rc) return rc;
-    if (B == 0) return daisy_bpr_step(h, P, Q, h->triples, 0, lr, wd, loss_accum, stream);
-    DeviceGuard g(h->device);
-    DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
-    // Double-buffered landing zone on a private copy stream: the H2D copy of batch n+1 overlaps the kernels of
-    // batch n (the caller's stream only waits for "its" copy; the copy only waits for the step that last read
-    // the same buffer).
-    cudaStream_t s = (cudaStream_t)stream;
-    const int b = h->h2d_idx;
-    h->h2d_idx ^= 1;
-    int32_t *dst = h->triples + (size_t)b * 3 * (size_t)h->maxB;
-    DAISY_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[b], 0));
-    DAISY_CUDA(cudaMemcpyAsync(dst, triples_host, (size_t)B * 3 * sizeof(int32_t), cudaMemcpyHostToDevice,
-                               h->copy_stream));
-    DAISY_CUDA(cudaEventRecord(h->ev_copied[b], h->copy_stream));
-    DAISY_CUDA(cudaStreamWaitEvent(s, h->ev_copied[b], 0));
-    rc = daisy_bpr_step(h, P, Q, dst, B, lr, wd, loss_accum, stream);
-    DAISY_CUDA(cudaEventRecord(h->ev_consumed[b], s));
-    return rc;
+    // landing buffer of the bookkeeping set this step will use; the H2D copy is issued on the side stream as the
+    // first node of the step's bookkeeping chain, so it overlaps the previous step's kernels
+    int32_t *dst = h->triples + (size_t)h->book_idx * 3 * (size_t)h->maxB;
+    return sgd_step(h, P, Q, dst, triples_host, B, lr, wd, loss_accum, stream);
 }
 
 extern "C" int daisy_bpr_adam_step(daisy_handle_t h, float *P, float *Q, float *mP, float *vP, float *mQ, float *vQ,
@@ -668,5 +731,6 @@ extern "C" int daisy_bpr_adam_step(daisy_handle_t h, float *P, float *Q, float *
     opt.step_size = (float)((double)lr / bc1);
     opt.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
     opt.eps = eps;
-    return run_step<AdamOpt>(h, P, Q, triples, B, opt, 1.0f, loss_accum, (cudaStream_t)stream);
+    return run_step<AdamOpt>(h, P, Q, triples, B, opt, 1.0f, loss_accum, (cudaStream_t)stream, nullptr,
+                             h->inputs_ready != 0);
 }

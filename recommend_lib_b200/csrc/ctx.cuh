@@ -9,6 +9,7 @@
 #include "../../include/daisy_b200.h"
 
 #define DAISY_DIRECT 0xFFFFFFFFu  // slot value: "this row has a single contribution -> update it in place"
+#define DAISY_SLICE 64     // contributions per level-1 slice of a very hot row
 #define DAISY_EVPOOL 2048  // main-kernel event pairs kept between two daisy_main_kernel_ms() calls
 
 // Phases of one BPR step, in launch order (daisy_last_step_phases).
@@ -27,6 +28,13 @@ enum {
     PH_COUNT
 };
 
+struct BookSet {
+    int32_t *st;                    // [maxB,3]  triples in positive-item order
+    uint32_t *ukey_s, *qkey_s;      // [maxB], [2*maxB]  sorted user / item ref keys (rows)
+    uint32_t *uslot, *jslot, *islot;  // [maxB]  per sorted triple: DAISY_DIRECT or staging slot
+    cudaEvent_t ready, freed;
+};
+
 struct daisy_ctx {
     int device;
     int num_sms;
@@ -36,24 +44,34 @@ struct daisy_ctx {
     double scale;  // lazy L2 decay factor c: true tables = c * stored tables
 
     // --- workspace (device) ---
-    int32_t *triples;       // [2][maxB,3]  double-buffered H2D landing zone of daisy_bpr_step_host
-    cudaStream_t copy_stream;
-    cudaEvent_t ev_copied[2], ev_consumed[2];
-    int h2d_idx;
-    int32_t *st;            // [maxB,3]  triples in positive-item order
-    uint32_t *key_in, *key_out, *val_in, *val_out;      // [2*maxB] item refs (negatives + run heads), unsorted / sorted
-    uint32_t *ukey_in, *ukey_out, *uval_in, *uval_out;  // [maxB]   user refs, unsorted / sorted
+    int32_t *triples;       // [2][maxB,3]  H2D landing zones of daisy_bpr_step_host (one per bookkeeping set)
+    // Bookkeeping products the table-touching kernels read; double-buffered so that the bookkeeping of step n+1
+    // (side stream) overlaps the kernels of step n (caller's stream).
+    BookSet book[2];
+    int book_idx;
+    cudaStream_t side_stream;
+    cudaEvent_t ev_call;
+    int pipeline;           // 1: bookkeeping on the side stream (default), 0: everything on the caller's stream
+    int inputs_ready;       // 1: device triples passed to daisy_bpr_step are complete at call time (no stream dependency)
+    // bookkeeping scratch, used on the bookkeeping stream only
+    uint32_t *key_in, *val_in, *val_out;    // [2*maxB] item refs (negatives + run heads): unsorted keys/values, sorted values
+    uint32_t *ukey_in, *uval_in, *uval_out; // [maxB]   user refs
     uint32_t *ikey_in, *ikey_out, *ival_in, *ival_out;  // [maxB]   (positive item, triple id), unsorted / sorted
-    uint32_t *uslot, *jslot, *islot;                    // [maxB]   per sorted triple: DIRECT or staging slot
-    float *stageU;          // [maxB, D]   staged user-row gradient contributions (by sorted user-ref position)
-    float *stageQ;          // [2*maxB, D] staged item-row contributions (by sorted item-ref position)
-    float *loss_part;       // [maxB] per-warp loss partials
-    uint32_t *heavy;        // [0] = count, [1..] = (table, first sorted position) of very hot rows
-    int *err;               // [2]: flag, first bad position
-    int *err_host;          // pinned mirror
     void *cub_tmp;
     size_t cub_tmp_bytes;
-    int heavy_cap;
+    // staging, used on the caller's stream only
+    float *stageU;          // [maxB, D]   staged user-row gradient contributions (by sorted user-ref position)
+    float *stageQ;          // [2*maxB, D] staged item-row contributions (by sorted item-ref position)
+    float *stage2;          // [slice_cap, D] level-1 partial sums of very hot rows
+    float *loss_part;       // [maxB] per-warp loss partials
+    uint32_t *heavy;        // [0] = #hot rows, [1] = #slices, then 5 words per hot row: table, row, first pos, len, first slice
+    int heavy_cap, slice_cap;
+    int *err;               // [2]: flag, first bad position
+    int *err_host;          // pinned mirror
+    // full-catalogue top-K workspace (grown on demand by daisy_topk_full)
+    float *scores;          // [tile_users, item_num] score tile
+    size_t scores_cap;      // floats
+    unsigned *sel_hist;     // unused placeholder for a fused histogram (kept null)
 
     // tuning (env overridable, see api.cu)
     int chunk;       // max positive-item run length handled by one warp in the main kernel (0 = auto)

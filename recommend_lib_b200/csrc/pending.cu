@@ -7,15 +7,3 @@ extern "C" int daisy_topk_full(daisy_handle_t, const float *, const float *, con
     daisy_set_error("daisy_topk_full: kernel not built in this revision");
     return DAISY_EUNSUPPORTED;
 }
-
-extern "C" int daisy_mf_fit(daisy_handle_t, double *, double *, double *, double *, const int32_t *, const int32_t *,
-                            const double *, int64_t, int, const daisy_mf_params *, double *, daisy_stream_t) {
-    daisy_set_error("daisy_mf_fit: kernel not built in this revision");
-    return DAISY_EUNSUPPORTED;
-}
-
-extern "C" int daisy_mf_predict(daisy_handle_t, const double *, const double *, const double *, const double *,
-                                const int32_t *, const int32_t *, int64_t, int, double, double *, daisy_stream_t) {
-    daisy_set_error("daisy_mf_predict: kernel not built in this revision");
-    return DAISY_EUNSUPPORTED;
-}
