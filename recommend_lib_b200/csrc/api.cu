@@ -136,7 +136,11 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
         }
         k_err_reset<<<1, 1>>>(h->err);
         for (int i = 0; i <= PH_COUNT; ++i) cudaEventCreate(&h->ev[i]);
-        cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
+        // highest priority: the short bookkeeping kernels of step n+1 must get SM slots while the long
+        // bandwidth-bound kernels of step n are still dispatching blocks
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, prio_hi);
         cudaEventCreateWithFlags(&h->ev_call, cudaEventDisableTiming);
         for (int i = 0; i < 2; ++i) {
             cudaEventCreateWithFlags(&h->book[i].ready, cudaEventDisableTiming);

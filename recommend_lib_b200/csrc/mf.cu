@@ -79,6 +79,12 @@ __global__ void __launch_bounds__(128) k_mf_dataflow(MfArgs a) {
         }
         bail = __shfl_sync(FULL, bail, 0);
         if (bail) break;
+        // Every lane acquires the two versions itself (satisfied at once: lane 0 has just seen them).  A shuffle is
+        // not a memory barrier -- without this the compiler may hoist the bias / row loads above the wait.
+        if (ld_acquire_u32(&a.ver_u[u]) != want_u || ld_acquire_u32(&a.ver_i[i]) != want_i) {
+            atomicExch(a.abort_flag, 2);  // cannot happen: versions only advance through this warp
+        }
+        __syncwarp();
         double *p = a.pu + (size_t)u * D;
         double *q = a.qi + (size_t)i * D;
         // rows live in L2 (ld.cg): other SMs wrote them
