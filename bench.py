@@ -220,9 +220,11 @@ def run_single(args):
     clocks.start()
     torch.cuda.synchronize()
     ev0.record()
+    t_host0 = time.perf_counter()
     device_resident_pass(W, K)
     model.materialize()                                    # the lazy L2 decay is paid inside the timed region
     ev1.record()
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / K
     torch.cuda.synchronize()
     clocks.stop()
     ms_total = ev0.elapsed_time(ev1)
@@ -257,6 +259,12 @@ def run_single(args):
     assert np.isfinite(losses).all() and (losses > 0).all(), "e2e losses not finite"
 
     # ---- optional per-phase breakdown (not part of the timed numbers) ----
+    trace = None
+    if args.trace:
+        torch.cuda.synchronize()
+        h.trace_start()
+        device_resident_pass(0, min(nb, 12))
+        trace = [[round(x, 4) for x in row] for row in h.trace_dump()]
     phases = None
     if args.phases:
         h.set_timing(2)
@@ -299,8 +307,11 @@ def run_single(args):
                          "whole_step_frac": (abytes / (ms_total / K * 1e-3) / 1e9) / peak},
             "cpu_baseline": cpu,
             "final_loss_per_triple": float(losses[-1] / B)}
+    line["host_enqueue_ms_per_step"] = round(host_enqueue_ms, 4)
     if phases:
         line["phase_ms"] = {k: round(v, 4) for k, v in phases.items()}
+    if trace:
+        line["trace_ms(book_begin,book_end,kernels_begin,kernels_end)"] = trace
     print(json.dumps(line), flush=True)
 
 
@@ -314,6 +325,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="debug only: override the batch size")
     ap.add_argument("--materialize-every", type=int, default=50)
     ap.add_argument("--phases", action="store_true", help="also print the per-phase breakdown of the step")
+    ap.add_argument("--trace", action="store_true", help="also print a timeline of bookkeeping vs table kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     args = ap.parse_args()

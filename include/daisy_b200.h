@@ -165,6 +165,10 @@ DAISY_API int daisy_main_kernel_ms(daisy_handle_t h, double *avg_ms, int64_t *co
  * prep, sort_i, refs, sort_u, sort_q, slots, main, seg_u, seg_q, heavy, loss (11 values). */
 #define DAISY_NUM_PHASES 11
 DAISY_API int daisy_phase_ms(daisy_handle_t h, double *avg_ms, int n, int64_t *steps);
+/* Timeline of the first 48 steps after daisy_trace(h, 1, NULL, 0, NULL): per step 4 offsets in ms from the first
+ * event -- bookkeeping begin, bookkeeping end (bookkeeping stream), table kernels begin, end (caller's stream).
+ * A call with ms != NULL dumps what was recorded (synchronises) before applying `on`. */
+DAISY_API int daisy_trace(daisy_handle_t h, int on, double *ms, int cap, int *n_steps);
 /* Pin rows [0, n_rows) of the item table in L2 through a stream access-policy window
  * (hot items first when the catalogue is popularity-ordered).  n_rows = 0 clears the window. */
 DAISY_API int daisy_set_l2_window(daisy_handle_t h, const float *Q, int64_t n_rows, float hit_ratio,

@@ -50,6 +50,7 @@ SIGNATURES = {
     "daisy_main_kernel_ms": [c_vp, ctypes.POINTER(c_f64), ctypes.POINTER(c_i64)],
     "daisy_phase_ms": [c_vp, ctypes.POINTER(c_f64), c_i32, ctypes.POINTER(c_i64)],
     "daisy_set_l2_window": [c_vp, c_vp, c_i64, c_f32, c_vp],
+    "daisy_trace": [c_vp, c_i32, ctypes.POINTER(c_f64), c_i32, ctypes.POINTER(c_i32)],
 }
 
 _lib = None
@@ -176,6 +177,16 @@ class Handle:
 
     def set_inputs_ready(self, on):
         check(self.L.daisy_set_inputs_ready(self.ptr, int(bool(on))))
+
+    def trace_start(self):
+        check(self.L.daisy_trace(self.ptr, 1, None, 0, None))
+
+    def trace_dump(self):
+        """[(book_begin, book_end, kernels_begin, kernels_end)] in ms for the traced steps; stops tracing."""
+        arr = (c_f64 * (4 * 48))()
+        n = c_i32()
+        check(self.L.daisy_trace(self.ptr, 0, arr, 4 * 48, ctypes.byref(n)))
+        return [tuple(arr[4 * i:4 * i + 4]) for i in range(n.value)]
 
     def set_timing(self, mode):
         check(self.L.daisy_set_timing(self.ptr, int(mode)))

@@ -183,6 +183,8 @@ extern "C" int daisy_destroy(daisy_handle_t h) {
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (int i = 0; i < 2 * DAISY_EVPOOL; ++i)
         if (h->evpool[i]) cudaEventDestroy(h->evpool[i]);
+    for (int i = 0; i < 4 * DAISY_TRACE_STEPS; ++i)
+        if (h->tr_ev[i]) cudaEventDestroy(h->tr_ev[i]);
     free(h);
     return DAISY_OK;
 }
@@ -227,6 +229,26 @@ extern "C" int daisy_materialize(daisy_handle_t h, float *P, float *Q, daisy_str
     k_scale2<<<grid, 256, 0, (cudaStream_t)stream>>>((float4 *)P, na4, (float4 *)Q, nb4, (float)h->scale);
     DAISY_LAUNCH_CHECK(h);
     h->scale = 1.0;
+    return DAISY_OK;
+}
+
+extern "C" int daisy_trace(daisy_handle_t h, int on, double *ms, int cap, int *n_steps) {
+    DAISY_REQUIRE(h != nullptr, DAISY_EINVAL, "null handle");
+    DeviceGuard g(h->device);
+    if (ms && n_steps) {  // dump what was recorded: 4 offsets (ms from the first event) per step
+        DAISY_CUDA(cudaDeviceSynchronize());
+        int n = h->tr_n < cap / 4 ? h->tr_n : cap / 4;
+        for (int i = 0; i < 4 * n; ++i) {
+            float v = 0.f;
+            DAISY_CUDA(cudaEventElapsedTime(&v, h->tr_ev[0], h->tr_ev[i]));
+            ms[i] = v;
+        }
+        *n_steps = n;
+    }
+    if (on && !h->tr_ev[0])
+        for (int i = 0; i < 4 * DAISY_TRACE_STEPS; ++i) DAISY_CUDA(cudaEventCreate(&h->tr_ev[i]));
+    h->trace = on ? 1 : 0;
+    h->tr_n = 0;
     return DAISY_OK;
 }
 

@@ -562,6 +562,8 @@ static int run_step_v(daisy_ctx *h, const float *P, const float *Q, const int32_
         }
         DAISY_CUDA(cudaStreamWaitEvent(bs, k.freed, 0));  // the step that last used this set has finished
     }
+    const bool tr = h->trace && h->tr_n < DAISY_TRACE_STEPS;
+    if (tr) cudaEventRecord(h->tr_ev[4 * h->tr_n + 0], bs);
     if (host_src) {  // daisy_bpr_step_host: the H2D copy is the first node of the bookkeeping chain
         DAISY_CUDA(cudaMemcpyAsync((void *)triples, host_src, (size_t)B * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, bs));
     }
@@ -601,6 +603,10 @@ static int run_step_v(daisy_ctx *h, const float *P, const float *Q, const int32_
         DAISY_CUDA(cudaStreamWaitEvent(s, k.ready, 0));
     }
     // main
+    if (tr) {
+        cudaEventRecord(h->tr_ev[4 * h->tr_n + 1], bs);
+        cudaEventRecord(h->tr_ev[4 * h->tr_n + 2], s);
+    }
     DAISY_CUDA(cudaMemsetAsync(h->heavy, 0, 2 * sizeof(uint32_t), s));
     MainArgs a;
     a.P = P; a.Q = Q; a.st = k.st; a.uslot = k.uslot; a.jslot = k.jslot; a.islot = k.islot;
@@ -637,6 +643,10 @@ static int run_step_v(daisy_ctx *h, const float *P, const float *Q, const int32_
     }
     phase_mark(h, PH_LOSS, s);
     if (piped) DAISY_CUDA(cudaEventRecord(k.freed, s));
+    if (tr) {
+        cudaEventRecord(h->tr_ev[4 * h->tr_n + 3], s);
+        h->tr_n++;
+    }
     if (h->timing == 2) {
         h->ev_pending = 1;
         h->ev_stream = s;

@@ -10,6 +10,7 @@
 
 #define DAISY_DIRECT 0xFFFFFFFFu  // slot value: "this row has a single contribution -> update it in place"
 #define DAISY_SLICE 64     // contributions per level-1 slice of a very hot row
+#define DAISY_TRACE_STEPS 48
 #define DAISY_EVPOOL 2048  // main-kernel event pairs kept between two daisy_main_kernel_ms() calls
 
 // Phases of one BPR step, in launch order (daisy_last_step_phases).
@@ -89,6 +90,10 @@ struct daisy_ctx {
     int pool_used;
     double main_ms_sum;
     int64_t main_count;
+    // optional timeline of the first DAISY_TRACE_STEPS steps (DAISY_TRACE=1): bookkeeping begin/end on the
+    // bookkeeping stream, table kernels begin/end on the caller's stream
+    int trace, tr_n;
+    cudaEvent_t tr_ev[4 * DAISY_TRACE_STEPS];
 };
 
 void daisy_set_error(const char *fmt, ...);

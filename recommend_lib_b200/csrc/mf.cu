@@ -92,15 +92,24 @@ __global__ void __launch_bounds__(128) k_mf_dataflow(MfArgs a) {
         for (int f = lane; f < D; f += 32) dot += __ldcg(q + f) * __ldcg(p + f);
         dot = warp_sum_d(dot);
         double err;
+        // the two biases are read by lane 0 alone and broadcast: one load each, taken strictly before lane 0's
+        // stores below whatever the intra-warp schedule is
+        double b0 = 0.0, b1 = 0.0;
+        if (lane == 0) {
+            b0 = __ldcg(a.bu + u);
+            b1 = __ldcg(a.bi + i);
+        }
+        b0 = __shfl_sync(FULL, b0, 0);
+        b1 = __shfl_sync(FULL, b1, 0);
         if (prm.variant == 0) {  // SVD, util/matrix_factorization.pyx:140-151
-            const double b_u = __ldcg(a.bu + u), b_i = __ldcg(a.bi + i);
+            const double b_u = b0, b_i = b1;
             err = r - (prm.global_mean + b_u + b_i + dot);
             if (prm.biased && lane == 0) {
                 __stcg(a.bu + u, b_u + prm.lr_bu * (err - prm.reg_bu * b_u));
                 __stcg(a.bi + i, b_i + prm.lr_bi * (err - prm.reg_bi * b_i));
             }
         } else {  // RSVD, :49-61
-            const double c_i = __ldcg(a.bu + u), d_j = __ldcg(a.bi + i);
+            const double c_i = b0, d_j = b1;
             err = r - (c_i + d_j + dot);
             if (prm.variant == 2 && lane == 0) {
                 const double inc = prm.lr_bu * (err - prm.reg2 * (c_i + d_j - prm.global_mean));
