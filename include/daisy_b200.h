@@ -100,6 +100,23 @@ DAISY_API int daisy_set_inputs_ready(daisy_handle_t h, int on);
 DAISY_API int daisy_bpr_step_host(daisy_handle_t h, float *P, float *Q, const int32_t *triples_host, int64_t B, float lr,
                         float wd, double *loss_accum, daisy_stream_t stream);
 
+/* ---- row-sharded tables (no Daisy counterpart) --------------------------------
+ * One process per GPU owns a block of user rows and a block of item rows.  Triples are routed to the owner of
+ * their user, so P is local; the item rows a batch needs are fetched from their owners into `cache`
+ * [cache_rows, dim] (exchange done by the host code over NCCL) and the triples' item ids are indices into it.
+ * daisy_bpr_shard_step runs the same fused pipeline as daisy_bpr_step: users get SGD + lazy L2 in place, and
+ * instead of updating the cache it writes the complete descent sum of every cache row to grad_out [cache_rows, dim]
+ * (every cache row must be referenced by at least one triple).  The handle is created with the LOCAL table sizes;
+ * cache_rows <= 2 * max_batch. */
+DAISY_API int daisy_bpr_shard_step(daisy_handle_t h, float *P_local, const float *cache, int64_t cache_rows,
+                                   const int32_t *triples, int64_t B, float lr, float wd, float *grad_out,
+                                   double *loss_accum, daisy_stream_t stream);
+/* Owner side: rows [n] (local item row ids, concatenated in sender-rank order, each sender's list duplicate-free)
+ * and grads [n, dim] (their descent sums).  Applies Q_local[row] += lr/(1-lr*wd) * sum over senders, contributions
+ * of a row summed in sender-rank order (stable sort): deterministic. */
+DAISY_API int daisy_owner_apply(daisy_handle_t h, float *Q_local, const int32_t *rows, const float *grads, int64_t n,
+                                float lr, float wd, daisy_stream_t stream);
+
 /* Lazy sparse Adam variant of the step (no Daisy counterpart -- BPR-MF uses SGD only; semantics =
  * torch.optim.SparseAdam: only rows present in the batch change, weights and moments alike).
  * mP,vP [user_num,dim], mQ,vQ [item_num,dim] fp32 moments owned by the caller; step_no is 1-based. */

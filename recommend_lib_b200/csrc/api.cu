@@ -165,7 +165,8 @@ extern "C" int daisy_destroy(daisy_handle_t h) {
     cudaDeviceSynchronize();
     void *ptrs[] = {h->triples, h->key_in, h->val_in, h->val_out, h->ukey_in, h->uval_in, h->uval_out, h->ikey_in,
                     h->ikey_out, h->ival_in, h->ival_out, h->stageU, h->stageQ, h->stage2, h->loss_part, h->heavy,
-                    h->err, h->cub_tmp, h->scores, h->sel_hist};
+                    h->err, h->cub_tmp, h->scores, h->sel_hist, h->own_key, h->own_key_s, h->own_val, h->own_val_s,
+                    h->own_tmp};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 2; ++i) {

@@ -71,6 +71,23 @@ struct AdamOpt {
     }
 };
 
+// Row-sharded step: users are local (SGD + lazy L2 as above); the "item table" is a cache of rows fetched
+// from their owners, and instead of updating it the step emits the complete descent sum of every cache row -- the
+// owners apply them (k_owner_apply).  Every cache row is referenced by at least one triple, so every row of G is
+// written exactly once.
+struct ShardOpt {
+    float *P, *G;
+    float alpha;
+    __device__ __forceinline__ void apply(int tbl, size_t idx, float4 old, float4 d) const {
+        if (tbl) {
+            st_row(G, idx, d);
+        } else {
+            st_row(P, idx, make_float4(fmaf(alpha, d.x, old.x), fmaf(alpha, d.y, old.y), fmaf(alpha, d.z, old.z),
+                                       fmaf(alpha, d.w, old.w)));
+        }
+    }
+};
+
 // ------------------------------------------------------------------------------------------------
 // prep: validate, emit sort keys
 // ------------------------------------------------------------------------------------------------
@@ -488,6 +505,67 @@ __global__ void __launch_bounds__(256) k_heavy_final(const float *__restrict__ P
 }
 
 // ------------------------------------------------------------------------------------------------
+// owner side of the sharded step: received (row, gradient-sum) pairs from all ranks, concatenated in rank order.
+// A stable sort by row keeps the rank order inside each row; one warp per window of 32 sorted entries sums each
+// row's contributions in that order and applies  Q[row] += alpha * sum  once.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_owner_keys(const int32_t *__restrict__ rows, int n, uint32_t I, uint32_t *__restrict__ key,
+                             uint32_t *__restrict__ val, int *err) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t r = (uint32_t)rows[p];
+    if (r >= I) {
+        atomicOr(&err[0], 1);
+        atomicMin(&err[1], p);
+        r = 0;
+    }
+    key[p] = r;
+    val[p] = (uint32_t)p;
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) k_owner_apply(float *__restrict__ Q, const uint32_t *__restrict__ keys,
+                                                      const uint32_t *__restrict__ perm, int n,
+                                                      const float *__restrict__ grads, int D4, float alpha) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const long long base = (long long)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5) * 32;
+    if (base >= n) return;
+    const long long p = base + lane;
+    const uint32_t key = (p < n) ? keys[p] : 0xFFFFFFFFu;
+    uint32_t prev = __shfl_up_sync(FULL, key, 1);
+    if (lane == 0) prev = (p > 0) ? keys[p - 1] : ~key;
+    const bool start = (p < n) && (prev != key);
+    unsigned todo = __ballot_sync(FULL, start);
+    bool act[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
+    while (todo) {
+        const int b = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t row = __shfl_sync(FULL, key, b);
+        float4 acc[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] = f4_zero();
+        for (long long q = base + b; q < n; ++q) {  // contributions of this row: at most one per rank
+            if (keys[q] != row) break;
+            const size_t src = perm[q];
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if (act[v]) acc[v] = f4_add(acc[v], ld_stream(grads, src * D4 + lane + 32 * v));
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            if (act[v]) {
+                const size_t e = (size_t)row * D4 + lane + 32 * v;
+                const float4 old = ld_row(Q, e);
+                st_row(Q, e, make_float4(fmaf(alpha, acc[v].x, old.x), fmaf(alpha, acc[v].y, old.y),
+                                         fmaf(alpha, acc[v].z, old.z), fmaf(alpha, acc[v].w, old.w)));
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // loss: fixed-order reduction of per-warp partials (double accumulation), added to *loss_accum
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_loss(const float *__restrict__ part, int n, double *loss_accum) {
@@ -532,7 +610,8 @@ static int run_step_v(daisy_ctx *h, const float *P, const float *Q, const int32_
     const int B = (int)B64;
     const int D4 = h->D / 4;
     const int C = auto_chunk(h, B);
-    const uint32_t U = (uint32_t)h->U, I = (uint32_t)h->I;
+    // the sharded step runs against a cache of fetched item rows whose row count differs from the local item shard
+    const uint32_t U = (uint32_t)h->U, I = (uint32_t)(h->item_rows_override ? h->item_rows_override : h->I);
     const int T = 256;
     // The integer bookkeeping of a step (prep .. slots) depends on the triples only, never on the tables.  It
     // runs on the handle's side stream into one of two bookkeeping sets, so that for step n+1 it overlaps the
@@ -719,6 +798,91 @@ extern "C" int daisy_bpr_step_host(daisy_handle_t h, float *P, float *Q, const i
     // first node of the step's bookkeeping chain, so it overlaps the previous step's kernels
     int32_t *dst = h->triples + (size_t)h->book_idx * 3 * (size_t)h->maxB;
     return sgd_step(h, P, Q, dst, triples_host, B, lr, wd, loss_accum, stream);
+}
+
+extern "C" int daisy_bpr_shard_step(daisy_handle_t h, float *P_local, const float *cache, int64_t cache_rows,
+                                    const int32_t *triples, int64_t B, float lr, float wd, float *grad_out,
+                                    double *loss_accum, daisy_stream_t stream) {
+    if (h && B == 0) {  // a rank without triples this step still decays its rows
+        const double sh = 1.0 - (double)lr * (double)wd;
+        DAISY_REQUIRE(sh > 0.0, DAISY_EINVAL, "lr*wd = %g >= 1", (double)lr * wd);
+        h->scale *= sh;
+        return DAISY_OK;
+    }
+    int rc = check_step_args(h, P_local, cache, triples, B);
+    if (rc) return rc;
+    DAISY_REQUIRE(grad_out != nullptr, DAISY_EINVAL, "null grad_out");
+    DAISY_REQUIRE(cache_rows > 0 && cache_rows <= 2 * h->maxB, DAISY_EINVAL,
+                  "cache_rows %lld must be in [1, 2 * max_batch]", (long long)cache_rows);
+    DAISY_REQUIRE((uintptr_t)grad_out % 16 == 0, DAISY_EINVAL, "grad_out must be 16-byte aligned");
+    const double shrink = 1.0 - (double)lr * (double)wd;
+    DAISY_REQUIRE(shrink > 0.0, DAISY_EINVAL, "lr*wd = %g >= 1", (double)lr * wd);
+    if (B == 0) {
+        h->scale *= shrink;
+        return DAISY_OK;
+    }
+    DeviceGuard g(h->device);
+    DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
+    ShardOpt opt;
+    opt.P = P_local;
+    opt.G = grad_out;
+    opt.alpha = (float)((double)lr / shrink);
+    h->item_rows_override = cache_rows;
+    rc = run_step<ShardOpt>(h, P_local, cache, triples, B, opt, (float)(h->scale * h->scale), loss_accum,
+                            (cudaStream_t)stream, nullptr, h->inputs_ready != 0);
+    h->item_rows_override = 0;
+    if (rc) return rc;
+    h->scale *= shrink;
+    return DAISY_OK;
+}
+
+extern "C" int daisy_owner_apply(daisy_handle_t h, float *Q_local, const int32_t *rows, const float *grads, int64_t n,
+                                 float lr, float wd, daisy_stream_t stream) {
+    DAISY_REQUIRE(h && Q_local, DAISY_EINVAL, "null argument");
+    DAISY_REQUIRE(h->D % 4 == 0 && h->D <= 512, DAISY_EUNSUPPORTED, "dim %d unsupported", h->D);
+    DAISY_REQUIRE(n >= 0 && n < (1LL << 30), DAISY_EINVAL, "bad row count");
+    const double shrink = 1.0 - (double)lr * (double)wd;
+    DAISY_REQUIRE(shrink > 0.0, DAISY_EINVAL, "lr*wd = %g >= 1", (double)lr * wd);
+    if (n == 0) return DAISY_OK;
+    DAISY_REQUIRE(rows && grads, DAISY_EINVAL, "null argument");
+    DeviceGuard g(h->device);
+    DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->own_cap < n) {  // grow-only scratch: (key, value) ping/pong + CUB temp
+        DAISY_CUDA(cudaStreamSynchronize(s));
+        for (void *p : {(void *)h->own_key, (void *)h->own_key_s, (void *)h->own_val, (void *)h->own_val_s, h->own_tmp})
+            if (p) cudaFree(p);
+        h->own_key = h->own_key_s = h->own_val = h->own_val_s = nullptr;
+        h->own_tmp = nullptr;
+        const size_t cap = (size_t)n + (size_t)n / 4 + 1024;
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                        (uint32_t *)nullptr, (int)cap, 0, 32, s);
+        bool ok = cudaMalloc((void **)&h->own_key, cap * 4) == cudaSuccess &&
+                  cudaMalloc((void **)&h->own_key_s, cap * 4) == cudaSuccess &&
+                  cudaMalloc((void **)&h->own_val, cap * 4) == cudaSuccess &&
+                  cudaMalloc((void **)&h->own_val_s, cap * 4) == cudaSuccess &&
+                  cudaMalloc(&h->own_tmp, tb + 256) == cudaSuccess;
+        DAISY_REQUIRE(ok, DAISY_ENOMEM, "owner-side scratch allocation failed");
+        h->own_cap = (int64_t)cap;
+        h->own_tmp_bytes = tb + 256;
+    }
+    const int T = 256;
+    k_owner_keys<<<daisy_ceil_div(n, T), T, 0, s>>>(rows, (int)n, (uint32_t)h->I, h->own_key, h->own_val, h->err);
+    DAISY_LAUNCH_CHECK(h);
+    size_t tb = h->own_tmp_bytes;
+    DAISY_CUDA(cub::DeviceRadixSort::SortPairs(h->own_tmp, tb, h->own_key, h->own_key_s, h->own_val, h->own_val_s, (int)n,
+                                               0, bits_for((uint64_t)h->I - 1), s));
+    h->launches += 4;
+    const int D4 = h->D / 4;
+    const float alpha = (float)((double)lr / shrink);
+    const int grid = daisy_ceil_div(daisy_ceil_div(n, 32), 8);
+    if (D4 <= 32) k_owner_apply<1><<<grid, 256, 0, s>>>(Q_local, h->own_key_s, h->own_val_s, (int)n, grads, D4, alpha);
+    else if (D4 <= 64) k_owner_apply<2><<<grid, 256, 0, s>>>(Q_local, h->own_key_s, h->own_val_s, (int)n, grads, D4, alpha);
+    else if (D4 <= 96) k_owner_apply<3><<<grid, 256, 0, s>>>(Q_local, h->own_key_s, h->own_val_s, (int)n, grads, D4, alpha);
+    else k_owner_apply<4><<<grid, 256, 0, s>>>(Q_local, h->own_key_s, h->own_val_s, (int)n, grads, D4, alpha);
+    DAISY_LAUNCH_CHECK(h);
+    return DAISY_OK;
 }
 
 extern "C" int daisy_bpr_adam_step(daisy_handle_t h, float *P, float *Q, float *mP, float *vP, float *mQ, float *vQ,

@@ -69,6 +69,13 @@ struct daisy_ctx {
     int heavy_cap, slice_cap;
     int *err;               // [2]: flag, first bad position
     int *err_host;          // pinned mirror
+    // sharded step: row count of the fetched-row cache standing in for the item table (0 = use I)
+    int64_t item_rows_override;
+    // owner-side apply scratch (grown on demand by daisy_owner_apply)
+    uint32_t *own_key, *own_key_s, *own_val, *own_val_s;
+    void *own_tmp;
+    size_t own_tmp_bytes;
+    int64_t own_cap;
     // full-catalogue top-K workspace (grown on demand by daisy_topk_full)
     float *scores;          // [tile_users, item_num] score tile
     size_t scores_cap;      // floats
