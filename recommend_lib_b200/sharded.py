@@ -173,7 +173,8 @@ class ShardedBPR:
         self.backend = backend if backend is not None else CudaBackend(self.layout, self.rank, self.dim, max_batch,
                                                                        self.device)
         self._bounds = self.layout.item_bounds(self.device)
-        self.wire_rows = 0          # rows received + sent over the interconnect (both exchanges), for reporting
+        self.profile = None
+        self.wire_rows = 0         # rows received + sent over the interconnect (both exchanges), for reporting
 
     # ---- phases (also driven one by one by the in-process multi-rank emulation in the tests) --------------------
     def plan(self, triples):
@@ -195,18 +196,49 @@ class ShardedBPR:
         self.backend.owner_apply(self.Q, (recv_ids - self.i0).to(torch.int32).contiguous(), grads_in, self.lr, self.wd)
 
     # ---- one full step over torch.distributed -----------------------------------------------------------------------
+    PHASES = ("plan", "counts", "ids", "serve", "rows", "compute", "grads", "apply")
+
+    def _mark(self, name):
+        if self.profile is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.profile.append((name, e, time.perf_counter()))
+
     def step(self, triples):
         c = self.comm
+        self._mark("start")
         ids, send_counts, tri_local = self.plan(triples)
+        self._mark("plan")
         recv_counts = c.counts(send_counts, self.device)
+        self._mark("counts")
         recv_ids = c.exchange(ids, send_counts, recv_counts)
+        self._mark("ids")
         rows = self.serve(recv_ids)
+        self._mark("serve")
         cache = c.exchange(rows, recv_counts, send_counts)
+        self._mark("rows")
         grads = self.compute(tri_local, cache)
+        self._mark("compute")
         grads_in = c.exchange(grads, send_counts, recv_counts)
+        self._mark("grads")
         self.apply(recv_ids, grads_in)
+        self._mark("apply")
         remote = sum(send_counts) - send_counts[self.rank]
         self.wire_rows += 2 * remote
+
+    def profile_summary(self):
+        """Mean device ms and host ms per phase over the profiled steps (enable with ``self.profile = []``)."""
+        torch.cuda.synchronize(self.device)
+        dev, host, n = {}, {}, 0
+        prev = None
+        for name, ev, t in self.profile:
+            if name == "start":
+                n += 1
+            else:
+                dev[name] = dev.get(name, 0.0) + prev[1].elapsed_time(ev)
+                host[name] = host.get(name, 0.0) + (t - prev[2]) * 1e3
+            prev = (name, ev, t)
+        return {k: (round(dev[k] / n, 3), round(host[k] / n, 3)) for k in dev}
 
     def materialize(self):
         self.backend.materialize(self.P, self.Q)
@@ -295,6 +327,12 @@ def bench_sharded(args, cfg, metric, unit):
     ms2 = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     model.backend.check()
+    phases = None
+    if args.phases:
+        model.profile = []
+        run(0, min(nb, 10), devtri)
+        phases = model.profile_summary()
+        model.profile = None
     if rank == 0:
         ms_total, ms_e2e = float(ms), float(ms2)
         value = B * world * K / (ms_total * 1e-3)
@@ -312,5 +350,7 @@ def bench_sharded(args, cfg, metric, unit):
                 "nvlink": {"rows_exchanged_per_step_per_gpu": wire_rows / K, "bytes_per_step_per_gpu_each_way": wire_bytes / 2,
                            "achieved_GBs_each_way": wire_bytes / 2 / (ms_total / K * 1e-3) / 1e9,
                            "measured_peer_copy_GBs": 770.0}}
+        if phases:
+            line["phase_ms(device,host)"] = phases
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()
