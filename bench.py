@@ -327,6 +327,8 @@ def main():
     ap.add_argument("--phases", action="store_true", help="also print the per-phase breakdown of the step")
     ap.add_argument("--trace", action="store_true", help="also print a timeline of bookkeeping vs table kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: peer = fused peer-memory step (product), nccl = all-to-all exchange (comparison)")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -117,6 +117,45 @@ DAISY_API int daisy_bpr_shard_step(daisy_handle_t h, float *P_local, const float
 DAISY_API int daisy_owner_apply(daisy_handle_t h, float *Q_local, const int32_t *rows, const float *grads, int64_t n,
                                 float lr, float wd, daisy_stream_t stream);
 
+/* ---- row-sharded tables over PEER MEMORY (NVLink / NVSwitch), one process per GPU -------------------------
+ * The fused compute + exchange path for catalogues larger than one GPU (BASELINE.json configs[4]): no collective
+ * library on the data path.  Rows are block-sharded: rank r owns items [r*i_per, (r+1)*i_per), i_per =
+ * ceil(item_num_global / world), and a block of users; a triple is (LOCAL user row, GLOBAL positive item, GLOBAL
+ * negative item) and is fed to the rank that owns its user.  The handle is created with the LOCAL row counts.
+ *
+ *   daisy_shard_init    allocates this rank's ARENA (its item rows + receive regions + barrier flags) in one
+ *                       cudaMalloc;  daisy_shard_arena returns it and the item-shard pointer q_local [item rows, dim]
+ *                       (fill it before the first step; it is the rank's block of BPR.embed_item.weight)
+ *   daisy_shard_ipc_handle / daisy_shard_attach   exchange the 64-byte CUDA IPC handles of all ranks (any transport,
+ *                       e.g. torch.distributed.all_gather) and map the peers' arenas; ranks living in ONE process
+ *                       (single-GPU emulation in the tests) pass their arena pointers instead
+ *   daisy_shard_step    one training step of this rank: pre-step item rows are READ from their owners by peer loads,
+ *                       the fused step kernels STORE every finished item-row sum straight into its owner's memory,
+ *                       a flag barrier across the GPUs, the owner-side deterministic merge + update, a second barrier.
+ *                       Every rank must call it the same number of times (B may be 0).  Asynchronous, no host sync.
+ *   daisy_shard_compute / _barrier / _apply   the phases of daisy_shard_step, for callers that drive several ranks
+ *                       from one process in lockstep (all computes, then all applies; no barrier kernels).
+ *   daisy_shard_materialize   daisy_materialize on (P_local, q_local) + barrier (peers read q_local).
+ * Semantics = daisy_bpr_step on the global batch (gradients at the pre-step tables, repeated rows accumulate);
+ * contributions to a row are added in sender-rank order, so results are bit-reproducible. */
+DAISY_API int daisy_shard_init(daisy_handle_t h, int rank, int world, int64_t item_num_global);
+DAISY_API int daisy_shard_arena(daisy_handle_t h, void **arena, float **q_local, int64_t *arena_bytes);
+DAISY_API int daisy_shard_ipc_handle(daisy_handle_t h, void *out64);
+DAISY_API int daisy_shard_attach(daisy_handle_t h, const void *ipc_handles /* [world][64] or NULL */,
+                                 void *const *arena_ptrs /* [world] or NULL */);
+DAISY_API int daisy_shard_step(daisy_handle_t h, float *P_local, const int32_t *triples, int64_t B, float lr, float wd,
+                               double *loss_accum, daisy_stream_t stream);
+DAISY_API int daisy_shard_step_host(daisy_handle_t h, float *P_local, const int32_t *triples_host, int64_t B, float lr,
+                                    float wd, double *loss_accum, daisy_stream_t stream);
+DAISY_API int daisy_shard_compute(daisy_handle_t h, float *P_local, const int32_t *triples, int64_t B, float lr, float wd,
+                                  double *loss_accum, daisy_stream_t stream);
+DAISY_API int daisy_shard_barrier(daisy_handle_t h, daisy_stream_t stream);
+DAISY_API int daisy_shard_apply(daisy_handle_t h, float lr, float wd, daisy_stream_t stream);
+DAISY_API int daisy_shard_materialize(daisy_handle_t h, float *P_local, daisy_stream_t stream);
+/* Reporting: owner_off_out [world+1] = first cache row of every owner in the most recent step of this rank, so
+ * owner_off_out[o+1] - owner_off_out[o] distinct item rows were fetched from / pushed to rank o.  Synchronises. */
+DAISY_API int daisy_shard_last_counts(daisy_handle_t h, uint32_t *owner_off_out, daisy_stream_t stream);
+
 /* Lazy sparse Adam variant of the step (no Daisy counterpart -- BPR-MF uses SGD only; semantics =
  * torch.optim.SparseAdam: only rows present in the batch change, weights and moments alike).
  * mP,vP [user_num,dim], mQ,vQ [item_num,dim] fp32 moments owned by the caller; step_no is 1-based. */

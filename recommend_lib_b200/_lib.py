@@ -39,6 +39,17 @@ SIGNATURES = {
     "daisy_bpr_step_host": [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp],
     "daisy_bpr_shard_step": [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp, c_vp],
     "daisy_owner_apply": [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp],
+    "daisy_shard_init": [c_vp, c_i32, c_i32, c_i64],
+    "daisy_shard_arena": [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_i64)],
+    "daisy_shard_ipc_handle": [c_vp, c_vp],
+    "daisy_shard_attach": [c_vp, c_vp, c_vp],
+    "daisy_shard_step": [c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp],
+    "daisy_shard_step_host": [c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp],
+    "daisy_shard_compute": [c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp],
+    "daisy_shard_barrier": [c_vp, c_vp],
+    "daisy_shard_apply": [c_vp, c_f32, c_f32, c_vp],
+    "daisy_shard_materialize": [c_vp, c_vp, c_vp],
+    "daisy_shard_last_counts": [c_vp, c_vp, c_vp],
     "daisy_bpr_adam_step": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32,
                             c_i64, c_vp, c_vp],
     "daisy_topk_candidates": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp],

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "ctx.cuh"
 
@@ -122,7 +123,11 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
         size_t need = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, need, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
                                         (uint32_t *)nullptr, (int)(2 * B), 0, 32, (cudaStream_t)0);
-        h->cub_tmp_bytes = need + 256;
+        size_t need_scan = 0;  // the sharded bookkeeping also scans 2B flags (step_kernels.cuh)
+        cub::DeviceScan::InclusiveSum(nullptr, need_scan, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)(2 * B),
+                                      (cudaStream_t)0);
+        if (need_scan > need) need = need_scan;
+        h->cub_tmp_bytes = need + 4096;
         rc = dalloc((char **)&h->cub_tmp, h->cub_tmp_bytes);
     }
     if (!rc && cudaMallocHost((void **)&h->err_host, 2 * sizeof(int)) != cudaSuccess) {
@@ -163,6 +168,7 @@ extern "C" int daisy_destroy(daisy_handle_t h) {
     if (!h) return DAISY_OK;
     DeviceGuard g(h->device);
     cudaDeviceSynchronize();
+    daisy_shard_free(h);
     void *ptrs[] = {h->triples, h->key_in, h->val_in, h->val_out, h->ukey_in, h->uval_in, h->uval_out, h->ikey_in,
                     h->ikey_out, h->ival_in, h->ival_out, h->stageU, h->stageQ, h->stage2, h->loss_part, h->heavy,
                     h->err, h->cub_tmp, h->scores, h->sel_hist, h->own_key, h->own_key_s, h->own_val, h->own_val_s,
@@ -198,8 +204,17 @@ extern "C" int daisy_check(daisy_handle_t h, daisy_stream_t stream) {
     DAISY_CUDA(cudaStreamSynchronize(s));
     if (h->err_host[0]) {
         const int pos = h->err_host[1];
+        const int bits = h->err_host[0];
         k_err_reset<<<1, 1, 0, s>>>(h->err);
         cudaStreamSynchronize(s);
+        if (bits & 16) {
+            daisy_set_error("sharded step: a peer rank did not reach the barrier within 20 s (ranks out of step or a peer died)");
+            return DAISY_ECUDA;
+        }
+        if (bits & 32) {
+            daisy_set_error("sharded step: a receive region overflowed");
+            return DAISY_ECUDA;
+        }
         daisy_set_error("index out of range in self (first offending position %d; user ids must be < %lld, item ids < %lld)",
                         pos, (long long)h->U, (long long)h->I);
         return DAISY_EINDEX;

@@ -8,7 +8,9 @@
 
 #include "../../include/daisy_b200.h"
 
-#define DAISY_DIRECT 0xFFFFFFFFu  // slot value: "this row has a single contribution -> update it in place"
+#define DAISY_DIRECT 0xFFFFFFFFu    // slot value: "this row has a single contribution -> update it in place"
+#define DAISY_NOT_HEAD 0xFFFFFFFEu  // positive-item slot of a sorted triple that continues the run of its predecessor
+#define DAISY_MAX_RANKS 16          // ranks of a row-sharded model (one node)
 #define DAISY_SLICE 64     // contributions per level-1 slice of a very hot row
 #define DAISY_TRACE_STEPS 48
 #define DAISY_EVPOOL 2048  // main-kernel event pairs kept between two daisy_main_kernel_ms() calls
@@ -34,6 +36,44 @@ struct BookSet {
     uint32_t *ukey_s, *qkey_s;      // [maxB], [2*maxB]  sorted user / item ref keys (rows)
     uint32_t *uslot, *jslot, *islot;  // [maxB]  per sorted triple: DAISY_DIRECT or staging slot
     cudaEvent_t ready, freed;
+};
+
+// ---- row-sharded tables over peer memory (shard.cu) ----------------------------------------------------------------
+// Every rank allocates one ARENA (a single cudaMalloc, exported through CUDA IPC) laid out identically on all ranks:
+//   q        [i_per, D]      fp32   this rank's block of item rows
+//   recv_g   [G][cap][D]     fp32   descent sums pushed by rank s for rows this rank owns (region s)
+//   recv_ids [G][cap]        int32  the LOCAL row ids those sums belong to (ascending, duplicate-free per sender)
+//   recv_cnt [G]             uint32 how many entries sender s pushed this step
+//   flags    [G]             uint32 barrier arrivals (epoch numbers), written by the peers
+struct ShardPeers {  // the same regions of every rank's arena, as mapped into THIS process; passed to kernels by value
+    float *q[DAISY_MAX_RANKS];
+    float *recv_g[DAISY_MAX_RANKS];
+    int32_t *recv_ids[DAISY_MAX_RANKS];
+    uint32_t *recv_cnt[DAISY_MAX_RANKS];
+    uint32_t *flags[DAISY_MAX_RANKS];
+};
+
+struct ShardSet {         // per bookkeeping set (double-buffered like BookSet)
+    uint32_t *uniq_gid;   // [2*maxB]  global id of cache row c (ascending => grouped by owner block)
+    const float **src;    // [2*maxB]  where cache row c lives in its owner's q (a peer or local address)
+    float **dst;          // [2*maxB]  where this rank's descent sum of cache row c goes in its owner's recv_g
+    uint32_t *owner_off;  // [G+1]     first cache row owned by rank o; [G] = number of cache rows
+};
+
+struct daisy_shard {
+    int rank, world;
+    int64_t I_global, i_per, cap;  // cap = entries per sender region = 2 * maxB (a batch references at most 2B item rows)
+    char *arena;
+    size_t arena_bytes, off_q, off_g, off_ids, off_cnt, off_flags;
+    char *peer_arena[DAISY_MAX_RANKS];
+    int ipc_opened[DAISY_MAX_RANKS];
+    int attached;
+    int in_process;  // peers live in this process (lockstep emulation): the caller orders the phases, no barrier kernels
+    ShardPeers peers;
+    ShardSet set[2];
+    uint32_t *cidx;   // [2*maxB] scan scratch (bookkeeping stream only)
+    float *cache;     // [2*maxB, D] fetched pre-step item rows of the current batch
+    uint32_t epoch;   // barrier epoch (same sequence on every rank)
 };
 
 struct daisy_ctx {
@@ -71,6 +111,7 @@ struct daisy_ctx {
     int *err_host;          // pinned mirror
     // sharded step: row count of the fetched-row cache standing in for the item table (0 = use I)
     int64_t item_rows_override;
+    daisy_shard *sh;        // peer-memory sharding state (daisy_shard_init), else null
     // owner-side apply scratch (grown on demand by daisy_owner_apply)
     uint32_t *own_key, *own_key_s, *own_val, *own_val_s;
     void *own_tmp;
@@ -104,6 +145,7 @@ struct daisy_ctx {
 };
 
 void daisy_set_error(const char *fmt, ...);
+void daisy_shard_free(daisy_ctx *h);  // shard.cu
 
 #define DAISY_CUDA(call)                                                                     \
     do {                                                                                     \

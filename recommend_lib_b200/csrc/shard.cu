@@ -1,0 +1,682 @@
+// Row-sharded BPR step: see the header comment of each section.
+#include "step_kernels.cuh"
+
+namespace {
+
+// Row-sharded step: users are local (SGD + lazy L2 as above); the "item table" is a cache of rows fetched
+// from their owners, and instead of updating it the step emits the complete descent sum of every cache row -- the
+// owners apply them (k_owner_apply).  Every cache row is referenced by at least one triple, so every row of G is
+// written exactly once.
+struct ShardOpt {
+    static constexpr bool kNeedOldItem = false;
+    float *P, *G;
+    float alpha;
+    int D4;
+    __device__ __forceinline__ void apply(int tbl, size_t row, int e, float4 old, float4 d) const {
+        const size_t idx = row * D4 + e;
+        if (tbl) {
+            st_row(G, idx, d);
+        } else {
+            st_row(P, idx, make_float4(fmaf(alpha, d.x, old.x), fmaf(alpha, d.y, old.y), fmaf(alpha, d.z, old.z),
+                                       fmaf(alpha, d.w, old.w)));
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// owner side of the sharded step: received (row, gradient-sum) pairs from all ranks, concatenated in rank order.
+// A stable sort by row keeps the rank order inside each row; one warp per window of 32 sorted entries sums each
+// row's contributions in that order and applies  Q[row] += alpha * sum  once.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_owner_keys(const int32_t *__restrict__ rows, int n, uint32_t I, uint32_t *__restrict__ key,
+                             uint32_t *__restrict__ val, int *err) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t r = (uint32_t)rows[p];
+    if (r >= I) {
+        atomicOr(&err[0], 1);
+        atomicMin(&err[1], p);
+        r = 0;
+    }
+    key[p] = r;
+    val[p] = (uint32_t)p;
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) k_owner_apply(float *__restrict__ Q, const uint32_t *__restrict__ keys,
+                                                      const uint32_t *__restrict__ perm, int n,
+                                                      const float *__restrict__ grads, int D4, float alpha) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const long long base = (long long)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5) * 32;
+    if (base >= n) return;
+    const long long p = base + lane;
+    const uint32_t key = (p < n) ? keys[p] : 0xFFFFFFFFu;
+    uint32_t prev = __shfl_up_sync(FULL, key, 1);
+    if (lane == 0) prev = (p > 0) ? keys[p - 1] : ~key;
+    const bool start = (p < n) && (prev != key);
+    unsigned todo = __ballot_sync(FULL, start);
+    bool act[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
+    while (todo) {
+        const int b = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t row = __shfl_sync(FULL, key, b);
+        float4 acc[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] = f4_zero();
+        for (long long q = base + b; q < n; ++q) {  // contributions of this row: at most one per rank
+            if (keys[q] != row) break;
+            const size_t src = perm[q];
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if (act[v]) acc[v] = f4_add(acc[v], ld_stream(grads, src * D4 + lane + 32 * v));
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            if (act[v]) {
+                const size_t e = (size_t)row * D4 + lane + 32 * v;
+                const float4 old = ld_row(Q, e);
+                st_row(Q, e, make_float4(fmaf(alpha, acc[v].x, old.x), fmaf(alpha, acc[v].y, old.y),
+                                         fmaf(alpha, acc[v].z, old.z), fmaf(alpha, acc[v].w, old.w)));
+            }
+    }
+}
+
+}  // namespace
+
+extern "C" int daisy_bpr_shard_step(daisy_handle_t h, float *P_local, const float *cache, int64_t cache_rows,
+                                    const int32_t *triples, int64_t B, float lr, float wd, float *grad_out,
+                                    double *loss_accum, daisy_stream_t stream) {
+    if (h && B == 0) {  // a rank without triples this step still decays its rows
+        const double sh = 1.0 - (double)lr * (double)wd;
+        DAISY_REQUIRE(sh > 0.0, DAISY_EINVAL, "lr*wd = %g >= 1", (double)lr * wd);
+        h->scale *= sh;
+        return DAISY_OK;
+    }
+    int rc = check_step_args(h, P_local, cache, triples, B);
+    if (rc) return rc;
+    DAISY_REQUIRE(grad_out != nullptr, DAISY_EINVAL, "null grad_out");
+    DAISY_REQUIRE(cache_rows > 0 && cache_rows <= 2 * h->maxB, DAISY_EINVAL,
+                  "cache_rows %lld must be in [1, 2 * max_batch]", (long long)cache_rows);
+    DAISY_REQUIRE((uintptr_t)grad_out % 16 == 0, DAISY_EINVAL, "grad_out must be 16-byte aligned");
+    const double shrink = 1.0 - (double)lr * (double)wd;
+    DAISY_REQUIRE(shrink > 0.0, DAISY_EINVAL, "lr*wd = %g >= 1", (double)lr * wd);
+    if (B == 0) {
+        h->scale *= shrink;
+        return DAISY_OK;
+    }
+    DeviceGuard g(h->device);
+    DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
+    ShardOpt opt;
+    opt.P = P_local;
+    opt.G = grad_out;
+    opt.alpha = (float)((double)lr / shrink);
+    opt.D4 = h->D / 4;
+    h->item_rows_override = cache_rows;
+    rc = run_step<ShardOpt>(h, P_local, cache, triples, B, opt, (float)(h->scale * h->scale), loss_accum,
+                            (cudaStream_t)stream, nullptr, h->inputs_ready != 0);
+    h->item_rows_override = 0;
+    if (rc) return rc;
+    h->scale *= shrink;
+    return DAISY_OK;
+}
+
+extern "C" int daisy_owner_apply(daisy_handle_t h, float *Q_local, const int32_t *rows, const float *grads, int64_t n,
+                                 float lr, float wd, daisy_stream_t stream) {
+    DAISY_REQUIRE(h && Q_local, DAISY_EINVAL, "null argument");
+    DAISY_REQUIRE(h->D % 4 == 0 && h->D <= 512, DAISY_EUNSUPPORTED, "dim %d unsupported", h->D);
+    DAISY_REQUIRE(n >= 0 && n < (1LL << 30), DAISY_EINVAL, "bad row count");
+    const double shrink = 1.0 - (double)lr * (double)wd;
+    DAISY_REQUIRE(shrink > 0.0, DAISY_EINVAL, "lr*wd = %g >= 1", (double)lr * wd);
+    if (n == 0) return DAISY_OK;
+    DAISY_REQUIRE(rows && grads, DAISY_EINVAL, "null argument");
+    DeviceGuard g(h->device);
+    DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->own_cap < n) {  // grow-only scratch: (key, value) ping/pong + CUB temp
+        DAISY_CUDA(cudaStreamSynchronize(s));
+        for (void *p : {(void *)h->own_key, (void *)h->own_key_s, (void *)h->own_val, (void *)h->own_val_s, h->own_tmp})
+            if (p) cudaFree(p);
+        h->own_key = h->own_key_s = h->own_val = h->own_val_s = nullptr;
+        h->own_tmp = nullptr;
+        const size_t cap = (size_t)n + (size_t)n / 4 + 1024;
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                        (uint32_t *)nullptr, (int)cap, 0, 32, s);
+        bool ok = cudaMalloc((void **)&h->own_key, cap * 4) == cudaSuccess &&
+                  cudaMalloc((void **)&h->own_key_s, cap * 4) == cudaSuccess &&
+                  cudaMalloc((void **)&h->own_val, cap * 4) == cudaSuccess &&
+                  cudaMalloc((void **)&h->own_val_s, cap * 4) == cudaSuccess &&
+                  cudaMalloc(&h->own_tmp, tb + 256) == cudaSuccess;
+        DAISY_REQUIRE(ok, DAISY_ENOMEM, "owner-side scratch allocation failed");
+        h->own_cap = (int64_t)cap;
+        h->own_tmp_bytes = tb + 256;
+    }
+    const int T = 256;
+    k_owner_keys<<<daisy_ceil_div(n, T), T, 0, s>>>(rows, (int)n, (uint32_t)h->I, h->own_key, h->own_val, h->err);
+    DAISY_LAUNCH_CHECK(h);
+    size_t tb = h->own_tmp_bytes;
+    DAISY_CUDA(cub::DeviceRadixSort::SortPairs(h->own_tmp, tb, h->own_key, h->own_key_s, h->own_val, h->own_val_s, (int)n,
+                                               0, bits_for((uint64_t)h->I - 1), s));
+    h->launches += 4;
+    const int D4 = h->D / 4;
+    const float alpha = (float)((double)lr / shrink);
+    const int grid = daisy_ceil_div(daisy_ceil_div(n, 32), 8);
+    if (D4 <= 32) k_owner_apply<1><<<grid, 256, 0, s>>>(Q_local, h->own_key_s, h->own_val_s, (int)n, grads, D4, alpha);
+    else if (D4 <= 64) k_owner_apply<2><<<grid, 256, 0, s>>>(Q_local, h->own_key_s, h->own_val_s, (int)n, grads, D4, alpha);
+    else if (D4 <= 96) k_owner_apply<3><<<grid, 256, 0, s>>>(Q_local, h->own_key_s, h->own_val_s, (int)n, grads, D4, alpha);
+    else k_owner_apply<4><<<grid, 256, 0, s>>>(Q_local, h->own_key_s, h->own_val_s, (int)n, grads, D4, alpha);
+    DAISY_LAUNCH_CHECK(h);
+    return DAISY_OK;
+}
+
+
+// =====================================================================================================================
+// Row-sharded step over PEER MEMORY (NVLink / NVSwitch): no collective library on the data path.
+//
+// Every rank owns a block of user rows (local tensor) and a block of item rows that lives in its ARENA (ctx.cuh:
+// daisy_shard), which all ranks of the node map through CUDA IPC.  Triples are routed to the owner of their user.
+// One step of rank `me`, all asynchronous on the caller's stream, no host synchronisation:
+//
+//   bookkeeping  (side stream, overlaps the previous step)  the single-GPU bookkeeping on GLOBAL item ids + cache-row
+//                assignment: the batch's distinct item ids, ascending = grouped by owner, each with the address it is
+//                fetched from (owner's q) and the address its descent sum is pushed to (owner's recv_g, region `me`)
+//   fetch        k_shard_fetch: pre-step rows of the batch's distinct items are READ from their owners' memory
+//                (128-bit peer loads over NVLink, several rows in flight per warp) into the local cache; the ids and
+//                counts of what this rank will push are WRITTEN into the owners' recv_ids / recv_cnt
+//   compute      the fused step kernels against (P_local, cache); a finished item-row sum is stored straight into the
+//                owner's memory by the kernel that completes it (PushOpt: k_bpr_main for rows referenced once,
+//                k_seg_reduce / k_heavy_final for repeated rows) -- the transfer overlaps the arithmetic
+//   barrier      k_shard_barrier: arrival flags written into every peer's arena, acquire-spin on the own flags
+//   apply        k_owner_merge: per owned row, the senders' sums are added in sender-rank order (each sender's id list
+//                is ascending, so membership is a binary search) and the row is updated once -> deterministic
+//   barrier      owners are done: peers may fetch the next step's rows and overwrite the receive regions
+// =====================================================================================================================
+namespace {
+
+struct PushOpt {
+    static constexpr bool kNeedOldItem = false;
+    float *P;
+    float *const *dst;  // per cache row: where its descent sum goes (peer or local address)
+    float alpha;
+    int D4;
+    __device__ __forceinline__ void apply(int tbl, size_t row, int e, float4 old, float4 d) const {
+        if (tbl) {
+            reinterpret_cast<float4 *>(dst[row])[e] = d;
+        } else {
+            st_row(P, row * D4 + e,
+                   make_float4(fmaf(alpha, d.x, old.x), fmaf(alpha, d.y, old.y), fmaf(alpha, d.z, old.z),
+                               fmaf(alpha, d.w, old.w)));
+        }
+    }
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// R rows in flight per warp: a peer load takes ~2000 cycles (NVLink + remote L2/DRAM), so bandwidth needs depth.
+template <int V, int R>
+__global__ void __launch_bounds__(256) k_shard_fetch(const float *const *__restrict__ src,
+                                                      const uint32_t *__restrict__ owner_off, int G,
+                                                      float *__restrict__ cache, int D4,
+                                                      const uint32_t *__restrict__ uniq_gid, uint32_t i_per, int me,
+                                                      size_t cap, ShardPeers peers) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const uint32_t nwarps = (uint32_t)((gridDim.x * (size_t)blockDim.x) >> 5);
+    const uint32_t nuniq = owner_off[G];
+    if (blockIdx.x == 0 && threadIdx.x < G)  // how many entries this rank pushes to every owner this step
+        peers.recv_cnt[threadIdx.x][me] = owner_off[threadIdx.x + 1] - owner_off[threadIdx.x];
+    bool act[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
+    for (uint32_t c0 = warp * R; c0 < nuniq; c0 += nwarps * R) {
+        float4 r[R][V];
+#pragma unroll
+        for (int jj = 0; jj < R; ++jj) {
+            const uint32_t c = c0 + jj;
+            if (c < nuniq) {
+                const float *p = src[c];
+#pragma unroll
+                for (int v = 0; v < V; ++v)
+                    if (act[v]) r[jj][v] = ld_stream(p, lane + 32 * v);
+            }
+        }
+        if (lane < R && c0 + lane < nuniq) {  // the id list the owner merges by
+            const uint32_t c = c0 + lane;
+            const uint32_t g = uniq_gid[c];
+            const uint32_t o = g / i_per;
+            peers.recv_ids[o][(size_t)me * cap + (c - owner_off[o])] = (int32_t)(g - o * i_per);
+        }
+#pragma unroll
+        for (int jj = 0; jj < R; ++jj) {
+            const uint32_t c = c0 + jj;
+            if (c < nuniq) {
+#pragma unroll
+                for (int v = 0; v < V; ++v)
+                    if (act[v]) st_row(cache, (size_t)c * D4 + lane + 32 * v, r[jj][v]);
+            }
+        }
+    }
+}
+
+// A rank without triples this step pushes nothing: tell every owner so.
+__global__ void k_shard_push_none(int G, int me, ShardPeers peers) {
+    if (threadIdx.x < G) peers.recv_cnt[threadIdx.x][me] = 0u;
+}
+
+// Cross-GPU barrier on the stream: everything this rank wrote to peer memory in earlier kernels of the stream is
+// complete (kernel boundary) and made visible system-wide before the arrival flag (release); the spin acquires the
+// peers' arrivals.  Epochs only grow, so flags are never reset.  One rank per GPU: the waiting kernels run on different
+// devices (never several of them on one GPU).
+__global__ void k_shard_barrier(ShardPeers peers, int me, int G, uint32_t epoch, unsigned long long timeout_ns, int *err) {
+    const int t = threadIdx.x;
+    if (t >= G) return;
+    __threadfence_system();
+    st_release_sys(peers.flags[t] + me, epoch);
+    const unsigned long long t0 = global_ns();
+    while ((int32_t)(ld_acquire_sys(peers.flags[me] + t) - epoch) < 0) {
+        if (global_ns() - t0 > timeout_ns) {
+            atomicOr(&err[0], 16);
+            break;
+        }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+// Owner side.  Region s of recv_ids holds the ascending, duplicate-free local row ids sender s pushed sums for
+// (recv_cnt[s] of them), recv_g the sums.  One lane per entry: it is the row's LEADER if no lower-ranked sender
+// pushed the same row (binary searches); the warp then handles its leaders one at a time, adding the senders'
+// sums in rank order and updating the row once.
+template <int V>
+__global__ void __launch_bounds__(256) k_owner_merge(float *__restrict__ Q, const float *__restrict__ recv_g,
+                                                      const int32_t *__restrict__ recv_ids,
+                                                      const uint32_t *__restrict__ recv_cnt, int G, size_t cap, int D4,
+                                                      float alpha, uint32_t rows_local, int *err) {
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t NONE = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const uint32_t nwarps = (uint32_t)((gridDim.x * (size_t)blockDim.x) >> 5);
+    uint32_t cnt_l = (lane < G) ? recv_cnt[lane] : 0u;
+    if (cnt_l > cap) {  // cannot happen (a sender has at most 2*maxB = cap distinct rows); never read out of bounds
+        atomicOr(&err[0], 32);
+        cnt_l = (uint32_t)cap;
+    }
+    uint32_t total = 0;
+    for (int s = 0; s < G; ++s) total += (__shfl_sync(FULL, cnt_l, s) + 31u) >> 5;
+    bool act[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
+
+    for (uint32_t task = warp; task < total; task += nwarps) {
+        int s = 0;
+        uint32_t rem = task;
+        while (true) {
+            const uint32_t ch = (__shfl_sync(FULL, cnt_l, s) + 31u) >> 5;
+            if (rem < ch) break;
+            rem -= ch;
+            ++s;
+        }
+        const uint32_t n_s = __shfl_sync(FULL, cnt_l, s);
+        const uint32_t k = rem * 32u + lane;
+        const bool valid = k < n_s;
+        uint32_t r = valid ? (uint32_t)recv_ids[(size_t)s * cap + k] : NONE;
+        bool leader = valid;
+        if (valid && r >= rows_local) {
+            atomicOr(&err[0], 1);
+            leader = false;
+        }
+        uint32_t pos[DAISY_MAX_RANKS];
+#pragma unroll
+        for (int sp = 0; sp < DAISY_MAX_RANKS; ++sp) {
+            pos[sp] = NONE;
+            if (sp < G && sp != s) {  // warp-uniform
+                const uint32_t n2 = __shfl_sync(FULL, cnt_l, sp);
+                const int32_t *ids2 = recv_ids + (size_t)sp * cap;
+                uint32_t lo = 0, hi = n2;
+                while (__any_sync(FULL, lo < hi)) {
+                    if (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if ((uint32_t)ids2[mid] < r) lo = mid + 1; else hi = mid;
+                    }
+                }
+                const bool found = valid && lo < n2 && (uint32_t)ids2[lo] == r;
+                if (found) {
+                    if (sp < s) leader = false; else pos[sp] = lo;
+                }
+            }
+        }
+        unsigned todo = __ballot_sync(FULL, leader);
+        while (todo) {
+            const int b = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t row = __shfl_sync(FULL, r, b);
+            float4 acc[V];
+            const size_t own = ((size_t)s * cap + rem * 32u + b) * D4;
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] = act[v] ? ld_stream(recv_g, own + lane + 32 * v) : f4_zero();
+#pragma unroll
+            for (int sp = 0; sp < DAISY_MAX_RANKS; ++sp) {
+                const uint32_t pp = __shfl_sync(FULL, pos[sp], b);
+                if (pp != NONE) {  // warp-uniform; sp > s ascending = sender-rank order
+                    const size_t at = ((size_t)sp * cap + pp) * D4;
+#pragma unroll
+                    for (int v = 0; v < V; ++v)
+                        if (act[v]) acc[v] = f4_add(acc[v], ld_stream(recv_g, at + lane + 32 * v));
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if (act[v]) {
+                    const size_t e = (size_t)row * D4 + lane + 32 * v;
+                    const float4 old = ld_row(Q, e);
+                    st_row(Q, e, make_float4(fmaf(alpha, acc[v].x, old.x), fmaf(alpha, acc[v].y, old.y),
+                                             fmaf(alpha, acc[v].z, old.z), fmaf(alpha, acc[v].w, old.w)));
+                }
+        }
+    }
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static void shard_set_peers(daisy_shard *sh, int r, char *base) {
+    sh->peer_arena[r] = base;
+    sh->peers.q[r] = (float *)(base + sh->off_q);
+    sh->peers.recv_g[r] = (float *)(base + sh->off_g);
+    sh->peers.recv_ids[r] = (int32_t *)(base + sh->off_ids);
+    sh->peers.recv_cnt[r] = (uint32_t *)(base + sh->off_cnt);
+    sh->peers.flags[r] = (uint32_t *)(base + sh->off_flags);
+}
+
+static int shard_ready(daisy_ctx *h) {
+    DAISY_REQUIRE(h != nullptr, DAISY_EINVAL, "null handle");
+    DAISY_REQUIRE(h->sh != nullptr, DAISY_EINVAL, "handle is not sharded: call daisy_shard_init first");
+    DAISY_REQUIRE(h->sh->attached, DAISY_EINVAL, "peers are not attached: call daisy_shard_attach first");
+    return DAISY_OK;
+}
+
+template <int V>
+static void launch_fetch(daisy_ctx *h, const ShardSet &ss, cudaStream_t s) {
+    daisy_shard *sh = h->sh;
+    k_shard_fetch<V, 4><<<h->num_sms * 4, 256, 0, s>>>(ss.src, ss.owner_off, sh->world, sh->cache, h->D / 4, ss.uniq_gid,
+                                                        (uint32_t)sh->i_per, sh->rank, (size_t)sh->cap, sh->peers);
+}
+
+template <int V>
+static void launch_merge(daisy_ctx *h, float alpha, cudaStream_t s) {
+    daisy_shard *sh = h->sh;
+    const int me = sh->rank;
+    k_owner_merge<V><<<h->num_sms * 8, 256, 0, s>>>(sh->peers.q[me], sh->peers.recv_g[me], sh->peers.recv_ids[me],
+                                                    sh->peers.recv_cnt[me], sh->world, (size_t)sh->cap, h->D / 4, alpha,
+                                                    (uint32_t)h->I, h->err);
+}
+
+static int shard_compute(daisy_ctx *h, float *P_local, const int32_t *triples_dev, const int32_t *host_src, int64_t B,
+                         float lr, float wd, double *loss_accum, cudaStream_t s) {
+    daisy_shard *sh = h->sh;
+    const double shrink = 1.0 - (double)lr * (double)wd;
+    DAISY_REQUIRE(shrink > 0.0, DAISY_EINVAL, "lr*wd = %g >= 1: the L2 shrink factor is not positive", (double)lr * wd);
+    DeviceGuard g(h->device);
+    DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
+    if (B == 0) {  // no triples here this step: the rank's rows still decay, and the owners must see empty regions
+        k_shard_push_none<<<1, 32, 0, s>>>(sh->world, sh->rank, sh->peers);
+        DAISY_LAUNCH_CHECK(h);
+        h->scale *= shrink;
+        return DAISY_OK;
+    }
+    StepPlan pl;
+    int rc = book_phase(h, pl, triples_dev, B, (uint32_t)h->U, (uint32_t)sh->I_global, s, host_src,
+                        host_src != nullptr || h->inputs_ready, sh);
+    if (rc) return rc;
+    const ShardSet &ss = sh->set[pl.set];
+    const int D4 = h->D / 4;
+    if (D4 <= 32) launch_fetch<1>(h, ss, s);
+    else if (D4 <= 64) launch_fetch<2>(h, ss, s);
+    else if (D4 <= 96) launch_fetch<3>(h, ss, s);
+    else launch_fetch<4>(h, ss, s);
+    DAISY_LAUNCH_CHECK(h);
+    PushOpt opt;
+    opt.P = P_local;
+    opt.dst = ss.dst;
+    opt.alpha = (float)((double)lr / shrink);
+    opt.D4 = D4;
+    rc = table_phase<PushOpt>(h, pl, P_local, sh->cache, opt, (float)(h->scale * h->scale), loss_accum);
+    if (rc) return rc;
+    h->scale *= shrink;
+    return DAISY_OK;
+}
+
+static int shard_apply(daisy_ctx *h, float lr, float wd, cudaStream_t s) {
+    const double shrink = 1.0 - (double)lr * (double)wd;
+    DAISY_REQUIRE(shrink > 0.0, DAISY_EINVAL, "lr*wd = %g >= 1", (double)lr * wd);
+    DeviceGuard g(h->device);
+    DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
+    const float alpha = (float)((double)lr / shrink);
+    const int D4 = h->D / 4;
+    if (D4 <= 32) launch_merge<1>(h, alpha, s);
+    else if (D4 <= 64) launch_merge<2>(h, alpha, s);
+    else if (D4 <= 96) launch_merge<3>(h, alpha, s);
+    else launch_merge<4>(h, alpha, s);
+    DAISY_LAUNCH_CHECK(h);
+    return DAISY_OK;
+}
+
+static int shard_barrier(daisy_ctx *h, cudaStream_t s) {
+    daisy_shard *sh = h->sh;
+    if (sh->world == 1) return DAISY_OK;
+    DeviceGuard g(h->device);
+    DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
+    sh->epoch++;
+    k_shard_barrier<<<1, 32, 0, s>>>(sh->peers, sh->rank, sh->world, sh->epoch, 20ull * 1000000000ull, h->err);
+    DAISY_LAUNCH_CHECK(h);
+    return DAISY_OK;
+}
+
+}  // namespace
+
+void daisy_shard_free(daisy_ctx *h) {
+    daisy_shard *sh = h->sh;
+    if (!sh) return;
+    for (int r = 0; r < sh->world; ++r)
+        if (sh->ipc_opened[r] && sh->peer_arena[r]) cudaIpcCloseMemHandle(sh->peer_arena[r]);
+    for (int i = 0; i < 2; ++i) {
+        void *ptrs[] = {sh->set[i].uniq_gid, (void *)sh->set[i].src, (void *)sh->set[i].dst, sh->set[i].owner_off};
+        for (void *p : ptrs)
+            if (p) cudaFree(p);
+    }
+    if (sh->cidx) cudaFree(sh->cidx);
+    if (sh->cache) cudaFree(sh->cache);
+    if (sh->arena) cudaFree(sh->arena);
+    free(sh);
+    h->sh = nullptr;
+}
+
+extern "C" int daisy_shard_init(daisy_handle_t h, int rank, int world, int64_t item_num_global) {
+    DAISY_REQUIRE(h != nullptr, DAISY_EINVAL, "null handle");
+    DAISY_REQUIRE(h->sh == nullptr, DAISY_EINVAL, "handle is already sharded");
+    DAISY_REQUIRE(world >= 1 && world <= DAISY_MAX_RANKS && rank >= 0 && rank < world, DAISY_EINVAL,
+                  "rank %d / world %d out of range (at most %d ranks)", rank, world, DAISY_MAX_RANKS);
+    DAISY_REQUIRE(h->maxB > 0 && h->D % 4 == 0 && h->D <= 512, DAISY_EUNSUPPORTED,
+                  "sharding needs a handle with max_batch > 0, dim %% 4 == 0, dim <= 512");
+    DAISY_REQUIRE(item_num_global > 0 && item_num_global < 0x7ffffffeLL, DAISY_EINVAL, "bad global item count");
+    const int64_t i_per = (item_num_global + world - 1) / world;
+    int64_t lo = (int64_t)rank * i_per, hi = lo + i_per;
+    if (lo > item_num_global) lo = item_num_global;
+    if (hi > item_num_global) hi = item_num_global;
+    DAISY_REQUIRE(h->I == (hi - lo > 0 ? hi - lo : 1), DAISY_EINVAL,
+                  "handle was created with item_num %lld but rank %d of %d owns %lld of %lld items", (long long)h->I, rank,
+                  world, (long long)(hi - lo), (long long)item_num_global);
+    DeviceGuard g(h->device);
+    DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
+    daisy_shard *sh = (daisy_shard *)calloc(1, sizeof(daisy_shard));
+    DAISY_REQUIRE(sh != nullptr, DAISY_ENOMEM, "host allocation failed");
+    sh->rank = rank;
+    sh->world = world;
+    sh->I_global = item_num_global;
+    sh->i_per = i_per;
+    sh->cap = 2 * h->maxB;
+    const size_t D = (size_t)h->D, cap = (size_t)sh->cap, G = (size_t)world;
+    size_t off = 0;
+    sh->off_q = off;      off = align_up(off + (size_t)i_per * D * sizeof(float), 256);
+    sh->off_g = off;      off = align_up(off + G * cap * D * sizeof(float), 256);
+    sh->off_ids = off;    off = align_up(off + G * cap * sizeof(int32_t), 256);
+    sh->off_cnt = off;    off = align_up(off + DAISY_MAX_RANKS * sizeof(uint32_t), 256);
+    sh->off_flags = off;  off = align_up(off + DAISY_MAX_RANKS * sizeof(uint32_t), 256);
+    sh->arena_bytes = off;
+    h->sh = sh;
+    bool ok = cudaMalloc((void **)&sh->arena, sh->arena_bytes) == cudaSuccess;
+    ok = ok && cudaMalloc((void **)&sh->cidx, cap * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMalloc((void **)&sh->cache, cap * D * sizeof(float)) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i) {
+        ok = ok && cudaMalloc((void **)&sh->set[i].uniq_gid, cap * sizeof(uint32_t)) == cudaSuccess;
+        ok = ok && cudaMalloc((void **)&sh->set[i].src, cap * sizeof(float *)) == cudaSuccess;
+        ok = ok && cudaMalloc((void **)&sh->set[i].dst, cap * sizeof(float *)) == cudaSuccess;
+        ok = ok && cudaMalloc((void **)&sh->set[i].owner_off, (DAISY_MAX_RANKS + 1) * sizeof(uint32_t)) == cudaSuccess;
+    }
+    if (!ok) {
+        cudaGetLastError();
+        daisy_set_error("sharding workspace allocation failed (arena of %zu bytes)", sh->arena_bytes);
+        daisy_shard_free(h);
+        return DAISY_ENOMEM;
+    }
+    // counts, flags and the tail of the arena start at zero; q is filled by the caller
+    DAISY_CUDA(cudaMemset(sh->arena + sh->off_cnt, 0, sh->arena_bytes - sh->off_cnt));
+    DAISY_CUDA(cudaDeviceSynchronize());
+    shard_set_peers(sh, rank, sh->arena);
+    if (world == 1) sh->attached = 1;
+    return DAISY_OK;
+}
+
+extern "C" int daisy_shard_arena(daisy_handle_t h, void **arena, float **q_local, int64_t *arena_bytes) {
+    DAISY_REQUIRE(h && h->sh, DAISY_EINVAL, "handle is not sharded");
+    if (arena) *arena = h->sh->arena;
+    if (q_local) *q_local = (float *)(h->sh->arena + h->sh->off_q);
+    if (arena_bytes) *arena_bytes = (int64_t)h->sh->arena_bytes;
+    return DAISY_OK;
+}
+
+extern "C" int daisy_shard_ipc_handle(daisy_handle_t h, void *out64) {
+    DAISY_REQUIRE(h && h->sh && out64, DAISY_EINVAL, "null argument or handle not sharded");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    DeviceGuard g(h->device);
+    cudaIpcMemHandle_t m;
+    DAISY_CUDA(cudaIpcGetMemHandle(&m, h->sh->arena));
+    memcpy(out64, &m, 64);
+    return DAISY_OK;
+}
+
+extern "C" int daisy_shard_attach(daisy_handle_t h, const void *ipc_handles, void *const *arena_ptrs) {
+    DAISY_REQUIRE(h && h->sh, DAISY_EINVAL, "handle is not sharded");
+    DAISY_REQUIRE((ipc_handles != nullptr) != (arena_ptrs != nullptr) || h->sh->world == 1, DAISY_EINVAL,
+                  "pass either the ranks' IPC handles or (same process) their arena pointers");
+    daisy_shard *sh = h->sh;
+    DAISY_REQUIRE(!sh->attached || sh->world == 1, DAISY_EINVAL, "peers are already attached");
+    DeviceGuard g(h->device);
+    DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
+    for (int r = 0; r < sh->world; ++r) {
+        if (r == sh->rank) continue;
+        if (arena_ptrs) {
+            DAISY_REQUIRE(arena_ptrs[r] != nullptr, DAISY_EINVAL, "null arena pointer for rank %d", r);
+            sh->in_process = 1;
+            shard_set_peers(sh, r, (char *)arena_ptrs[r]);
+        } else {
+            cudaIpcMemHandle_t m;
+            memcpy(&m, (const char *)ipc_handles + 64 * (size_t)r, 64);
+            void *p = nullptr;
+            DAISY_CUDA(cudaIpcOpenMemHandle(&p, m, cudaIpcMemLazyEnablePeerAccess));
+            sh->ipc_opened[r] = 1;
+            shard_set_peers(sh, r, (char *)p);
+        }
+    }
+    sh->attached = 1;
+    return DAISY_OK;
+}
+
+extern "C" int daisy_shard_compute(daisy_handle_t h, float *P_local, const int32_t *triples, int64_t B, float lr,
+                                   float wd, double *loss_accum, daisy_stream_t stream) {
+    int rc = shard_ready(h);
+    if (rc) return rc;
+    rc = check_step_args(h, P_local, h->sh->cache, triples, B);
+    if (rc) return rc;
+    return shard_compute(h, P_local, triples, nullptr, B, lr, wd, loss_accum, (cudaStream_t)stream);
+}
+
+extern "C" int daisy_shard_apply(daisy_handle_t h, float lr, float wd, daisy_stream_t stream) {
+    int rc = shard_ready(h);
+    if (rc) return rc;
+    return shard_apply(h, lr, wd, (cudaStream_t)stream);
+}
+
+extern "C" int daisy_shard_barrier(daisy_handle_t h, daisy_stream_t stream) {
+    int rc = shard_ready(h);
+    if (rc) return rc;
+    return shard_barrier(h, (cudaStream_t)stream);
+}
+
+static int shard_step_impl(daisy_handle_t h, float *P_local, const int32_t *triples_dev, const int32_t *host_src,
+                           int64_t B, float lr, float wd, double *loss_accum, daisy_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = shard_compute(h, P_local, triples_dev, host_src, B, lr, wd, loss_accum, s);
+    if (!rc) rc = shard_barrier(h, s);
+    if (!rc) rc = shard_apply(h, lr, wd, s);
+    if (!rc) rc = shard_barrier(h, s);
+    if (!rc && h->scale < 1e-4) rc = daisy_shard_materialize(h, P_local, stream);  // same step on every rank
+    return rc;
+}
+
+extern "C" int daisy_shard_step(daisy_handle_t h, float *P_local, const int32_t *triples, int64_t B, float lr, float wd,
+                                double *loss_accum, daisy_stream_t stream) {
+    int rc = shard_ready(h);
+    if (rc) return rc;
+    rc = check_step_args(h, P_local, h->sh->cache, triples, B);
+    if (rc) return rc;
+    return shard_step_impl(h, P_local, triples, nullptr, B, lr, wd, loss_accum, stream);
+}
+
+extern "C" int daisy_shard_step_host(daisy_handle_t h, float *P_local, const int32_t *triples_host, int64_t B, float lr,
+                                     float wd, double *loss_accum, daisy_stream_t stream) {
+    int rc = shard_ready(h);
+    if (rc) return rc;
+    rc = check_step_args(h, P_local, h->sh->cache, triples_host, B);
+    if (rc) return rc;
+    int32_t *dst = h->triples + (size_t)h->book_idx * 3 * (size_t)h->maxB;
+    return shard_step_impl(h, P_local, dst, triples_host, B, lr, wd, loss_accum, stream);
+}
+
+extern "C" int daisy_shard_materialize(daisy_handle_t h, float *P_local, daisy_stream_t stream) {
+    int rc = shard_ready(h);
+    if (rc) return rc;
+    DAISY_REQUIRE(P_local != nullptr, DAISY_EINVAL, "null argument");
+    // peers fetch rows of this rank's q: the in-place rescale must not overlap their next fetch
+    rc = daisy_materialize(h, P_local, h->sh->peers.q[h->sh->rank], stream);
+    if (!rc && !h->sh->in_process)
+        rc = shard_barrier(h, (cudaStream_t)stream);
+    return rc;
+}
+
+extern "C" int daisy_shard_last_counts(daisy_handle_t h, uint32_t *owner_off_out, daisy_stream_t stream) {
+    int rc = shard_ready(h);
+    if (rc) return rc;
+    DAISY_REQUIRE(owner_off_out != nullptr, DAISY_EINVAL, "null argument");
+    DeviceGuard g(h->device);
+    DAISY_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    DAISY_CUDA(cudaStreamSynchronize(h->side_stream));
+    const ShardSet &ss = h->sh->set[h->book_idx ^ 1];  // the set the most recent step used
+    DAISY_CUDA(cudaMemcpy(owner_off_out, ss.owner_off, (h->sh->world + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return DAISY_OK;
+}

@@ -1,0 +1,744 @@
+// Shared pipeline of the fused BPR step (kernels + host orchestration), included by bpr_step.cu (single GPU:
+// SGD / lazy sparse Adam) and shard.cu (row-sharded tables).  The optimiser / destination of a finished row sum is a
+// functor `Opt` with
+//     apply(int tbl, size_t row, int e, float4 old, float4 d)
+// tbl 0 = user table, 1 = item table; e = float4 index inside the row; old = the row slice as read before the step;
+// d = the complete descent direction (-gradient sum) of that slice.  `Opt::kNeedOldItem` tells the reduce kernels
+// whether `old` of an item row has to be loaded at all.
+#pragma once
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
+
+#include "ctx.cuh"
+
+namespace {
+// ------------------------------------------------------------------------------------------------
+// prep: validate, emit sort keys
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_triple(const int32_t *__restrict__ triples, int t, uint32_t U, uint32_t I,
+                                            uint32_t &u, uint32_t &i, uint32_t &j, bool &bad) {
+    u = (uint32_t)triples[3 * (size_t)t];
+    i = (uint32_t)triples[3 * (size_t)t + 1];
+    j = (uint32_t)triples[3 * (size_t)t + 2];
+    bad = (u >= U) | (i >= I) | (j >= I);
+    if (bad) {  // never fault: park the triple on row 0, the error flag tells the caller
+        u = u < U ? u : 0u;
+        i = i < I ? i : 0u;
+        j = j < I ? j : 0u;
+    }
+}
+
+__global__ void k_prep(const int32_t *__restrict__ triples, int B, uint32_t U, uint32_t I, uint32_t *__restrict__ key,
+                       uint32_t *__restrict__ val, int *err) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B) return;
+    uint32_t u, i, j;
+    bool bad;
+    load_triple(triples, t, U, I, u, i, j, bad);
+    if (bad) {
+        atomicOr(&err[0], 1);
+        atomicMin(&err[1], t);
+    }
+    key[t] = i;
+    val[t] = (uint32_t)t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// refs: sorted triples + reference lists
+// ------------------------------------------------------------------------------------------------
+__global__ void k_refs(const int32_t *__restrict__ triples, const uint32_t *__restrict__ order,
+                       const uint32_t *__restrict__ sorted_i, int B, uint32_t U, uint32_t I, int C,
+                       int32_t *__restrict__ st, uint32_t *__restrict__ ukey, uint32_t *__restrict__ uval,
+                       uint32_t *__restrict__ qkey, uint32_t *__restrict__ qval, uint32_t *__restrict__ islot) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= B) return;
+    uint32_t u, i, j;
+    bool bad;
+    load_triple(triples, (int)order[k], U, I, u, i, j, bad);
+    st[3 * (size_t)k] = (int32_t)u;
+    st[3 * (size_t)k + 1] = (int32_t)i;
+    st[3 * (size_t)k + 2] = (int32_t)j;
+    ukey[k] = u;
+    uval[k] = (uint32_t)k;
+    qkey[k] = j;  // negative-item ref of sorted triple k
+    qval[k] = (uint32_t)k;
+    const bool head = (k % C == 0) || (sorted_i[k - 1] != i);
+    qkey[B + k] = head ? i : I;  // I = sentinel, sorts after every real row
+    qval[B + k] = (uint32_t)(B + k);
+    if (!head) islot[k] = DAISY_NOT_HEAD;  // heads get their slot from k_slots_item
+}
+
+// ------------------------------------------------------------------------------------------------
+// slots: DIRECT (single contribution in the batch) or staging slot = sorted position
+// ------------------------------------------------------------------------------------------------
+__global__ void k_slots_user(const uint32_t *__restrict__ key, const uint32_t *__restrict__ val, int n,
+                             uint32_t *__restrict__ uslot) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t r = key[p];
+    const bool first = (p == 0) || (key[p - 1] != r);
+    const bool last = (p == n - 1) || (key[p + 1] != r);
+    uslot[val[p]] = (first && last) ? DAISY_DIRECT : (uint32_t)p;
+}
+
+__global__ void k_slots_item(const uint32_t *__restrict__ key, const uint32_t *__restrict__ val, int n, int B,
+                             uint32_t sentinel, uint32_t *__restrict__ jslot, uint32_t *__restrict__ islot) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t r = key[p];
+    if (r == sentinel) return;
+    const bool first = (p == 0) || (key[p - 1] != r);
+    const bool last = (p == n - 1) || (key[p + 1] != r);
+    const uint32_t slot = (first && last) ? DAISY_DIRECT : (uint32_t)p;
+    const uint32_t v = val[p];
+    if (v < (uint32_t)B)
+        jslot[v] = slot;
+    else
+        islot[v - B] = slot;
+}
+
+// ------------------------------------------------------------------------------------------------
+// main fused kernel
+// ------------------------------------------------------------------------------------------------
+struct MainArgs {
+    const float *P;
+    const float *Q;
+    const int32_t *st;
+    const uint32_t *uslot, *jslot, *islot;
+    float *stageU, *stageQ;
+    float *loss_part;
+    int B, D4, C;
+    float c2;  // score scale = c^2
+};
+
+template <int V, class Opt>
+__global__ void __launch_bounds__(256) k_bpr_main(MainArgs a, Opt opt) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int warp = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const int C = a.C;
+    const long long k0 = (long long)warp * C;
+    if (k0 >= a.B) return;  // warp-uniform
+    const int n = (int)min((long long)C, (long long)a.B - k0);
+    const int D4 = a.D4;
+
+    // chunk metadata: lane l holds sorted triple k0 + l (C <= 32)
+    int mu = 0, mi = 0, mj = 0;
+    uint32_t mus = 0, mjs = 0, mis = 0;
+    if (lane < n) {
+        const size_t k = (size_t)(k0 + lane);
+        mu = a.st[3 * k];
+        mi = a.st[3 * k + 1];
+        mj = a.st[3 * k + 2];
+        mus = a.uslot[k];
+        mjs = a.jslot[k];
+        mis = a.islot[k];  // DAISY_NOT_HEAD unless this triple starts a positive-item run
+    }
+    bool act[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
+
+    float4 pu[V], qj[V], qi[V], acc[V], pu_n[V], qj_n[V], qi_n[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) pu[v] = qj[v] = qi[v] = acc[v] = pu_n[v] = qj_n[v] = qi_n[v] = f4_zero();
+    {
+        const int u = __shfl_sync(FULL, mu, 0), i = __shfl_sync(FULL, mi, 0), j = __shfl_sync(FULL, mj, 0);
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            if (act[v]) {
+                pu_n[v] = ld_row(a.P, (size_t)u * D4 + lane + 32 * v);
+                qj_n[v] = ld_row(a.Q, (size_t)j * D4 + lane + 32 * v);
+                qi_n[v] = ld_row(a.Q, (size_t)i * D4 + lane + 32 * v);
+            }
+    }
+    int cur_i = -1;
+    uint32_t cur_is = 0;
+    float loss = 0.f;
+
+    for (int t = 0; t < n; ++t) {
+        const int u = __shfl_sync(FULL, mu, t), i = __shfl_sync(FULL, mi, t), j = __shfl_sync(FULL, mj, t);
+        const uint32_t us = __shfl_sync(FULL, mus, t), js = __shfl_sync(FULL, mjs, t);
+        const uint32_t is_t = __shfl_sync(FULL, mis, t);
+        if (is_t != DAISY_NOT_HEAD) {  // a new positive-item run starts here (warp-uniform; t == 0 is always a head)
+            if (t > 0) {
+#pragma unroll
+                for (int v = 0; v < V; ++v)
+                    if (act[v]) {
+                        const int e = lane + 32 * v;
+                        if (cur_is == DAISY_DIRECT)
+                            opt.apply(1, (size_t)cur_i, e, qi[v], acc[v]);
+                        else
+                            st_stream(a.stageQ, (size_t)cur_is * D4 + e, acc[v]);
+                    }
+            }
+            cur_i = i;
+            cur_is = is_t;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                qi[v] = qi_n[v];
+                acc[v] = f4_zero();
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            pu[v] = pu_n[v];
+            qj[v] = qj_n[v];
+        }
+        // prefetch the rows of sorted triple t+1 before touching triple t.  Safe: a row that is written in
+        // place below is referenced exactly once in the whole batch, so no later triple reads it.
+        if (t + 1 < n) {
+            const int un = __shfl_sync(FULL, mu, t + 1), in = __shfl_sync(FULL, mi, t + 1),
+                      jn = __shfl_sync(FULL, mj, t + 1);
+            const bool head_n = __shfl_sync(FULL, mis, t + 1) != DAISY_NOT_HEAD;
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if (act[v]) {
+                    pu_n[v] = ld_row(a.P, (size_t)un * D4 + lane + 32 * v);
+                    qj_n[v] = ld_row(a.Q, (size_t)jn * D4 + lane + 32 * v);
+                    if (head_n) qi_n[v] = ld_row(a.Q, (size_t)in * D4 + lane + 32 * v);
+                }
+        }
+        // x = c^2 <P[u], Q[i] - Q[j]>;  s = sigmoid(-x) = -d(loss)/dx
+        float d = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            if (act[v]) d += f4_dot(pu[v], f4_sub(qi[v], qj[v]));
+        d = warp_sum(d);
+        const float x = d * a.c2;
+        const float s = 1.f / (1.f + expf(x));
+        loss += fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x)));  // -log sigmoid(x), overflow-safe
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            if (act[v]) {
+                const int e = lane + 32 * v;
+                // user row: descent direction +s (Q[i] - Q[j])
+                const float4 gu = f4_scale(f4_sub(qi[v], qj[v]), s);
+                if (us == DAISY_DIRECT)
+                    opt.apply(0, (size_t)u, e, pu[v], gu);
+                else
+                    st_stream(a.stageU, (size_t)us * D4 + e, gu);
+                // negative item row: descent direction -s P[u]
+                const float4 gj = f4_scale(pu[v], -s);
+                if (js == DAISY_DIRECT)
+                    opt.apply(1, (size_t)j, e, qj[v], gj);
+                else
+                    st_stream(a.stageQ, (size_t)js * D4 + e, gj);
+                // positive item row: +s P[u], accumulated over the run in sorted order
+                acc[v].x = fmaf(s, pu[v].x, acc[v].x);
+                acc[v].y = fmaf(s, pu[v].y, acc[v].y);
+                acc[v].z = fmaf(s, pu[v].z, acc[v].z);
+                acc[v].w = fmaf(s, pu[v].w, acc[v].w);
+            }
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+        if (act[v]) {
+            const int e = lane + 32 * v;
+            if (cur_is == DAISY_DIRECT)
+                opt.apply(1, (size_t)cur_i, e, qi[v], acc[v]);
+            else
+                st_stream(a.stageQ, (size_t)cur_is * D4 + e, acc[v]);
+        }
+    if (lane == 0) a.loss_part[warp] = loss;
+}
+
+// ------------------------------------------------------------------------------------------------
+// segmented reduce + row update for rows with several contributions
+// ------------------------------------------------------------------------------------------------
+template <int V>
+__device__ __forceinline__ void sum_staged(const float *__restrict__ stage, size_t q0, int len, int D4, int lane,
+                                           const bool (&act)[V], float4 (&acc)[V]) {
+    constexpr int UN = (V == 1) ? 8 : (V == 2 ? 4 : 2);
+    for (int c = 0; c < len; c += UN) {
+        float4 r[UN][V];
+#pragma unroll
+        for (int jj = 0; jj < UN; ++jj)
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                r[jj][v] = (c + jj < len && act[v]) ? ld_stream(stage, (q0 + c + jj) * D4 + lane + 32 * v) : f4_zero();
+#pragma unroll
+        for (int jj = 0; jj < UN; ++jj)  // fixed order: sorted position ascending
+            if (c + jj < len) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[v] = f4_add(acc[v], r[jj][v]);
+            }
+    }
+}
+
+template <int V, class Opt>
+__global__ void __launch_bounds__(256) k_seg_reduce(int tbl, const float *__restrict__ table,
+                                                     const uint32_t *__restrict__ keys, int n, uint32_t sentinel,
+                                                     const float *__restrict__ stage, int D4, Opt opt, int heavy_len,
+                                                     uint32_t *heavy, int heavy_cap) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const long long w = (long long)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const long long base = w * 32;
+    if (base >= n) return;
+    const long long p = base + lane;
+    const uint32_t key = (p < n) ? keys[p] : sentinel;
+    uint32_t prev = __shfl_up_sync(FULL, key, 1);
+    if (lane == 0) prev = (p > 0) ? keys[p - 1] : ~key;
+    uint32_t next = __shfl_down_sync(FULL, key, 1);
+    if (lane == 31) next = (p + 1 < n) ? keys[p + 1] : sentinel;
+    const bool valid = (p < n) && (key != sentinel);
+    const bool start = valid && (prev != key);
+    const bool multi = start && (next == key) && (p + 1 < n);
+    const unsigned boundary = __ballot_sync(FULL, start || !valid);
+    unsigned todo = __ballot_sync(FULL, multi);
+    bool act[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
+
+    while (todo) {
+        const int b = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t row = __shfl_sync(FULL, key, b);
+        const unsigned after = (b == 31) ? 0u : (boundary & ~((2u << b) - 1u));
+        int len;
+        if (after) {
+            len = (__ffs(after) - 1) - b;
+        } else {  // the segment runs past this window: count matching keys in the following windows
+            len = 32 - b;
+            long long q = base + 32;
+            while (true) {
+                const bool ok = (q + lane < n) && (keys[q + lane] == row);
+                const unsigned m = __ballot_sync(FULL, ok);
+                const int c = (m == FULL) ? 32 : (__ffs(~m) - 1);
+                len += c;
+                if (c < 32 || len > heavy_len) break;
+                q += 32;
+            }
+        }
+        const size_t q0 = (size_t)(base + b);
+        if (len > heavy_len) {  // very hot row: reduced in two levels by k_heavy_slices / k_heavy_final
+            // exact length by a 32-ary search over the sorted keys: keys[q] == row for q in [q0, q0 + len)
+            long long lo = (long long)q0 + len, hi = n;
+            while (lo < hi) {
+                const long long step = (hi - lo + 31) / 32;
+                const long long probe = lo + lane * step;
+                const bool ok = (probe < hi) && (keys[probe] == row);
+                const unsigned m = __ballot_sync(FULL, ok);
+                const int c = (m == FULL) ? 32 : (__ffs(~m) - 1);
+                if (c == 0) break;
+                const long long nhi = lo + c * step;
+                lo = lo + (c - 1) * step + 1;
+                hi = nhi < hi ? nhi : hi;
+            }
+            const uint32_t full = (uint32_t)(lo - (long long)q0);
+            if (lane == 0) {
+                const uint32_t nsl = (full + DAISY_SLICE - 1) / DAISY_SLICE;
+                const uint32_t idx = atomicAdd(&heavy[0], 1u);
+                const uint32_t sl0 = atomicAdd(&heavy[1], nsl);
+                if ((int)idx < heavy_cap) {
+                    uint32_t *rec = heavy + 2 + 5 * (size_t)idx;
+                    rec[0] = (uint32_t)tbl;
+                    rec[1] = row;
+                    rec[2] = (uint32_t)q0;
+                    rec[3] = full;
+                    rec[4] = sl0;
+                }
+            }
+            continue;
+        }
+        float4 old[V], acc[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            old[v] = (act[v] && (tbl == 0 || Opt::kNeedOldItem)) ? ld_row(table, (size_t)row * D4 + lane + 32 * v) : f4_zero();
+            acc[v] = f4_zero();
+        }
+        sum_staged<V>(stage, q0, len, D4, lane, act, acc);
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            if (act[v]) opt.apply(tbl, (size_t)row, lane + 32 * v, old[v], acc[v]);
+    }
+}
+
+// Level 1: every slice of DAISY_SLICE consecutive staged contributions of a hot row is summed by one warp into
+// stage2[first_slice + j].  SPLIT blocks share one hot row so that even the hottest row is spread over
+// SPLIT * 8 warps.
+template <int V>
+__global__ void __launch_bounds__(256) k_heavy_slices(const float *__restrict__ stageU, const float *__restrict__ stageQ,
+                                                       float *__restrict__ stage2, int D4,
+                                                       const uint32_t *__restrict__ heavy, int heavy_cap, int split) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int count = min((int)heavy[0], heavy_cap);
+    bool act[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
+    for (int w = blockIdx.x; w < count * split; w += gridDim.x) {
+        const uint32_t *rec = heavy + 2 + 5 * (size_t)(w / split);
+        const int part = w % split;
+        const float *stage = rec[0] ? stageQ : stageU;
+        const size_t q0 = rec[2];
+        const int len = (int)rec[3];
+        const size_t sl0 = rec[4];
+        const int nsl = (len + DAISY_SLICE - 1) / DAISY_SLICE;
+        for (int j = part + split * wid; j < nsl; j += split * 8) {
+            const int c0 = j * DAISY_SLICE;
+            const int cn = min(DAISY_SLICE, len - c0);
+            float4 acc[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] = f4_zero();
+            sum_staged<V>(stage, q0 + c0, cn, D4, lane, act, acc);
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if (act[v]) st_stream(stage2, (sl0 + j) * D4 + lane + 32 * v, acc[v]);
+        }
+    }
+}
+
+// Level 2: one block per hot row sums the row's slice partials (fixed split over 8 warps, fixed combine order)
+// and applies the update.
+template <int V, class Opt>
+__global__ void __launch_bounds__(256) k_heavy_final(const float *__restrict__ P, const float *__restrict__ Q,
+                                                      const float *__restrict__ stage2, int D4, Opt opt,
+                                                      const uint32_t *__restrict__ heavy, int heavy_cap) {
+    __shared__ float4 part[8][32 * V];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int count = min((int)heavy[0], heavy_cap);
+    bool act[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
+    for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
+        const uint32_t *rec = heavy + 2 + 5 * (size_t)idx;
+        const int tbl = (int)rec[0];
+        const uint32_t row = rec[1];
+        const int nsl = ((int)rec[3] + DAISY_SLICE - 1) / DAISY_SLICE;
+        const size_t sl0 = rec[4];
+        const float *table = tbl ? Q : P;
+        const int per = (nsl + 7) / 8;
+        const int c0 = min(nsl, wid * per), c1 = min(nsl, c0 + per);
+        float4 acc[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] = f4_zero();
+        sum_staged<V>(stage2, sl0 + c0, c1 - c0, D4, lane, act, acc);
+#pragma unroll
+        for (int v = 0; v < V; ++v) part[wid][lane + 32 * v] = acc[v];
+        __syncthreads();
+        if (wid == 0) {
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if (act[v]) {
+                    float4 tot = part[0][lane + 32 * v];
+                    for (int ww = 1; ww < 8; ++ww) tot = f4_add(tot, part[ww][lane + 32 * v]);  // fixed order
+                    const int e = lane + 32 * v;
+                    const float4 old = (tbl == 0 || Opt::kNeedOldItem) ? ld_row(table, (size_t)row * D4 + e) : f4_zero();
+                    opt.apply(tbl, (size_t)row, e, old, tot);
+                }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// loss: fixed-order reduction of per-warp partials (double accumulation), added to *loss_accum
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_loss(const float *__restrict__ part, int n, double *loss_accum) {
+    __shared__ double sh[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) s += (double)part[i];
+    s = warp_sum_d(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = sh[threadIdx.x];
+        t = warp_sum_d(t);
+        if (threadIdx.x == 0) *loss_accum += t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int bits_for(uint64_t max_value) {  // number of low bits needed to represent max_value
+    int b = 1;
+    while (b < 32 && (max_value >> b)) ++b;
+    return b;
+}
+
+static int auto_chunk(const daisy_ctx *h, int64_t B) {
+    if (h->chunk > 0) return h->chunk;
+    // keep >= ~4 waves of 32 resident warps per SM before growing the chunk
+    const int64_t want_warps = (int64_t)h->num_sms * 32 * 4;
+    int c = 1;
+    while (c < 16 && B / (2 * c) >= want_warps) c *= 2;
+    return c;
+}
+
+static inline void phase_mark(daisy_ctx *h, int ph, cudaStream_t s) {
+    if (h->timing == 2) cudaEventRecord(h->ev[ph + 1], s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// row-sharded bookkeeping (shard.cu): item refs carry GLOBAL ids; the sorted, de-duplicated ids of the batch are
+// its CACHE rows (cache row c = c-th smallest id => grouped by owner block)
+// ------------------------------------------------------------------------------------------------
+struct StartFlag {  // 1 where a new row starts in the sorted item refs
+    const uint32_t *key;
+    uint32_t sentinel;
+    __host__ __device__ __forceinline__ uint32_t operator()(int p) const {
+        const uint32_t r = key[p];
+        return (r != sentinel && (p == 0 || key[p - 1] != r)) ? 1u : 0u;
+    }
+};
+
+// k_slots_item + cache-row assignment: cidx[p] = inclusive count of row starts up to p, so the cache row of sorted
+// ref p is cidx[p] - 1.  Rewrites the item columns of the sorted triples from global ids to cache rows, lists the
+// global id of every cache row and the first cache row of every owner.
+__global__ void k_slots_item_shard(const uint32_t *__restrict__ key, const uint32_t *__restrict__ val,
+                                   const uint32_t *__restrict__ cidx, int n, int B, uint32_t sentinel, uint32_t i_per,
+                                   int G, uint32_t *__restrict__ jslot, uint32_t *__restrict__ islot,
+                                   int32_t *__restrict__ st, uint32_t *__restrict__ uniq_gid,
+                                   uint32_t *__restrict__ owner_off) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t r = key[p];
+    if (r == sentinel) return;
+    const bool first = (p == 0) || (key[p - 1] != r);
+    const bool last = (p == n - 1) || (key[p + 1] != r);
+    const uint32_t slot = (first && last) ? DAISY_DIRECT : (uint32_t)p;
+    const uint32_t c = cidx[p] - 1u;
+    const uint32_t v = val[p];
+    if (v < (uint32_t)B) {
+        jslot[v] = slot;
+        st[3 * (size_t)v + 2] = (int32_t)c;
+    } else {
+        islot[v - B] = slot;
+        st[3 * (size_t)(v - B) + 1] = (int32_t)c;
+    }
+    if (first) {
+        uniq_gid[c] = r;
+        const int o_cur = (int)(r / i_per);
+        const int o_prev = (p == 0) ? -1 : (int)(key[p - 1] / i_per);
+        for (int o = o_prev + 1; o <= o_cur; ++o) owner_off[o] = c;
+    }
+    if (last && (p == n - 1 || key[p + 1] == sentinel)) {  // the last real ref: close the offsets
+        for (int o = (int)(r / i_per) + 1; o <= G; ++o) owner_off[o] = c + 1u;
+    }
+}
+
+// Sorted item-ref keys become cache rows (same grouping and order: the map gid -> cache row is monotone), and every
+// cache row gets the address it is fetched from (owner's q) and the address its descent sum is pushed to (region
+// `me` of the owner's recv_g).
+__global__ void k_shard_finish(uint32_t *__restrict__ key, const uint32_t *__restrict__ cidx, int n, uint32_t sentinel,
+                               const uint32_t *__restrict__ uniq_gid, const uint32_t *__restrict__ owner_off, int G,
+                               uint32_t i_per, int me, size_t cap, int D, ShardPeers peers,
+                               const float **__restrict__ src, float **__restrict__ dst) {
+    const uint32_t nuniq = owner_off[G];
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        if (key[p] != sentinel) key[p] = cidx[p] - 1u;
+        if ((uint32_t)p < nuniq) {
+            const uint32_t g = uniq_gid[p];
+            const uint32_t o = g / i_per;
+            src[p] = peers.q[o] + (size_t)(g - o * i_per) * D;
+            dst[p] = peers.recv_g[o] + ((size_t)me * cap + ((uint32_t)p - owner_off[o])) * D;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host orchestration: bookkeeping phase (depends on the triples only) + table phase
+// ------------------------------------------------------------------------------------------------
+struct StepPlan {
+    int B, C;
+    uint32_t U, I;        // id bounds: user rows, item ids (I is also the sentinel key of the item refs)
+    bool piped;
+    cudaStream_t bs, s;   // bookkeeping stream, caller's stream
+    BookSet *k;
+    int set;              // index of k in h->book
+};
+
+// The integer bookkeeping of a step (prep .. slots) depends on the triples only, never on the tables.  It runs on
+// the handle's side stream into one of two bookkeeping sets, so that for step n+1 it overlaps the bandwidth-bound
+// kernels of step n on the caller's stream.  Per-phase timing (mode 2) serialises everything on the caller's
+// stream so that phase times do not overlap.
+static int book_phase(daisy_ctx *h, StepPlan &pl, const int32_t *triples, int64_t B64, uint32_t U, uint32_t I,
+                      cudaStream_t s, const int32_t *host_src, bool inputs_ready, const daisy_shard *sh) {
+    const int B = (int)B64;
+    const int C = auto_chunk(h, B);
+    const int T = 256;
+    const bool piped = h->pipeline && h->timing != 2;
+    cudaStream_t bs = piped ? h->side_stream : s;
+    pl.B = B; pl.C = C; pl.U = U; pl.I = I; pl.piped = piped; pl.bs = bs; pl.s = s;
+    pl.set = h->book_idx;
+    BookSet &k = h->book[h->book_idx];
+    pl.k = &k;
+    h->book_idx ^= 1;
+    if (h->timing == 2) {
+        if (h->ev_pending) {  // fold the previous step's phase times in
+            cudaEventSynchronize(h->ev[PH_COUNT]);
+            for (int ph = 0; ph < PH_COUNT; ++ph) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, h->ev[ph], h->ev[ph + 1]);
+                h->phase_ms_sum[ph] += ms;
+            }
+            h->timed_steps++;
+            h->ev_pending = 0;
+        }
+        cudaEventRecord(h->ev[0], s);
+    }
+    if (piped) {
+        if (!inputs_ready) {  // the triples may have been produced by earlier work on the caller's stream
+            DAISY_CUDA(cudaEventRecord(h->ev_call, s));
+            DAISY_CUDA(cudaStreamWaitEvent(bs, h->ev_call, 0));
+        }
+        DAISY_CUDA(cudaStreamWaitEvent(bs, k.freed, 0));  // the step that last used this set has finished
+    }
+    const bool tr = h->trace && h->tr_n < DAISY_TRACE_STEPS;
+    if (tr) cudaEventRecord(h->tr_ev[4 * h->tr_n + 0], bs);
+    if (host_src) {  // *_step_host: the H2D copy is the first node of the bookkeeping chain
+        DAISY_CUDA(cudaMemcpyAsync((void *)triples, host_src, (size_t)B * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, bs));
+    }
+    // prep
+    k_prep<<<daisy_ceil_div(B, T), T, 0, bs>>>(triples, B, U, I, h->ikey_in, h->ival_in, h->err);
+    DAISY_LAUNCH_CHECK(h);
+    phase_mark(h, PH_PREP, s);
+    // sort by positive item
+    size_t tmp = h->cub_tmp_bytes;
+    DAISY_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->ikey_in, h->ikey_out, h->ival_in, h->ival_out, B, 0,
+                                               bits_for(I - 1), bs));
+    h->launches += 4;
+    phase_mark(h, PH_SORT_I, s);
+    // refs
+    k_refs<<<daisy_ceil_div(B, T), T, 0, bs>>>(triples, h->ival_out, h->ikey_out, B, U, I, C, k.st, h->ukey_in,
+                                               h->uval_in, h->key_in, h->val_in, k.islot);
+    DAISY_LAUNCH_CHECK(h);
+    phase_mark(h, PH_REFS, s);
+    tmp = h->cub_tmp_bytes;
+    DAISY_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->ukey_in, k.ukey_s, h->uval_in, h->uval_out, B, 0,
+                                               bits_for(U - 1), bs));
+    h->launches += 4;
+    phase_mark(h, PH_SORT_U, s);
+    tmp = h->cub_tmp_bytes;
+    DAISY_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->key_in, k.qkey_s, h->val_in, h->val_out, 2 * B, 0,
+                                               bits_for(I), bs));
+    h->launches += 4;
+    phase_mark(h, PH_SORT_Q, s);
+    // slots
+    k_slots_user<<<daisy_ceil_div(B, T), T, 0, bs>>>(k.ukey_s, h->uval_out, B, k.uslot);
+    DAISY_LAUNCH_CHECK(h);
+    if (!sh) {
+        k_slots_item<<<daisy_ceil_div(2 * (int64_t)B, T), T, 0, bs>>>(k.qkey_s, h->val_out, 2 * B, B, I, k.jslot, k.islot);
+        DAISY_LAUNCH_CHECK(h);
+    } else {
+        const ShardSet &ss = sh->set[pl.set];
+        auto flags = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), StartFlag{k.qkey_s, I});
+        tmp = h->cub_tmp_bytes;
+        DAISY_CUDA(cub::DeviceScan::InclusiveSum(h->cub_tmp, tmp, flags, sh->cidx, 2 * B, bs));
+        h->launches += 2;
+        k_slots_item_shard<<<daisy_ceil_div(2 * (int64_t)B, T), T, 0, bs>>>(
+            k.qkey_s, h->val_out, sh->cidx, 2 * B, B, I, (uint32_t)sh->i_per, sh->world, k.jslot, k.islot, k.st,
+            ss.uniq_gid, ss.owner_off);
+        DAISY_LAUNCH_CHECK(h);
+        k_shard_finish<<<daisy_ceil_div(2 * (int64_t)B, T), T, 0, bs>>>(k.qkey_s, sh->cidx, 2 * B, I, ss.uniq_gid,
+                                                                         ss.owner_off, sh->world, (uint32_t)sh->i_per,
+                                                                         sh->rank, (size_t)sh->cap, h->D, sh->peers,
+                                                                         ss.src, ss.dst);
+        DAISY_LAUNCH_CHECK(h);
+    }
+    phase_mark(h, PH_SLOTS, s);
+    if (piped) {
+        DAISY_CUDA(cudaEventRecord(k.ready, bs));
+        DAISY_CUDA(cudaStreamWaitEvent(s, k.ready, 0));
+    }
+    if (tr) {
+        cudaEventRecord(h->tr_ev[4 * h->tr_n + 1], bs);
+        cudaEventRecord(h->tr_ev[4 * h->tr_n + 2], s);
+    }
+    return DAISY_OK;
+}
+
+// The table-touching kernels of a step, on the caller's stream: main, segmented reduces, hot rows, loss.
+// Q is the item table (or, sharded, the cache of fetched rows; the sorted item-ref keys then hold cache rows).
+template <int V, class Opt>
+static int table_phase_v(daisy_ctx *h, const StepPlan &pl, const float *P, const float *Q, const Opt &opt, float c2,
+                         double *loss_accum) {
+    const int B = pl.B, C = pl.C;
+    const int D4 = h->D / 4;
+    cudaStream_t s = pl.s;
+    BookSet &k = *pl.k;
+    DAISY_CUDA(cudaMemsetAsync(h->heavy, 0, 2 * sizeof(uint32_t), s));
+    MainArgs a;
+    a.P = P; a.Q = Q; a.st = k.st; a.uslot = k.uslot; a.jslot = k.jslot; a.islot = k.islot;
+    a.stageU = h->stageU; a.stageQ = h->stageQ; a.loss_part = h->loss_part;
+    a.B = B; a.D4 = D4; a.C = C; a.c2 = c2;
+    const int warps = daisy_ceil_div(B, C);
+    const bool pool = (h->timing == 1 && h->pool_used < DAISY_EVPOOL);
+    if (pool) cudaEventRecord(h->evpool[2 * h->pool_used], s);
+    k_bpr_main<V, Opt><<<daisy_ceil_div(warps, 8), 256, 0, s>>>(a, opt);
+    DAISY_LAUNCH_CHECK(h);
+    if (pool) {
+        cudaEventRecord(h->evpool[2 * h->pool_used + 1], s);
+        h->pool_used++;
+    }
+    phase_mark(h, PH_MAIN, s);
+    // segmented reduces
+    k_seg_reduce<V, Opt><<<daisy_ceil_div(daisy_ceil_div(B, 32), 8), 256, 0, s>>>(
+        0, P, k.ukey_s, B, 0xFFFFFFFFu, h->stageU, D4, opt, h->heavy_len, h->heavy, h->heavy_cap);
+    DAISY_LAUNCH_CHECK(h);
+    phase_mark(h, PH_SEG_U, s);
+    k_seg_reduce<V, Opt><<<daisy_ceil_div(daisy_ceil_div(2 * (int64_t)B, 32), 8), 256, 0, s>>>(
+        1, Q, k.qkey_s, 2 * B, pl.I, h->stageQ, D4, opt, h->heavy_len, h->heavy, h->heavy_cap);
+    DAISY_LAUNCH_CHECK(h);
+    phase_mark(h, PH_SEG_Q, s);
+    const int split = 8;
+    k_heavy_slices<V><<<h->num_sms * 4, 256, 0, s>>>(h->stageU, h->stageQ, h->stage2, D4, h->heavy, h->heavy_cap, split);
+    DAISY_LAUNCH_CHECK(h);
+    k_heavy_final<V, Opt><<<h->num_sms, 256, 0, s>>>(P, Q, h->stage2, D4, opt, h->heavy, h->heavy_cap);
+    DAISY_LAUNCH_CHECK(h);
+    phase_mark(h, PH_HEAVY, s);
+    if (loss_accum) {
+        k_loss<<<1, 1024, 0, s>>>(h->loss_part, warps, loss_accum);
+        DAISY_LAUNCH_CHECK(h);
+    }
+    phase_mark(h, PH_LOSS, s);
+    if (pl.piped) DAISY_CUDA(cudaEventRecord(k.freed, s));
+    if (h->trace && h->tr_n < DAISY_TRACE_STEPS) {
+        cudaEventRecord(h->tr_ev[4 * h->tr_n + 3], s);
+        h->tr_n++;
+    }
+    if (h->timing == 2) {
+        h->ev_pending = 1;
+        h->ev_stream = s;
+    }
+    return DAISY_OK;
+}
+
+template <class Opt>
+static int table_phase(daisy_ctx *h, const StepPlan &pl, const float *P, const float *Q, const Opt &opt, float c2,
+                       double *loss_accum) {
+    const int D4 = h->D / 4;
+    if (D4 <= 32) return table_phase_v<1, Opt>(h, pl, P, Q, opt, c2, loss_accum);
+    if (D4 <= 64) return table_phase_v<2, Opt>(h, pl, P, Q, opt, c2, loss_accum);
+    if (D4 <= 96) return table_phase_v<3, Opt>(h, pl, P, Q, opt, c2, loss_accum);
+    return table_phase_v<4, Opt>(h, pl, P, Q, opt, c2, loss_accum);
+}
+
+template <class Opt>
+static int run_step(daisy_ctx *h, const float *P, const float *Q, const int32_t *triples, int64_t B, const Opt &opt,
+                    float c2, double *loss_accum, cudaStream_t s, const int32_t *host_src, bool inputs_ready) {
+    // the NCCL-exchange sharded step runs against a cache of fetched item rows whose row count differs from the
+    // local item shard
+    const uint32_t U = (uint32_t)h->U, I = (uint32_t)(h->item_rows_override ? h->item_rows_override : h->I);
+    StepPlan pl;
+    int rc = book_phase(h, pl, triples, B, U, I, s, host_src, inputs_ready, nullptr);
+    if (rc) return rc;
+    return table_phase<Opt>(h, pl, P, Q, opt, c2, loss_accum);
+}
+
+static int check_step_args(daisy_ctx *h, const void *P, const void *Q, const void *triples, int64_t B) {
+    DAISY_REQUIRE(h != nullptr, DAISY_EINVAL, "null handle");
+    DAISY_REQUIRE(P && Q && (triples || B == 0), DAISY_EINVAL, "null table or triples pointer");
+    DAISY_REQUIRE(h->maxB > 0 && h->D % 4 == 0 && h->D <= 512, DAISY_EUNSUPPORTED,
+                  "BPR step needs a handle created with max_batch > 0 and dim %% 4 == 0, dim <= 512 (dim is %d)", h->D);
+    DAISY_REQUIRE(B >= 0 && B <= h->maxB, DAISY_EINVAL, "batch of %lld triples exceeds max_batch %lld", (long long)B,
+                  (long long)h->maxB);
+    DAISY_REQUIRE(((uintptr_t)P % 16 == 0) && ((uintptr_t)Q % 16 == 0), DAISY_EINVAL, "tables must be 16-byte aligned");
+    return DAISY_OK;
+}
+
+
+}  // namespace

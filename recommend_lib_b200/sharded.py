@@ -20,6 +20,7 @@ single-GPU step up to fp32 summation order.  The collectives are NCCL all-to-all
 """
 from __future__ import annotations
 
+import ctypes
 import math
 import os
 import time
@@ -260,6 +261,157 @@ class ShardedBPR:
         return out[0], out[1]
 
 
+class _DeviceView:
+    """A [rows, dim] fp32 window on device memory owned by the library (the item shard inside the rank's arena),
+    exposed to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, rows, dim):
+        self.__cuda_array_interface__ = {"shape": (int(rows), int(dim)), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def exchange_ipc_handles(blob, group=None, device=None):
+    """All-gather one 64-byte CUDA IPC handle per rank over torch.distributed (any backend) -> list of bytes."""
+    world = dist.get_world_size(group)
+    dev = device if (device is not None and dist.get_backend(group) == "nccl") else torch.device("cpu")
+    mine = torch.tensor(list(blob), dtype=torch.uint8, device=dev)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    return [bytes(p.cpu().tolist()) for p in parts]
+
+
+class PeerShardedBPR:
+    """One rank's share of a row-sharded BPR-MF model whose exchange runs over PEER MEMORY (NVLink) inside the step
+    kernels -- the product path of BASELINE.json configs[4] (include/daisy_b200.h, daisy_shard_*).  No CPU fallback.
+
+    ``P`` [local users, D] is an ordinary CUDA tensor; ``Q`` [local items, D] is a view of the item shard inside the
+    rank's arena (library-owned memory that the peer GPUs map through CUDA IPC).  ``step(triples)``: int32 [B, 3] with
+    columns (LOCAL user index, GLOBAL positive item, GLOBAL negative item), on the device or in pinned host memory.
+    Every rank must call ``step`` the same number of times.
+    """
+
+    def __init__(self, user_num, item_num, factor_num, lr=0.01, wd=0.001, max_batch=4096, rank=None, world=None,
+                 device=None, P_full=None, Q_full=None, seed=2019):
+        from . import _lib
+        _lib.require_cuda()
+        self._lib = _lib
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.layout = ShardLayout(user_num, item_num, self.world)
+        self.dim, self.lr, self.wd = int(factor_num), float(lr), float(wd)
+        self.device = torch.device(device if device is not None else "cuda")
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        u0, u1 = self.layout.user_range(self.rank)
+        i0, i1 = self.layout.item_range(self.rank)
+        self.u0, self.i0 = u0, i0
+        self.h = _lib.Handle(idx, max(u1 - u0, 1), max(i1 - i0, 1), self.dim, max_batch)
+        L, vp = self.h.L, _lib.c_vp
+        _lib.check(L.daisy_shard_init(self.h.ptr, self.rank, self.world, int(item_num)))
+        arena, q, nbytes = vp(), vp(), _lib.c_i64()
+        _lib.check(L.daisy_shard_arena(self.h.ptr, ctypes.byref(arena), ctypes.byref(q), ctypes.byref(nbytes)))
+        self.arena_ptr, self.arena_bytes = arena.value, nbytes.value
+        with torch.cuda.device(self.device):
+            self.Q = torch.as_tensor(_DeviceView(q.value, max(i1 - i0, 1), self.dim), device=self.device)[:i1 - i0]
+            if P_full is not None:
+                self.P = torch.as_tensor(P_full)[u0:u1].to(self.device, torch.float32).contiguous()
+                self.Q.copy_(torch.as_tensor(Q_full)[i0:i1].to(self.device, torch.float32))
+            else:
+                g = torch.Generator(device=self.device).manual_seed(seed * 1000 + self.rank)
+                self.P = torch.empty((u1 - u0, self.dim), device=self.device).normal_(0, 0.01, generator=g)
+                self.Q.normal_(0, 0.01, generator=g)
+            if self.P.shape[0] == 0:
+                self.P = torch.zeros((1, self.dim), device=self.device)[:0]
+            self.loss = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._P_ptr = self.P.data_ptr() if self.P.shape[0] else torch.zeros((1, self.dim), device=self.device).data_ptr()
+        self.attached = self.world == 1
+        torch.cuda.synchronize(self.device)
+
+    # ---- wiring ---------------------------------------------------------------------------------------------------
+    def ipc_handle(self):
+        buf = (ctypes.c_ubyte * 64)()
+        self._lib.check(self.h.L.daisy_shard_ipc_handle(self.h.ptr, ctypes.cast(buf, ctypes.c_void_p)))
+        return bytes(buf)
+
+    def connect(self, group=None):
+        """Exchange the ranks' IPC handles over torch.distributed and map the peers' arenas."""
+        if self.world > 1:
+            blobs = exchange_ipc_handles(self.ipc_handle(), group, self.device)
+            raw = b"".join(blobs)
+            buf = (ctypes.c_ubyte * len(raw)).from_buffer_copy(raw)
+            self._lib.check(self.h.L.daisy_shard_attach(self.h.ptr, ctypes.cast(buf, ctypes.c_void_p), None))
+            self.attached = True
+            dist.barrier(group)
+        return self
+
+    @staticmethod
+    def connect_in_process(shards):
+        """All ranks live in this process on one device (tests): hand every rank the others' arena pointers."""
+        G = len(shards)
+        arr = (ctypes.c_void_p * G)(*[s.arena_ptr for s in shards])
+        for s in shards:
+            if G > 1:
+                s._lib.check(s.h.L.daisy_shard_attach(s.h.ptr, None, arr))
+            s.attached = True
+
+    def _s(self):
+        return self._lib.stream_ptr(torch, self.device)
+
+    # ---- the step ---------------------------------------------------------------------------------------------------
+    def step(self, triples):
+        vp = self._lib.c_vp
+        B = int(triples.shape[0])
+        fn = self.h.L.daisy_shard_step if triples.is_cuda else self.h.L.daisy_shard_step_host
+        self._lib.check(fn(self.h.ptr, vp(self._P_ptr), vp(triples.data_ptr() if B else 0), B, self.lr, self.wd,
+                           vp(self.loss.data_ptr()), self._s()))
+
+    def compute(self, triples):
+        vp = self._lib.c_vp
+        B = int(triples.shape[0])
+        self._lib.check(self.h.L.daisy_shard_compute(self.h.ptr, vp(self._P_ptr), vp(triples.data_ptr() if B else 0), B,
+                                                     self.lr, self.wd, vp(self.loss.data_ptr()), self._s()))
+
+    def apply(self):
+        self._lib.check(self.h.L.daisy_shard_apply(self.h.ptr, self.lr, self.wd, self._s()))
+
+    def materialize(self):
+        self._lib.check(self.h.L.daisy_shard_materialize(self.h.ptr, self._lib.c_vp(self._P_ptr), self._s()))
+
+    def check(self):
+        self._lib.check(self.h.L.daisy_check(self.h.ptr, self._s()))
+
+    def last_counts(self):
+        """Distinct item rows the most recent step exchanged with every owner (list of `world` ints).  Synchronises."""
+        buf = (ctypes.c_uint32 * (self.world + 1))()
+        self._lib.check(self.h.L.daisy_shard_last_counts(self.h.ptr, ctypes.cast(buf, ctypes.c_void_p), self._s()))
+        return [int(buf[o + 1]) - int(buf[o]) for o in range(self.world)]
+
+    def loss_sum(self, reset=True, group=None, reduce=False):
+        t = self.loss.clone()
+        if reduce and self.world > 1:
+            dist.all_reduce(t, group=group)
+        if reset:
+            self.loss.zero_()
+        return float(t.item())
+
+    def full_tables(self):
+        """All-gather the (materialised) shards: (P [U, D], Q [I, D]) on every rank.  Test / small-model helper."""
+        self.materialize()
+        out = []
+        for t, per in ((self.P, self.layout.u_per), (self.Q, self.layout.i_per)):
+            pad = torch.zeros((per, self.dim), device=self.device)
+            pad[:t.shape[0]] = t
+            parts = [torch.empty_like(pad) for _ in range(self.world)]
+            dist.all_gather(parts, pad)
+            out.append(torch.cat(parts))
+        return out[0][:self.layout.user_num], out[1][:self.layout.item_num]
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        self.Q = None
+        self.h.close()
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # bench.py --gpus N  (launched by torchrun, one rank per GPU)
 # ----------------------------------------------------------------------------------------------------------------
@@ -276,9 +428,18 @@ def bench_sharded(args, cfg, metric, unit):
     U, I, D, B = cfg["user_num"], cfg["item_num"], cfg["dim"], cfg["batch"]
     if args.scale != 1.0:
         U, I = int(U * args.scale), int(I * args.scale)
+    if args.batch:
+        B = args.batch
     K, W = args.steps, max(args.warmup, 3)
-    model = ShardedBPR(U, I, D, lr=cfg["lr"], wd=cfg["wd"], max_batch=B, rank=rank, world=world, device=dev,
-                       comm=DistComm(), seed=2019)
+    peer = args.exchange == "peer"
+    if peer:
+        model = PeerShardedBPR(U, I, D, lr=cfg["lr"], wd=cfg["wd"], max_batch=B, rank=rank, world=world, device=dev,
+                               seed=2019).connect()
+        handle, loss_dev, check = model.h, model.loss, model.check
+    else:
+        model = ShardedBPR(U, I, D, lr=cfg["lr"], wd=cfg["wd"], max_batch=B, rank=rank, world=world, device=dev,
+                           comm=DistComm(), seed=2019)
+        handle, loss_dev, check = model.backend.h, model.backend.loss, model.backend.check
     u0, u1 = model.layout.user_range(rank)
     nb = K + W
     g = _rng(2019, 40, rank)
@@ -288,29 +449,50 @@ def bench_sharded(args, cfg, metric, unit):
     host[:, 2] = g.integers(0, I, size=nb * B)
     host = torch.from_numpy(host.reshape(nb, B, 3)).pin_memory()
     devtri = host.to(dev)
+    if peer:
+        handle.set_inputs_ready(True)      # device triples are uploaded and synchronised before they are used
 
     def run(first, count, src):
         for s in range(first, first + count):
-            model.step(src[s] if src is devtri else src[s].to(dev, non_blocking=True))
+            if peer:
+                model.step(src[s])
+            else:
+                model.step(src[s] if src is devtri else src[s].to(dev, non_blocking=True))
 
     run(0, W, devtri)
-    model.backend.check()
+    check()
     torch.cuda.synchronize()
     dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    model.wire_rows = 0
-    launches0 = model.backend.h.launches
+    if not peer:
+        model.wire_rows = 0
+    launches0 = handle.launches
+    clocks = None
+    if rank == 0:
+        try:
+            import bench as _bench
+            clocks = _bench.ClockSampler(local)
+            clocks.start()
+        except Exception:
+            clocks = None
     torch.cuda.synchronize()
     ev0.record()
     run(W, K, devtri)
     model.materialize()
     ev1.record()
     torch.cuda.synchronize()
+    if clocks is not None:
+        clocks.stop()
     dist.barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    launches = model.backend.h.launches - launches0
-    wire_rows = model.wire_rows
+    launches = handle.launches - launches0
+    if peer:
+        cnt = model.last_counts()
+        remote = sum(cnt) - cnt[rank]
+        wire_rows = 2 * remote * K         # fetched rows in + pushed sums out, per rank (last step's count, every step alike)
+    else:
+        wire_rows = model.wire_rows
     # e2e: host triples, per-step loss read-back
     loss_host = torch.zeros(nb, dtype=torch.float64).pin_memory()
     run(0, W, host)
@@ -318,17 +500,20 @@ def bench_sharded(args, cfg, metric, unit):
     dist.barrier()
     ev0.record()
     for s in range(W, W + K):
-        model.step(host[s].to(dev, non_blocking=True))
-        loss_host[s:s + 1].copy_(model.backend.loss, non_blocking=True)
+        if peer:
+            model.step(host[s])
+        else:
+            model.step(host[s].to(dev, non_blocking=True))
+        loss_host[s:s + 1].copy_(loss_dev, non_blocking=True)
     model.materialize()
     ev1.record()
     torch.cuda.synchronize()
     dist.barrier()
     ms2 = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    model.backend.check()
+    check()
     phases = None
-    if args.phases:
+    if args.phases and not peer:
         model.profile = []
         run(0, min(nb, 10), devtri)
         phases = model.profile_summary()
@@ -337,19 +522,30 @@ def bench_sharded(args, cfg, metric, unit):
         ms_total, ms_e2e = float(ms), float(ms2)
         value = B * world * K / (ms_total * 1e-3)
         wire_bytes = wire_rows / K * 4 * D                      # per step, this rank, rows in + rows out
+        peak_nvl = 770.0
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": cfg["workload"], "user_num": U, "item_num": I, "dim": D,
                            "batch_per_gpu": B, "global_batch": B * world, "lr": cfg["lr"], "wd": cfg["wd"],
-                           "sharding": "block rows, triples routed to the user's owner, item rows + row gradients "
-                                       "exchanged by NCCL all-to-all", "l2": "inputs larger than L2"},
+                           "sharding": ("block rows, triples routed to the user's owner; item rows read from / row "
+                                        "sums stored to the owners' memory by the step kernels over NVLink (CUDA IPC "
+                                        "peer pointers), flag barriers, deterministic owner-side merge") if peer else
+                                       ("block rows, triples routed to the user's owner, item rows + row gradients "
+                                        "exchanged by NCCL all-to-all"),
+                           "exchange": args.exchange, "l2": "inputs larger than L2",
+                           "lazy_decay_materialized_in_timed_region": True},
+                "clocks": clocks.summary() if clocks is not None else None,
                 "e2e": {"value": B * world * K / (ms_e2e * 1e-3), "unit": unit, "ms_per_step": ms_e2e / K,
                         "h2d_bytes_per_step": B * 12 * world, "d2h_bytes_per_step": 8 * world},
                 "gpu_launches": int(launches),
-                "nvlink": {"rows_exchanged_per_step_per_gpu": wire_rows / K, "bytes_per_step_per_gpu_each_way": wire_bytes / 2,
-                           "achieved_GBs_each_way": wire_bytes / 2 / (ms_total / K * 1e-3) / 1e9,
-                           "measured_peer_copy_GBs": 770.0}}
+                "roofline": {"bound": "nvlink", "achieved": wire_bytes / 2 / (ms_total / K * 1e-3) / 1e9, "peak": peak_nvl,
+                             "unit": "GB/s per direction per GPU",
+                             "frac": wire_bytes / 2 / (ms_total / K * 1e-3) / 1e9 / peak_nvl,
+                             "traffic": None, "peak_source": "measured peer copy (B200_PROFILING.md)",
+                             "rows_exchanged_per_step_per_gpu": wire_rows / K,
+                             "bytes_per_step_per_gpu_each_way": wire_bytes / 2,
+                             "hbm_whole_step_frac": (B * (24 * D + 12) / (ms_total / K * 1e-3) / 1e9) / 6461.8}}
         if phases:
             line["phase_ms(device,host)"] = phases
         print(json.dumps(line), flush=True)

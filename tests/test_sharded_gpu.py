@@ -81,3 +81,149 @@ def test_sharded_step_is_deterministic():
             s.materialize()
         outs.append((torch.cat([s.P for s in shards]).clone(), torch.cat([s.Q for s in shards]).clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# peer-memory path (daisy_shard_*): G ranks in this process on one device, phases in lockstep (no barrier kernels)
+# ----------------------------------------------------------------------------------------------------------------
+def _peer_lockstep(shards, batches_per_rank):
+    for s, b in zip(shards, batches_per_rank):
+        s.compute(b)
+    for s in shards:
+        s.apply()
+
+
+def _make_peer_shards(G, U, I, D, B, P0, Q0, lr=0.05, wd=0.01):
+    from recommend_lib_b200.sharded import PeerShardedBPR
+    dev = torch.device("cuda:0")
+    shards = [PeerShardedBPR(U, I, D, lr=lr, wd=wd, max_batch=B, rank=r, world=G, device=dev, P_full=P0, Q_full=Q0)
+              for r in range(G)]
+    PeerShardedBPR.connect_in_process(shards)
+    return shards
+
+
+@pytest.mark.parametrize("G,U,I,D,B", [(1, 300, 200, 64, 3000), (2, 400, 300, 64, 6000), (3, 1000, 701, 128, 20000),
+                                       (4, 64, 50, 32, 37), (8, 5000, 3001, 128, 40000), (2, 500, 4000, 256, 3000)])
+def test_peer_sharded_lockstep_matches_oracle_and_unsharded(G, U, I, D, B):
+    assert torch.cuda.is_available()
+    from oracle import bpr_oracle
+    from recommend_lib_b200.bpr import BPR, BPRSGD
+    from sharded_testing import route
+    dev = torch.device("cuda:0")
+    lr, wd, steps = 0.05, 0.01, 3
+    P0, Q0, batches = _problem(U, I, D, B, steps, seed=G)
+    shards = _make_peer_shards(G, U, I, D, B, P0, Q0, lr, wd)
+    for b in batches:
+        _peer_lockstep(shards, [torch.from_numpy(route(b, s.layout, s.rank)).to(dev) for s in shards])
+    for s in shards:
+        s.check()
+        s.materialize()
+    P = torch.cat([s.P for s in shards]).cpu().numpy()
+    Q = torch.cat([s.Q for s in shards]).cpu().numpy()
+    loss = sum(s.loss_sum() for s in shards)
+    Pr, Qr, losses = bpr_oracle.bpr_run_closed_form(P0, Q0, batches, lr, wd, np.float64)
+    assert rel_err(P, Pr) <= 1e-5 and rel_err(Q, Qr) <= 1e-5
+    assert abs(loss - sum(losses)) / sum(losses) < 1e-5
+    m = BPR(U, I, D, max_batch=B)
+    with torch.no_grad():
+        m.embed_user.weight.copy_(torch.from_numpy(P0))
+        m.embed_item.weight.copy_(torch.from_numpy(Q0))
+    m = m.to(dev)
+    opt = BPRSGD(m, lr=lr, weight_decay=wd)
+    for b in batches:
+        opt.step(torch.from_numpy(b).to(dev))
+    m.materialize()
+    assert rel_err(P, m.embed_user.weight.detach().cpu().numpy()) <= 1e-5
+    assert rel_err(Q, m.embed_item.weight.detach().cpu().numpy()) <= 1e-5
+    for s in shards:
+        s.close()
+
+
+def test_peer_sharded_is_deterministic_and_handles_empty_ranks():
+    from sharded_testing import route
+    dev = torch.device("cuda:0")
+    G, U, I, D, B = 4, 3000, 2000, 128, 50000
+    P0, Q0, batches = _problem(U, I, D, B, 2, seed=9)
+    batches[1][:, 0] = batches[1][:, 0] % 700          # second step: only rank 0 has triples, the others push nothing
+    outs = []
+    for _ in range(2):
+        shards = _make_peer_shards(G, U, I, D, B, P0, Q0)
+        for b in batches:
+            _peer_lockstep(shards, [torch.from_numpy(route(b, s.layout, s.rank)).to(dev) for s in shards])
+        for s in shards:
+            s.check()
+            s.materialize()
+        outs.append((torch.cat([s.P for s in shards]).clone(), torch.cat([s.Q for s in shards]).clone()))
+        for s in shards:
+            s.close()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    from oracle import bpr_oracle
+    Pr, Qr, _ = bpr_oracle.bpr_run_closed_form(P0, Q0, batches, 0.05, 0.01, np.float64)
+    assert rel_err(outs[0][0].cpu().numpy(), Pr) <= 1e-5 and rel_err(outs[0][1].cpu().numpy(), Qr) <= 1e-5
+
+
+def test_peer_sharded_reports_bad_ids():
+    dev = torch.device("cuda:0")
+    G, U, I, D, B = 2, 100, 80, 32, 64
+    P0, Q0, _ = _problem(U, I, D, B, 1, seed=1)
+    shards = _make_peer_shards(G, U, I, D, B, P0, Q0)
+    bad = torch.tensor([[0, 5, 80]], dtype=torch.int32, device=dev)      # negative item id == item_num (global)
+    shards[0].compute(bad)
+    shards[1].compute(bad[:0])
+    for s in shards:
+        s.apply()
+    with pytest.raises(IndexError):
+        shards[0].check()
+    for s in shards:
+        s.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the real thing: one process per GPU, CUDA IPC + flag barriers (needs >= 2 GPUs; run with gpurun --gpus 2)
+# ----------------------------------------------------------------------------------------------------------------
+def _mp_worker(rank, world, port, U, I, D, B, steps, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from recommend_lib_b200.sharded import PeerShardedBPR
+        from sharded_testing import route
+        P0, Q0, batches = _problem(U, I, D, B, steps, seed=5)
+        m = PeerShardedBPR(U, I, D, lr=0.05, wd=0.01, max_batch=B, rank=rank, world=world, device=dev, P_full=P0,
+                           Q_full=Q0).connect()
+        for n, b in enumerate(batches):
+            t = torch.from_numpy(route(b, m.layout, rank))
+            m.step(t.pin_memory() if n % 2 else t.to(dev))          # alternate host-fed / device-fed steps
+        m.check()
+        P, Q = m.full_tables()
+        loss = m.loss_sum(reduce=True)
+        if rank == 0:
+            np.savez(out, P=P.cpu().numpy(), Q=Q.cpu().numpy(), loss=loss)
+        dist.barrier()
+        m.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_peer_sharded_multiprocess_ipc(tmp_path, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    from oracle import bpr_oracle
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    U, I, D, B, steps = 4000, 3001, 128, 30000, 4
+    out = str(tmp_path / "res.npz")
+    mp.spawn(_mp_worker, args=(world, port, U, I, D, B, steps, out), nprocs=world, join=True)
+    r = np.load(out)
+    P0, Q0, batches = _problem(U, I, D, B, steps, seed=5)
+    Pr, Qr, losses = bpr_oracle.bpr_run_closed_form(P0, Q0, batches, 0.05, 0.01, np.float64)
+    assert rel_err(r["P"], Pr) <= 1e-5 and rel_err(r["Q"], Qr) <= 1e-5
+    assert abs(float(r["loss"]) - sum(losses)) / sum(losses) < 1e-5
