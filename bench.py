@@ -62,7 +62,8 @@ class ClockSampler:
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, index):
+    def __init__(self, index, period_s=None):
+        self.period_s = float(os.environ.get("DAISY_CLOCK_PERIOD_S", "0.02")) if period_s is None else period_s
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._thread = None
@@ -89,7 +90,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(self.period_s)
 
     def start(self):
         if self._h is not None:
@@ -327,6 +328,8 @@ def main():
     ap.add_argument("--phases", action="store_true", help="also print the per-phase breakdown of the step")
     ap.add_argument("--trace", action="store_true", help="also print a timeline of bookkeeping vs table kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mapping", default="symm", choices=["symm", "ipc"],
+                    help="N > 1, peer exchange: how the ranks map each other's arenas")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: peer = fused peer-memory step (product), nccl = all-to-all exchange (comparison)")
     ap.add_argument("--cpu-budget", type=float, default=25.0)

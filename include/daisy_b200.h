@@ -123,12 +123,19 @@ DAISY_API int daisy_owner_apply(daisy_handle_t h, float *Q_local, const int32_t 
  * ceil(item_num_global / world), and a block of users; a triple is (LOCAL user row, GLOBAL positive item, GLOBAL
  * negative item) and is fed to the rank that owns its user.  The handle is created with the LOCAL row counts.
  *
- *   daisy_shard_init    allocates this rank's ARENA (its item rows + receive regions + barrier flags) in one
- *                       cudaMalloc;  daisy_shard_arena returns it and the item-shard pointer q_local [item rows, dim]
+ *   daisy_shard_init    sets up this rank's ARENA (its item rows + receive regions + barrier flags, one contiguous
+ *                       buffer of daisy_shard_arena_size bytes with the same layout on every rank).  arena != NULL:
+ *                       caller-owned memory that the caller has mapped into the peer processes -- the product path
+ *                       passes a torch symmetric-memory buffer (cuMem VMM mapping; measured 625 GB/s per direction
+ *                       for random 512-byte row reads from the peer).  arena == NULL: the library cudaMallocs it and
+ *                       exports it through legacy CUDA IPC (daisy_shard_ipc_handle; that mapping was measured at
+ *                       300 GB/s for the same reads, profiles/r01_peer_mapping_bw.md).
+ *                       daisy_shard_arena returns the arena and the item-shard pointer q_local [item rows, dim]
  *                       (fill it before the first step; it is the rank's block of BPR.embed_item.weight)
- *   daisy_shard_ipc_handle / daisy_shard_attach   exchange the 64-byte CUDA IPC handles of all ranks (any transport,
- *                       e.g. torch.distributed.all_gather) and map the peers' arenas; ranks living in ONE process
- *                       (single-GPU emulation in the tests) pass their arena pointers instead
+ *   daisy_shard_attach  gives the library the peers' arenas as mapped into THIS process: either the ranks' 64-byte
+ *                       CUDA IPC handles (exchanged by any transport, e.g. torch.distributed.all_gather) or their
+ *                       addresses (arena_ptrs [world]).  in_process = 1: all ranks live in this process on one
+ *                       device (single-GPU emulation in the tests) -- the caller orders the phases, no barriers.
  *   daisy_shard_step    one training step of this rank: pre-step item rows are READ from their owners by peer loads,
  *                       the fused step kernels STORE every finished item-row sum straight into its owner's memory,
  *                       a flag barrier across the GPUs, the owner-side deterministic merge + update, a second barrier.
@@ -138,11 +145,12 @@ DAISY_API int daisy_owner_apply(daisy_handle_t h, float *Q_local, const int32_t 
  *   daisy_shard_materialize   daisy_materialize on (P_local, q_local) + barrier (peers read q_local).
  * Semantics = daisy_bpr_step on the global batch (gradients at the pre-step tables, repeated rows accumulate);
  * contributions to a row are added in sender-rank order, so results are bit-reproducible. */
-DAISY_API int daisy_shard_init(daisy_handle_t h, int rank, int world, int64_t item_num_global);
+DAISY_API int daisy_shard_arena_size(int dim, int64_t max_batch, int world, int64_t item_num_global, int64_t *bytes);
+DAISY_API int daisy_shard_init(daisy_handle_t h, int rank, int world, int64_t item_num_global, void *arena);
 DAISY_API int daisy_shard_arena(daisy_handle_t h, void **arena, float **q_local, int64_t *arena_bytes);
 DAISY_API int daisy_shard_ipc_handle(daisy_handle_t h, void *out64);
 DAISY_API int daisy_shard_attach(daisy_handle_t h, const void *ipc_handles /* [world][64] or NULL */,
-                                 void *const *arena_ptrs /* [world] or NULL */);
+                                 void *const *arena_ptrs /* [world] or NULL */, int in_process);
 DAISY_API int daisy_shard_step(daisy_handle_t h, float *P_local, const int32_t *triples, int64_t B, float lr, float wd,
                                double *loss_accum, daisy_stream_t stream);
 DAISY_API int daisy_shard_step_host(daisy_handle_t h, float *P_local, const int32_t *triples_host, int64_t B, float lr,
@@ -154,6 +162,16 @@ DAISY_API int daisy_shard_apply(daisy_handle_t h, float lr, float wd, daisy_stre
 DAISY_API int daisy_shard_materialize(daisy_handle_t h, float *P_local, daisy_stream_t stream);
 /* Reporting: owner_off_out [world+1] = first cache row of every owner in the most recent step of this rank, so
  * owner_off_out[o+1] - owner_off_out[o] distinct item rows were fetched from / pushed to rank o.  Synchronises. */
+/* The item shard of `rank` as mapped into this process (diagnostics). */
+DAISY_API int daisy_shard_peer_q(daisy_handle_t h, int rank, float **q);
+/* Row gather dst[c] = src[idx[c]] (rows of `dim` floats; src may be a peer address mapped into this process):
+ * the building block of the fetch, exposed for bandwidth diagnostics (tools/peer_map_bw.py). */
+DAISY_API int daisy_gather_rows(daisy_handle_t h, const float *src, const int32_t *idx, int64_t n, float *dst,
+                                daisy_stream_t stream);
+/* With daisy_set_timing(h, 2): average device ms of the phases of daisy_shard_step since the last call, in order
+ * bookkeeping, fetch, compute+push, barrier, apply, barrier (the step is then serialised on the caller's stream and
+ * synchronised once per step -- a diagnostic, not a bench mode). */
+DAISY_API int daisy_shard_phase_ms(daisy_handle_t h, double *avg_ms6, int64_t *steps);
 DAISY_API int daisy_shard_last_counts(daisy_handle_t h, uint32_t *owner_off_out, daisy_stream_t stream);
 
 /* Lazy sparse Adam variant of the step (no Daisy counterpart -- BPR-MF uses SGD only; semantics =

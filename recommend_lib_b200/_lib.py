@@ -39,10 +39,11 @@ SIGNATURES = {
     "daisy_bpr_step_host": [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp],
     "daisy_bpr_shard_step": [c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp, c_vp],
     "daisy_owner_apply": [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp],
-    "daisy_shard_init": [c_vp, c_i32, c_i32, c_i64],
+    "daisy_shard_arena_size": [c_i32, c_i64, c_i32, c_i64, ctypes.POINTER(c_i64)],
+    "daisy_shard_init": [c_vp, c_i32, c_i32, c_i64, c_vp],
     "daisy_shard_arena": [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_i64)],
     "daisy_shard_ipc_handle": [c_vp, c_vp],
-    "daisy_shard_attach": [c_vp, c_vp, c_vp],
+    "daisy_shard_attach": [c_vp, c_vp, c_vp, c_i32],
     "daisy_shard_step": [c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp],
     "daisy_shard_step_host": [c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp],
     "daisy_shard_compute": [c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp],
@@ -50,6 +51,9 @@ SIGNATURES = {
     "daisy_shard_apply": [c_vp, c_f32, c_f32, c_vp],
     "daisy_shard_materialize": [c_vp, c_vp, c_vp],
     "daisy_shard_last_counts": [c_vp, c_vp, c_vp],
+    "daisy_shard_peer_q": [c_vp, c_i32, ctypes.POINTER(c_vp)],
+    "daisy_gather_rows": [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp],
+    "daisy_shard_phase_ms": [c_vp, ctypes.POINTER(c_f64), ctypes.POINTER(c_i64)],
     "daisy_bpr_adam_step": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32,
                             c_i64, c_vp, c_vp],
     "daisy_topk_candidates": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp],

@@ -58,12 +58,16 @@ struct ShardSet {         // per bookkeeping set (double-buffered like BookSet)
     const float **src;    // [2*maxB]  where cache row c lives in its owner's q (a peer or local address)
     float **dst;          // [2*maxB]  where this rank's descent sum of cache row c goes in its owner's recv_g
     uint32_t *owner_off;  // [G+1]     first cache row owned by rank o; [G] = number of cache rows
+    uint8_t *multi;       // [2*maxB]  1: cache row c is referenced more than once in the batch => fetched into the cache
+    const float **jsrc;   // [maxB]    per sorted triple: where its negative-item row is read from
+    const float **isrc;   // [maxB]    per sorted triple that heads a positive-item run: where that row is read from
 };
 
 struct daisy_shard {
     int rank, world;
     int64_t I_global, i_per, cap;  // cap = entries per sender region = 2 * maxB (a batch references at most 2B item rows)
     char *arena;
+    int arena_owned;  // 1: cudaMalloc'ed by daisy_shard_init (legacy CUDA IPC export), 0: provided by the caller
     size_t arena_bytes, off_q, off_g, off_ids, off_cnt, off_flags;
     char *peer_arena[DAISY_MAX_RANKS];
     int ipc_opened[DAISY_MAX_RANKS];
@@ -74,6 +78,10 @@ struct daisy_shard {
     uint32_t *cidx;   // [2*maxB] scan scratch (bookkeeping stream only)
     float *cache;     // [2*maxB, D] fetched pre-step item rows of the current batch
     uint32_t epoch;   // barrier epoch (same sequence on every rank)
+    // phase profile (daisy_set_timing(h, 2)): bookkeeping, fetch, compute+push, barrier, apply, barrier
+    cudaEvent_t pev[7];
+    double pms[6];
+    int64_t psteps;
 };
 
 struct daisy_ctx {
@@ -225,6 +233,10 @@ __device__ __forceinline__ void st_stream(float *base, size_t f4_index, float4 v
                      reinterpret_cast<float4 *>(base) + f4_index),
                  "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
+}
+
+__device__ __forceinline__ const float *shfl_ptr(const float *p, int src_lane) {
+    return reinterpret_cast<const float *>(__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)p, src_lane));
 }
 
 __device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }

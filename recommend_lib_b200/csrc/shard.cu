@@ -227,44 +227,51 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
+// The id list every owner merges by: one thread per cache row => consecutive rows of one owner coalesce into full
+// 128-byte peer stores.  Also tells every owner how many entries this rank pushes this step.
+__global__ void k_shard_push_ids(const uint32_t *__restrict__ owner_off, int G, const uint32_t *__restrict__ uniq_gid,
+                                 uint32_t i_per, int me, size_t cap, ShardPeers peers) {
+    const uint32_t nuniq = owner_off[G];
+    if (blockIdx.x == 0 && threadIdx.x < G)
+        peers.recv_cnt[threadIdx.x][me] = owner_off[threadIdx.x + 1] - owner_off[threadIdx.x];
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nuniq; c += gridDim.x * blockDim.x) {
+        const uint32_t g = uniq_gid[c];
+        const uint32_t o = g / i_per;
+        peers.recv_ids[o][(size_t)me * cap + (c - owner_off[o])] = (int32_t)(g - o * i_per);
+    }
+}
+
 // R rows in flight per warp: a peer load takes ~2000 cycles (NVLink + remote L2/DRAM), so bandwidth needs depth.
 template <int V, int R>
 __global__ void __launch_bounds__(256) k_shard_fetch(const float *const *__restrict__ src,
+                                                      const uint8_t *__restrict__ multi,
                                                       const uint32_t *__restrict__ owner_off, int G,
-                                                      float *__restrict__ cache, int D4,
-                                                      const uint32_t *__restrict__ uniq_gid, uint32_t i_per, int me,
-                                                      size_t cap, ShardPeers peers) {
+                                                      float *__restrict__ cache, int D4) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
     const uint32_t nwarps = (uint32_t)((gridDim.x * (size_t)blockDim.x) >> 5);
     const uint32_t nuniq = owner_off[G];
-    if (blockIdx.x == 0 && threadIdx.x < G)  // how many entries this rank pushes to every owner this step
-        peers.recv_cnt[threadIdx.x][me] = owner_off[threadIdx.x + 1] - owner_off[threadIdx.x];
     bool act[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
     for (uint32_t c0 = warp * R; c0 < nuniq; c0 += nwarps * R) {
         float4 r[R][V];
+        bool take[R];  // rows referenced once are read by the main kernel straight from their owner
 #pragma unroll
         for (int jj = 0; jj < R; ++jj) {
             const uint32_t c = c0 + jj;
-            if (c < nuniq) {
+            take[jj] = c < nuniq && multi[c];
+            if (take[jj]) {
                 const float *p = src[c];
 #pragma unroll
                 for (int v = 0; v < V; ++v)
                     if (act[v]) r[jj][v] = ld_stream(p, lane + 32 * v);
             }
         }
-        if (lane < R && c0 + lane < nuniq) {  // the id list the owner merges by
-            const uint32_t c = c0 + lane;
-            const uint32_t g = uniq_gid[c];
-            const uint32_t o = g / i_per;
-            peers.recv_ids[o][(size_t)me * cap + (c - owner_off[o])] = (int32_t)(g - o * i_per);
-        }
 #pragma unroll
         for (int jj = 0; jj < R; ++jj) {
             const uint32_t c = c0 + jj;
-            if (c < nuniq) {
+            if (take[jj]) {
 #pragma unroll
                 for (int v = 0; v < V; ++v)
                     if (act[v]) st_row(cache, (size_t)c * D4 + lane + 32 * v, r[jj][v]);
@@ -394,6 +401,22 @@ __global__ void __launch_bounds__(256) k_owner_merge(float *__restrict__ Q, cons
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Arena layout (identical on every rank): a function of (dim, max_batch, world, item_num_global) only.
+static void shard_layout(daisy_shard *sh, int dim, int64_t max_batch, int world, int64_t item_num_global) {
+    sh->world = world;
+    sh->I_global = item_num_global;
+    sh->i_per = (item_num_global + world - 1) / world;
+    sh->cap = 2 * max_batch;
+    const size_t D = (size_t)dim, cap = (size_t)sh->cap, G = (size_t)world;
+    size_t off = 0;
+    sh->off_q = off;      off = align_up(off + (size_t)sh->i_per * D * sizeof(float), 256);
+    sh->off_g = off;      off = align_up(off + G * cap * D * sizeof(float), 256);
+    sh->off_ids = off;    off = align_up(off + G * cap * sizeof(int32_t), 256);
+    sh->off_cnt = off;    off = align_up(off + DAISY_MAX_RANKS * sizeof(uint32_t), 256);
+    sh->off_flags = off;  off = align_up(off + DAISY_MAX_RANKS * sizeof(uint32_t), 256);
+    sh->arena_bytes = off;
+}
+
 static void shard_set_peers(daisy_shard *sh, int r, char *base) {
     sh->peer_arena[r] = base;
     sh->peers.q[r] = (float *)(base + sh->off_q);
@@ -413,8 +436,10 @@ static int shard_ready(daisy_ctx *h) {
 template <int V>
 static void launch_fetch(daisy_ctx *h, const ShardSet &ss, cudaStream_t s) {
     daisy_shard *sh = h->sh;
-    k_shard_fetch<V, 4><<<h->num_sms * 4, 256, 0, s>>>(ss.src, ss.owner_off, sh->world, sh->cache, h->D / 4, ss.uniq_gid,
-                                                        (uint32_t)sh->i_per, sh->rank, (size_t)sh->cap, sh->peers);
+    k_shard_push_ids<<<h->num_sms * 2, 256, 0, s>>>(ss.owner_off, sh->world, ss.uniq_gid, (uint32_t)sh->i_per, sh->rank,
+                                                    (size_t)sh->cap, sh->peers);
+    h->launches++;
+    k_shard_fetch<V, 4><<<h->num_sms * 4, 256, 0, s>>>(ss.src, ss.multi, ss.owner_off, sh->world, sh->cache, h->D / 4);
 }
 
 template <int V>
@@ -440,9 +465,16 @@ static int shard_compute(daisy_ctx *h, float *P_local, const int32_t *triples_de
         return DAISY_OK;
     }
     StepPlan pl;
+    const bool prof = h->timing == 2;
+    if (prof) {
+        if (!sh->pev[0])
+            for (int i = 0; i < 7; ++i) cudaEventCreate(&sh->pev[i]);
+        cudaEventRecord(sh->pev[0], s);
+    }
     int rc = book_phase(h, pl, triples_dev, B, (uint32_t)h->U, (uint32_t)sh->I_global, s, host_src,
                         host_src != nullptr || h->inputs_ready, sh);
     if (rc) return rc;
+    if (prof) cudaEventRecord(sh->pev[1], s);
     const ShardSet &ss = sh->set[pl.set];
     const int D4 = h->D / 4;
     if (D4 <= 32) launch_fetch<1>(h, ss, s);
@@ -450,6 +482,7 @@ static int shard_compute(daisy_ctx *h, float *P_local, const int32_t *triples_de
     else if (D4 <= 96) launch_fetch<3>(h, ss, s);
     else launch_fetch<4>(h, ss, s);
     DAISY_LAUNCH_CHECK(h);
+    if (prof) cudaEventRecord(sh->pev[2], s);
     PushOpt opt;
     opt.P = P_local;
     opt.dst = ss.dst;
@@ -457,6 +490,7 @@ static int shard_compute(daisy_ctx *h, float *P_local, const int32_t *triples_de
     opt.D4 = D4;
     rc = table_phase<PushOpt>(h, pl, P_local, sh->cache, opt, (float)(h->scale * h->scale), loss_accum);
     if (rc) return rc;
+    if (prof) cudaEventRecord(sh->pev[3], s);
     h->scale *= shrink;
     return DAISY_OK;
 }
@@ -492,21 +526,35 @@ static int shard_barrier(daisy_ctx *h, cudaStream_t s) {
 void daisy_shard_free(daisy_ctx *h) {
     daisy_shard *sh = h->sh;
     if (!sh) return;
+    for (int i = 0; i < 7; ++i)
+        if (sh->pev[i]) cudaEventDestroy(sh->pev[i]);
     for (int r = 0; r < sh->world; ++r)
         if (sh->ipc_opened[r] && sh->peer_arena[r]) cudaIpcCloseMemHandle(sh->peer_arena[r]);
     for (int i = 0; i < 2; ++i) {
-        void *ptrs[] = {sh->set[i].uniq_gid, (void *)sh->set[i].src, (void *)sh->set[i].dst, sh->set[i].owner_off};
+        void *ptrs[] = {sh->set[i].uniq_gid, (void *)sh->set[i].src, (void *)sh->set[i].dst, sh->set[i].owner_off,
+                        sh->set[i].multi, (void *)sh->set[i].jsrc, (void *)sh->set[i].isrc};
         for (void *p : ptrs)
             if (p) cudaFree(p);
     }
     if (sh->cidx) cudaFree(sh->cidx);
     if (sh->cache) cudaFree(sh->cache);
-    if (sh->arena) cudaFree(sh->arena);
+    if (sh->arena && sh->arena_owned) cudaFree(sh->arena);
     free(sh);
     h->sh = nullptr;
 }
 
-extern "C" int daisy_shard_init(daisy_handle_t h, int rank, int world, int64_t item_num_global) {
+extern "C" int daisy_shard_arena_size(int dim, int64_t max_batch, int world, int64_t item_num_global, int64_t *bytes) {
+    DAISY_REQUIRE(bytes != nullptr, DAISY_EINVAL, "null argument");
+    DAISY_REQUIRE(dim > 0 && dim % 4 == 0 && dim <= 512 && max_batch > 0 && world >= 1 && world <= DAISY_MAX_RANKS &&
+                      item_num_global > 0, DAISY_EINVAL, "bad shape");
+    daisy_shard tmp;
+    memset(&tmp, 0, sizeof(tmp));
+    shard_layout(&tmp, dim, max_batch, world, item_num_global);
+    *bytes = (int64_t)tmp.arena_bytes;
+    return DAISY_OK;
+}
+
+extern "C" int daisy_shard_init(daisy_handle_t h, int rank, int world, int64_t item_num_global, void *arena) {
     DAISY_REQUIRE(h != nullptr, DAISY_EINVAL, "null handle");
     DAISY_REQUIRE(h->sh == nullptr, DAISY_EINVAL, "handle is already sharded");
     DAISY_REQUIRE(world >= 1 && world <= DAISY_MAX_RANKS && rank >= 0 && rank < world, DAISY_EINVAL,
@@ -514,6 +562,7 @@ extern "C" int daisy_shard_init(daisy_handle_t h, int rank, int world, int64_t i
     DAISY_REQUIRE(h->maxB > 0 && h->D % 4 == 0 && h->D <= 512, DAISY_EUNSUPPORTED,
                   "sharding needs a handle with max_batch > 0, dim %% 4 == 0, dim <= 512");
     DAISY_REQUIRE(item_num_global > 0 && item_num_global < 0x7ffffffeLL, DAISY_EINVAL, "bad global item count");
+    DAISY_REQUIRE((uintptr_t)arena % 256 == 0, DAISY_EINVAL, "a caller-provided arena must be 256-byte aligned");
     const int64_t i_per = (item_num_global + world - 1) / world;
     int64_t lo = (int64_t)rank * i_per, hi = lo + i_per;
     if (lo > item_num_global) lo = item_num_global;
@@ -526,20 +575,16 @@ extern "C" int daisy_shard_init(daisy_handle_t h, int rank, int world, int64_t i
     daisy_shard *sh = (daisy_shard *)calloc(1, sizeof(daisy_shard));
     DAISY_REQUIRE(sh != nullptr, DAISY_ENOMEM, "host allocation failed");
     sh->rank = rank;
-    sh->world = world;
-    sh->I_global = item_num_global;
-    sh->i_per = i_per;
-    sh->cap = 2 * h->maxB;
-    const size_t D = (size_t)h->D, cap = (size_t)sh->cap, G = (size_t)world;
-    size_t off = 0;
-    sh->off_q = off;      off = align_up(off + (size_t)i_per * D * sizeof(float), 256);
-    sh->off_g = off;      off = align_up(off + G * cap * D * sizeof(float), 256);
-    sh->off_ids = off;    off = align_up(off + G * cap * sizeof(int32_t), 256);
-    sh->off_cnt = off;    off = align_up(off + DAISY_MAX_RANKS * sizeof(uint32_t), 256);
-    sh->off_flags = off;  off = align_up(off + DAISY_MAX_RANKS * sizeof(uint32_t), 256);
-    sh->arena_bytes = off;
+    shard_layout(sh, h->D, h->maxB, world, item_num_global);
+    const size_t D = (size_t)h->D, cap = (size_t)sh->cap;
     h->sh = sh;
-    bool ok = cudaMalloc((void **)&sh->arena, sh->arena_bytes) == cudaSuccess;
+    bool ok = true;
+    if (arena) {  // caller-owned (e.g. a torch symmetric-memory buffer the peers have mapped)
+        sh->arena = (char *)arena;
+    } else {
+        ok = cudaMalloc((void **)&sh->arena, sh->arena_bytes) == cudaSuccess;
+        sh->arena_owned = ok ? 1 : 0;
+    }
     ok = ok && cudaMalloc((void **)&sh->cidx, cap * sizeof(uint32_t)) == cudaSuccess;
     ok = ok && cudaMalloc((void **)&sh->cache, cap * D * sizeof(float)) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i) {
@@ -547,6 +592,9 @@ extern "C" int daisy_shard_init(daisy_handle_t h, int rank, int world, int64_t i
         ok = ok && cudaMalloc((void **)&sh->set[i].src, cap * sizeof(float *)) == cudaSuccess;
         ok = ok && cudaMalloc((void **)&sh->set[i].dst, cap * sizeof(float *)) == cudaSuccess;
         ok = ok && cudaMalloc((void **)&sh->set[i].owner_off, (DAISY_MAX_RANKS + 1) * sizeof(uint32_t)) == cudaSuccess;
+        ok = ok && cudaMalloc((void **)&sh->set[i].multi, cap) == cudaSuccess;
+        ok = ok && cudaMalloc((void **)&sh->set[i].jsrc, (size_t)h->maxB * sizeof(float *)) == cudaSuccess;
+        ok = ok && cudaMalloc((void **)&sh->set[i].isrc, (size_t)h->maxB * sizeof(float *)) == cudaSuccess;
     }
     if (!ok) {
         cudaGetLastError();
@@ -572,6 +620,7 @@ extern "C" int daisy_shard_arena(daisy_handle_t h, void **arena, float **q_local
 
 extern "C" int daisy_shard_ipc_handle(daisy_handle_t h, void *out64) {
     DAISY_REQUIRE(h && h->sh && out64, DAISY_EINVAL, "null argument or handle not sharded");
+    DAISY_REQUIRE(h->sh->arena_owned, DAISY_EINVAL, "the arena is caller-owned: the caller maps it into the peers");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     DeviceGuard g(h->device);
     cudaIpcMemHandle_t m;
@@ -580,7 +629,7 @@ extern "C" int daisy_shard_ipc_handle(daisy_handle_t h, void *out64) {
     return DAISY_OK;
 }
 
-extern "C" int daisy_shard_attach(daisy_handle_t h, const void *ipc_handles, void *const *arena_ptrs) {
+extern "C" int daisy_shard_attach(daisy_handle_t h, const void *ipc_handles, void *const *arena_ptrs, int in_process) {
     DAISY_REQUIRE(h && h->sh, DAISY_EINVAL, "handle is not sharded");
     DAISY_REQUIRE((ipc_handles != nullptr) != (arena_ptrs != nullptr) || h->sh->world == 1, DAISY_EINVAL,
                   "pass either the ranks' IPC handles or (same process) their arena pointers");
@@ -592,7 +641,6 @@ extern "C" int daisy_shard_attach(daisy_handle_t h, const void *ipc_handles, voi
         if (r == sh->rank) continue;
         if (arena_ptrs) {
             DAISY_REQUIRE(arena_ptrs[r] != nullptr, DAISY_EINVAL, "null arena pointer for rank %d", r);
-            sh->in_process = 1;
             shard_set_peers(sh, r, (char *)arena_ptrs[r]);
         } else {
             cudaIpcMemHandle_t m;
@@ -603,6 +651,7 @@ extern "C" int daisy_shard_attach(daisy_handle_t h, const void *ipc_handles, voi
             shard_set_peers(sh, r, (char *)p);
         }
     }
+    sh->in_process = (arena_ptrs && in_process) ? 1 : 0;
     sh->attached = 1;
     return DAISY_OK;
 }
@@ -631,10 +680,24 @@ extern "C" int daisy_shard_barrier(daisy_handle_t h, daisy_stream_t stream) {
 static int shard_step_impl(daisy_handle_t h, float *P_local, const int32_t *triples_dev, const int32_t *host_src,
                            int64_t B, float lr, float wd, double *loss_accum, daisy_stream_t stream) {
     cudaStream_t s = (cudaStream_t)stream;
+    daisy_shard *sh = h->sh;
+    const bool prof = h->timing == 2 && B > 0;
     int rc = shard_compute(h, P_local, triples_dev, host_src, B, lr, wd, loss_accum, s);
     if (!rc) rc = shard_barrier(h, s);
+    if (!rc && prof) cudaEventRecord(sh->pev[4], s);
     if (!rc) rc = shard_apply(h, lr, wd, s);
+    if (!rc && prof) cudaEventRecord(sh->pev[5], s);
     if (!rc) rc = shard_barrier(h, s);
+    if (!rc && prof) {
+        cudaEventRecord(sh->pev[6], s);
+        cudaEventSynchronize(sh->pev[6]);
+        for (int i = 0; i < 6; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, sh->pev[i], sh->pev[i + 1]);
+            sh->pms[i] += ms;
+        }
+        sh->psteps++;
+    }
     if (!rc && h->scale < 1e-4) rc = daisy_shard_materialize(h, P_local, stream);  // same step on every rank
     return rc;
 }
@@ -678,5 +741,67 @@ extern "C" int daisy_shard_last_counts(daisy_handle_t h, uint32_t *owner_off_out
     DAISY_CUDA(cudaStreamSynchronize(h->side_stream));
     const ShardSet &ss = h->sh->set[h->book_idx ^ 1];  // the set the most recent step used
     DAISY_CUDA(cudaMemcpy(owner_off_out, ss.owner_off, (h->sh->world + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return DAISY_OK;
+}
+
+extern "C" int daisy_shard_phase_ms(daisy_handle_t h, double *avg_ms6, int64_t *steps) {
+    DAISY_REQUIRE(h && h->sh && avg_ms6 && steps, DAISY_EINVAL, "null argument or handle not sharded");
+    for (int i = 0; i < 6; ++i) avg_ms6[i] = h->sh->psteps ? h->sh->pms[i] / (double)h->sh->psteps : 0.0;
+    *steps = h->sh->psteps;
+    for (int i = 0; i < 6; ++i) h->sh->pms[i] = 0.0;
+    h->sh->psteps = 0;
+    return DAISY_OK;
+}
+
+// Diagnostic / building block: dst[c] = src[idx[c]] for rows of h->D floats; src may be a peer address.
+namespace {
+template <int V, int R>
+__global__ void __launch_bounds__(256) k_gather_rows(const float *__restrict__ src, const int32_t *__restrict__ idx,
+                                                      int n, float *__restrict__ dst, int D4) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const uint32_t nwarps = (uint32_t)((gridDim.x * (size_t)blockDim.x) >> 5);
+    for (uint32_t c0 = warp * R; c0 < (uint32_t)n; c0 += nwarps * R) {
+        float4 r[R][V];
+#pragma unroll
+        for (int jj = 0; jj < R; ++jj)
+            if (c0 + jj < (uint32_t)n) {
+                const size_t row = (size_t)idx[c0 + jj];
+#pragma unroll
+                for (int v = 0; v < V; ++v)
+                    if (lane + 32 * v < D4) r[jj][v] = ld_stream(src, row * D4 + lane + 32 * v);
+            }
+#pragma unroll
+        for (int jj = 0; jj < R; ++jj)
+            if (c0 + jj < (uint32_t)n) {
+#pragma unroll
+                for (int v = 0; v < V; ++v)
+                    if (lane + 32 * v < D4) st_row(dst, (size_t)(c0 + jj) * D4 + lane + 32 * v, r[jj][v]);
+            }
+    }
+}
+}  // namespace
+
+extern "C" int daisy_gather_rows(daisy_handle_t h, const float *src, const int32_t *idx, int64_t n, float *dst,
+                                 daisy_stream_t stream) {
+    DAISY_REQUIRE(h && src && idx && dst, DAISY_EINVAL, "null argument");
+    DAISY_REQUIRE(h->D % 4 == 0 && h->D <= 512 && n >= 0 && n < (1LL << 31), DAISY_EUNSUPPORTED, "unsupported shape");
+    if (n == 0) return DAISY_OK;
+    DeviceGuard g(h->device);
+    const int D4 = h->D / 4;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (D4 <= 32) k_gather_rows<1, 4><<<h->num_sms * 4, 256, 0, s>>>(src, idx, (int)n, dst, D4);
+    else if (D4 <= 64) k_gather_rows<2, 4><<<h->num_sms * 4, 256, 0, s>>>(src, idx, (int)n, dst, D4);
+    else if (D4 <= 96) k_gather_rows<3, 2><<<h->num_sms * 4, 256, 0, s>>>(src, idx, (int)n, dst, D4);
+    else k_gather_rows<4, 2><<<h->num_sms * 4, 256, 0, s>>>(src, idx, (int)n, dst, D4);
+    DAISY_LAUNCH_CHECK(h);
+    return DAISY_OK;
+}
+
+extern "C" int daisy_shard_peer_q(daisy_handle_t h, int rank, float **q) {
+    int rc = shard_ready(h);
+    if (rc) return rc;
+    DAISY_REQUIRE(q && rank >= 0 && rank < h->sh->world, DAISY_EINVAL, "bad rank");
+    *q = h->sh->peers.q[rank];
     return DAISY_OK;
 }

@@ -111,15 +111,18 @@ struct MainArgs {
     float *loss_part;
     int B, D4, C;
     float c2;  // score scale = c^2
+    // PTR mode (row-sharded step): where to read the item rows of sorted triple k from -- the owner's memory (peer
+    // or local address) for rows referenced once, the fetched-row cache otherwise.  st then holds cache rows.
+    const float *const *jsrc, *const *isrc;
 };
 
-template <int V, class Opt>
+template <int V, class Opt, bool PTR>
 __global__ void __launch_bounds__(256) k_bpr_main(MainArgs a, Opt opt) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int warp = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
     const int C = a.C;
-    const long long k0 = (long long)warp * C;
+    const long long k0 = (long long)warp * C;  // (k0 + lane fits size_t below: k0 < B)
     if (k0 >= a.B) return;  // warp-uniform
     const int n = (int)min((long long)C, (long long)a.B - k0);
     const int D4 = a.D4;
@@ -136,6 +139,11 @@ __global__ void __launch_bounds__(256) k_bpr_main(MainArgs a, Opt opt) {
         mjs = a.jslot[k];
         mis = a.islot[k];  // DAISY_NOT_HEAD unless this triple starts a positive-item run
     }
+    const float *pj = nullptr, *pi = nullptr;
+    if (PTR && lane < n) {
+        pj = a.jsrc[k0 + lane];
+        if (mis != DAISY_NOT_HEAD) pi = a.isrc[k0 + lane];
+    }
     bool act[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
@@ -145,12 +153,14 @@ __global__ void __launch_bounds__(256) k_bpr_main(MainArgs a, Opt opt) {
     for (int v = 0; v < V; ++v) pu[v] = qj[v] = qi[v] = acc[v] = pu_n[v] = qj_n[v] = qi_n[v] = f4_zero();
     {
         const int u = __shfl_sync(FULL, mu, 0), i = __shfl_sync(FULL, mi, 0), j = __shfl_sync(FULL, mj, 0);
+        const float *rj = PTR ? shfl_ptr(pj, 0) : a.Q + (size_t)j * (4 * D4);
+        const float *ri = PTR ? shfl_ptr(pi, 0) : a.Q + (size_t)i * (4 * D4);
 #pragma unroll
         for (int v = 0; v < V; ++v)
             if (act[v]) {
                 pu_n[v] = ld_row(a.P, (size_t)u * D4 + lane + 32 * v);
-                qj_n[v] = ld_row(a.Q, (size_t)j * D4 + lane + 32 * v);
-                qi_n[v] = ld_row(a.Q, (size_t)i * D4 + lane + 32 * v);
+                qj_n[v] = ld_row(rj, lane + 32 * v);
+                qi_n[v] = ld_row(ri, lane + 32 * v);
             }
     }
     int cur_i = -1;
@@ -192,12 +202,14 @@ __global__ void __launch_bounds__(256) k_bpr_main(MainArgs a, Opt opt) {
             const int un = __shfl_sync(FULL, mu, t + 1), in = __shfl_sync(FULL, mi, t + 1),
                       jn = __shfl_sync(FULL, mj, t + 1);
             const bool head_n = __shfl_sync(FULL, mis, t + 1) != DAISY_NOT_HEAD;
+            const float *rj = PTR ? shfl_ptr(pj, t + 1) : a.Q + (size_t)jn * (4 * D4);
+            const float *ri = PTR ? shfl_ptr(pi, t + 1) : a.Q + (size_t)in * (4 * D4);
 #pragma unroll
             for (int v = 0; v < V; ++v)
                 if (act[v]) {
                     pu_n[v] = ld_row(a.P, (size_t)un * D4 + lane + 32 * v);
-                    qj_n[v] = ld_row(a.Q, (size_t)jn * D4 + lane + 32 * v);
-                    if (head_n) qi_n[v] = ld_row(a.Q, (size_t)in * D4 + lane + 32 * v);
+                    qj_n[v] = ld_row(rj, lane + 32 * v);
+                    if (head_n) qi_n[v] = ld_row(ri, lane + 32 * v);
                 }
         }
         // x = c^2 <P[u], Q[i] - Q[j]>;  s = sigmoid(-x) = -d(loss)/dx
@@ -492,7 +504,9 @@ __global__ void k_slots_item_shard(const uint32_t *__restrict__ key, const uint3
                                    const uint32_t *__restrict__ cidx, int n, int B, uint32_t sentinel, uint32_t i_per,
                                    int G, uint32_t *__restrict__ jslot, uint32_t *__restrict__ islot,
                                    int32_t *__restrict__ st, uint32_t *__restrict__ uniq_gid,
-                                   uint32_t *__restrict__ owner_off) {
+                                   uint32_t *__restrict__ owner_off, ShardPeers peers, const float *__restrict__ cache,
+                                   int D, const float **__restrict__ jsrc, const float **__restrict__ isrc,
+                                   uint8_t *__restrict__ uniq_multi) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const uint32_t r = key[p];
@@ -502,15 +516,22 @@ __global__ void k_slots_item_shard(const uint32_t *__restrict__ key, const uint3
     const uint32_t slot = (first && last) ? DAISY_DIRECT : (uint32_t)p;
     const uint32_t c = cidx[p] - 1u;
     const uint32_t v = val[p];
+    // where the main kernel reads this ref's pre-step row: a row referenced once in the batch is read straight from
+    // its owner (peer load over NVLink, or local); a repeated row from the cache the fetch kernel fills once
+    const uint32_t o_r = r / i_per;
+    const float *from = (first && last) ? peers.q[o_r] + (size_t)(r - o_r * i_per) * D : cache + (size_t)c * D;
     if (v < (uint32_t)B) {
         jslot[v] = slot;
         st[3 * (size_t)v + 2] = (int32_t)c;
+        jsrc[v] = from;
     } else {
         islot[v - B] = slot;
         st[3 * (size_t)(v - B) + 1] = (int32_t)c;
+        isrc[v - B] = from;
     }
     if (first) {
         uniq_gid[c] = r;
+        uniq_multi[c] = last ? 0 : 1;
         const int o_cur = (int)(r / i_per);
         const int o_prev = (p == 0) ? -1 : (int)(key[p - 1] / i_per);
         for (int o = o_prev + 1; o <= o_cur; ++o) owner_off[o] = c;
@@ -549,6 +570,7 @@ struct StepPlan {
     cudaStream_t bs, s;   // bookkeeping stream, caller's stream
     BookSet *k;
     int set;              // index of k in h->book
+    const float *const *jsrc, *const *isrc;  // row-sharded step only (else null)
 };
 
 // The integer bookkeeping of a step (prep .. slots) depends on the triples only, never on the tables.  It runs on
@@ -564,6 +586,8 @@ static int book_phase(daisy_ctx *h, StepPlan &pl, const int32_t *triples, int64_
     cudaStream_t bs = piped ? h->side_stream : s;
     pl.B = B; pl.C = C; pl.U = U; pl.I = I; pl.piped = piped; pl.bs = bs; pl.s = s;
     pl.set = h->book_idx;
+    pl.jsrc = sh ? sh->set[pl.set].jsrc : nullptr;
+    pl.isrc = sh ? sh->set[pl.set].isrc : nullptr;
     BookSet &k = h->book[h->book_idx];
     pl.k = &k;
     h->book_idx ^= 1;
@@ -631,7 +655,7 @@ static int book_phase(daisy_ctx *h, StepPlan &pl, const int32_t *triples, int64_
         h->launches += 2;
         k_slots_item_shard<<<daisy_ceil_div(2 * (int64_t)B, T), T, 0, bs>>>(
             k.qkey_s, h->val_out, sh->cidx, 2 * B, B, I, (uint32_t)sh->i_per, sh->world, k.jslot, k.islot, k.st,
-            ss.uniq_gid, ss.owner_off);
+            ss.uniq_gid, ss.owner_off, sh->peers, sh->cache, h->D, ss.jsrc, ss.isrc, ss.multi);
         DAISY_LAUNCH_CHECK(h);
         k_shard_finish<<<daisy_ceil_div(2 * (int64_t)B, T), T, 0, bs>>>(k.qkey_s, sh->cidx, 2 * B, I, ss.uniq_gid,
                                                                          ss.owner_off, sh->world, (uint32_t)sh->i_per,
@@ -665,10 +689,14 @@ static int table_phase_v(daisy_ctx *h, const StepPlan &pl, const float *P, const
     a.P = P; a.Q = Q; a.st = k.st; a.uslot = k.uslot; a.jslot = k.jslot; a.islot = k.islot;
     a.stageU = h->stageU; a.stageQ = h->stageQ; a.loss_part = h->loss_part;
     a.B = B; a.D4 = D4; a.C = C; a.c2 = c2;
+    a.jsrc = pl.jsrc; a.isrc = pl.isrc;
     const int warps = daisy_ceil_div(B, C);
     const bool pool = (h->timing == 1 && h->pool_used < DAISY_EVPOOL);
     if (pool) cudaEventRecord(h->evpool[2 * h->pool_used], s);
-    k_bpr_main<V, Opt><<<daisy_ceil_div(warps, 8), 256, 0, s>>>(a, opt);
+    if (pl.jsrc)
+        k_bpr_main<V, Opt, true><<<daisy_ceil_div(warps, 8), 256, 0, s>>>(a, opt);
+    else
+        k_bpr_main<V, Opt, false><<<daisy_ceil_div(warps, 8), 256, 0, s>>>(a, opt);
     DAISY_LAUNCH_CHECK(h);
     if (pool) {
         cudaEventRecord(h->evpool[2 * h->pool_used + 1], s);

@@ -96,8 +96,8 @@ def _peer_lockstep(shards, batches_per_rank):
 def _make_peer_shards(G, U, I, D, B, P0, Q0, lr=0.05, wd=0.01):
     from recommend_lib_b200.sharded import PeerShardedBPR
     dev = torch.device("cuda:0")
-    shards = [PeerShardedBPR(U, I, D, lr=lr, wd=wd, max_batch=B, rank=r, world=G, device=dev, P_full=P0, Q_full=Q0)
-              for r in range(G)]
+    shards = [PeerShardedBPR(U, I, D, lr=lr, wd=wd, max_batch=B, rank=r, world=G, device=dev, P_full=P0, Q_full=Q0,
+                             mapping="local") for r in range(G)]
     PeerShardedBPR.connect_in_process(shards)
     return shards
 
@@ -181,7 +181,7 @@ def test_peer_sharded_reports_bad_ids():
 # ----------------------------------------------------------------------------------------------------------------
 # the real thing: one process per GPU, CUDA IPC + flag barriers (needs >= 2 GPUs; run with gpurun --gpus 2)
 # ----------------------------------------------------------------------------------------------------------------
-def _mp_worker(rank, world, port, U, I, D, B, steps, out):
+def _mp_worker(rank, world, port, U, I, D, B, steps, out, mapping):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -193,7 +193,7 @@ def _mp_worker(rank, world, port, U, I, D, B, steps, out):
         from sharded_testing import route
         P0, Q0, batches = _problem(U, I, D, B, steps, seed=5)
         m = PeerShardedBPR(U, I, D, lr=0.05, wd=0.01, max_batch=B, rank=rank, world=world, device=dev, P_full=P0,
-                           Q_full=Q0).connect()
+                           Q_full=Q0, mapping=mapping).connect()
         for n, b in enumerate(batches):
             t = torch.from_numpy(route(b, m.layout, rank))
             m.step(t.pin_memory() if n % 2 else t.to(dev))          # alternate host-fed / device-fed steps
@@ -208,8 +208,8 @@ def _mp_worker(rank, world, port, U, I, D, B, steps, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_peer_sharded_multiprocess_ipc(tmp_path, world):
+@pytest.mark.parametrize("world,mapping", [(2, "symm"), (2, "ipc"), (4, "symm"), (8, "symm")])
+def test_peer_sharded_multiprocess(tmp_path, world, mapping):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import socket
@@ -219,11 +219,25 @@ def test_peer_sharded_multiprocess_ipc(tmp_path, world):
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    U, I, D, B, steps = 4000, 3001, 128, 30000, 4
+    U, I, D, B, steps = 4000, 3001, 128, 30000, 3
     out = str(tmp_path / "res.npz")
-    mp.spawn(_mp_worker, args=(world, port, U, I, D, B, steps, out), nprocs=world, join=True)
+    mp.spawn(_mp_worker, args=(world, port, U, I, D, B, steps, out, mapping), nprocs=world, join=True)
     r = np.load(out)
     P0, Q0, batches = _problem(U, I, D, B, steps, seed=5)
     Pr, Qr, losses = bpr_oracle.bpr_run_closed_form(P0, Q0, batches, 0.05, 0.01, np.float64)
     assert rel_err(r["P"], Pr) <= 1e-5 and rel_err(r["Q"], Qr) <= 1e-5
     assert abs(float(r["loss"]) - sum(losses)) / sum(losses) < 1e-5
+    # the same ranks driven in lockstep from this process run the same kernels in the same order: any difference
+    # would be a cross-GPU ordering bug (a fetch overtaking an owner's update, a push overwriting a region in use)
+    from sharded_testing import route
+    dev = torch.device("cuda:0")
+    shards = _make_peer_shards(world, U, I, D, B, P0, Q0)
+    for b in batches:
+        _peer_lockstep(shards, [torch.from_numpy(route(b, s.layout, s.rank)).to(dev) for s in shards])
+    for s in shards:
+        s.materialize()
+    P = torch.cat([s.P for s in shards]).cpu().numpy()
+    Q = torch.cat([s.Q for s in shards]).cpu().numpy()
+    assert np.array_equal(P, r["P"]) and np.array_equal(Q, r["Q"])
+    for s in shards:
+        s.close()
