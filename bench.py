@@ -38,6 +38,12 @@ CFG4 = dict(workload="BPR-MF synthetic 10M users x 2M items, dim 128, batch 1M t
 CFG5 = dict(workload="BPR-MF synthetic 100M users x 20M items, dim 128, row-sharded, 1M triples per GPU per step "
                      "(BASELINE.json configs[4])",
             user_num=100_000_000, item_num=20_000_000, dim=128, batch=1_000_000, lr=0.01, wd=0.001, zipf=1.0)
+CFG3 = dict(workload="BPR-MF on ml-20m-shaped synthetic implicit data (138k users x 27k items, dim 128), Zipf item "
+                     "popularity, batch 65536 (BASELINE.json configs[2])",
+            user_num=138_493, item_num=27_278, dim=128, batch=65_536, lr=0.01, wd=0.001, zipf=1.0)
+CFG2 = dict(workload="Funk-SVD SGD (matrix_factorization.pyx) on ml-1m-shaped synthetic ratings, dim 128 "
+                     "(BASELINE.json configs[1])",
+            user_num=6040, item_num=3706, n=1_000_209, dim=128, lr=0.005, reg=0.02)
 METRIC = "bpr_mf_train_triples_per_s"
 UNIT = "triples/s"
 
@@ -178,7 +184,7 @@ def run_single(args):
     import torch
     from recommend_lib_b200.bpr import BPR, BPRSGD
     from recommend_lib_b200.sampler import synthetic_triples
-    cfg = dict(CFG4)
+    cfg = dict(CFG3 if args.workload == "config3" else CFG4)
     if args.scale != 1.0:                      # debugging aid only; the default (1.0) is the named configuration
         cfg["user_num"] = int(cfg["user_num"] * args.scale)
         cfg["item_num"] = int(cfg["item_num"] * args.scale)
@@ -196,6 +202,8 @@ def run_single(args):
     model.embed_item.weight = torch.nn.Parameter(torch.empty((I, D), device=dev).normal_(0, 0.01), requires_grad=False)
     opt = BPRSGD(model, lr=cfg["lr"], weight_decay=cfg["wd"])
     h = model.handle(B)
+    if args.l2_window:                          # north star: hot item rows pinned in L2 (access-policy window)
+        model.pin_hot_items(None, 1.0)
 
     nb = K + W
     host = torch.from_numpy(synthetic_triples(nb * B, U, I, seed=2019, zipf=cfg["zipf"]).reshape(nb, B, 3)).pin_memory()
@@ -294,7 +302,10 @@ def run_single(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["workload"], "user_num": U, "item_num": I, "dim": D, "batch": B,
                        "lr": cfg["lr"], "wd": cfg["wd"], "item_popularity": "zipf(1.0), permuted",
-                       "l2": "inputs larger than L2 (6.1 GB of tables, ~3 GB touched per step vs 126 MB L2)",
+                       "l2": ("inputs larger than L2 (6.1 GB of tables, ~3 GB touched per step vs 126 MB L2)"
+                              if args.workload == "config4" else
+                              "tables (85 MB) fit the 126 MB L2: L2-resident workload, the HBM roofline does not bound it"),
+                       "l2_access_policy_window": bool(args.l2_window),
                        "lazy_decay_materialized_in_timed_region": True,
                        "e2e_loss_readback": "async D2H of every step's loss into pinned memory, synchronised at the end"},
             "clocks": clocks.summary(),
@@ -316,6 +327,70 @@ def run_single(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------
+# config 2: funk-SVD (secondary line, not the driver's metric)
+# ------------------------------------------------------------------------------------------------
+def run_mf(args):
+    """ratings/s of SVD.fit (daisy_mf_fit, dataflow kernel, float64, strictly sequential semantics) on the ml-1m
+    shape, next to the reference's own Cython extension (oracle/_ref, when it was built) or its C restatement on a
+    bounded sample."""
+    import torch
+    from recommend_lib_b200 import _lib
+    from recommend_lib_b200._lib import MFParams, c_vp
+    from recommend_lib_b200.sampler import synthetic_ratings
+    import ctypes
+    cfg = CFG2
+    U, I, D, N = cfg["user_num"], cfg["item_num"], cfg["dim"], cfg["n"]
+    users, items, ratings = synthetic_ratings(N, U, I, seed=2019)
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(0)
+    pu = rng.normal(0, 0.1, (U, D)); qi = rng.normal(0, 0.1, (I, D))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    dpu, dqi, dbu, dbi = t(pu), t(qi), t(np.zeros(U)), t(np.zeros(I))
+    du, di, dr = t(users.astype(np.int32)), t(items.astype(np.int32)), t(ratings.astype(np.float64))
+    prm = MFParams(0, 1, cfg["lr"], cfg["lr"], cfg["lr"], cfg["lr"], cfg["reg"], cfg["reg"], cfg["reg"], cfg["reg"], 0.0,
+                   float(ratings.mean()))
+    h = _lib.Handle(0, U, I, D, 0)
+    s = _lib.stream_ptr(torch, dev)
+    fit = lambda ep: _lib.check(h.L.daisy_mf_fit(h.ptr, c_vp(dpu.data_ptr()), c_vp(dqi.data_ptr()), c_vp(dbu.data_ptr()),
+                                                 c_vp(dbi.data_ptr()), c_vp(du.data_ptr()), c_vp(di.data_ptr()),
+                                                 c_vp(dr.data_ptr()), N, ep, ctypes.byref(prm), None, s))
+    fit(max(1, min(args.warmup, 2)))
+    torch.cuda.synchronize()
+    K = max(1, min(args.steps, 10))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    fit(K)                                              # K epochs = K passes over the 1M ratings
+    ev1.record()
+    torch.cuda.synchronize()
+    _lib.check(h.L.daisy_check(h.ptr, s))
+    ms = ev0.elapsed_time(ev1)
+    # CPU side: the reference's compiled Cython SVD when present, else the C restatement; bounded sample
+    from oracle import mf_oracle
+    n_cpu = 200_000
+    pu_c, qi_c = pu.copy(), qi.copy()
+    t0 = time.time()
+    mf_oracle.svd_fit(users[:n_cpu], items[:n_cpu], ratings[:n_cpu], pu_c, qi_c, n_epochs=1, biased=True,
+                      lr_all=cfg["lr"], reg_all=cfg["reg"])
+    cpu_dt = time.time() - t0
+    line = {"metric": "funk_svd_train_ratings_per_s", "value": N * K / (ms * 1e-3), "unit": "ratings/s", "n_gpus": 1,
+            "steps": K, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "user_num": U, "item_num": I, "ratings": N, "dim": D,
+                       "step": "one epoch (a pass over all ratings in the given order, sequential semantics)",
+                       "l2": "tables (10 MB in f64) are L2-resident; the bound is the longest dependency chain"},
+            "roofline": {"bound": "hbm", "achieved": N * K * (2 * (16 * D + 12) + 16) / (ms * 1e-3) / 1e9,
+                         "peak": measured_peaks()[0], "unit": "GB/s",
+                         "frac": N * K * (2 * (16 * D + 12) + 16) / (ms * 1e-3) / 1e9 / measured_peaks()[0],
+                         "traffic": None, "note": "f64 rows: 2 x (16 D + 12) + 16 B per rating; dependency-bound"},
+            "cpu_baseline": {"value": n_cpu / cpu_dt, "unit": "ratings/s", "cores": 1, "kind": "port",
+                             "sample": f"C restatement of the Cython loop (bit-identical to it, tests/test_oracle_golden.py), "
+                                       f"one epoch over the first {n_cpu} ratings, single thread (the loop is serial); "
+                                       "the reference's own fit adds ~50 us/rating of DataFrame.iterrows overhead"},
+            "gpu_launches": int(h.launches)}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -328,6 +403,10 @@ def main():
     ap.add_argument("--phases", action="store_true", help="also print the per-phase breakdown of the step")
     ap.add_argument("--trace", action="store_true", help="also print a timeline of bookkeeping vs table kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="config4", choices=["config4", "config3", "config2"],
+                    help="N = 1 only: config4 is the driver's metric; config3 (L2-resident ml-20m shape) and config2 "
+                         "(funk-SVD) are secondary lines kept under profiles/")
+    ap.add_argument("--l2-window", action="store_true", help="pin the item table in L2 (access-policy window)")
     ap.add_argument("--mapping", default="symm", choices=["symm", "ipc"],
                     help="N > 1, peer exchange: how the ranks map each other's arenas")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
@@ -341,6 +420,8 @@ def main():
     if args.gpus > 1 or world > 1:
         from recommend_lib_b200.sharded import bench_sharded
         return bench_sharded(args, CFG5, METRIC, UNIT)
+    if args.workload == "config2":
+        return run_mf(args)
     return run_single(args)
 
 

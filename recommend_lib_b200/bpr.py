@@ -90,6 +90,18 @@ class BPR(nn.Module):
                                          _lib.stream_ptr(torch, P.device)))
         return self
 
+    def pin_hot_items(self, n_rows=None, hit_ratio=1.0):
+        """Pin rows [0, n_rows) of the item table in L2 through an access-policy window on the current stream
+        (``daisy_set_l2_window``): with a popularity-ordered catalogue these are the hot items of the Zipf head.
+        ``n_rows=None`` pins the whole item table (as much as the device's persisting-L2 carve-out allows);
+        ``n_rows=0`` clears the window."""
+        P, Q = self._tables()
+        h = self.handle()
+        n = self.item_num if n_rows is None else int(n_rows)
+        _lib.check(h.L.daisy_set_l2_window(h.ptr, c_vp(Q.data_ptr()), n, float(hit_ratio),
+                                           _lib.stream_ptr(torch, P.device)))
+        return self
+
     def check(self):
         """Synchronise and raise IndexError if any id seen since the last check was out of range."""
         if self._handle is not None:

@@ -96,6 +96,9 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
     h->heavy_cap = (int)(3 * max_batch / h->heavy_len) + 4;
     h->slice_cap = (int)(3 * max_batch / DAISY_SLICE) + h->heavy_cap + 4;
     h->pipeline = env_int("DAISY_PIPELINE", 1) ? 1 : 0;
+    h->main_stages = env_int("DAISY_MAIN_STAGES", 3);
+    if (h->main_stages < 0) h->main_stages = 0;
+    if (h->main_stages > 16) h->main_stages = 16;
     h->inputs_ready = 0;
 
     const size_t B = (size_t)max_batch;

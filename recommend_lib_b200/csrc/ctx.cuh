@@ -133,6 +133,7 @@ struct daisy_ctx {
     // tuning (env overridable, see api.cu)
     int chunk;       // max positive-item run length handled by one warp in the main kernel (0 = auto)
     int heavy_len;   // segments longer than this go to the block-per-row kernel
+    int main_stages; // > 0: TMA-pipelined main kernel with this many stages (triples in flight) per warp; 0: register prefetch
 
     // --- instrumentation ---
     int64_t launches;

@@ -257,6 +257,180 @@ __global__ void __launch_bounds__(256) k_bpr_main(MainArgs a, Opt opt) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// main fused kernel, TMA-pipelined: the same arithmetic in the same order as k_bpr_main (bit-identical results), but
+// the rows of the next S sorted triples of a warp are in flight at once.  Every warp owns a ring of S stages in
+// shared memory (3 rows each); one elected lane issues one bulk async copy per row (cp.async.bulk global ->
+// shared, completion on the stage's mbarrier), the warp waits on the stage's phase, reads its float4 slices
+// (conflict-free 16-byte-per-lane shared loads) and immediately refills the stage with triple t + S.
+// With register prefetching one triple ahead, a warp's next loads are only issued once the previous ones have
+// landed, which makes the sharded step latency-bound on peer loads (~2-3 us over NVLink); here the depth is S
+// triples per warp and the loads cost no registers.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+template <int V, class Opt, bool PTR>
+__global__ void __launch_bounds__(256) k_bpr_main_tma(MainArgs a, Opt opt, int S) {
+    extern __shared__ __align__(128) unsigned char dsm[];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int warp = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const int C = a.C;
+    const long long k0 = (long long)warp * C;
+    if (k0 >= a.B) return;  // warp-uniform; no block-wide barrier is used below
+    const int n = (int)min((long long)C, (long long)a.B - k0);
+    const int D4 = a.D4;
+    const uint32_t rowB = (uint32_t)D4 * 16u;
+    // ring of this warp: S stages x 3 rows; the mbarriers of all warps sit behind the rings
+    unsigned char *ring = dsm + (size_t)wid * S * 3 * rowB;
+    const uint32_t ring_s = smem_u32(ring);
+    const uint32_t bars = smem_u32(dsm + (size_t)8 * S * 3 * rowB) + (uint32_t)(wid * S) * 8u;
+    if (lane == 0) {
+        for (int st = 0; st < S; ++st) mbar_init(bars + 8u * st, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    int mu = 0, mi = 0, mj = 0;
+    uint32_t mus = 0, mjs = 0, mis = 0;
+    const float *pj = nullptr, *pi = nullptr;
+    if (lane < n) {
+        const size_t k = (size_t)(k0 + lane);
+        mu = a.st[3 * k];
+        mi = a.st[3 * k + 1];
+        mj = a.st[3 * k + 2];
+        mus = a.uslot[k];
+        mjs = a.jslot[k];
+        mis = a.islot[k];
+        if (PTR) {
+            pj = a.jsrc[k];
+            if (mis != DAISY_NOT_HEAD) pi = a.isrc[k];
+        }
+    }
+    bool act[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
+
+    // issue the copies of sorted triple t into stage t % S (warp-uniform arguments; lane 0 elected)
+    auto issue = [&](int t) {
+        const int u = __shfl_sync(FULL, mu, t), i = __shfl_sync(FULL, mi, t), j = __shfl_sync(FULL, mj, t);
+        const bool head = __shfl_sync(FULL, mis, t) != DAISY_NOT_HEAD;
+        const float *rj = PTR ? shfl_ptr(pj, t) : a.Q + (size_t)j * (4 * D4);
+        const float *ri = PTR ? shfl_ptr(pi, t) : a.Q + (size_t)i * (4 * D4);
+        if (lane == 0) {
+            const int stg = t % S;
+            const uint32_t bar = bars + 8u * stg, dst = ring_s + (uint32_t)stg * 3u * rowB;
+            mbar_expect_tx(bar, head ? 3u * rowB : 2u * rowB);
+            bulk_g2s(dst, a.P + (size_t)u * (4 * D4), rowB, bar);
+            bulk_g2s(dst + rowB, rj, rowB, bar);
+            if (head) bulk_g2s(dst + 2u * rowB, ri, rowB, bar);
+        }
+    };
+    for (int t = 0; t < S && t < n; ++t) issue(t);
+
+    float4 pu[V], qj[V], qi[V], acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) pu[v] = qj[v] = qi[v] = acc[v] = f4_zero();
+    int cur_i = -1;
+    uint32_t cur_is = 0;
+    float loss = 0.f;
+
+    for (int t = 0; t < n; ++t) {
+        const int u = __shfl_sync(FULL, mu, t), i = __shfl_sync(FULL, mi, t), j = __shfl_sync(FULL, mj, t);
+        const uint32_t us = __shfl_sync(FULL, mus, t), js = __shfl_sync(FULL, mjs, t);
+        const uint32_t is_t = __shfl_sync(FULL, mis, t);
+        const bool head = is_t != DAISY_NOT_HEAD;
+        if (head && t > 0) {  // flush the finished positive-item run
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if (act[v]) {
+                    const int e = lane + 32 * v;
+                    if (cur_is == DAISY_DIRECT)
+                        opt.apply(1, (size_t)cur_i, e, qi[v], acc[v]);
+                    else
+                        st_stream(a.stageQ, (size_t)cur_is * D4 + e, acc[v]);
+                }
+        }
+        const int stg = t % S;
+        mbar_wait(bars + 8u * stg, (uint32_t)(t / S) & 1u);
+        const float4 *sp = reinterpret_cast<const float4 *>(ring + (size_t)stg * 3 * rowB);
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            if (act[v]) {
+                pu[v] = sp[lane + 32 * v];
+                qj[v] = sp[D4 + lane + 32 * v];
+                if (head) {
+                    qi[v] = sp[2 * D4 + lane + 32 * v];
+                    acc[v] = f4_zero();
+                }
+            }
+        if (head) {
+            cur_i = i;
+            cur_is = is_t;
+        }
+        __syncwarp();                   // every lane has read the stage: it can be refilled
+        if (t + S < n) issue(t + S);
+        float d = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            if (act[v]) d += f4_dot(pu[v], f4_sub(qi[v], qj[v]));
+        d = warp_sum(d);
+        const float x = d * a.c2;
+        const float s = 1.f / (1.f + expf(x));
+        loss += fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x)));
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            if (act[v]) {
+                const int e = lane + 32 * v;
+                const float4 gu = f4_scale(f4_sub(qi[v], qj[v]), s);
+                if (us == DAISY_DIRECT)
+                    opt.apply(0, (size_t)u, e, pu[v], gu);
+                else
+                    st_stream(a.stageU, (size_t)us * D4 + e, gu);
+                const float4 gj = f4_scale(pu[v], -s);
+                if (js == DAISY_DIRECT)
+                    opt.apply(1, (size_t)j, e, qj[v], gj);
+                else
+                    st_stream(a.stageQ, (size_t)js * D4 + e, gj);
+                acc[v].x = fmaf(s, pu[v].x, acc[v].x);
+                acc[v].y = fmaf(s, pu[v].y, acc[v].y);
+                acc[v].z = fmaf(s, pu[v].z, acc[v].z);
+                acc[v].w = fmaf(s, pu[v].w, acc[v].w);
+            }
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+        if (act[v]) {
+            const int e = lane + 32 * v;
+            if (cur_is == DAISY_DIRECT)
+                opt.apply(1, (size_t)cur_i, e, qi[v], acc[v]);
+            else
+                st_stream(a.stageQ, (size_t)cur_is * D4 + e, acc[v]);
+        }
+    if (lane == 0) a.loss_part[warp] = loss;
+}
+
+// ------------------------------------------------------------------------------------------------
 // segmented reduce + row update for rows with several contributions
 // ------------------------------------------------------------------------------------------------
 template <int V>
@@ -693,10 +867,26 @@ static int table_phase_v(daisy_ctx *h, const StepPlan &pl, const float *P, const
     const int warps = daisy_ceil_div(B, C);
     const bool pool = (h->timing == 1 && h->pool_used < DAISY_EVPOOL);
     if (pool) cudaEventRecord(h->evpool[2 * h->pool_used], s);
-    if (pl.jsrc)
-        k_bpr_main<V, Opt, true><<<daisy_ceil_div(warps, 8), 256, 0, s>>>(a, opt);
-    else
-        k_bpr_main<V, Opt, false><<<daisy_ceil_div(warps, 8), 256, 0, s>>>(a, opt);
+    const int blocks = daisy_ceil_div(warps, 8);
+    // TMA-pipelined variant: S stages of 3 rows per warp in shared memory, at most ~56 KB per block so that four
+    // blocks stay resident per SM; rows too long for two stages fall back to the register-prefetch kernel
+    const size_t stage_bytes = (size_t)8 * 3 * D4 * 16;
+    int S = h->main_stages;
+    if ((size_t)S * stage_bytes > (size_t)56 * 1024) S = (int)((size_t)56 * 1024 / stage_bytes);
+    if (S >= 2) {
+        const size_t smem = S * stage_bytes + (size_t)8 * S * 8;
+        if (pl.jsrc) {
+            DAISY_CUDA(cudaFuncSetAttribute(k_bpr_main_tma<V, Opt, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_bpr_main_tma<V, Opt, true><<<blocks, 256, smem, s>>>(a, opt, S);
+        } else {
+            DAISY_CUDA(cudaFuncSetAttribute(k_bpr_main_tma<V, Opt, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_bpr_main_tma<V, Opt, false><<<blocks, 256, smem, s>>>(a, opt, S);
+        }
+    } else if (pl.jsrc) {
+        k_bpr_main<V, Opt, true><<<blocks, 256, 0, s>>>(a, opt);
+    } else {
+        k_bpr_main<V, Opt, false><<<blocks, 256, 0, s>>>(a, opt);
+    }
     DAISY_LAUNCH_CHECK(h);
     if (pool) {
         cudaEventRecord(h->evpool[2 * h->pool_used + 1], s);

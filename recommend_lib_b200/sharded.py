@@ -582,31 +582,35 @@ def bench_sharded(args, cfg, metric, unit):
     if rank == 0:
         ms_total, ms_e2e = float(ms), float(ms2)
         value = B * world * K / (ms_total * 1e-3)
-        wire_bytes = wire_rows / K * 4 * D                      # per step, this rank, rows in + rows out
+        # NVLink bytes per step and direction at one GPU: it RECEIVES the rows it fetches and SERVES the rows its peers
+        # fetch from it (egress), and it PUSHES its row sums (egress) and receives its peers' (ingress); by symmetry
+        # every direction carries (remote rows) x 4D bytes twice.  wire_rows = 2 x remote rows of this rank.
+        each_way = wire_rows / K * 4 * D
         peak_nvl = 770.0
+        step_s = ms_total / K * 1e-3
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": cfg["workload"], "user_num": U, "item_num": I, "dim": D,
                            "batch_per_gpu": B, "global_batch": B * world, "lr": cfg["lr"], "wd": cfg["wd"],
                            "sharding": ("block rows, triples routed to the user's owner; item rows read from / row "
-                                        "sums stored to the owners' memory by the step kernels over NVLink (CUDA IPC "
-                                        "peer pointers), flag barriers, deterministic owner-side merge") if peer else
+                                        "sums stored to the owners' memory by the step kernels over NVLink (peer "
+                                        "pointers), flag barriers, deterministic owner-side merge") if peer else
                                        ("block rows, triples routed to the user's owner, item rows + row gradients "
                                         "exchanged by NCCL all-to-all"),
-                           "exchange": args.exchange, "peer_mapping": args.mapping if peer else None, "l2": "inputs larger than L2",
-                           "lazy_decay_materialized_in_timed_region": True},
+                           "exchange": args.exchange, "peer_mapping": args.mapping if peer else None,
+                           "l2": "inputs larger than L2", "lazy_decay_materialized_in_timed_region": True},
                 "clocks": clocks.summary() if clocks is not None else None,
                 "e2e": {"value": B * world * K / (ms_e2e * 1e-3), "unit": unit, "ms_per_step": ms_e2e / K,
                         "h2d_bytes_per_step": B * 12 * world, "d2h_bytes_per_step": 8 * world},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "nvlink", "achieved": wire_bytes / 2 / (ms_total / K * 1e-3) / 1e9, "peak": peak_nvl,
-                             "unit": "GB/s per direction per GPU",
-                             "frac": wire_bytes / 2 / (ms_total / K * 1e-3) / 1e9 / peak_nvl,
+                "roofline": {"bound": "nvlink", "achieved": each_way / step_s / 1e9, "peak": peak_nvl,
+                             "unit": "GB/s per direction per GPU", "frac": each_way / step_s / 1e9 / peak_nvl,
                              "traffic": None, "peak_source": "measured peer copy (B200_PROFILING.md)",
-                             "rows_exchanged_per_step_per_gpu": wire_rows / K,
-                             "bytes_per_step_per_gpu_each_way": wire_bytes / 2,
-                             "hbm_whole_step_frac": (B * (24 * D + 12) / (ms_total / K * 1e-3) / 1e9) / 6461.8}}
+                             "remote_rows_per_step_per_gpu": wire_rows / K / 2,
+                             "nvlink_bytes_per_step_per_gpu_each_way": each_way,
+                             "note": "whole step (compute + barriers + owner merge), not the fused kernel alone",
+                             "hbm_whole_step_frac": (B * (24 * D + 12) / step_s / 1e9) / 6461.8}}
         if phases:
             line["phase_ms(device,host)"] = phases
         print(json.dumps(line), flush=True)
