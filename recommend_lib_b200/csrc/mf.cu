@@ -132,6 +132,291 @@ __global__ void __launch_bounds__(128) k_mf_dataflow(MfArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Item-owner schedule (default).  The ticket schedule above pays a full L2 hand-off (poll, acquire, row loads,
+// stores, fence, release: ~10 us measured) for EVERY link of the longest dependency chain -- and with a Zipf
+// catalogue the hottest item's chain is ~12 % of all ratings.  Here every item belongs to one warp for the whole
+// fit: item of hotness rank r -> warp r mod W (W = resident warps), so the hottest W items have a warp of their
+// own.  A warp walks the ratings of its items in sequence order, epoch after epoch, and keeps the current item's
+// row and bias IN REGISTERS from one rating to the next: an item chain link costs a dot product and an update,
+// no memory round trip.  Only user rows travel through memory, guarded by the per-user version counters exactly
+// as above (expected version = e * #ratings(u) + rank of the rating among u's ratings); the next link's user row
+// is loaded speculatively behind an acquire load of its version while the current link computes.
+// Deadlock-free: the earliest unprocessed rating of the whole sequence has its user predecessor done (it is
+// earlier) and its item predecessor done (same warp, earlier in that warp's list), so its owner can proceed;
+// all W warps are resident (persistent launch sized by the occupancy query).
+// Same arithmetic as the reference loop: the result is the sequential result up to the rounding of the warp-tree
+// dot product, identical to the ticket schedule's.
+// ------------------------------------------------------------------------------------------------
+struct OwnArgs {
+    double *pu, *qi, *bu, *bi;
+    const int *lk_u, *lk_i;        // per link: links are grouped by owner warp, in sequence order inside a warp
+    const double *lk_r;
+    const unsigned *lk_need, *lk_cnt, *lk_t;  // rank among the user's ratings, #ratings of the user, position t
+    const unsigned *wptr;          // [W + 1] first link of every warp
+    unsigned *ver_u;
+    double *err2;
+    int *abort_flag;
+    unsigned long long *stats;  // optional (DAISY_MF_STATS=1): [0] links, [1] links that took the blocking path, [2] item switches
+    long long n;
+    int epochs, D;
+    daisy_mf_params prm;
+    unsigned spin_cap;
+};
+
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(unsigned *p, unsigned v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// Links are processed in GROUPS of K.  A memory fence costs a warp ~0.4 us whatever it covers, so a group shares ONE:
+// after the K links of group g are done (their user rows stored, K version updates pending), lanes j < K read the
+// versions of group g+1's users (relaxed), every lane executes one fence.acq_rel -- it orders this warp's row stores
+// before the K pending version stores (release pattern) and the version reads before the row reads that follow
+// (acquire pattern) -- then the pending versions are published and the K user rows of group g+1 are loaded for the
+// links whose version was already the expected one.  A link whose user row is not ready yet (its previous rating is
+// held by another warp, or by an earlier link of the same group) takes the blocking path; pending versions are
+// always published BEFORE blocking, so no warp ever waits on a version that its owner is holding back.
+template <int DV>
+__global__ void __launch_bounds__(128) k_mf_owner(OwnArgs a) {
+    constexpr int K = DV <= 4 ? 8 : (DV == 8 ? 4 : 2);
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned w = (unsigned)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const unsigned beg = a.wptr[w], end = a.wptr[w + 1];
+    if (beg == end) return;  // warp-uniform
+    const unsigned len = end - beg;
+    const unsigned long long L = (unsigned long long)len * (unsigned long long)a.epochs;  // links of this warp, all epochs
+    const int D = a.D;
+    const daisy_mf_params prm = a.prm;
+    bool act[DV];
+#pragma unroll
+    for (int v = 0; v < DV; ++v) act[v] = (lane + 32 * v) < D;
+
+    double q[DV];
+#pragma unroll
+    for (int v = 0; v < DV; ++v) q[v] = 0.0;
+    double b_i = 0.0;
+    int cur_item = -1;
+
+    // metadata of the current group (M0) and the next one (M1): lane j < K holds link x0 + j
+    int u0 = -1, i0 = 0, u1 = -1, i1 = 0;
+    double r0 = 0.0, r1 = 0.0;
+    unsigned want0 = 0, want1 = 0, t0 = 0, t1 = 0, e0 = 0, e1 = 0;
+    // (epoch, offset) of the link x the next load_meta call starts at; advanced by K per call (no 64-bit divisions)
+    unsigned meta_e = 0, meta_off = 0;
+    auto load_meta = [&](unsigned long long x, int &mu, int &mi, double &mr, unsigned &mw, unsigned &mt, unsigned &me) {
+        mu = -1;
+        unsigned e = meta_e, off = meta_off + (unsigned)lane;
+        while (off >= len) { off -= len; ++e; }
+        meta_off += K;
+        while (meta_off >= len) { meta_off -= len; ++meta_e; }
+        if (lane < K && x + lane < L) {
+            const unsigned k = beg + off;
+            mu = a.lk_u[k];
+            mi = a.lk_i[k];
+            mr = a.lk_r[k];
+            mw = e * a.lk_cnt[k] + a.lk_need[k];
+            mt = a.lk_t[k];
+            me = e;
+        }
+    };
+    load_meta(0, u0, i0, r0, want0, t0, e0);
+    load_meta(K, u1, i1, r1, want1, t1, e1);
+
+    double R[K][DV], Bu[K];  // prefetched user rows / biases of the current group (valid where `valid` has the bit)
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        Bu[j] = 0.0;
+#pragma unroll
+        for (int v = 0; v < DV; ++v) R[j][v] = 0.0;
+    }
+    unsigned valid = 0;
+    unsigned long long n_slow = 0, n_switch = 0;
+    int pend_u = -1;         // lane j: user whose version update from link j of the current group is not published yet
+    unsigned pend_v = 0;
+
+    for (unsigned long long x0 = 0; x0 < L; x0 += K) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int u = __shfl_sync(FULL, u0, j);
+            if (u < 0) break;  // warp-uniform: past the end of the list
+            const int i = __shfl_sync(FULL, i0, j);
+            const double r = __shfl_sync(FULL, r0, j);
+            const unsigned want = __shfl_sync(FULL, want0, j);
+            if (i != cur_item) {  // another item of this warp: park the current row, fetch the other
+                ++n_switch;
+                if (cur_item >= 0) {
+#pragma unroll
+                    for (int v = 0; v < DV; ++v)
+                        if (act[v]) __stcg(a.qi + (size_t)cur_item * D + lane + 32 * v, q[v]);
+                    if (lane == 0) __stcg(a.bi + cur_item, b_i);
+                }
+#pragma unroll
+                for (int v = 0; v < DV; ++v) q[v] = act[v] ? __ldcg(a.qi + (size_t)i * D + lane + 32 * v) : 0.0;
+                b_i = __ldcg(a.bi + i);
+                cur_item = i;
+            }
+            double p[DV], b_u;
+            if (valid & (1u << j)) {
+#pragma unroll
+                for (int v = 0; v < DV; ++v) p[v] = R[j][v];
+                b_u = Bu[j];
+            } else {
+                ++n_slow;
+                // blocking path.  Publish what this warp holds back first (another warp may be waiting for it, and
+                // the version we are about to wait for may even be one of ours).
+                fence_acq_rel_gpu();
+                __syncwarp();
+                if (pend_u >= 0) st_relaxed_u32(&a.ver_u[pend_u], pend_v);
+                pend_u = -1;
+                int bail = 0;
+                if (lane == 0) {
+                    unsigned spins = 0;
+                    while (ld_acquire_u32(&a.ver_u[u]) != want) {
+                        __nanosleep(20);
+                        if (++spins > a.spin_cap || *(volatile int *)a.abort_flag) {
+                            atomicExch(a.abort_flag, 1);
+                            bail = 1;
+                            break;
+                        }
+                    }
+                }
+                bail = __shfl_sync(FULL, bail, 0);
+                if (bail) return;
+                if (ld_acquire_u32(&a.ver_u[u]) != want) atomicExch(a.abort_flag, 2);  // every lane acquires itself
+#pragma unroll
+                for (int v = 0; v < DV; ++v) p[v] = act[v] ? __ldcg(a.pu + (size_t)u * D + lane + 32 * v) : 0.0;
+                b_u = __ldcg(a.bu + u);
+            }
+            double dot = 0.0;
+#pragma unroll
+            for (int v = 0; v < DV; ++v)
+                if (act[v]) dot += q[v] * p[v];
+            dot = warp_sum_d(dot);
+            double err;
+            double nb_u = b_u, nb_i = b_i;
+            if (prm.variant == 0) {  // SVD, util/matrix_factorization.pyx:140-151
+                err = r - (prm.global_mean + b_u + b_i + dot);
+                if (prm.biased) {
+                    nb_u = b_u + prm.lr_bu * (err - prm.reg_bu * b_u);
+                    nb_i = b_i + prm.lr_bi * (err - prm.reg_bi * b_i);
+                }
+            } else {  // RSVD, :49-61
+                err = r - (b_u + b_i + dot);
+                if (prm.variant == 2) {
+                    const double inc = prm.lr_bu * (err - prm.reg2 * (b_u + b_i - prm.global_mean));
+                    nb_u = b_u + inc;
+                    nb_i = b_i + inc;
+                }
+            }
+            b_i = nb_i;
+#pragma unroll
+            for (int v = 0; v < DV; ++v)
+                if (act[v]) {
+                    const double puf = p[v], qif = q[v];
+                    __stcg(a.pu + (size_t)u * D + lane + 32 * v, puf + prm.lr_pu * (err * qif - prm.reg_pu * puf));
+                    q[v] = qif + prm.lr_qi * (err * puf - prm.reg_qi * qif);
+                }
+            if (lane == 0) {
+                if (nb_u != b_u) __stcg(a.bu + u, nb_u);
+            }
+            if (a.err2) {
+                const unsigned t = __shfl_sync(FULL, t0, j), e = __shfl_sync(FULL, e0, j);
+                if (lane == 0) a.err2[(size_t)e * a.n + t] = err * err;
+            }
+            if (lane == j) {  // version update of this link: published with the group's fence
+                pend_u = u;
+                pend_v = want + 1;
+            }
+        }
+        // ---- one fence for the group: publish its versions, pick up the next group's user rows ----------------
+        unsigned vnext = 0;
+        if (u1 >= 0) vnext = ld_relaxed_u32(&a.ver_u[u1]);
+        fence_acq_rel_gpu();
+        __syncwarp();
+        if (pend_u >= 0) st_relaxed_u32(&a.ver_u[pend_u], pend_v);
+        pend_u = -1;
+        valid = __ballot_sync(FULL, u1 >= 0 && vnext == want1);
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            if (valid & (1u << j)) {  // warp-uniform
+                const int un = __shfl_sync(FULL, u1, j);
+#pragma unroll
+                for (int v = 0; v < DV; ++v) R[j][v] = act[v] ? __ldcg(a.pu + (size_t)un * D + lane + 32 * v) : 0.0;
+                Bu[j] = __ldcg(a.bu + un);
+            }
+        }
+        u0 = u1; i0 = i1; r0 = r1; want0 = want1; t0 = t1; e0 = e1;
+        load_meta(x0 + 2 * K, u1, i1, r1, want1, t1, e1);
+    }
+    // (the loop's last iteration published every pending version)
+    if (a.stats && lane == 0) {
+        atomicAdd(&a.stats[0], L);
+        atomicAdd(&a.stats[1], n_slow);
+        atomicAdd(&a.stats[2], n_switch);
+        if (w == 0) {  // the hottest item's warp
+            a.stats[3] = L;
+            a.stats[4] = n_slow;
+            a.stats[5] = n_switch;
+        }
+    }
+    if (cur_item >= 0) {
+#pragma unroll
+        for (int v = 0; v < DV; ++v)
+            if (act[v]) __stcg(a.qi + (size_t)cur_item * D + lane + 32 * v, q[v]);
+        if (lane == 0) __stcg(a.bi + cur_item, b_i);
+    }
+}
+
+__global__ void k_mf_hot_keys(const int *__restrict__ cnt_i, unsigned I, uint32_t *key, uint32_t *val) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= I) return;
+    key[i] = 0xFFFFFFFFu - (uint32_t)cnt_i[i];  // ascending sort = hottest first
+    val[i] = i;
+}
+__global__ void k_mf_hot_rank(const uint32_t *__restrict__ val_s, unsigned I, uint32_t *rank) {
+    unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < I) rank[val_s[p]] = p;
+}
+__global__ void k_mf_owner_keys(const int32_t *__restrict__ items, long long n, const uint32_t *__restrict__ rank,
+                                unsigned W, uint32_t *key, uint32_t *val) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    key[t] = rank[items[t]] % W;
+    val[t] = (uint32_t)t;
+}
+__global__ void k_mf_links(const uint32_t *__restrict__ order, long long n, const int32_t *__restrict__ users,
+                           const int32_t *__restrict__ items, const double *__restrict__ ratings,
+                           const int *__restrict__ need_u, const int *__restrict__ cnt_u, int *lk_u, int *lk_i,
+                           double *lk_r, unsigned *lk_need, unsigned *lk_cnt, unsigned *lk_t) {
+    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t t = order[p];
+    const int u = users[t];
+    lk_u[p] = u;
+    lk_i[p] = items[t];
+    lk_r[p] = ratings[t];
+    lk_need[p] = (unsigned)need_u[t];
+    lk_cnt[p] = (unsigned)cnt_u[u];
+    lk_t[p] = t;
+}
+__global__ void k_mf_wptr(const uint32_t *__restrict__ okey_s, long long n, unsigned W, unsigned *wptr) {
+    unsigned w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w > W) return;
+    long long lo = 0, hi = n;  // first position with key >= w
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (okey_s[mid] < w) lo = mid + 1; else hi = mid;
+    }
+    wptr[w] = (unsigned)lo;
+}
+
 // ---- rank of each rating among the ratings of its row, and per-row counts ------------------------
 __global__ void k_mf_keys(const int32_t *__restrict__ ids, long long n, unsigned rows, uint32_t *key, uint32_t *val,
                           int *err) {
@@ -196,22 +481,32 @@ __global__ void k_mf_predict(const double *__restrict__ pu, const double *__rest
     }
 }
 
-struct Scratch {  // frees everything on scope exit
-    void *p[16];
+// Stream-ordered scratch (cudaMallocAsync from the device's default pool, kept cached between fits): ~45 buffers per
+// fit cost microseconds instead of the ~100 ms of as many cudaMalloc / cudaFree pairs.  Freed on scope exit.
+struct Scratch {
+    void *p[64];
     int n = 0;
+    cudaStream_t s;
+    explicit Scratch(cudaStream_t stream, int device) : s(stream) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     template <class T>
     int get(T **out, size_t count) {
         *out = nullptr;
-        cudaError_t e = cudaMalloc((void **)out, (count ? count : 1) * sizeof(T));
+        cudaError_t e = cudaMallocAsync((void **)out, (count ? count : 1) * sizeof(T), s);
         if (e != cudaSuccess) {
-            daisy_set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+            daisy_set_error("cudaMallocAsync of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
             return DAISY_ENOMEM;
         }
         p[n++] = *out;
         return DAISY_OK;
     }
     ~Scratch() {
-        for (int i = 0; i < n; ++i) cudaFree(p[i]);
+        for (int i = 0; i < n; ++i) cudaFreeAsync(p[i], s);
     }
 };
 
@@ -252,7 +547,7 @@ extern "C" int daisy_mf_fit(daisy_handle_t h, double *pu, double *qi, double *bu
     DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
     cudaStream_t s = (cudaStream_t)stream;
     const size_t N = (size_t)n;
-    Scratch ws;
+    Scratch ws(s, h->device);
     uint32_t *key, *key_s, *val, *val_s;
     int *start, *start_scan, *need_u, *need_i, *cnt_u, *cnt_i, *abort_flag;
     unsigned *ver_u, *ver_i;
@@ -293,21 +588,93 @@ extern "C" int daisy_mf_fit(daisy_handle_t h, double *pu, double *qi, double *bu
         daisy_set_error("Invalid user or item code at rating %d", h->err_host[1]);
         return DAISY_EINDEX;
     }
-    MfArgs a;
-    a.pu = pu; a.qi = qi; a.bu = bu; a.bi = bi;
-    a.users = users; a.items = items; a.ratings = ratings;
-    a.need_u = need_u; a.need_i = need_i; a.cnt_u = cnt_u; a.cnt_i = cnt_i;
-    a.ver_u = ver_u; a.ver_i = ver_i; a.ticket = ticket; a.err2 = err2; a.abort_flag = abort_flag;
-    a.n = n; a.epochs = n_epochs; a.D = h->D; a.prm = *prm;
-    a.spin_cap = 1u << 24;  // ~1 s of polling: a correct schedule never gets near it
-    int occ = 0;
-    DAISY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mf_dataflow, 128, 0));
-    if (occ < 1) occ = 1;
-    int per_sm = occ < 8 ? occ : 8;
-    const char *env = getenv("DAISY_MF_BLOCKS_PER_SM");
-    if (env && atoi(env) > 0) per_sm = atoi(env) < occ ? atoi(env) : occ;
-    k_mf_dataflow<<<h->num_sms * per_sm, 128, 0, s>>>(a);
-    DAISY_LAUNCH_CHECK(h);
+    unsigned long long *dbg_stats = nullptr;
+    const char *sched = getenv("DAISY_MF_SCHEDULE");
+    const bool owner = !(sched && strcmp(sched, "ticket") == 0) && h->D <= 512;
+    if (owner) {
+        int occ = 0;
+        const int DVsel = h->D <= 32 ? 1 : h->D <= 64 ? 2 : h->D <= 128 ? 4 : h->D <= 256 ? 8 : 16;
+#define OCC_(DVV) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mf_owner<DVV>, 128, 0)
+        DAISY_CUDA(DVsel == 1 ? OCC_(1) : DVsel == 2 ? OCC_(2) : DVsel == 4 ? OCC_(4) : DVsel == 8 ? OCC_(8) : OCC_(16));
+#undef OCC_
+        if (occ < 1) occ = 1;
+        int per_sm = occ < 8 ? occ : 8;
+        const unsigned W = (unsigned)(h->num_sms * per_sm * 4);
+        uint32_t *hkey, *hkey_s, *hval, *hval_s, *rank;
+        int *lk_u, *lk_i;
+        double *lk_r;
+        unsigned *lk_need, *lk_cnt, *lk_t, *wptr;
+        const size_t I = (size_t)h->I;
+        rc = DAISY_OK;
+#define G2_(x, c) if (!rc) rc = ws.get(&x, (c))
+        G2_(hkey, I); G2_(hkey_s, I); G2_(hval, I); G2_(hval_s, I); G2_(rank, I);
+        G2_(lk_u, N); G2_(lk_i, N); G2_(lk_r, N); G2_(lk_need, N); G2_(lk_cnt, N); G2_(lk_t, N); G2_(wptr, (size_t)W + 1);
+#undef G2_
+        if (rc) return rc;
+        const int T = 256;
+        k_mf_hot_keys<<<daisy_ceil_div((int64_t)I, T), T, 0, s>>>(cnt_i, (unsigned)I, hkey, hval);
+        DAISY_LAUNCH_CHECK(h);
+        size_t tb = tmp_bytes;
+        if (I > (size_t)n) {  // the shared CUB scratch was sized for n pairs
+            size_t need = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, need, hkey, hkey_s, hval, hval_s, (int)I, 0, 32, s);
+            DAISY_REQUIRE(need <= tmp_bytes, DAISY_EUNSUPPORTED, "item table much larger than the rating list");
+        }
+        DAISY_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, hkey, hkey_s, hval, hval_s, (int)I, 0, 32, s));
+        k_mf_hot_rank<<<daisy_ceil_div((int64_t)I, T), T, 0, s>>>(hval_s, (unsigned)I, rank);
+        DAISY_LAUNCH_CHECK(h);
+        k_mf_owner_keys<<<daisy_ceil_div(n, T), T, 0, s>>>(items, n, rank, W, key, val);
+        DAISY_LAUNCH_CHECK(h);
+        int wbits = 1;
+        while (wbits < 32 && ((uint64_t)(W - 1) >> wbits)) ++wbits;
+        tb = tmp_bytes;
+        DAISY_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, key, key_s, val, val_s, (int)n, 0, wbits, s));
+        k_mf_links<<<daisy_ceil_div(n, T), T, 0, s>>>(val_s, n, users, items, ratings, need_u, cnt_u, lk_u, lk_i, lk_r,
+                                                      lk_need, lk_cnt, lk_t);
+        DAISY_LAUNCH_CHECK(h);
+        k_mf_wptr<<<daisy_ceil_div((int64_t)W + 1, T), T, 0, s>>>(key_s, n, W, wptr);
+        DAISY_LAUNCH_CHECK(h);
+        h->launches += 8;
+        OwnArgs o;
+        o.pu = pu; o.qi = qi; o.bu = bu; o.bi = bi;
+        o.lk_u = lk_u; o.lk_i = lk_i; o.lk_r = lk_r; o.lk_need = lk_need; o.lk_cnt = lk_cnt; o.lk_t = lk_t;
+        o.wptr = wptr; o.ver_u = ver_u; o.err2 = err2; o.abort_flag = abort_flag;
+        o.n = n; o.epochs = n_epochs; o.D = h->D; o.prm = *prm;
+        o.spin_cap = 1u << 26;
+        o.stats = nullptr;
+        const char *st_env = getenv("DAISY_MF_STATS");
+        if (st_env && atoi(st_env) > 0) {
+            rc = ws.get(&o.stats, 8);
+            if (rc) return rc;
+            DAISY_CUDA(cudaMemsetAsync(o.stats, 0, 8 * sizeof(unsigned long long), s));
+            dbg_stats = o.stats;
+        }
+        const int grid = h->num_sms * per_sm;
+        switch (DVsel) {
+            case 1: k_mf_owner<1><<<grid, 128, 0, s>>>(o); break;
+            case 2: k_mf_owner<2><<<grid, 128, 0, s>>>(o); break;
+            case 4: k_mf_owner<4><<<grid, 128, 0, s>>>(o); break;
+            case 8: k_mf_owner<8><<<grid, 128, 0, s>>>(o); break;
+            default: k_mf_owner<16><<<grid, 128, 0, s>>>(o); break;
+        }
+        DAISY_LAUNCH_CHECK(h);
+    } else {
+        MfArgs a;
+        a.pu = pu; a.qi = qi; a.bu = bu; a.bi = bi;
+        a.users = users; a.items = items; a.ratings = ratings;
+        a.need_u = need_u; a.need_i = need_i; a.cnt_u = cnt_u; a.cnt_i = cnt_i;
+        a.ver_u = ver_u; a.ver_i = ver_i; a.ticket = ticket; a.err2 = err2; a.abort_flag = abort_flag;
+        a.n = n; a.epochs = n_epochs; a.D = h->D; a.prm = *prm;
+        a.spin_cap = 1u << 24;  // ~1 s of polling: a correct schedule never gets near it
+        int occ = 0;
+        DAISY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mf_dataflow, 128, 0));
+        if (occ < 1) occ = 1;
+        int per_sm = occ < 8 ? occ : 8;
+        const char *env = getenv("DAISY_MF_BLOCKS_PER_SM");
+        if (env && atoi(env) > 0) per_sm = atoi(env) < occ ? atoi(env) : occ;
+        k_mf_dataflow<<<h->num_sms * per_sm, 128, 0, s>>>(a);
+        DAISY_LAUNCH_CHECK(h);
+    }
     if (sse_out) {
         k_mf_sse<<<n_epochs, 256, 0, s>>>(err2, n, n_epochs, sse_out);
         DAISY_LAUNCH_CHECK(h);
@@ -315,6 +682,12 @@ extern "C" int daisy_mf_fit(daisy_handle_t h, double *pu, double *qi, double *bu
     int aborted = 0;
     DAISY_CUDA(cudaMemcpyAsync(&aborted, abort_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
     DAISY_CUDA(cudaStreamSynchronize(s));
+    if (dbg_stats) {
+        unsigned long long hs[8];
+        DAISY_CUDA(cudaMemcpy(hs, dbg_stats, sizeof(hs), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[daisy_mf_fit] links %llu blocking %llu item-switches %llu | hottest warp: links %llu blocking %llu switches %llu\n",
+                hs[0], hs[1], hs[2], hs[3], hs[4], hs[5]);
+    }
     DAISY_REQUIRE(!aborted, DAISY_ECUDA, "daisy_mf_fit: dataflow schedule stalled (spin cap reached) -- tables are partial");
     return DAISY_OK;
 }

@@ -22,6 +22,13 @@ def _need_gpu():
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
 
 
+@pytest.fixture(params=["owner", "ticket"], autouse=True)
+def _schedule(request, monkeypatch):
+    """Both dataflow schedules of daisy_mf_fit (csrc/mf.cu): item-owner warps (default) and the ticket schedule."""
+    monkeypatch.setenv("DAISY_MF_SCHEDULE", request.param)
+    return request.param
+
+
 def frame(g):
     return pd.DataFrame({"user": g["users"].astype(np.int64), "item": g["items"].astype(np.int64),
                          "rating": g["ratings"]})
@@ -158,3 +165,23 @@ def test_live_reference_extension_when_present():
     a = RSVD(U, I, n_factors=D, n_epochs=2, version=2, verbose=False)
     a.fit(df)
     assert rel_err(a.ui, r.ui) <= TOL and rel_err(a.vj, r.vj) <= TOL and rel_err(a.ci, r.ci) <= TOL
+
+
+def test_many_items_per_warp_and_wide_rows():
+    """More items than resident warps (every warp multiplexes several items) and D = 200 (7 doubles per lane)."""
+    from oracle import mf_oracle
+    from recommend_lib_b200.mf import SVD
+    rng = np.random.default_rng(1)
+    U, I, D, N = 3000, 60000, 200, 150_000
+    users = rng.integers(0, U, N).astype(np.int32)
+    items = (rng.zipf(1.3, N) % I).astype(np.int32)
+    ratings = rng.integers(1, 6, N).astype(np.float64)
+    df = pd.DataFrame({"user": users, "item": items, "rating": ratings})
+    np.random.seed(11)
+    a = SVD(U, I, n_factors=D, n_epochs=2, verbose=False)
+    a.fit(df)
+    np.random.seed(11)
+    p0, q0 = mf_oracle.draw_init(U, I, D)
+    o = mf_oracle.svd_fit(users, items, ratings, p0, q0, n_epochs=2)
+    for x, y in zip((a.pu, a.qi, a.bu, a.bi), (o["pu"], o["qi"], o["bu"], o["bi"])):
+        assert rel_err(x, y) <= 1e-8
