@@ -392,6 +392,60 @@ def run_mf(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------
+# device-side negative sampler (secondary line)
+# ------------------------------------------------------------------------------------------------
+def run_sampler(args):
+    """triples/s of daisy_sample_triples (rejection sampling + epoch shuffle, in device memory) on the ml-20m shape
+    (config 3: 138 493 x 27 278, 20 M positives x num_ng 4 = 80 M triples per epoch), next to the reference's
+    per-positive Python loop (ng_sample) on a bounded sample."""
+    import torch
+    from recommend_lib_b200.sampler import DeviceTripleSampler, zipf_items, _rng
+    U, I, NP, NG = CFG3["user_num"], CFG3["item_num"], 20_000_263, 4
+    g = _rng(2019, 77)
+    pairs = np.stack([g.integers(0, U, NP), zipf_items(g, NP, I, 1.0, perm_seed=2019)], 1)
+    pairs = np.unique(pairs, axis=0)
+    smp = DeviceTripleSampler(pairs, I, U, num_ng=NG, seed=2019, device="cuda:0")
+    n = len(smp)
+    out = torch.empty((n, 3), dtype=torch.int32, device="cuda:0")
+    K, W = max(1, min(args.steps, 10)), max(1, min(args.warmup, 3))
+    for e in range(W):
+        smp.sample_epoch(e, out=out)
+    smp.check()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for e in range(W, W + K):
+        smp.sample_epoch(e, out=out)
+    ev1.record()
+    torch.cuda.synchronize()
+    smp.check()
+    ms = ev0.elapsed_time(ev1) / K
+    from oracle import sampler_oracle
+    n_cpu = 50_000
+    sub = pairs[:n_cpu]
+    pos = set(map(tuple, pairs[pairs[:, 0] <= sub[:, 0].max()].tolist()))
+    t0 = time.time()
+    sampler_oracle.ng_sample_loop(sub, I, NG, positives=pos)
+    cpu_dt = time.time() - t0
+    line = {"metric": "bpr_negative_sampling_triples_per_s", "value": n / (ms * 1e-3), "unit": "triples/s", "n_gpus": 1,
+            "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "negative sampling + epoch shuffle for config 3 (ml-20m shape)", "user_num": U,
+                       "item_num": I, "positives": int(len(pairs)), "num_ng": NG, "triples_per_epoch": int(n),
+                       "step": "one epoch of triples written to device memory, shuffled"},
+            "roofline": {"bound": "hbm", "achieved": n * (12 * 3 + 16 * 4) / (ms * 1e-3) / 1e9, "peak": measured_peaks()[0],
+                         "unit": "GB/s", "frac": n * (12 * 3 + 16 * 4) / (ms * 1e-3) / 1e9 / measured_peaks()[0],
+                         "traffic": None,
+                         "note": "per triple: write 12 + read 12 + write 12 B of triples, ~4 radix passes over 8 B "
+                                 "(key, slot) pairs; the rejection test is a binary search in L2"},
+            "cpu_baseline": {"value": n_cpu * NG / cpu_dt, "unit": "triples/s", "cores": 1, "kind": "port",
+                             "sample": f"the reference's ng_sample loop (util/data_loader.py:680-690) restated, "
+                                       f"{n_cpu} positives x {NG}, single thread as in the reference"},
+            "gpu_launches": int(smp.h.launches)}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -404,7 +458,7 @@ def main():
     ap.add_argument("--phases", action="store_true", help="also print the per-phase breakdown of the step")
     ap.add_argument("--trace", action="store_true", help="also print a timeline of bookkeeping vs table kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="config4", choices=["config4", "config3", "config2"],
+    ap.add_argument("--workload", default="config4", choices=["config4", "config3", "config2", "sampler"],
                     help="N = 1 only: config4 is the driver's metric; config3 (L2-resident ml-20m shape) and config2 "
                          "(funk-SVD) are secondary lines kept under profiles/")
     ap.add_argument("--l2-window", action="store_true", help="pin the item table in L2 (access-policy window)")
@@ -423,6 +477,8 @@ def main():
         return bench_sharded(args, CFG5, METRIC, UNIT)
     if args.workload == "config2":
         return run_mf(args)
+    if args.workload == "sampler":
+        return run_sampler(args)
     return run_single(args)
 
 

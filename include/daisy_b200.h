@@ -197,6 +197,20 @@ DAISY_API int daisy_topk_full(daisy_handle_t h, const float *P, const float *Q, 
                     const int64_t *excl_ptr, const int32_t *excl_idx, int32_t *out_item, float *out_score,
                     daisy_stream_t stream);
 
+/* ---- device-side negative sampler ------------------------------------
+ * Replaces BPRData.ng_sample (util/data_loader.py:680-690) + the DataLoader(shuffle=True) permutation
+ * (BPRMFRecommender.py:141-142) for one epoch: for every training positive pairs[p] = (u, i), num_ng triples
+ * (u, i, j) with j uniform over [0, item_num) re-drawn while (u, j) is a training positive; triples_out is
+ * int32 [n_pairs * num_ng, 3] on the device, in the reference's features_fill order (positive-major) or, with
+ * shuffle != 0, permuted by one epoch-keyed permutation.  pos_keys: the sorted, duplicate-free int64 keys
+ * u * item_num + i of the training positives on the device (the role of train_mat).  Deterministic: every draw is
+ * Philox4x32-10(key = seed, counter = (slot, epoch, attempt)) -- the rule is restated in oracle/sampler_oracle.py
+ * and the two agree bit for bit.  A user whose items are (almost) all positive raises the sticky error flag
+ * (daisy_check -> DAISY_EINDEX) after 4096 rejected draws. */
+DAISY_API int daisy_sample_triples(daisy_handle_t h, const int32_t *pairs, int64_t n_pairs, int num_ng,
+                                   const int64_t *pos_keys, int64_t n_keys, uint64_t seed, uint32_t epoch, int shuffle,
+                                   int32_t *triples_out, daisy_stream_t stream);
+
 /* ---- funk-SVD / RSVD (util/matrix_factorization.pyx) ---------------------------------------------
  * variant: 0 = SVD (:132-151), 1 = RSVD version 1, 2 = RSVD version 2 (:41-61).
  * One call runs `n_epochs` passes over the n ratings IN THE GIVEN ORDER with the reference's strictly

@@ -20,8 +20,8 @@ _LAZY = {
     "BPR": ".bpr", "BPRMFRecommender": ".bpr", "BPRSGD": ".bpr", "BPRAdam": ".bpr",
     "metric_eval": ".metrics", "topk_candidates": ".metrics", "topk_full": ".metrics",
     "SVD": ".mf", "RSVD": ".mf", "MFRecommender": ".mf",
-    "TripleSampler": ".sampler",
-    "ShardedBPR": ".sharded",
+    "TripleSampler": ".sampler", "DeviceTripleSampler": ".sampler",
+    "ShardedBPR": ".sharded", "PeerShardedBPR": ".sharded",
     "lib": "._lib",
 }
 

@@ -241,7 +241,7 @@ class BPRMFRecommender:
     """
 
     def __init__(self, user_num, item_num, factor_num=32, lr=0.01, wd=0.001, batch_size=4096, epochs=20, num_ng=4,
-                 topk=10, seed=2019, device="cuda", optimizer="sgd"):
+                 topk=10, seed=2019, device="cuda", optimizer="sgd", sampler="host"):
         _lib.require_cuda()
         self.user_num, self.item_num, self.factor_num = int(user_num), int(item_num), int(factor_num)
         self.lr, self.wd, self.batch_size, self.epochs = float(lr), float(wd), int(batch_size), int(epochs)
@@ -252,21 +252,33 @@ class BPRMFRecommender:
         self.optimizer = (BPRSGD(self.model, lr=self.lr, weight_decay=self.wd) if optimizer == "sgd"
                           else BPRAdam(self.model, lr=self.lr))
         self.history = []
+        assert sampler in ("host", "device")
+        self.sampler = sampler     # "device": negatives drawn on the GPU (daisy_sample_triples), no H2D of triples
 
     def fit(self, train_pairs, eval_users=None, eval_cands=None, verbose=False):
         import time
         from .metrics import topk_candidates, hr_ndcg
-        from .sampler import TripleSampler
-        sampler = TripleSampler(train_pairs, self.item_num, num_ng=self.num_ng, seed=self.seed)
-        n = len(sampler)
-        pinned = torch.empty((n, 3), dtype=torch.int32).pin_memory()
+        from .sampler import TripleSampler, DeviceTripleSampler
+        on_device = self.sampler == "device"
+        if on_device:
+            sampler = DeviceTripleSampler(train_pairs, self.item_num, self.user_num, num_ng=self.num_ng,
+                                          seed=self.seed, device=self.device)
+            n = len(sampler)
+            epoch_triples = torch.empty((n, 3), dtype=torch.int32, device=self.device)
+        else:
+            sampler = TripleSampler(train_pairs, self.item_num, num_ng=self.num_ng, seed=self.seed)
+            n = len(sampler)
+            epoch_triples = torch.empty((n, 3), dtype=torch.int32).pin_memory()
         for ep in range(self.epochs):
             t0 = time.time()
-            pinned.numpy()[:] = sampler.sample_epoch(ep)
+            if on_device:
+                sampler.sample_epoch(ep, out=epoch_triples)
+            else:
+                epoch_triples.numpy()[:] = sampler.sample_epoch(ep)
             torch.cuda.synchronize(self.device)
             t1 = time.time()
             for s in range(0, n, self.batch_size):
-                self.optimizer.step(pinned[s:s + self.batch_size])
+                self.optimizer.step(epoch_triples[s:s + self.batch_size])
             self.model.materialize()
             loss = self.optimizer.loss_sum()          # synchronises
             self.model.check()

@@ -214,6 +214,10 @@ extern "C" int daisy_check(daisy_handle_t h, daisy_stream_t stream) {
             daisy_set_error("sharded step: a peer rank did not reach the barrier within 20 s (ranks out of step or a peer died)");
             return DAISY_ECUDA;
         }
+        if (bits & 64) {
+            daisy_set_error("negative sampler: a user has no item left to draw as a negative (4096 rejected draws)");
+            return DAISY_EINDEX;
+        }
         if (bits & 32) {
             daisy_set_error("sharded step: a receive region overflowed");
             return DAISY_ECUDA;

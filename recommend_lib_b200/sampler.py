@@ -77,6 +77,53 @@ class TripleSampler:
             yield t[s:s + batch_size]
 
 
+class DeviceTripleSampler:
+    """The same job on the GPU (``daisy_sample_triples``, csrc/sampler.cu): one epoch of
+    ``(u, i, j)`` triples is produced directly in device memory -- no host sampling, no H2D copy.
+
+    Same constructor as ``TripleSampler``.  Deterministic: every draw is Philox4x32-10 keyed by
+    ``(seed, epoch, slot, attempt)``; the rule (a different stream than the host sampler's numpy generator, same
+    distribution and order conventions) is restated in ``oracle/sampler_oracle.py`` and checked bit for bit.
+    No CPU fallback.
+    """
+
+    def __init__(self, train_pairs, item_num, user_num=None, num_ng=4, seed=2019, reject=True, device="cuda"):
+        import torch
+        from . import _lib
+        _lib.require_cuda()
+        self._lib, self._torch = _lib, torch
+        self.device = torch.device(device)
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        p = np.ascontiguousarray(np.asarray(train_pairs)[:, :2], dtype=np.int64)
+        self.item_num, self.num_ng, self.seed = int(item_num), int(num_ng), int(seed)
+        self.user_num = int(user_num) if user_num is not None else int(p[:, 0].max()) + 1 if len(p) else 1
+        self.n_pairs = len(p)
+        self.pairs = torch.from_numpy(p.astype(np.int32)).to(self.device)
+        keys = np.unique(p[:, 0] * self.item_num + p[:, 1]) if reject else np.zeros(0, np.int64)
+        self.pos_keys = torch.from_numpy(keys).to(self.device)
+        self.h = _lib.Handle(idx, self.user_num, self.item_num, 4, 0)
+
+    def __len__(self):
+        return self.num_ng * self.n_pairs
+
+    def sample_epoch(self, epoch, shuffle=True, out=None):
+        """int32 [num_ng * |train|, 3] on the device (asynchronous on the current stream)."""
+        torch, _lib = self._torch, self._lib
+        n = len(self)
+        if out is None:
+            out = torch.empty((n, 3), dtype=torch.int32, device=self.device)
+        vp = _lib.c_vp
+        _lib.check(self.h.L.daisy_sample_triples(self.h.ptr, vp(self.pairs.data_ptr()), self.n_pairs, self.num_ng,
+                                                 vp(self.pos_keys.data_ptr()) if self.pos_keys.numel() else None,
+                                                 int(self.pos_keys.numel()), self.seed, int(epoch), int(bool(shuffle)),
+                                                 vp(out.data_ptr()), _lib.stream_ptr(torch, self.device)))
+        return out
+
+    def check(self):
+        self._lib.check(self.h.L.daisy_check(self.h.ptr, self._lib.stream_ptr(self._torch, self.device)))
+
+
 # --------------------------------------------------------------------------
 # synthetic workloads of BASELINE.json configs 2-5 (SURVEY.md section 8d)
 # --------------------------------------------------------------------------

@@ -148,3 +148,40 @@ def test_live_reference_extension_when_present():
     pu0, qi0 = mf_oracle.draw_init(U, I, D)
     o = mf_oracle.svd_fit(users, items, ratings, pu0, qi0, n_epochs=2)
     assert np.array_equal(o["pu"], a.pu) and np.array_equal(o["qi"], a.qi)
+
+
+# ------------------------------------------------------------------------------------------------
+# device sampler rule (oracle/sampler_oracle.py): the generator against published known answers, the rule's
+# semantics against util/data_loader.py:680-690
+# ------------------------------------------------------------------------------------------------
+def test_philox4x32_10_known_answers():
+    """Random123 (Salmon et al., SC'11) kat_vectors for philox4x32-10."""
+    from oracle.sampler_oracle import philox4x32_10
+    a = lambda *v: tuple(np.array([x], dtype=np.uint64) for x in v)
+    kat = [((0, 0), a(0, 0, 0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff, 0xffffffff), a(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff),
+            (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0xa4093822, 0x299f31d0), a(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for key, ctr, want in kat:
+        got = tuple(int(x[0]) for x in philox4x32_10(key, ctr))
+        assert got == want
+
+
+def test_sampler_rule_semantics():
+    from oracle.sampler_oracle import sample_epoch
+    rng = np.random.default_rng(0)
+    U, I, num_ng = 60, 50, 4
+    pairs = np.unique(np.stack([rng.integers(0, U, 1500), rng.integers(0, I, 1500)], 1), axis=0)
+    flat = sample_epoch(pairs, I, num_ng, 2019, 0, shuffle=False)
+    assert np.array_equal(flat[:, :2], np.repeat(pairs, num_ng, axis=0))          # features_fill order (:684-690)
+    pos = set(map(tuple, pairs.tolist()))
+    assert not any((int(u), int(j)) in pos for u, _, j in flat)                    # re-drawn while (u, j) in train_mat
+    assert flat[:, 2].min() >= 0 and flat[:, 2].max() < I
+    sh = sample_epoch(pairs, I, num_ng, 2019, 0, shuffle=True)
+    assert sorted(map(tuple, sh.tolist())) == sorted(map(tuple, flat.tolist()))
+    assert not np.array_equal(sample_epoch(pairs, I, num_ng, 2019, 1, shuffle=False), flat)
+    # negatives of one user are uniform over its non-positives
+    big = sample_epoch(np.array([[0, 1], [0, 2]] * 1), 10, 4000, 5, 0, shuffle=False)
+    c = np.bincount(big[:, 2], minlength=10)
+    assert c[1] == 0 and c[2] == 0 and c[[0, 3, 4, 5, 6, 7, 8, 9]].min() > 0.8 * 8000 / 8
