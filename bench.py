@@ -446,6 +446,61 @@ def run_sampler(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------
+# full-catalogue top-K evaluation of config 4 (secondary line)
+# ------------------------------------------------------------------------------------------------
+def run_eval(args):
+    """users/s of daisy_topk_full: top-100 of all 2 M items for a seeded sample of 16 384 users (SURVEY 8d, config 4's
+    evaluation), fp32 scores on CUDA cores (ranking parity) + exact radix select."""
+    import torch
+    from recommend_lib_b200.bpr import BPR
+    from recommend_lib_b200.metrics import topk_full
+    U, I, D, N, K = 1_000_000, CFG4["item_num"], CFG4["dim"], args.eval_users, 100
+    dev = torch.device("cuda:0")
+    torch.manual_seed(2019)
+    model = BPR(1, 1, D, max_batch=0)
+    model.user_num, model.item_num = U, I
+    model.embed_user.weight = torch.nn.Parameter(torch.empty((U, D), device=dev).normal_(0, 0.01), requires_grad=False)
+    model.embed_item.weight = torch.nn.Parameter(torch.empty((I, D), device=dev).normal_(0, 0.01), requires_grad=False)
+    users = torch.from_numpy(np.random.default_rng(2019).choice(U, N, replace=False).astype(np.int32)).to(dev)
+    K_steps, W = max(1, min(args.steps, 3)), 1
+    for _ in range(W):
+        items, scores = topk_full(model, users[:2048], K)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(K_steps):
+        items, scores = topk_full(model, users, K)
+    ev1.record()
+    torch.cuda.synchronize()
+    model.check()
+    ms = ev0.elapsed_time(ev1) / K_steps
+    flops = 2.0 * N * I * D
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    # bounded CPU sample: exact fp32 scores + argpartition for a few users (what a vectorised CPU ranking costs)
+    from oracle import bpr_oracle
+    Pc = model.embed_user.weight[users[:8].long()].cpu().numpy()
+    Qc = model.embed_item.weight.cpu().numpy()
+    t0 = time.time()
+    ref_items, _ = bpr_oracle.full_topk(Pc, Qc, np.arange(8), K)
+    cpu_dt = time.time() - t0
+    agree = float((items[:8].cpu().numpy() == ref_items).mean())
+    line = {"metric": "bpr_full_catalogue_topk_users_per_s", "value": N / (ms * 1e-3), "unit": "users/s", "n_gpus": 1,
+            "steps": K_steps, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "full-catalogue top-100 for 16 384 users of config 4 (2 M items, dim 128)", "users": N,
+                       "item_num": I, "dim": D, "top_k": K, "step": "one evaluation of all sampled users"},
+            "roofline": {"bound": "fp32-fma", "achieved": flops / (ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": flops / (ms * 1e-3) / 1e12 / fp32_peak, "traffic": None,
+                         "note": "CUDA-core fp32 (scores must be fp32 sums of fp32 products for ranking parity); peak = "
+                                 "148 SMs x 128 FMA/clk x 1.965 GHz (nominal, not in MEASURED_PEAKS.json)"},
+            "cpu_baseline": {"value": 8 / cpu_dt, "unit": "users/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": "numpy fp32 scores + exact top-100 for 8 users (oracle full_topk), agreement "
+                                       f"with the device's items {agree:.3f}"},
+            "gpu_launches": int(model.handle().launches)}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -458,9 +513,10 @@ def main():
     ap.add_argument("--phases", action="store_true", help="also print the per-phase breakdown of the step")
     ap.add_argument("--trace", action="store_true", help="also print a timeline of bookkeeping vs table kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="config4", choices=["config4", "config3", "config2", "sampler"],
+    ap.add_argument("--workload", default="config4", choices=["config4", "config3", "config2", "sampler", "eval"],
                     help="N = 1 only: config4 is the driver's metric; config3 (L2-resident ml-20m shape) and config2 "
                          "(funk-SVD) are secondary lines kept under profiles/")
+    ap.add_argument("--eval-users", type=int, default=16384)
     ap.add_argument("--l2-window", action="store_true", help="pin the item table in L2 (access-policy window)")
     ap.add_argument("--mapping", default="symm", choices=["symm", "ipc"],
                     help="N > 1, peer exchange: how the ranks map each other's arenas")
@@ -479,6 +535,8 @@ def main():
         return run_mf(args)
     if args.workload == "sampler":
         return run_sampler(args)
+    if args.workload == "eval":
+        return run_eval(args)
     return run_single(args)
 
 

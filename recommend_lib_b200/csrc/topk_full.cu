@@ -9,90 +9,133 @@
 //                  K-th largest score, then collection and a (score desc, item asc) ordering of the K winners.
 // The score tile lives in the handle's workspace (<= ~1 GiB), users are processed tile by tile.
 #include <float.h>
+#include <string.h>
 
 #include "ctx.cuh"
 
 namespace {
 
-constexpr int BM = 64, BN = 128, BK = 16;
+constexpr int BM = 128, BN = 128, BK = 16;
 
-__global__ void __launch_bounds__(256) k_score_tile(const float *__restrict__ P, const float *__restrict__ Q,
-                                                     const int32_t *__restrict__ users, int n_users, uint32_t U,
-                                                     int64_t I, int D, float c2, float *__restrict__ S, int *err) {
+__device__ __forceinline__ uint32_t okey(float f) {  // order-preserving float -> uint32
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float okey_inv(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// FILTER = false: scores are written to S [n_users, I].
+// FILTER = true : nothing is materialised -- a score at or above the user's threshold thr[m] is appended to the user's
+//                 candidate list (cand_key [n_users, cap], count in cnt[m]); see daisy_topk_full.
+// 128 x 128 x 16 block tile, 256 threads, 8 x 8 register tile per thread (two 4-wide groups 64 apart in each
+// direction, so that the shared-memory operand loads are conflict-free 128-bit loads): 4 LDS.128 per 64 FMA.
+template <bool FILTER>
+__global__ void __launch_bounds__(256, 2) k_score_tile(const float *__restrict__ P, const float *__restrict__ Q,
+                                                        const int32_t *__restrict__ users, int n_users, uint32_t U,
+                                                        int64_t I, int D, float c2, float *__restrict__ S, int *err,
+                                                        const float *__restrict__ thr, int *__restrict__ cnt,
+                                                        unsigned long long *__restrict__ cand_key, int cap) {
     __shared__ __align__(16) float As[2][BK][BM + 4];
     __shared__ __align__(16) float Bs[2][BK][BN + 4];
     const int tid = threadIdx.x;
     const int m0 = blockIdx.y * BM;
     const int64_t i0 = (int64_t)blockIdx.x * BN;
-    const int lr = tid >> 2, lk = (tid & 3) * 4;  // loader coordinates: row 0..63, k offset 0,4,8,12
-    // resolve the user row this thread loads (once)
-    int64_t urow = -1;
-    if (m0 + lr < n_users) {
-        uint32_t u = (uint32_t)users[m0 + lr];
-        if (u >= U) {
-            atomicOr(&err[0], 1);
-            atomicMin(&err[1], m0 + lr);
-            u = 0;
-        }
-        urow = (int64_t)u;
-    }
-    const int64_t it0 = i0 + lr, it1 = i0 + lr + 64;
-    const int ty = tid >> 4, tx = tid & 15;
-    float acc[4][8];
+    const int lr = tid >> 2, lk = (tid & 3) * 4;  // loader coordinates: rows lr and lr + 64, k offset 0,4,8,12
+    int64_t urow[2] = {-1, -1};
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int hh = 0; hh < 2; ++hh)
+        if (m0 + lr + 64 * hh < n_users) {
+            uint32_t u = (uint32_t)users[m0 + lr + 64 * hh];
+            if (u >= U) {
+                atomicOr(&err[0], 1);
+                atomicMin(&err[1], m0 + lr + 64 * hh);
+                u = 0;
+            }
+            urow[hh] = (int64_t)u;
+        }
+    const int64_t it[2] = {i0 + lr, i0 + lr + 64};
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
 #pragma unroll
         for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
 
-    auto gload = [&](int k0, float4 &a, float4 &b0, float4 &b1) {
+    float4 ra[2], rb[2];
+    auto gload = [&](int k0) {
         const int k = k0 + lk;
-        a = (urow >= 0 && k < D) ? *reinterpret_cast<const float4 *>(P + urow * D + k) : f4_zero();
-        b0 = (it0 < I && k < D) ? *reinterpret_cast<const float4 *>(Q + it0 * D + k) : f4_zero();
-        b1 = (it1 < I && k < D) ? *reinterpret_cast<const float4 *>(Q + it1 * D + k) : f4_zero();
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            ra[hh] = (urow[hh] >= 0 && k < D) ? *reinterpret_cast<const float4 *>(P + urow[hh] * D + k) : f4_zero();
+            rb[hh] = (it[hh] < I && k < D) ? *reinterpret_cast<const float4 *>(Q + it[hh] * D + k) : f4_zero();
+        }
     };
-    auto sstore = [&](int buf, const float4 &a, const float4 &b0, const float4 &b1) {
-        As[buf][lk + 0][lr] = a.x; As[buf][lk + 1][lr] = a.y; As[buf][lk + 2][lr] = a.z; As[buf][lk + 3][lr] = a.w;
-        Bs[buf][lk + 0][lr] = b0.x; Bs[buf][lk + 1][lr] = b0.y; Bs[buf][lk + 2][lr] = b0.z; Bs[buf][lk + 3][lr] = b0.w;
-        Bs[buf][lk + 0][lr + 64] = b1.x; Bs[buf][lk + 1][lr + 64] = b1.y; Bs[buf][lk + 2][lr + 64] = b1.z;
-        Bs[buf][lk + 3][lr + 64] = b1.w;
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int r = lr + 64 * hh;
+            As[buf][lk + 0][r] = ra[hh].x; As[buf][lk + 1][r] = ra[hh].y; As[buf][lk + 2][r] = ra[hh].z; As[buf][lk + 3][r] = ra[hh].w;
+            Bs[buf][lk + 0][r] = rb[hh].x; Bs[buf][lk + 1][r] = rb[hh].y; Bs[buf][lk + 2][r] = rb[hh].z; Bs[buf][lk + 3][r] = rb[hh].w;
+        }
     };
-    float4 ra, rb0, rb1;
-    gload(0, ra, rb0, rb1);
-    sstore(0, ra, rb0, rb1);
+    gload(0);
+    sstore(0);
     __syncthreads();
     const int nk = (D + BK - 1) / BK;
     for (int kt = 0; kt < nk; ++kt) {
         const int buf = kt & 1;
-        if (kt + 1 < nk) gload((kt + 1) * BK, ra, rb0, rb1);
+        if (kt + 1 < nk) gload((kt + 1) * BK);
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
-            const float4 a = *reinterpret_cast<const float4 *>(&As[buf][kk][ty * 4]);
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][kk][64 + ty * 4]);
             const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[buf][kk][tx * 4]);
             const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[buf][kk][64 + tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int x = 0; x < 4; ++x)
+            for (int x = 0; x < 8; ++x)
 #pragma unroll
                 for (int y = 0; y < 8; ++y) acc[x][y] = fmaf(av[x], bv[y], acc[x][y]);
         }
         if (kt + 1 < nk) {
-            sstore(buf ^ 1, ra, rb0, rb1);
+            sstore(buf ^ 1);
             __syncthreads();
         }
     }
 #pragma unroll
-    for (int x = 0; x < 4; ++x) {
-        const int m = m0 + ty * 4 + x;
+    for (int x = 0; x < 8; ++x) {
+        const int m = m0 + (x >> 2) * 64 + ty * 4 + (x & 3);
         if (m >= n_users) continue;
-        float *row = S + (size_t)m * (size_t)I;
+        if (FILTER) {
+            const float t = thr[m];
 #pragma unroll
-        for (int half = 0; half < 2; ++half)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) {
-                const int64_t i = i0 + half * 64 + tx * 4 + y;
-                if (i < I) row[i] = acc[x][half * 4 + y] * c2;
+            for (int y = 0; y < 8; ++y) {
+                const int64_t i = i0 + (y >> 2) * 64 + tx * 4 + (y & 3);
+                const float v = acc[x][y] * c2;
+                if (i < I && v >= t) {
+                    const int pos = atomicAdd(&cnt[m], 1);
+                    if (pos < cap)  // (score desc, item asc) as one descending 64-bit key
+                        cand_key[(size_t)m * cap + pos] =
+                            ((unsigned long long)okey(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
+                }
             }
+        } else {
+            float *row = S + (size_t)m * (size_t)I;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int64_t i = i0 + half * 64 + tx * 4;
+                if (i + 3 < I && (((size_t)m * (size_t)I + (size_t)i) & 3) == 0) {
+                    *reinterpret_cast<float4 *>(row + i) = make_float4(acc[x][half * 4 + 0] * c2, acc[x][half * 4 + 1] * c2,
+                                                                       acc[x][half * 4 + 2] * c2, acc[x][half * 4 + 3] * c2);
+                } else {
+#pragma unroll
+                    for (int y = 0; y < 4; ++y)
+                        if (i + y < I) row[i + y] = acc[x][half * 4 + y] * c2;
+                }
+            }
+        }
     }
 }
 
@@ -112,13 +155,6 @@ __global__ void k_mask(float *__restrict__ S, int64_t I, const int64_t *__restri
     }
 }
 
-__device__ __forceinline__ uint32_t okey(float f) {  // order-preserving float -> uint32
-    const uint32_t u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float okey_inv(uint32_t k) {
-    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
 
 // From a histogram (bins ascending), find the bin holding the `need`-th largest element; returns the bin and
 // updates need to the rank inside that bin (1-based count still required from it).
@@ -249,6 +285,77 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select_topk(const float *__rest
     }
 }
 
+// rows of a strided sample of the catalogue, gathered contiguously: Qs[j] = Q[j * stride]
+__global__ void k_sample_rows(const float *__restrict__ Q, int64_t stride, int Ms, int D4, float *__restrict__ Qs) {
+    const int lane = threadIdx.x & 31;
+    const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    if (w >= Ms) return;
+    for (int e = lane; e < D4; e += 32) st_row(Qs, (size_t)w * D4 + e, ld_row(Q, (size_t)w * stride * D4 + e));
+}
+
+__global__ void k_thr_from_topk(const float *__restrict__ top_scores, int r, int n, float *__restrict__ thr,
+                                int *__restrict__ cnt) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    thr[m] = top_scores[(size_t)m * r + (r - 1)];  // r-th largest score of the user's sample
+    cnt[m] = 0;
+}
+
+// Exact top-K of one user's candidate list: bitonic sort of the 64-bit (score desc, item asc) keys in shared memory.
+// Excluded items (the user's training positives, CSR) are dropped first.  A user whose list overflowed, or holds
+// fewer than K admissible candidates, is handed to the exact fallback (flag in redo[m]).
+__global__ void __launch_bounds__(1024) k_select_cand(const unsigned long long *__restrict__ cand_key,
+                                                       const int *__restrict__ cnt, int cap, int K, int64_t first_user,
+                                                       const int64_t *__restrict__ excl_ptr,
+                                                       const int32_t *__restrict__ excl_idx, int32_t *__restrict__ out_item,
+                                                       float *__restrict__ out_score, int *__restrict__ redo) {
+    extern __shared__ unsigned long long keys[];
+    const int m = blockIdx.x, tid = threadIdx.x;
+    const int n = cnt[m];
+    if (n > cap || n < K) {
+        if (tid == 0) redo[m] = 1;
+        return;
+    }
+    int P2 = 1;
+    while (P2 < n) P2 <<= 1;
+    const int64_t ea = excl_ptr ? excl_ptr[first_user + m] : 0, eb = excl_ptr ? excl_ptr[first_user + m + 1] : 0;
+    for (int p = tid; p < P2; p += blockDim.x) {
+        unsigned long long k = (p < n) ? cand_key[(size_t)m * cap + p] : 0ull;
+        if (p < n && eb > ea) {
+            const int32_t item = (int32_t)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+            for (int64_t e = ea; e < eb; ++e)
+                if (excl_idx[e] == item) {
+                    k = 0ull;
+                    break;
+                }
+        }
+        keys[p] = k;
+    }
+    __syncthreads();
+    for (int size = 2; size <= P2; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int p = tid; p < P2 / 2; p += blockDim.x) {
+                const int lo = 2 * p - (p & (stride - 1)), hi = lo + stride;
+                const bool desc = ((lo & size) == 0);
+                const unsigned long long a = keys[lo], b = keys[hi];
+                if ((a < b) == desc) {
+                    keys[lo] = b;
+                    keys[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    if (keys[K - 1] == 0ull) {  // fewer than K admissible candidates after the exclusions
+        if (tid == 0) redo[m] = 1;
+        return;
+    }
+    if (tid < K) {
+        const unsigned long long k = keys[tid];
+        out_item[(size_t)(first_user + m) * K + tid] = (int32_t)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+        out_score[(size_t)(first_user + m) * K + tid] = okey_inv((uint32_t)(k >> 32));
+    }
+}
+
 }  // namespace
 
 extern "C" int daisy_topk_full(daisy_handle_t h, const float *P, const float *Q, const int32_t *users, int64_t N, int K,
@@ -271,29 +378,115 @@ extern "C" int daisy_topk_full(daisy_handle_t h, const float *P, const float *Q,
     if (tile < 1) tile = 1;
     if (tile > 4096) tile = 4096;
     if (tile > N) tile = N;
-    const size_t need = (size_t)tile * (size_t)I;
-    if (h->scores_cap < need) {
-        DAISY_CUDA(cudaStreamSynchronize(s));
-        if (h->scores) cudaFree(h->scores);
-        h->scores = nullptr;
-        h->scores_cap = 0;
-        cudaError_t e = cudaMalloc((void **)&h->scores, need * sizeof(float));
-        DAISY_REQUIRE(e == cudaSuccess, DAISY_ENOMEM, "cudaMalloc of the %zu-byte score tile failed: %s", need * sizeof(float),
-                      cudaGetErrorString(e));
-        h->scores_cap = need;
-    }
     const float c2 = (float)(h->scale * h->scale);
-    for (int64_t first = 0; first < N; first += tile) {
-        const int nu = (int)((N - first < tile) ? (N - first) : tile);
-        dim3 grid((unsigned)((I + BN - 1) / BN), (unsigned)((nu + BM - 1) / BM));
-        k_score_tile<<<grid, 256, 0, s>>>(P, Q, users + first, nu, (uint32_t)h->U, I, h->D, c2, h->scores, h->err);
-        DAISY_LAUNCH_CHECK(h);
-        if (excl_ptr && excl_idx) {
-            k_mask<<<nu, 128, 0, s>>>(h->scores, I, excl_ptr, excl_idx, first, nu, h->err);
+    // ---- exact path over a user range (materialised score tile + radix select); used for small catalogues and as
+    //      the fallback of the filtered path ----
+    auto exact_range = [&](const int32_t *us, int64_t n_us, int64_t out_first) -> int {
+        const int64_t rows = tile < n_us ? tile : n_us;
+        const size_t need = (size_t)rows * (size_t)I;
+        if (h->scores_cap < need) {  // grow-only score tile in the handle's workspace
+            DAISY_CUDA(cudaStreamSynchronize(s));
+            if (h->scores) cudaFree(h->scores);
+            h->scores = nullptr;
+            h->scores_cap = 0;
+            cudaError_t e = cudaMalloc((void **)&h->scores, need * sizeof(float));
+            DAISY_REQUIRE(e == cudaSuccess, DAISY_ENOMEM, "cudaMalloc of the %zu-byte score tile failed: %s",
+                          need * sizeof(float), cudaGetErrorString(e));
+            h->scores_cap = need;
+        }
+        for (int64_t first = 0; first < n_us; first += tile) {
+            const int nu = (int)((n_us - first < tile) ? (n_us - first) : tile);
+            dim3 grid((unsigned)((I + BN - 1) / BN), (unsigned)((nu + BM - 1) / BM));
+            k_score_tile<false><<<grid, 256, 0, s>>>(P, Q, us + first, nu, (uint32_t)h->U, I, h->D, c2, h->scores, h->err,
+                                                     nullptr, nullptr, nullptr, 0);
+            DAISY_LAUNCH_CHECK(h);
+            if (excl_ptr && excl_idx) {
+                k_mask<<<nu, 128, 0, s>>>(h->scores, I, excl_ptr, excl_idx, out_first + first, nu, h->err);
+                DAISY_LAUNCH_CHECK(h);
+            }
+            k_select_topk<<<nu, SEL_THREADS, 0, s>>>(h->scores, I, K, out_first + first, out_item, out_score);
             DAISY_LAUNCH_CHECK(h);
         }
-        k_select_topk<<<nu, SEL_THREADS, 0, s>>>(h->scores, I, K, first, out_item, out_score);
-        DAISY_LAUNCH_CHECK(h);
+        return DAISY_OK;
+    };
+    // ---- filtered path (large catalogues): no score matrix is materialised.
+    //   1. scores of a strided SAMPLE of Ms items per user -> the r-th largest is the user's threshold; r is chosen so
+    //      that about E >= 16 K items of the full catalogue exceed it (Beta(r, Ms - r + 1) fraction: E +- E / sqrt(r))
+    //   2. the full score GEMM appends every item at or above the threshold to the user's candidate list
+    //   3. exact (score desc, item asc) top-K of the list; a user whose list is short of K admissible items or
+    //      overflowed (never seen in practice) is redone by the exact path.
+    const int Ms = 8192;
+    const char *force = getenv("DAISY_TOPK_PATH");
+    const bool want_filter = force ? (strcmp(force, "filter") == 0) : (I >= 16 * (int64_t)Ms);
+    if (!want_filter || I < 4 * (int64_t)Ms) {
+        return exact_range(users, N, 0);
     }
-    return DAISY_OK;
+    const int64_t stride = I / Ms;
+    const int E = K * 16 > 2048 ? K * 16 : 2048;
+    int r = (int)(((int64_t)E * Ms + I - 1) / I);
+    if (r < 8) r = 8;
+    if (r > 128) return exact_range(users, N, 0);
+    const int cap = 4 * E;  // 8192 at K <= 128: 64 KB of keys in shared memory for the final sort
+    const int64_t Tu = N < 4096 ? N : 4096;
+    float *Qs = nullptr, *Ss = nullptr, *tscore = nullptr, *thr = nullptr;
+    int32_t *titem = nullptr;
+    int *cnt = nullptr, *redo = nullptr;
+    unsigned long long *cand = nullptr;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    bool ok = cudaMallocAsync((void **)&Qs, (size_t)Ms * h->D * sizeof(float), s) == cudaSuccess;
+    ok = ok && cudaMallocAsync((void **)&Ss, (size_t)Tu * Ms * sizeof(float), s) == cudaSuccess;
+    ok = ok && cudaMallocAsync((void **)&tscore, (size_t)Tu * r * sizeof(float), s) == cudaSuccess;
+    ok = ok && cudaMallocAsync((void **)&titem, (size_t)Tu * r * sizeof(int32_t), s) == cudaSuccess;
+    ok = ok && cudaMallocAsync((void **)&thr, (size_t)Tu * sizeof(float), s) == cudaSuccess;
+    ok = ok && cudaMallocAsync((void **)&cnt, (size_t)Tu * sizeof(int), s) == cudaSuccess;
+    ok = ok && cudaMallocAsync((void **)&redo, (size_t)N * sizeof(int), s) == cudaSuccess;
+    ok = ok && cudaMallocAsync((void **)&cand, (size_t)Tu * cap * sizeof(unsigned long long), s) == cudaSuccess;
+    int rc = DAISY_OK;
+    int *redo_host = nullptr;
+    if (!ok) {
+        cudaGetLastError();
+        daisy_set_error("top-K workspace allocation failed");
+        rc = DAISY_ENOMEM;
+    } else {
+        cudaMemsetAsync(redo, 0, (size_t)N * sizeof(int), s);
+        k_sample_rows<<<daisy_ceil_div(Ms, 8), 256, 0, s>>>(Q, stride, Ms, h->D / 4, Qs);
+        h->launches++;
+        cudaFuncSetAttribute(k_select_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * (int)sizeof(unsigned long long));
+        for (int64_t first = 0; first < N; first += Tu) {
+            const int nu = (int)((N - first < Tu) ? (N - first) : Tu);
+            dim3 gs((unsigned)((Ms + BN - 1) / BN), (unsigned)((nu + BM - 1) / BM));
+            k_score_tile<false><<<gs, 256, 0, s>>>(P, Qs, users + first, nu, (uint32_t)h->U, Ms, h->D, c2, Ss, h->err, nullptr,
+                                                   nullptr, nullptr, 0);
+            k_select_topk<<<nu, SEL_THREADS, 0, s>>>(Ss, Ms, r, 0, titem, tscore);
+            k_thr_from_topk<<<daisy_ceil_div(nu, 256), 256, 0, s>>>(tscore, r, nu, thr, cnt);
+            dim3 gf((unsigned)((I + BN - 1) / BN), (unsigned)((nu + BM - 1) / BM));
+            k_score_tile<true><<<gf, 256, 0, s>>>(P, Q, users + first, nu, (uint32_t)h->U, I, h->D, c2, nullptr, h->err, thr, cnt,
+                                                  cand, cap);
+            k_select_cand<<<nu, 1024, cap * sizeof(unsigned long long), s>>>(cand, cnt, cap, K, first, excl_ptr, excl_idx,
+                                                                             out_item, out_score, redo + first);
+            h->launches += 5;
+        }
+        if (cudaGetLastError() != cudaSuccess) {
+            daisy_set_error("top-K launch failed");
+            rc = DAISY_ECUDA;
+        }
+        redo_host = (int *)malloc((size_t)N * sizeof(int));
+        if (!rc && (!redo_host || cudaMemcpyAsync(redo_host, redo, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                    cudaStreamSynchronize(s) != cudaSuccess)) {
+            daisy_set_error("top-K fallback list read-back failed");
+            rc = DAISY_ECUDA;
+        }
+    }
+    for (void *p : {(void *)Qs, (void *)Ss, (void *)tscore, (void *)titem, (void *)thr, (void *)cnt, (void *)redo, (void *)cand})
+        if (p) cudaFreeAsync(p, s);
+    if (!rc)
+        for (int64_t m = 0; m < N && !rc; ++m)
+            if (redo_host[m]) rc = exact_range(users + m, 1, m);
+    free(redo_host);
+    return rc;
 }
+
