@@ -18,7 +18,7 @@ __all__ = ["BPR", "BPRMFRecommender", "metric_eval", "SVD", "RSVD", "MFRecommend
 
 _LAZY = {
     "BPR": ".bpr", "BPRMFRecommender": ".bpr", "BPRSGD": ".bpr", "BPRAdam": ".bpr",
-    "metric_eval": ".metrics", "topk_candidates": ".metrics", "topk_full": ".metrics",
+    "metric_eval": ".metrics", "topk_candidates": ".metrics", "topk_full": ".metrics", "rank_metrics": ".metrics", "final_kpi": ".metrics",
     "SVD": ".mf", "RSVD": ".mf", "MFRecommender": ".mf",
     "TripleSampler": ".sampler", "DeviceTripleSampler": ".sampler",
     "ShardedBPR": ".sharded", "PeerShardedBPR": ".sharded",

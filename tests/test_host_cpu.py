@@ -136,3 +136,18 @@ def test_split_loo_ties_and_order():
     ts = np.array([5, 9, 9, 3, 1])
     tr, te = data.split_loo_by_time(users, np.arange(5), ts)
     assert list(te) == [1, 3] and list(tr) == [0, 2, 4]          # tie at ts=9: first row wins (rank method='first')
+
+
+def test_rank_metrics_match_the_reference_functions(golden):
+    """precision / recall / MAP / NDCG / HR / MRR @k against values computed by the reference's own functions
+    (util/metrics.py:99-195; fixture written by tests/golden/make_rank_metrics_golden.py)."""
+    from recommend_lib_b200.metrics import rank_metrics
+    g = golden("rank_metrics.npz")
+    for c in range(3):
+        rel, ptr, k = g[f"c{c}_rel"], g[f"c{c}_ur_ptr"], int(g[f"c{c}_k"])
+        got = rank_metrics(rel, np.diff(ptr), k)
+        want = dict(zip(("precision", "recall", "map", "ndcg", "hr", "mrr"), g[f"c{c}_kpi"]))
+        for name in want:
+            assert got[name] == pytest.approx(want[name], rel=1e-12, abs=1e-15), (c, name)
+    with pytest.raises(ValueError):
+        rank_metrics(np.zeros((3, 4)), np.ones(3), top_k=5)              # 'Relevance score length < k'
