@@ -214,6 +214,9 @@ def run_single(args):
     mat_every = args.materialize_every
 
     def device_resident_pass(first, count):
+        if args.epoch_api:                      # one daisy_bpr_epoch call runs all `count` steps (BPRSGD.epoch)
+            opt.epoch(devtri[first:first + count].reshape(-1, 3), B, loss_out=loss_dev[first:first + 1])
+            return
         for s in range(first, first + count):
             opt.step(devtri[s], loss_out=loss_dev[s:s + 1], ready=True)   # uploaded + synchronised before timing
             if mat_every and (s + 1) % mat_every == 0:
@@ -245,6 +248,10 @@ def run_single(args):
 
     # ---- e2e: host triples through the public API, loss read back every step ----
     def e2e_pass(first, count):
+        if args.epoch_api:                      # pinned host triples of `count` steps, loss read back once per call
+            opt.epoch(host[first:first + count].reshape(-1, 3), B, loss_out=loss_dev[first:first + 1])
+            loss_host[first:first + 1].copy_(loss_dev[first:first + 1], non_blocking=True)
+            return
         for s in range(first, first + count):
             opt.step(host[s], loss_out=loss_dev[s:s + 1])
             loss_host[s:s + 1].copy_(loss_dev[s:s + 1], non_blocking=True)
@@ -265,6 +272,8 @@ def run_single(args):
     model.check()
     e2e_value = B * K / (ms_e2e * 1e-3)
     losses = loss_host[W:W + K].numpy()
+    if args.epoch_api:
+        losses = losses[:1] / K                 # the call accumulates the loss of its K steps
     assert np.isfinite(losses).all() and (losses > 0).all(), "e2e losses not finite"
 
     # ---- optional per-phase breakdown (not part of the timed numbers) ----
@@ -286,7 +295,7 @@ def run_single(args):
     achieved = abytes / (main_ms * 1e-3) / 1e9 if main_ms > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "main_kernel_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and args.workload == "config4" and not args.batch and args.scale == 1.0:
         try:
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
@@ -307,10 +316,14 @@ def run_single(args):
                               "tables (85 MB) fit the 126 MB L2: L2-resident workload, the HBM roofline does not bound it"),
                        "l2_access_policy_window": bool(args.l2_window),
                        "lazy_decay_materialized_in_timed_region": True,
-                       "e2e_loss_readback": "async D2H of every step's loss into pinned memory, synchronised at the end"},
+                       "api": ("BPRSGD.epoch -> daisy_bpr_epoch: ONE library call runs the K timed steps"
+                               if args.epoch_api else "BPRSGD.step -> daisy_bpr_step[_host]: one library call per step"),
+                       "e2e_loss_readback": ("async D2H of the call's accumulated loss, once per daisy_bpr_epoch call"
+                                             if args.epoch_api else
+                                             "async D2H of every step's loss into pinned memory, synchronised at the end")},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": B * 12,
-                    "d2h_bytes_per_step": 8},
+                    "d2h_bytes_per_step": 8 / K if args.epoch_api else 8},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_bpr_main", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
@@ -517,6 +530,8 @@ def main():
                     help="N = 1 only: config4 is the driver's metric; config3 (L2-resident ml-20m shape) and config2 "
                          "(funk-SVD) are secondary lines kept under profiles/")
     ap.add_argument("--eval-users", type=int, default=16384)
+    ap.add_argument("--epoch-api", action="store_true",
+                    help="config3/config4: run the K timed steps through ONE daisy_bpr_epoch call (BPRSGD.epoch)")
     ap.add_argument("--l2-window", action="store_true", help="pin the item table in L2 (access-policy window)")
     ap.add_argument("--mapping", default="symm", choices=["symm", "ipc"],
                     help="N > 1, peer exchange: how the ranks map each other's arenas")

@@ -100,6 +100,16 @@ DAISY_API int daisy_set_inputs_ready(daisy_handle_t h, int on);
 DAISY_API int daisy_bpr_step_host(daisy_handle_t h, float *P, float *Q, const int32_t *triples_host, int64_t B, float lr,
                         float wd, double *loss_accum, daisy_stream_t stream);
 
+/* One epoch of steps = the body of `for user, item_i, item_j in train_loader:` (BPRMFRecommender.py:162-178) run
+ * by the library: triples is int32 [n,3] (every triple of the epoch, already shuffled), consumed in consecutive
+ * batches of `batch` (<= max_batch; the last one may be short), each one exactly daisy_bpr_step /
+ * daisy_bpr_step_host.  One call per epoch instead of one per step: with small batches (the reference's default is
+ * 4 096) the step takes ~20 us on the device and the per-call cost of the host language would dominate.
+ * on_host = 1: triples is host memory (pinned), each batch is copied in as the head of its bookkeeping chain.
+ * on_host = 0: device memory, produced by earlier work on `stream` at the latest (e.g. daisy_sample_triples). */
+DAISY_API int daisy_bpr_epoch(daisy_handle_t h, float *P, float *Q, const int32_t *triples, int64_t n, int64_t batch,
+                    int on_host, float lr, float wd, double *loss_accum, daisy_stream_t stream);
+
 /* ---- row-sharded tables (no Daisy counterpart) --------------------------------
  * One process per GPU owns a block of user rows and a block of item rows.  Triples are routed to the owner of
  * their user, so P is local; the item rows a batch needs are fetched from their owners into `cache`

@@ -186,6 +186,24 @@ class BPRSGD:
         _lib.check(fn(h.ptr, c_vp(P.data_ptr()), c_vp(Q.data_ptr()), c_vp(tri.data_ptr()), B, self.lr,
                       self.weight_decay, c_vp(loss.data_ptr()), _lib.stream_ptr(torch, P.device)))
 
+    def epoch(self, triples, batch_size, loss_out=None):
+        """Every step of one epoch in ONE library call (``daisy_bpr_epoch``): ``triples`` is the epoch's packed
+        int32 [n,3] tensor (device, or pinned host), consumed in consecutive batches of ``batch_size`` -- the loop
+        ``for user, item_i, item_j in train_loader`` of BPRMFRecommender.py:162-178.  Same result as calling
+        ``step`` per batch; what it saves is the per-call cost of Python, which at the reference's default batch of
+        4 096 triples is larger than the ~20 us the step takes on the device."""
+        m = self.model
+        P, Q = m._tables()
+        tri = triples
+        if tri.dtype != torch.int32 or tri.dim() != 2 or tri.shape[1] != 3 or not tri.is_contiguous():
+            raise ValueError("packed triples must be a contiguous int32 [n, 3] tensor")
+        n, batch = tri.shape[0], int(batch_size)
+        h = m.handle(min(batch, max(n, 1)))
+        loss = self._loss_buf(P.device) if loss_out is None else loss_out
+        _lib.check(h.L.daisy_bpr_epoch(h.ptr, c_vp(P.data_ptr()), c_vp(Q.data_ptr()), c_vp(tri.data_ptr()), n, batch,
+                                       0 if tri.is_cuda else 1, self.lr, self.weight_decay, c_vp(loss.data_ptr()),
+                                       _lib.stream_ptr(torch, P.device)))
+
     def loss_sum(self, reset=True):
         if self._loss is None:
             return 0.0
@@ -277,8 +295,11 @@ class BPRMFRecommender:
                 epoch_triples.numpy()[:] = sampler.sample_epoch(ep)
             torch.cuda.synchronize(self.device)
             t1 = time.time()
-            for s in range(0, n, self.batch_size):
-                self.optimizer.step(epoch_triples[s:s + self.batch_size])
+            if isinstance(self.optimizer, BPRSGD):
+                self.optimizer.epoch(epoch_triples, self.batch_size)
+            else:
+                for s in range(0, n, self.batch_size):
+                    self.optimizer.step(epoch_triples[s:s + self.batch_size])
             self.model.materialize()
             loss = self.optimizer.loss_sum()          # synchronises
             self.model.check()

@@ -94,12 +94,20 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
     if (h->heavy_len < 8) h->heavy_len = 8;
     // a row is "very hot" above heavy_len contributions; at most 3B contributions exist per step
     h->heavy_cap = (int)(3 * max_batch / h->heavy_len) + 4;
-    h->slice_cap = (int)(3 * max_batch / DAISY_SLICE) + h->heavy_cap + 4;
+    {   // small-batch path: rows with more than 16 (DAISY_SMALL_SLICE, step_kernels.cuh) contributions, slices of 16
+        const int64_t sb = max_batch < DAISY_SMALL_CAP ? max_batch : DAISY_SMALL_CAP;
+        h->longs_cap = (int)(3 * sb / 16) + 4;
+        h->slice_cap = (int)(3 * max_batch / DAISY_SLICE) + h->heavy_cap + 4;
+        if (h->slice_cap < 2 * h->longs_cap) h->slice_cap = 2 * h->longs_cap;
+    }
     h->pipeline = env_int("DAISY_PIPELINE", 1) ? 1 : 0;
     h->main_stages = env_int("DAISY_MAIN_STAGES", 3);
     if (h->main_stages < 0) h->main_stages = 0;
     if (h->main_stages > 16) h->main_stages = 16;
     h->inputs_ready = 0;
+    h->small_max = env_int("DAISY_SMALL_MAX", DAISY_SMALL_CAP);
+    if (h->small_max < 0) h->small_max = 0;
+    if (h->small_max > DAISY_SMALL_CAP) h->small_max = DAISY_SMALL_CAP;
 
     const size_t B = (size_t)max_batch;
     int rc = DAISY_OK;
@@ -111,6 +119,7 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
             A(book[i].st, 3 * B);
             A(book[i].ukey_s, B); A(book[i].qkey_s, 2 * B);
             A(book[i].uslot, B); A(book[i].jslot, B); A(book[i].islot, B);
+            A(book[i].longs, 2 + 5 * (size_t)h->longs_cap);
         }
         A(key_in, 2 * B); A(val_in, 2 * B); A(val_out, 2 * B);
         A(ukey_in, B); A(uval_in, B); A(uval_out, B);
@@ -120,6 +129,7 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
         A(stage2, (size_t)h->slice_cap * dim);
         A(loss_part, B);
         A(heavy, 2 + 5 * (size_t)h->heavy_cap);
+        A(small_ticket, (size_t)h->longs_cap);
     }
 #undef A
     if (!rc && B > 0) {
@@ -141,6 +151,7 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
         if (B > 0) {
             for (int i = 0; i < 2; ++i) cudaMemset(h->book[i].islot, 0xFF, B * sizeof(uint32_t));
             cudaMemset(h->heavy, 0, 2 * sizeof(uint32_t));
+            cudaMemset(h->small_ticket, 0, (size_t)h->longs_cap * sizeof(uint32_t));
         }
         k_err_reset<<<1, 1>>>(h->err);
         for (int i = 0; i <= PH_COUNT; ++i) cudaEventCreate(&h->ev[i]);
@@ -174,13 +185,13 @@ extern "C" int daisy_destroy(daisy_handle_t h) {
     daisy_shard_free(h);
     void *ptrs[] = {h->triples, h->key_in, h->val_in, h->val_out, h->ukey_in, h->uval_in, h->uval_out, h->ikey_in,
                     h->ikey_out, h->ival_in, h->ival_out, h->stageU, h->stageQ, h->stage2, h->loss_part, h->heavy,
-                    h->err, h->cub_tmp, h->scores, h->sel_hist, h->own_key, h->own_key_s, h->own_val, h->own_val_s,
+                    h->err, h->cub_tmp, h->small_ticket, h->scores, h->sel_hist, h->own_key, h->own_key_s, h->own_val, h->own_val_s,
                     h->own_tmp};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 2; ++i) {
         void *bp[] = {h->book[i].st, h->book[i].ukey_s, h->book[i].qkey_s, h->book[i].uslot, h->book[i].jslot,
-                      h->book[i].islot};
+                      h->book[i].islot, h->book[i].longs};
         for (void *p : bp)
             if (p) cudaFree(p);
         if (h->book[i].ready) cudaEventDestroy(h->book[i].ready);

@@ -78,7 +78,7 @@ struct AdamOpt {
 
 // shared body of daisy_bpr_step / daisy_bpr_step_host
 static int sgd_step(daisy_ctx *h, float *P, float *Q, const int32_t *triples_dev, const int32_t *host_src, int64_t B,
-                    float lr, float wd, double *loss_accum, daisy_stream_t stream) {
+                    float lr, float wd, double *loss_accum, daisy_stream_t stream, bool inputs_ready) {
     const double shrink = 1.0 - (double)lr * (double)wd;
     DAISY_REQUIRE(shrink > 0.0, DAISY_EINVAL, "lr*wd = %g >= 1: the L2 shrink factor is not positive", (double)lr * wd);
     if (B == 0) {  // an empty batch still decays every row (optim.SGD.step with zero gradients)
@@ -94,7 +94,7 @@ static int sgd_step(daisy_ctx *h, float *P, float *Q, const int32_t *triples_dev
     opt.D4 = h->D / 4;
     const float c2 = (float)(h->scale * h->scale);
     int rc = run_step<SgdOpt>(h, P, Q, triples_dev, B, opt, c2, loss_accum, (cudaStream_t)stream, host_src,
-                              host_src != nullptr || h->inputs_ready);
+                              host_src != nullptr || inputs_ready);
     if (rc) return rc;
     h->scale *= shrink;
     if ((h->flags & DAISY_FLAG_EAGER_DECAY) || h->scale < 1e-4) return daisy_materialize(h, P, Q, stream);
@@ -110,7 +110,7 @@ extern "C" int daisy_bpr_step(daisy_handle_t h, float *P, float *Q, const int32_
                               float wd, double *loss_accum, daisy_stream_t stream) {
     int rc = check_step_args(h, P, Q, triples, B);
     if (rc) return rc;
-    return sgd_step(h, P, Q, triples, nullptr, B, lr, wd, loss_accum, stream);
+    return sgd_step(h, P, Q, triples, nullptr, B, lr, wd, loss_accum, stream, h->inputs_ready != 0);
 }
 
 extern "C" int daisy_bpr_step_host(daisy_handle_t h, float *P, float *Q, const int32_t *triples_host, int64_t B,
@@ -120,7 +120,33 @@ extern "C" int daisy_bpr_step_host(daisy_handle_t h, float *P, float *Q, const i
     // landing buffer of the bookkeeping set this step will use; the H2D copy is issued on the side stream as the
     // first node of the step's bookkeeping chain, so it overlaps the previous step's kernels
     int32_t *dst = h->triples + (size_t)h->book_idx * 3 * (size_t)h->maxB;
-    return sgd_step(h, P, Q, dst, triples_host, B, lr, wd, loss_accum, stream);
+    return sgd_step(h, P, Q, dst, triples_host, B, lr, wd, loss_accum, stream, true);
+}
+
+extern "C" int daisy_bpr_epoch(daisy_handle_t h, float *P, float *Q, const int32_t *triples, int64_t n, int64_t batch,
+                               int on_host, float lr, float wd, double *loss_accum, daisy_stream_t stream) {
+    DAISY_REQUIRE(n >= 0 && batch > 0, DAISY_EINVAL, "epoch of %lld triples in batches of %lld", (long long)n, (long long)batch);
+    int rc = check_step_args(h, P, Q, triples, batch < n ? batch : n);
+    if (rc) return rc;
+    if (!on_host && n > 0 && h->pipeline && !h->inputs_ready) {
+        // the triples are complete once the work already queued on `stream` is: order the bookkeeping stream behind
+        // it ONCE, then every step's bookkeeping may run ahead of the previous step's kernels
+        DeviceGuard g(h->device);
+        DAISY_CUDA(cudaEventRecord(h->ev_call, (cudaStream_t)stream));
+        DAISY_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_call, 0));
+    }
+    for (int64_t s = 0; s < n; s += batch) {
+        const int64_t B = n - s < batch ? n - s : batch;
+        const int32_t *src = triples + 3 * s;
+        if (on_host) {
+            int32_t *dst = h->triples + (size_t)h->book_idx * 3 * (size_t)h->maxB;
+            rc = sgd_step(h, P, Q, dst, src, B, lr, wd, loss_accum, stream, true);
+        } else {
+            rc = sgd_step(h, P, Q, src, nullptr, B, lr, wd, loss_accum, stream, true);
+        }
+        if (rc) return rc;
+    }
+    return DAISY_OK;
 }
 
 extern "C" int daisy_bpr_adam_step(daisy_handle_t h, float *P, float *Q, float *mP, float *vP, float *mQ, float *vQ,

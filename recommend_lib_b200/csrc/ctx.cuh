@@ -13,6 +13,7 @@
 #define DAISY_MAX_RANKS 16          // ranks of a row-sharded model (one node)
 #define DAISY_SLICE 64     // contributions per level-1 slice of a very hot row
 #define DAISY_TRACE_STEPS 48
+#define DAISY_SMALL_CAP 8192  // largest batch of the small-batch path: 2B item refs are sorted by ONE thread block
 #define DAISY_EVPOOL 2048  // main-kernel event pairs kept between two daisy_main_kernel_ms() calls
 
 // Phases of one BPR step, in launch order (daisy_last_step_phases).
@@ -35,6 +36,8 @@ struct BookSet {
     int32_t *st;                    // [maxB,3]  triples in positive-item order
     uint32_t *ukey_s, *qkey_s;      // [maxB], [2*maxB]  sorted user / item ref keys (rows)
     uint32_t *uslot, *jslot, *islot;  // [maxB]  per sorted triple: DAISY_DIRECT or staging slot
+    uint32_t *longs;                // small-batch path: [0] = #rows longer than DAISY_SLICE, [1] = #slices, then 5 words
+                                    // per row (table, row, first sorted position, length, first slice), like `heavy`
     cudaEvent_t ready, freed;
 };
 
@@ -114,7 +117,8 @@ struct daisy_ctx {
     float *stage2;          // [slice_cap, D] level-1 partial sums of very hot rows
     float *loss_part;       // [maxB] per-warp loss partials
     uint32_t *heavy;        // [0] = #hot rows, [1] = #slices, then 5 words per hot row: table, row, first pos, len, first slice
-    int heavy_cap, slice_cap;
+    int heavy_cap, slice_cap, longs_cap;
+    uint32_t *small_ticket; // [longs_cap] finished-slice counters of the small-batch path's long rows (zero between steps)
     int *err;               // [2]: flag, first bad position
     int *err_host;          // pinned mirror
     // sharded step: row count of the fetched-row cache standing in for the item table (0 = use I)
@@ -134,6 +138,7 @@ struct daisy_ctx {
     int chunk;       // max positive-item run length handled by one warp in the main kernel (0 = auto)
     int heavy_len;   // segments longer than this go to the block-per-row kernel
     int main_stages; // > 0: TMA-pipelined main kernel with this many stages (triples in flight) per warp; 0: register prefetch
+    int small_max;   // batches up to this many triples take the 3-launch small-batch path (0 = never; <= DAISY_SMALL_CAP)
 
     // --- instrumentation ---
     int64_t launches;

@@ -436,14 +436,21 @@ __global__ void __launch_bounds__(256) k_bpr_main_tma(MainArgs a, Opt opt, int S
 template <int V>
 __device__ __forceinline__ void sum_staged(const float *__restrict__ stage, size_t q0, int len, int D4, int lane,
                                            const bool (&act)[V], float4 (&acc)[V]) {
+#ifdef DAISY_SEG_UN  // tools/small_book_probe.cu experiments
+    constexpr int UN = DAISY_SEG_UN;
+#else
     constexpr int UN = (V == 1) ? 8 : (V == 2 ? 4 : 2);
+#endif
+#ifndef DAISY_SEG_LD
+#define DAISY_SEG_LD ld_stream
+#endif
     for (int c = 0; c < len; c += UN) {
         float4 r[UN][V];
 #pragma unroll
         for (int jj = 0; jj < UN; ++jj)
 #pragma unroll
             for (int v = 0; v < V; ++v)
-                r[jj][v] = (c + jj < len && act[v]) ? ld_stream(stage, (q0 + c + jj) * D4 + lane + 32 * v) : f4_zero();
+                r[jj][v] = (c + jj < len && act[v]) ? DAISY_SEG_LD(stage, (q0 + c + jj) * D4 + lane + 32 * v) : f4_zero();
 #pragma unroll
         for (int jj = 0; jj < UN; ++jj)  // fixed order: sorted position ascending
             if (c + jj < len) {
@@ -453,15 +460,17 @@ __device__ __forceinline__ void sum_staged(const float *__restrict__ stage, size
     }
 }
 
-template <int V, class Opt>
-__global__ void __launch_bounds__(256) k_seg_reduce(int tbl, const float *__restrict__ table,
-                                                     const uint32_t *__restrict__ keys, int n, uint32_t sentinel,
-                                                     const float *__restrict__ stage, int D4, Opt opt, int heavy_len,
-                                                     uint32_t *heavy, int heavy_cap) {
+// One warp, window w of WIN sorted refs: every multi-contribution row that STARTS in the window is summed and updated.
+// The warp always looks at 32 refs from the window's first one; WIN < 32 only narrows which row starts it owns (the
+// small-batch path has SMs to spare and uses 8: a warp walks its rows one after the other, each an L2 round trip).
+template <int V, class Opt, int WIN = 32>
+__device__ __forceinline__ void seg_window(long long w, int tbl, const float *__restrict__ table,
+                                           const uint32_t *__restrict__ keys, int n, uint32_t sentinel,
+                                           const float *__restrict__ stage, int D4, const Opt &opt, int heavy_len,
+                                           uint32_t *heavy, int heavy_cap) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const long long w = (long long)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
-    const long long base = w * 32;
+    const long long base = w * WIN;
     if (base >= n) return;
     const long long p = base + lane;
     const uint32_t key = (p < n) ? keys[p] : sentinel;
@@ -473,7 +482,7 @@ __global__ void __launch_bounds__(256) k_seg_reduce(int tbl, const float *__rest
     const bool start = valid && (prev != key);
     const bool multi = start && (next == key) && (p + 1 < n);
     const unsigned boundary = __ballot_sync(FULL, start || !valid);
-    unsigned todo = __ballot_sync(FULL, multi);
+    unsigned todo = __ballot_sync(FULL, multi && lane < WIN);
     bool act[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
@@ -500,6 +509,7 @@ __global__ void __launch_bounds__(256) k_seg_reduce(int tbl, const float *__rest
         }
         const size_t q0 = (size_t)(base + b);
         if (len > heavy_len) {  // very hot row: reduced in two levels by k_heavy_slices / k_heavy_final
+            if (!heavy) continue;  // small-batch path: k_small_book listed it already, the slice blocks take it
             // exact length by a 32-ary search over the sorted keys: keys[q] == row for q in [q0, q0 + len)
             long long lo = (long long)q0 + len, hi = n;
             while (lo < hi) {
@@ -540,6 +550,15 @@ __global__ void __launch_bounds__(256) k_seg_reduce(int tbl, const float *__rest
         for (int v = 0; v < V; ++v)
             if (act[v]) opt.apply(tbl, (size_t)row, lane + 32 * v, old[v], acc[v]);
     }
+}
+
+template <int V, class Opt>
+__global__ void __launch_bounds__(256) k_seg_reduce(int tbl, const float *__restrict__ table,
+                                                     const uint32_t *__restrict__ keys, int n, uint32_t sentinel,
+                                                     const float *__restrict__ stage, int D4, Opt opt, int heavy_len,
+                                                     uint32_t *heavy, int heavy_cap) {
+    const long long w = (long long)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    seg_window<V, Opt>(w, tbl, table, keys, n, sentinel, stage, D4, opt, heavy_len, heavy, heavy_cap);
 }
 
 // Level 1: every slice of DAISY_SLICE consecutive staged contributions of a hot row is summed by one warp into
@@ -633,6 +652,406 @@ __global__ void __launch_bounds__(1024) k_loss(const float *__restrict__ part, i
         double t = sh[threadIdx.x];
         t = warp_sum_d(t);
         if (threadIdx.x == 0) *loss_accum += t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small-batch path (B <= DAISY_SMALL_CAP): the step is launch-bound, not bandwidth-bound (the 22 launches of the
+// general pipeline cost ~80 us for 4 096 triples), so the whole bookkeeping is ONE kernel and the table phase two.
+//
+//   k_small_book   block 0 sorts the B user refs, block 1 the 2B item refs (negatives, then positives), each with a
+//                  block-wide radix sort in shared memory.  A ref is one 32-bit word (row << vb | ref index), sorted
+//                  on the row bits only; the ref index rides along, so there is no value array.  Rows referenced once
+//                  are DIRECT, every other ref is staged at its sorted position -- the contract of the general path,
+//                  without the positive-item runs (every triple heads its own run: C = 1).
+//   k_bpr_main     the general main kernel with C = 1 (one warp per triple)
+//   k_small_seg    segmented reduces of both tables in one launch (no two-level hot-row path: at most 16 384
+//                  contributions exist) + the loss reduction
+//
+// The accumulation order of a row is its sorted-ref order, fixed by the sort => bit-reproducible.  It differs from
+// the general path's order (which groups triples by positive item first), so the two paths agree to rounding only.
+// ------------------------------------------------------------------------------------------------
+#ifdef DAISY_SMALL_PROBE  // tools/small_book_probe.cu: clock stamps of thread 0 of each block
+__device__ long long g_small_probe[32][32];
+#define SMALL_PROBE(n) do { if (threadIdx.x == 0) g_small_probe[blockIdx.x][n] = clock64(); } while (0)
+#else
+#define SMALL_PROBE(n) do { } while (0)
+#endif
+
+// Block-wide stable LSD radix sort of up to 1024 * IPT 32-bit words on bits [lo, lo + nbits), digits of up to 9 bits
+// ranked the way CUB's onesweep ranks them: a warp counts its digits by matching lanes (lanes holding the same digit
+// find each other, the lowest one bumps the warp's histogram), one block scan over (digit, warp) turns the
+// histograms into offsets.  Words live in registers in warp-striped order (word k < ipt of lane l of warp w is
+// position w*32*ipt + k*32 + l; ipt <= IPT is block-uniform); the sorted words are left in `out` (shared memory).
+// The whole block runs on ONE SM, 8 warps per scheduler, so the cost is the instruction count: ~70 per word and pass.
+template <int IPT>
+__device__ __forceinline__ void block_sort_words(uint32_t (&keys)[IPT], int ipt, int lo, int nbits,
+                                                 uint32_t *hist /*[32 * 513]*/, uint32_t *out,
+                                                 uint32_t *scan_tmp /*[33]*/) {
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    if (nbits < 1) nbits = 1;
+    const int passes = (nbits + 8) / 9;
+    int done = 0;
+    for (int p = 0; p < passes; ++p) {
+        int db = (nbits - done + (passes - p) - 1) / (passes - p);  // balanced digit widths, each <= 9
+        if (db < 5) db = 5;                                          // >= 32 bins: one (digit, warp) cell per thread at least
+        const int NB = 1 << db, shift = lo + done;
+        const uint32_t dmask = (uint32_t)NB - 1u;
+        const int HS = NB + 1;  // row stride: (digit, warp) cells of one scan step fall into 32 different banks
+        uint32_t *wh = hist + (size_t)w * HS;
+        SMALL_PROBE(2 + 6 * p);
+        for (int i = lane; i < NB; i += 32) wh[i] = 0;
+        __syncwarp();
+        uint32_t rank[IPT];
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            if (k < ipt) {
+                const uint32_t d = (keys[k] >> shift) & dmask;
+                // lanes holding the same digit, found with one ballot per digit bit (match.any serialises over the
+                // distinct values of the warp: no faster here)
+                unsigned m = FULL;
+                for (int bb = 0; bb < db; ++bb) {
+                    const bool bit = (d >> bb) & 1u;
+                    const unsigned v = __ballot_sync(FULL, bit);
+                    m &= bit ? v : ~v;
+                }
+                const int leader = __ffs(m) - 1;
+                uint32_t base = 0;
+                if (lane == leader) {
+                    base = wh[d];
+                    wh[d] = base + __popc(m);
+                }
+                base = __shfl_sync(FULL, base, leader);
+                rank[k] = base + __popc(m & lt);
+                __syncwarp();
+            }
+        }
+        SMALL_PROBE(3 + 6 * p);
+        __syncthreads();
+        SMALL_PROBE(4 + 6 * p);
+        // exclusive scan of the cells in (digit, warp) order: thread t owns E consecutive cells
+        const int E = NB / 32;
+        uint32_t sum = 0;
+        for (int e = 0; e < E; ++e) {
+            const int L = tid * E + e;
+            sum += hist[(size_t)(L & 31) * HS + (L >> 5)];
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) scan_tmp[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            const uint32_t tot = scan_tmp[lane];
+            uint32_t inc2 = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL, inc2, o);
+                if (lane >= o) inc2 += v;
+            }
+            scan_tmp[lane] = inc2 - tot;
+        }
+        __syncthreads();
+        uint32_t run = scan_tmp[w] + incl - sum;
+        for (int e = 0; e < E; ++e) {
+            const int L = tid * E + e;
+            uint32_t *cell = hist + (size_t)(L & 31) * HS + (L >> 5);
+            const uint32_t c = *cell;
+            *cell = run;
+            run += c;
+        }
+        SMALL_PROBE(5 + 6 * p);
+        __syncthreads();
+        SMALL_PROBE(6 + 6 * p);
+#pragma unroll
+        for (int k = 0; k < IPT; ++k)
+            if (k < ipt) out[wh[(keys[k] >> shift) & dmask] + rank[k]] = keys[k];
+        __syncthreads();
+        SMALL_PROBE(7 + 6 * p);
+        if (p + 1 < passes) {
+#pragma unroll
+            for (int k = 0; k < IPT; ++k)
+                if (k < ipt) keys[k] = out[w * 32 * ipt + k * 32 + lane];
+        }
+        done += db;
+    }
+}
+
+#define DAISY_SMALL_HIST_WORDS (32 * 513)
+#define DAISY_SMALL_WIN 8       // sorted refs per warp of k_small_seg
+#define DAISY_SMALL_SLICE 16   // contributions per slice of a long row (k_small_seg): short, so that a hot row's
+                               // sum is spread over many warps on many SMs and is not a latency chain
+#define DAISY_SMALL_CB 3        // k_small_book: rows are split over 2^CB blocks per table by their low CB bits
+// Grid: 2 << CB blocks; block b < 2^CB handles the user refs whose row has low bits b, the others the item refs
+// (negatives, then positives) likewise.  Only equal rows have to be adjacent in the "sorted" ref arrays, in a
+// reproducible order -- not ascending rows -- so the arrays are ordered by (low row bits, high row bits, ref index)
+// and every block can work alone: it reads ALL refs of its table (cheap), counts how many belong to lower classes
+// (its base position) and compacts its own class into shared memory, then sorts that eighth on the high row bits.
+// No block waits for another one, and the sort -- bound by the instruction throughput of one SM -- shrinks 8x.
+template <int IPT>
+__global__ void __launch_bounds__(1024) k_small_book(const int32_t *__restrict__ triples, int B, uint32_t U, uint32_t I,
+                                                      int vbU, int kbU, int vbQ, int kbQ, int32_t *__restrict__ st,
+                                                      uint32_t *__restrict__ ukey_s, uint32_t *__restrict__ qkey_s,
+                                                      uint32_t *__restrict__ uslot, uint32_t *__restrict__ jslot,
+                                                      uint32_t *__restrict__ islot, uint32_t *longs, int longs_cap,
+                                                      int *err) {
+    extern __shared__ __align__(16) unsigned char small_dsm[];
+    uint32_t *hist = reinterpret_cast<uint32_t *>(small_dsm);
+    uint32_t *sk = hist + DAISY_SMALL_HIST_WORDS;  // [1024 * IPT] compacted, then sorted words
+    __shared__ uint32_t scan_tmp[33], wcnt[32], wlow[32];
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    constexpr uint32_t NC = 1u << DAISY_SMALL_CB;
+    const bool items = blockIdx.x >= NC;
+    const uint32_t cls = blockIdx.x & (NC - 1);
+    const int n = items ? 2 * B : B;
+    const int vb = items ? vbQ : vbU, kb = items ? kbQ : kbU;
+    const uint32_t bound = items ? I : U;
+    uint32_t keys[IPT];
+    SMALL_PROBE(0);
+    // ---- every ref of the table: mine / lower class / neither ----
+    const bool checker = !items && cls == 0;  // this block also validates the triples and writes the clamped copy
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {  // the loads first, all in flight together
+        const int idx = w * 32 * IPT + k * 32 + lane;  // ref index; refs of a row keep this order
+        uint32_t row = 0;
+        if (idx < n) {
+            const int t = idx < B ? idx : idx - B;
+            if (checker) {
+                uint32_t u, i, j;
+                bool bad;
+                load_triple(triples, t, U, I, u, i, j, bad);
+                st[3 * (size_t)t] = (int32_t)u;
+                st[3 * (size_t)t + 1] = (int32_t)i;
+                st[3 * (size_t)t + 2] = (int32_t)j;
+                if (bad) {
+                    atomicOr(&err[0], 1);
+                    atomicMin(&err[1], t);
+                }
+                row = u;
+            } else {
+                row = (uint32_t)__ldg(triples + 3 * (size_t)t + (items ? (idx < B ? 2 : 1) : 0));
+            }
+        }
+        keys[k] = row;
+    }
+    uint32_t mine_cnt = 0, low_cnt = 0;
+    unsigned mine_mask[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        const int idx = w * 32 * IPT + k * 32 + lane;
+        uint32_t row = keys[k];
+        if (row >= bound) row = 0;  // parked on row 0 like load_triple does
+        const uint32_t c = row & (NC - 1);
+        const bool in = idx < n;
+        keys[k] = in ? ((row << vb) | (uint32_t)idx) : 0xFFFFFFFFu;
+        mine_mask[k] = __ballot_sync(FULL, in && c == cls);
+        mine_cnt += __popc(mine_mask[k]);
+        low_cnt += __popc(__ballot_sync(FULL, in && c < cls));
+    }
+    if (lane == 0) {
+        wcnt[w] = mine_cnt;
+        wlow[w] = low_cnt;
+    }
+    __syncthreads();
+    uint32_t wbase, n_c, base_c;
+    {
+        const uint32_t c = wcnt[lane];
+        uint32_t inc = c, lo = wlow[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lo += __shfl_xor_sync(FULL, lo, o);
+        n_c = __shfl_sync(FULL, inc, 31);
+        wbase = __shfl_sync(FULL, inc - c, w);
+        base_c = lo;  // refs of lower classes come first in the table's sorted array
+    }
+    {
+        uint32_t run = wbase;
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            if (mine_mask[k] >> lane & 1u) sk[run + __popc(mine_mask[k] & lt)] = keys[k];
+            run += __popc(mine_mask[k]);
+        }
+    }
+    __syncthreads();
+    const int ipt = (int)((n_c + 1023u) / 1024u);
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        const uint32_t q = (uint32_t)(w * 32 * ipt + k * 32 + lane);
+        keys[k] = (k < ipt && q < n_c) ? sk[q] : 0xFFFFFFFFu;  // padding behind the real refs; the sort is stable
+    }
+    __syncthreads();
+    SMALL_PROBE(1);
+    if (ipt > 0) block_sort_words<IPT>(keys, ipt, vb + DAISY_SMALL_CB, kb - DAISY_SMALL_CB, hist, sk, scan_tmp);
+    SMALL_PROBE(30);
+    const uint32_t vmask = (1u << vb) - 1u;
+    uint32_t *key_out = (items ? qkey_s : ukey_s) + base_c;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        const uint32_t p = (uint32_t)(k * 1024 + tid);
+        if (p >= n_c) continue;
+        const uint32_t wd = sk[p];
+        const uint32_t row = wd >> vb, idx = wd & vmask;
+        const bool first = (p == 0) || ((sk[p - 1] >> vb) != row);
+        const bool last = (p == n_c - 1) || ((sk[p + 1] >> vb) != row);
+        const uint32_t slot = (first && last) ? DAISY_DIRECT : base_c + p;
+        key_out[p] = row;
+        if (first && p + DAISY_SMALL_SLICE < n_c && (sk[p + DAISY_SMALL_SLICE] >> vb) == row) {
+            // a row with more than DAISY_SMALL_SLICE contributions: too much for one warp (and for the L2 port of one SM).
+            // List it -- (table, row, first sorted position, length, first slice) like the general path's heavy
+            // list -- for the slice blocks of k_small_seg.
+            uint32_t lo = p + DAISY_SMALL_SLICE, hi = n_c - 1;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if ((sk[mid] >> vb) == row) lo = mid; else hi = mid - 1;
+            }
+            const uint32_t len = lo - p + 1;
+            const uint32_t r = atomicAdd(&longs[0], 1u);
+            const uint32_t sl0 = atomicAdd(&longs[1], (len + DAISY_SMALL_SLICE - 1) / DAISY_SMALL_SLICE);
+            if ((int)r < longs_cap) {
+                uint32_t *rec = longs + 2 + 5 * (size_t)r;
+                rec[0] = items ? 1u : 0u;
+                rec[1] = row;
+                rec[2] = base_c + p;
+                rec[3] = len;
+                rec[4] = sl0;
+            }
+        }
+        if (!items)
+            uslot[idx] = slot;
+        else if (idx < (uint32_t)B)
+            jslot[idx] = slot;
+        else
+            islot[idx - B] = slot;
+    }
+    SMALL_PROBE(31);
+}
+
+template <int IPT>
+static int launch_small_book(daisy_ctx *h, cudaStream_t bs, const int32_t *triples, int B, uint32_t U, uint32_t I, int vbU,
+                             int kbU, int vbQ, int kbQ, BookSet &k) {
+    const size_t smem = sizeof(uint32_t) * (DAISY_SMALL_HIST_WORDS + 1024 * IPT);
+    static bool granted[64];
+    if (!granted[h->device & 63]) {
+        DAISY_CUDA(cudaFuncSetAttribute(k_small_book<IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        granted[h->device & 63] = true;
+    }
+    DAISY_CUDA(cudaMemsetAsync(k.longs, 0, 2 * sizeof(uint32_t), bs));
+    k_small_book<IPT><<<2 << DAISY_SMALL_CB, 1024, smem, bs>>>(triples, B, U, I, vbU, kbU, vbQ, kbQ, k.st, k.ukey_s,
+                                                             k.qkey_s, k.uslot, k.jslot, k.islot, k.longs,
+                                                             h->longs_cap, h->err);
+    DAISY_LAUNCH_CHECK(h);
+    return DAISY_OK;
+}
+
+#define DAISY_SMALL_SLICE_BLOCKS 64  // blocks of k_small_seg that sum the slices of long rows
+template <int V, class Opt>
+__global__ void __launch_bounds__(256) k_small_seg(const float *__restrict__ P, const float *__restrict__ Q,
+                                                    const uint32_t *__restrict__ ukey_s,
+                                                    const uint32_t *__restrict__ qkey_s, int B,
+                                                    const float *__restrict__ stageU, const float *__restrict__ stageQ,
+                                                    float *__restrict__ stage2, int D4, Opt opt, int blocksU, int blocksQ,
+                                                    const uint32_t *__restrict__ longs, int longs_cap, uint32_t *ticket,
+                                                    const float *__restrict__ loss_part, int n_part,
+                                                    double *loss_accum) {
+    // Blocks [0, blocksU + blocksQ): 8 windows of DAISY_SMALL_WIN sorted refs each; a warp reduces the rows of up to
+    // DAISY_SMALL_SLICE contributions that start in its window.
+    // The next DAISY_SMALL_SLICE_BLOCKS blocks: the rows k_small_book listed as longer than that.  One SM draws
+    // ~40 B/clk from L2 however many loads it has in flight (tools/small_book_probe.cu), so a hot row's staged
+    // contributions (195 KB for the top item of a 4 096-triple Zipf batch) are spread over the SMs slice by slice:
+    // a warp sums one slice of DAISY_SMALL_SLICE contributions into stage2, takes a ticket of its row, and the warp that
+    // draws the last ticket adds the slice sums in slice order and updates the row -- the order of the sum is fixed
+    // by the slice numbers, not by who arrives when.
+    // The last block: the loss reduction.
+    const int b = blockIdx.x, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const int nwin = blocksU + blocksQ;
+    if (b < nwin) {
+        const int tbl = b < blocksU ? 0 : 1;
+        seg_window<V, Opt, DAISY_SMALL_WIN>((long long)(tbl ? b - blocksU : b) * 8 + wid, tbl, tbl ? Q : P,
+                                            tbl ? qkey_s : ukey_s, tbl ? 2 * B : B, 0xFFFFFFFFu, tbl ? stageQ : stageU, D4,
+                                            opt, DAISY_SMALL_SLICE, nullptr, 0);
+        return;
+    }
+    if (b >= nwin + DAISY_SMALL_SLICE_BLOCKS) {  // fixed-order reduction of the per-warp loss partials (cf. k_loss)
+        if (!loss_accum) return;
+        __shared__ double sh[8];
+        double s = 0.0;
+        for (int i = threadIdx.x; i < n_part; i += 256) s += (double)loss_part[i];
+        s = warp_sum_d(s);
+        if (lane == 0) sh[wid] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int i = 0; i < 8; ++i) t += sh[i];
+            *loss_accum += t;
+        }
+        return;
+    }
+    const int count = min((int)longs[0], longs_cap);
+    if (count == 0) return;
+    const int total = (int)longs[1];
+    bool act[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
+    // consecutive slices go to different blocks (SMs): slice s is taken by warp (s / BLOCKS) % 8 of block s % BLOCKS
+    for (int s = (b - nwin) + DAISY_SMALL_SLICE_BLOCKS * wid; s < total; s += DAISY_SMALL_SLICE_BLOCKS * 8) {
+        int r = -1;
+        for (int r0 = 0; r0 < count && r < 0; r0 += 32) {  // the row this slice belongs to
+            bool hit = false;
+            if (r0 + lane < count) {
+                const uint32_t *rec = longs + 2 + 5 * (size_t)(r0 + lane);
+                const int sl0 = (int)rec[4], nsl = (int)((rec[3] + DAISY_SMALL_SLICE - 1) / DAISY_SMALL_SLICE);
+                hit = s >= sl0 && s < sl0 + nsl;
+            }
+            const unsigned m = __ballot_sync(FULL, hit);
+            if (m) r = r0 + __ffs(m) - 1;
+        }
+        if (r < 0) continue;  // a record beyond longs_cap was dropped (cannot happen: the cap covers 3B / DAISY_SMALL_SLICE rows)
+        const uint32_t *rec = longs + 2 + 5 * (size_t)r;
+        const int tbl = (int)rec[0];
+        const uint32_t row = rec[1];
+        const size_t q0 = rec[2];
+        const int len = (int)rec[3], sl0 = (int)rec[4];
+        const int nsl = (len + DAISY_SMALL_SLICE - 1) / DAISY_SMALL_SLICE, j = s - sl0;
+        float4 acc[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] = f4_zero();
+        sum_staged<V>(tbl ? stageQ : stageU, q0 + (size_t)j * DAISY_SMALL_SLICE, min(DAISY_SMALL_SLICE, len - j * DAISY_SMALL_SLICE), D4,
+                      lane, act, acc);
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            if (act[v]) __stcg(reinterpret_cast<float4 *>(stage2) + (size_t)s * D4 + lane + 32 * v, acc[v]);
+        __threadfence();
+        __syncwarp();
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(&ticket[r], 1u);
+        t = __shfl_sync(FULL, t, 0);
+        if ((int)t != nsl - 1) continue;
+        // last slice of the row to finish: every slice sum is in L2
+        __threadfence();
+        if (lane == 0) ticket[r] = 0;  // ready for the next step
+        const float *table = tbl ? Q : P;
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            if (act[v]) {
+                const int e = lane + 32 * v;
+                float4 tot = __ldcg(reinterpret_cast<const float4 *>(stage2) + (size_t)sl0 * D4 + e);
+                for (int jj = 1; jj < nsl; ++jj)  // fixed order: slice 0, 1, 2, ...
+                    tot = f4_add(tot, __ldcg(reinterpret_cast<const float4 *>(stage2) + (size_t)(sl0 + jj) * D4 + e));
+                const float4 old = (tbl == 0 || Opt::kNeedOldItem) ? ld_row(table, (size_t)row * D4 + e) : f4_zero();
+                opt.apply(tbl, (size_t)row, e, old, tot);
+            }
     }
 }
 
@@ -745,7 +1164,19 @@ struct StepPlan {
     BookSet *k;
     int set;              // index of k in h->book
     const float *const *jsrc, *const *isrc;  // row-sharded step only (else null)
+    bool small;           // small-batch path: k_small_book / C = 1 / k_small_seg
 };
+
+// Does a batch of B triples take the small-batch path?  Its refs must pack into 32 bits: row bits (of the VALUE U
+// resp. I, so that the all-ones padding sorts behind every real row) + ref-index bits.
+static bool small_path(const daisy_ctx *h, int64_t B, uint32_t U, uint32_t I, int *vbU, int *kbU, int *vbQ, int *kbQ) {
+    if (B <= 0 || B > h->small_max) return false;
+    *vbU = bits_for((uint64_t)(B - 1));
+    *vbQ = bits_for((uint64_t)(2 * B - 1));
+    *kbU = bits_for(U);
+    *kbQ = bits_for(I);
+    return *vbU + *kbU <= 32 && *vbQ + *kbQ <= 32;
+}
 
 // The integer bookkeeping of a step (prep .. slots) depends on the triples only, never on the tables.  It runs on
 // the handle's side stream into one of two bookkeeping sets, so that for step n+1 it overlaps the bandwidth-bound
@@ -754,12 +1185,15 @@ struct StepPlan {
 static int book_phase(daisy_ctx *h, StepPlan &pl, const int32_t *triples, int64_t B64, uint32_t U, uint32_t I,
                       cudaStream_t s, const int32_t *host_src, bool inputs_ready, const daisy_shard *sh) {
     const int B = (int)B64;
-    const int C = auto_chunk(h, B);
+    int vbU = 0, kbU = 0, vbQ = 0, kbQ = 0;
+    const bool small = !sh && small_path(h, B64, U, I, &vbU, &kbU, &vbQ, &kbQ);
+    const int C = small ? 1 : auto_chunk(h, B);
     const int T = 256;
     const bool piped = h->pipeline && h->timing != 2;
     cudaStream_t bs = piped ? h->side_stream : s;
     pl.B = B; pl.C = C; pl.U = U; pl.I = I; pl.piped = piped; pl.bs = bs; pl.s = s;
     pl.set = h->book_idx;
+    pl.small = small;
     pl.jsrc = sh ? sh->set[pl.set].jsrc : nullptr;
     pl.isrc = sh ? sh->set[pl.set].isrc : nullptr;
     BookSet &k = h->book[h->book_idx];
@@ -789,6 +1223,27 @@ static int book_phase(daisy_ctx *h, StepPlan &pl, const int32_t *triples, int64_
     if (tr) cudaEventRecord(h->tr_ev[4 * h->tr_n + 0], bs);
     if (host_src) {  // *_step_host: the H2D copy is the first node of the bookkeeping chain
         DAISY_CUDA(cudaMemcpyAsync((void *)triples, host_src, (size_t)B * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, bs));
+    }
+    if (small) {
+        for (int ph = PH_PREP; ph < PH_SLOTS; ++ph) phase_mark(h, ph, s);
+        int rc;
+        if (2 * B <= 4096)
+            rc = launch_small_book<4>(h, bs, triples, B, U, I, vbU, kbU, vbQ, kbQ, k);
+        else if (2 * B <= 8192)
+            rc = launch_small_book<8>(h, bs, triples, B, U, I, vbU, kbU, vbQ, kbQ, k);
+        else
+            rc = launch_small_book<16>(h, bs, triples, B, U, I, vbU, kbU, vbQ, kbQ, k);
+        if (rc) return rc;
+        phase_mark(h, PH_SLOTS, s);
+        if (piped) {
+            DAISY_CUDA(cudaEventRecord(k.ready, bs));
+            DAISY_CUDA(cudaStreamWaitEvent(s, k.ready, 0));
+        }
+        if (tr) {
+            cudaEventRecord(h->tr_ev[4 * h->tr_n + 1], bs);
+            cudaEventRecord(h->tr_ev[4 * h->tr_n + 2], s);
+        }
+        return DAISY_OK;
     }
     // prep
     k_prep<<<daisy_ceil_div(B, T), T, 0, bs>>>(triples, B, U, I, h->ikey_in, h->ival_in, h->err);
@@ -858,7 +1313,7 @@ static int table_phase_v(daisy_ctx *h, const StepPlan &pl, const float *P, const
     const int D4 = h->D / 4;
     cudaStream_t s = pl.s;
     BookSet &k = *pl.k;
-    DAISY_CUDA(cudaMemsetAsync(h->heavy, 0, 2 * sizeof(uint32_t), s));
+    if (!pl.small) DAISY_CUDA(cudaMemsetAsync(h->heavy, 0, 2 * sizeof(uint32_t), s));
     MainArgs a;
     a.P = P; a.Q = Q; a.st = k.st; a.uslot = k.uslot; a.jslot = k.jslot; a.islot = k.islot;
     a.stageU = h->stageU; a.stageQ = h->stageQ; a.loss_part = h->loss_part;
@@ -873,15 +1328,21 @@ static int table_phase_v(daisy_ctx *h, const StepPlan &pl, const float *P, const
     const size_t stage_bytes = (size_t)8 * 3 * D4 * 16;
     int S = h->main_stages;
     if ((size_t)S * stage_bytes > (size_t)56 * 1024) S = (int)((size_t)56 * 1024 / stage_bytes);
+    if (pl.small) S = 0;  // one triple per warp: nothing to pipeline
     if (S >= 2) {
         const size_t smem = S * stage_bytes + (size_t)8 * S * 8;
+        static size_t granted_tab[2][64];  // per instantiation (V, Opt): shared memory already granted, by PTR and device
+        size_t &granted = granted_tab[pl.jsrc ? 1 : 0][h->device & 63];
         if (pl.jsrc) {
-            DAISY_CUDA(cudaFuncSetAttribute(k_bpr_main_tma<V, Opt, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (granted != smem)
+                DAISY_CUDA(cudaFuncSetAttribute(k_bpr_main_tma<V, Opt, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_bpr_main_tma<V, Opt, true><<<blocks, 256, smem, s>>>(a, opt, S);
         } else {
-            DAISY_CUDA(cudaFuncSetAttribute(k_bpr_main_tma<V, Opt, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (granted != smem)
+                DAISY_CUDA(cudaFuncSetAttribute(k_bpr_main_tma<V, Opt, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_bpr_main_tma<V, Opt, false><<<blocks, 256, smem, s>>>(a, opt, S);
         }
+        granted = smem;
     } else if (pl.jsrc) {
         k_bpr_main<V, Opt, true><<<blocks, 256, 0, s>>>(a, opt);
     } else {
@@ -893,6 +1354,24 @@ static int table_phase_v(daisy_ctx *h, const StepPlan &pl, const float *P, const
         h->pool_used++;
     }
     phase_mark(h, PH_MAIN, s);
+    if (pl.small) {
+        const int blocksU = daisy_ceil_div(B, 8 * DAISY_SMALL_WIN), blocksQ = daisy_ceil_div(2 * B, 8 * DAISY_SMALL_WIN);
+        k_small_seg<V, Opt><<<blocksU + blocksQ + DAISY_SMALL_SLICE_BLOCKS + (loss_accum ? 1 : 0), 256, 0, s>>>(
+            P, Q, k.ukey_s, k.qkey_s, B, h->stageU, h->stageQ, h->stage2, D4, opt, blocksU, blocksQ, k.longs, h->longs_cap,
+            h->small_ticket, h->loss_part, warps, loss_accum);
+        DAISY_LAUNCH_CHECK(h);
+        for (int ph = PH_SEG_U; ph <= PH_LOSS; ++ph) phase_mark(h, ph, s);
+        if (pl.piped) DAISY_CUDA(cudaEventRecord(k.freed, s));
+        if (h->trace && h->tr_n < DAISY_TRACE_STEPS) {
+            cudaEventRecord(h->tr_ev[4 * h->tr_n + 3], s);
+            h->tr_n++;
+        }
+        if (h->timing == 2) {
+            h->ev_pending = 1;
+            h->ev_stream = s;
+        }
+        return DAISY_OK;
+    }
     // segmented reduces
     k_seg_reduce<V, Opt><<<daisy_ceil_div(daisy_ceil_div(B, 32), 8), 256, 0, s>>>(
         0, P, k.ukey_s, B, 0xFFFFFFFFu, h->stageU, D4, opt, h->heavy_len, h->heavy, h->heavy_cap);
