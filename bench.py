@@ -315,7 +315,8 @@ def run_single(args):
                               if args.workload == "config4" else
                               "tables (85 MB) fit the 126 MB L2: L2-resident workload, the HBM roofline does not bound it"),
                        "l2_access_policy_window": bool(args.l2_window),
-                       "lazy_decay_materialized_in_timed_region": True,
+                       "lazy_decay_materialized_in_timed_region": ("once, after the last timed step (as at an epoch end)" if not mat_every
+                                                                   else f"every {mat_every} steps and after the last timed step"),
                        "api": ("BPRSGD.epoch -> daisy_bpr_epoch: ONE library call runs the K timed steps"
                                if args.epoch_api else "BPRSGD.step -> daisy_bpr_step[_host]: one library call per step"),
                        "e2e_loss_readback": ("async D2H of the call's accumulated loss, once per daisy_bpr_epoch call"
@@ -337,6 +338,75 @@ def run_single(args):
         line["phase_ms"] = {k: round(v, 4) for k, v in phases.items()}
     if trace:
         line["trace_ms(book_begin,book_end,kernels_begin,kernels_end)"] = trace
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# config 1: ml-100k, 20 epochs + HR@10 / NDCG@10 (secondary line: the reference's own CPU-runnable case)
+# ------------------------------------------------------------------------------------------------
+def run_config1(args):
+    """BPRMFRecommender.fit on the real ml-100k split (tests/golden/ml100k_split.npz: loo-by-time, 99 057 train
+    pairs x num_ng 4 = 396 228 triples per epoch, B 4 096, D 64, lr 0.01, wd 0.001), 20 epochs, HR@10 / NDCG@10 on
+    1 + 999 candidates per user.  value = training triples/s over the epochs' step loops (daisy_bpr_epoch: H2D of
+    the epoch's triples + 97 steps + loss read-back; sampling and evaluation are timed separately).  The CPU line
+    beside it is the reference's loop restated (TorchPort == BPRMFRecommender.py:172-176) on the same triples."""
+    import torch
+    from recommend_lib_b200 import data
+    from recommend_lib_b200.bpr import BPRMFRecommender
+    from recommend_lib_b200.sampler import TripleSampler
+    s = np.load(os.path.join(ROOT, "tests", "golden", "ml100k_split.npz"))
+    tr, te = s["train_pairs"].astype(np.int64), s["test_pairs"].astype(np.int64)
+    U, I = int(s["user_num"]), int(s["item_num"])
+    allp = np.concatenate([tr, te])
+    eu, ec = data.eval_candidates(allp[:, 0], allp[:, 1], te[:, 0], te[:, 1], I, 999, 2019)
+    epochs = 20
+    clocks = ClockSampler(0)
+    rec = BPRMFRecommender(U, I, factor_num=64, lr=0.01, wd=0.001, batch_size=4096, epochs=2, num_ng=4, topk=10,
+                           seed=2019, device="cuda:0")
+    rec.fit(tr)                                            # warm-up: 2 epochs on a throw-away model
+    rec = BPRMFRecommender(U, I, factor_num=64, lr=0.01, wd=0.001, batch_size=4096, epochs=epochs, num_ng=4, topk=10,
+                           seed=2019, device="cuda:0")
+    h0 = rec.model.handle(4096).launches
+    clocks.start()
+    t0 = time.time()
+    rec.fit(tr, eu, ec)
+    wall = time.time() - t0
+    clocks.stop()
+    launches = rec.model.handle(4096).launches - h0
+    n = len(tr) * 4
+    train_s = sum(e["train_s"] for e in rec.history)
+    steps = epochs * ((n + 4095) // 4096)
+    # CPU: one epoch of the reference's loop on the same triples
+    from oracle.bpr_oracle import TorchPort
+    torch.manual_seed(2019)
+    cores = os.cpu_count() or 1
+    P0 = torch.empty((U, 64)).normal_(0, 0.01)
+    Q0 = torch.empty((I, 64)).normal_(0, 0.01)
+    port = TorchPort(P0, Q0, 0.01, 0.001, threads=cores)
+    tri = TripleSampler(tr, I, num_ng=4, seed=2019).sample_epoch(0)
+    t0 = time.time()
+    for b in range(0, len(tri), 4096):
+        port.step(tri[b:b + 4096])
+    cpu_dt = time.time() - t0
+    last = rec.history[-1]
+    line = {"metric": METRIC, "value": n * epochs / train_s, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": 2 * 97,
+            "ms_per_step": 1e3 * train_s / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "ml-100k (tests/golden/ml100k_split.npz)",
+            "config": {"workload": "BPR-MF on ml-100k (943 users x 1682 items, dim 64, fp32), 20 epochs + HR@10/NDCG@10 "
+                                   "(BASELINE.json configs[0])", "user_num": U, "item_num": I, "dim": 64, "batch": 4096,
+                       "lr": 0.01, "wd": 0.001, "num_ng": 4, "epochs": epochs, "triples_per_epoch": n,
+                       "timing": "host wall clock around each epoch's daisy_bpr_epoch call + loss read-back "
+                                 "(synchronised); latency-bound (0.67 MB of tables), no roofline",
+                       "l2": "tables are L2-resident"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": n * epochs / wall, "unit": UNIT, "h2d_bytes_per_step": 4096 * 12, "d2h_bytes_per_step": 8 / 97,
+                    "note": "whole fit(): host negative sampling + training + per-epoch metric_eval"},
+            "gpu_launches": int(launches),
+            "roofline": None,
+            "cpu_baseline": {"value": n / cpu_dt, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "one epoch (97 steps of 4 096 triples) of the reference loop, same triples"},
+            "final": {"loss": last["loss"], "hr@10": last["hr"], "ndcg@10": last["ndcg"]},
+            "sample_s_per_epoch": float(np.mean([e["sample_s"] for e in rec.history]))}
     print(json.dumps(line), flush=True)
 
 
@@ -522,11 +592,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="debug only: scale the table sizes")
     ap.add_argument("--batch", type=int, default=0, help="debug only: override the batch size")
-    ap.add_argument("--materialize-every", type=int, default=50)
+    ap.add_argument("--materialize-every", type=int, default=0,
+                    help="also fold the lazy L2 scale into the tables every N steps (0: only once, at the end of the "
+                         "timed region -- what an epoch end does; the library itself only needs it when c < 1e-4)")
     ap.add_argument("--phases", action="store_true", help="also print the per-phase breakdown of the step")
     ap.add_argument("--trace", action="store_true", help="also print a timeline of bookkeeping vs table kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="config4", choices=["config4", "config3", "config2", "sampler", "eval"],
+    ap.add_argument("--workload", default="config4", choices=["config4", "config3", "config2", "config1", "sampler", "eval"],
                     help="N = 1 only: config4 is the driver's metric; config3 (L2-resident ml-20m shape) and config2 "
                          "(funk-SVD) are secondary lines kept under profiles/")
     ap.add_argument("--eval-users", type=int, default=16384)
@@ -546,6 +618,8 @@ def main():
     if args.gpus > 1 or world > 1:
         from recommend_lib_b200.sharded import bench_sharded
         return bench_sharded(args, CFG5, METRIC, UNIT)
+    if args.workload == "config1":
+        return run_config1(args)
     if args.workload == "config2":
         return run_mf(args)
     if args.workload == "sampler":

@@ -97,6 +97,7 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
     {   // small-batch path: rows with more than 16 (DAISY_SMALL_SLICE, step_kernels.cuh) contributions, slices of 16
         const int64_t sb = max_batch < DAISY_SMALL_CAP ? max_batch : DAISY_SMALL_CAP;
         h->longs_cap = (int)(3 * sb / 16) + 4;
+        if (h->longs_cap < h->heavy_cap) h->longs_cap = h->heavy_cap;  // the general path lists rows longer than heavy_len
         h->slice_cap = (int)(3 * max_batch / DAISY_SLICE) + h->heavy_cap + 4;
         if (h->slice_cap < 2 * h->longs_cap) h->slice_cap = 2 * h->longs_cap;
     }
@@ -129,7 +130,7 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
         A(stage2, (size_t)h->slice_cap * dim);
         A(loss_part, B);
         A(heavy, 2 + 5 * (size_t)h->heavy_cap);
-        A(small_ticket, (size_t)h->longs_cap);
+        A(ticket, (size_t)h->longs_cap);
     }
 #undef A
     if (!rc && B > 0) {
@@ -151,7 +152,7 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
         if (B > 0) {
             for (int i = 0; i < 2; ++i) cudaMemset(h->book[i].islot, 0xFF, B * sizeof(uint32_t));
             cudaMemset(h->heavy, 0, 2 * sizeof(uint32_t));
-            cudaMemset(h->small_ticket, 0, (size_t)h->longs_cap * sizeof(uint32_t));
+            cudaMemset(h->ticket, 0, (size_t)h->longs_cap * sizeof(uint32_t));
         }
         k_err_reset<<<1, 1>>>(h->err);
         for (int i = 0; i <= PH_COUNT; ++i) cudaEventCreate(&h->ev[i]);
@@ -185,7 +186,7 @@ extern "C" int daisy_destroy(daisy_handle_t h) {
     daisy_shard_free(h);
     void *ptrs[] = {h->triples, h->key_in, h->val_in, h->val_out, h->ukey_in, h->uval_in, h->uval_out, h->ikey_in,
                     h->ikey_out, h->ival_in, h->ival_out, h->stageU, h->stageQ, h->stage2, h->loss_part, h->heavy,
-                    h->err, h->cub_tmp, h->small_ticket, h->scores, h->sel_hist, h->own_key, h->own_key_s, h->own_val, h->own_val_s,
+                    h->err, h->cub_tmp, h->ticket, h->scores, h->sel_hist, h->own_key, h->own_key_s, h->own_val, h->own_val_s,
                     h->own_tmp};
     for (void *p : ptrs)
         if (p) cudaFree(p);

@@ -36,8 +36,8 @@ struct BookSet {
     int32_t *st;                    // [maxB,3]  triples in positive-item order
     uint32_t *ukey_s, *qkey_s;      // [maxB], [2*maxB]  sorted user / item ref keys (rows)
     uint32_t *uslot, *jslot, *islot;  // [maxB]  per sorted triple: DAISY_DIRECT or staging slot
-    uint32_t *longs;                // small-batch path: [0] = #rows longer than DAISY_SLICE, [1] = #slices, then 5 words
-                                    // per row (table, row, first sorted position, length, first slice), like `heavy`
+    uint32_t *longs;                // rows too long for one warp (k_seg_all): [0] = #rows, [1] = #slices, then 5 words per
+                                    // row (table, row, first sorted position, length, first slice), like `heavy`
     cudaEvent_t ready, freed;
 };
 
@@ -118,7 +118,7 @@ struct daisy_ctx {
     float *loss_part;       // [maxB] per-warp loss partials
     uint32_t *heavy;        // [0] = #hot rows, [1] = #slices, then 5 words per hot row: table, row, first pos, len, first slice
     int heavy_cap, slice_cap, longs_cap;
-    uint32_t *small_ticket; // [longs_cap] finished-slice counters of the small-batch path's long rows (zero between steps)
+    uint32_t *ticket;       // [longs_cap] finished-slice counters of k_seg_all's long rows (zero between steps)
     int *err;               // [2]: flag, first bad position
     int *err_host;          // pinned mirror
     // sharded step: row count of the fetched-row cache standing in for the item table (0 = use I)

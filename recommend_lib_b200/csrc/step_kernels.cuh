@@ -73,18 +73,23 @@ __global__ void k_refs(const int32_t *__restrict__ triples, const uint32_t *__re
 // ------------------------------------------------------------------------------------------------
 // slots: DIRECT (single contribution in the batch) or staging slot = sorted position
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void list_long_row(const uint32_t *__restrict__ keys, int n, int p, uint32_t row, int tbl,
+                                              int long_len, int slice, uint32_t *longs, int longs_cap);
+
 __global__ void k_slots_user(const uint32_t *__restrict__ key, const uint32_t *__restrict__ val, int n,
-                             uint32_t *__restrict__ uslot) {
+                             uint32_t *__restrict__ uslot, uint32_t *longs, int longs_cap, int long_len) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const uint32_t r = key[p];
     const bool first = (p == 0) || (key[p - 1] != r);
     const bool last = (p == n - 1) || (key[p + 1] != r);
     uslot[val[p]] = (first && last) ? DAISY_DIRECT : (uint32_t)p;
+    if (first && longs) list_long_row(key, n, p, r, 0, long_len, DAISY_SLICE, longs, longs_cap);
 }
 
 __global__ void k_slots_item(const uint32_t *__restrict__ key, const uint32_t *__restrict__ val, int n, int B,
-                             uint32_t sentinel, uint32_t *__restrict__ jslot, uint32_t *__restrict__ islot) {
+                             uint32_t sentinel, uint32_t *__restrict__ jslot, uint32_t *__restrict__ islot,
+                             uint32_t *longs, int longs_cap, int long_len) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const uint32_t r = key[p];
@@ -97,6 +102,7 @@ __global__ void k_slots_item(const uint32_t *__restrict__ key, const uint32_t *_
         jslot[v] = slot;
     else
         islot[v - B] = slot;
+    if (first && longs) list_long_row(key, n, p, r, 1, long_len, DAISY_SLICE, longs, longs_cap);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -665,7 +671,7 @@ __global__ void __launch_bounds__(1024) k_loss(const float *__restrict__ part, i
 //                  are DIRECT, every other ref is staged at its sorted position -- the contract of the general path,
 //                  without the positive-item runs (every triple heads its own run: C = 1).
 //   k_bpr_main     the general main kernel with C = 1 (one warp per triple)
-//   k_small_seg    segmented reduces of both tables in one launch (no two-level hot-row path: at most 16 384
+//   k_seg_all      segmented reduces of both tables + hot-row slices + loss in one launch (at most 16 384
 //                  contributions exist) + the loss reduction
 //
 // The accumulation order of a row is its sorted-ref order, fixed by the sort => bit-reproducible.  It differs from
@@ -783,8 +789,8 @@ __device__ __forceinline__ void block_sort_words(uint32_t (&keys)[IPT], int ipt,
 }
 
 #define DAISY_SMALL_HIST_WORDS (32 * 513)
-#define DAISY_SMALL_WIN 8       // sorted refs per warp of k_small_seg
-#define DAISY_SMALL_SLICE 16   // contributions per slice of a long row (k_small_seg): short, so that a hot row's
+#define DAISY_SMALL_WIN 8       // sorted refs per warp of k_seg_all
+#define DAISY_SMALL_SLICE 16   // contributions per slice of a long row (k_seg_all): short, so that a hot row's
                                // sum is spread over many warps on many SMs and is not a latency chain
 #define DAISY_SMALL_CB 3        // k_small_book: rows are split over 2^CB blocks per table by their low CB bits
 // Grid: 2 << CB blocks; block b < 2^CB handles the user refs whose row has low bits b, the others the item refs
@@ -909,7 +915,7 @@ __global__ void __launch_bounds__(1024) k_small_book(const int32_t *__restrict__
         if (first && p + DAISY_SMALL_SLICE < n_c && (sk[p + DAISY_SMALL_SLICE] >> vb) == row) {
             // a row with more than DAISY_SMALL_SLICE contributions: too much for one warp (and for the L2 port of one SM).
             // List it -- (table, row, first sorted position, length, first slice) like the general path's heavy
-            // list -- for the slice blocks of k_small_seg.
+            // list -- for the slice blocks of k_seg_all.
             uint32_t lo = p + DAISY_SMALL_SLICE, hi = n_c - 1;
             while (lo < hi) {
                 const uint32_t mid = (lo + hi + 1) >> 1;
@@ -954,36 +960,31 @@ static int launch_small_book(daisy_ctx *h, cudaStream_t bs, const int32_t *tripl
     return DAISY_OK;
 }
 
-#define DAISY_SMALL_SLICE_BLOCKS 64  // blocks of k_small_seg that sum the slices of long rows
-template <int V, class Opt>
-__global__ void __launch_bounds__(256) k_small_seg(const float *__restrict__ P, const float *__restrict__ Q,
-                                                    const uint32_t *__restrict__ ukey_s,
-                                                    const uint32_t *__restrict__ qkey_s, int B,
-                                                    const float *__restrict__ stageU, const float *__restrict__ stageQ,
-                                                    float *__restrict__ stage2, int D4, Opt opt, int blocksU, int blocksQ,
-                                                    const uint32_t *__restrict__ longs, int longs_cap, uint32_t *ticket,
-                                                    const float *__restrict__ loss_part, int n_part,
-                                                    double *loss_accum) {
-    // Blocks [0, blocksU + blocksQ): 8 windows of DAISY_SMALL_WIN sorted refs each; a warp reduces the rows of up to
-    // DAISY_SMALL_SLICE contributions that start in its window.
-    // The next DAISY_SMALL_SLICE_BLOCKS blocks: the rows k_small_book listed as longer than that.  One SM draws
-    // ~40 B/clk from L2 however many loads it has in flight (tools/small_book_probe.cu), so a hot row's staged
-    // contributions (195 KB for the top item of a 4 096-triple Zipf batch) are spread over the SMs slice by slice:
-    // a warp sums one slice of DAISY_SMALL_SLICE contributions into stage2, takes a ticket of its row, and the warp that
-    // draws the last ticket adds the slice sums in slice order and updates the row -- the order of the sum is fixed
-    // by the slice numbers, not by who arrives when.
-    // The last block: the loss reduction.
+// ------------------------------------------------------------------------------------------------
+// Every row with several contributions, both tables, ONE launch (small-batch path and single-GPU general path; the
+// row-sharded step keeps k_seg_reduce / k_heavy_*, whose rows are finished by PushOpt over NVLink).
+//   blocks [0, NS)                  slice blocks: the rows the bookkeeping listed as longer than `long_len`.  One SM
+//        draws ~40 B/clk from L2 however many loads it has in flight (tools/small_book_probe.cu), so a hot row's
+//        staged contributions are spread over the SMs slice by slice: a warp sums one slice of SLICE contributions
+//        into stage2, takes a ticket of its row, and the warp that draws the row's last ticket adds the slice sums
+//        IN SLICE ORDER and updates the row -- the order of the sum is fixed by the slice numbers, not by who
+//        arrives when.  They come first in the grid so that they run under the window blocks, not after them.
+//   blocks [NS, NS + blocksU + blocksQ)   8 windows of WIN sorted refs each; a warp reduces the rows of up to
+//        `long_len` contributions that start in its window
+//   the last block                  the loss reduction
+// ------------------------------------------------------------------------------------------------
+template <int V, class Opt, int WIN, int SLICE>
+__global__ void __launch_bounds__(256) k_seg_all(const float *__restrict__ P, const float *__restrict__ Q,
+                                                  const uint32_t *__restrict__ ukey_s,
+                                                  const uint32_t *__restrict__ qkey_s, int B, uint32_t q_sentinel,
+                                                  const float *__restrict__ stageU, const float *__restrict__ stageQ,
+                                                  float *__restrict__ stage2, int D4, Opt opt, int NS, int blocksU,
+                                                  int blocksQ, int long_len, const uint32_t *__restrict__ longs,
+                                                  int longs_cap, uint32_t *ticket, const float *__restrict__ loss_part,
+                                                  int n_part, double *loss_accum) {
     const int b = blockIdx.x, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-    const int nwin = blocksU + blocksQ;
-    if (b < nwin) {
-        const int tbl = b < blocksU ? 0 : 1;
-        seg_window<V, Opt, DAISY_SMALL_WIN>((long long)(tbl ? b - blocksU : b) * 8 + wid, tbl, tbl ? Q : P,
-                                            tbl ? qkey_s : ukey_s, tbl ? 2 * B : B, 0xFFFFFFFFu, tbl ? stageQ : stageU, D4,
-                                            opt, DAISY_SMALL_SLICE, nullptr, 0);
-        return;
-    }
-    if (b >= nwin + DAISY_SMALL_SLICE_BLOCKS) {  // fixed-order reduction of the per-warp loss partials (cf. k_loss)
+    if (b >= NS + blocksU + blocksQ) {  // fixed-order reduction of the per-warp loss partials (cf. k_loss)
         if (!loss_accum) return;
         __shared__ double sh[8];
         double s = 0.0;
@@ -998,37 +999,44 @@ __global__ void __launch_bounds__(256) k_small_seg(const float *__restrict__ P, 
         }
         return;
     }
+    if (b >= NS) {
+        const int wb = b - NS;
+        const int tbl = wb < blocksU ? 0 : 1;
+        seg_window<V, Opt, WIN>((long long)(tbl ? wb - blocksU : wb) * 8 + wid, tbl, tbl ? Q : P, tbl ? qkey_s : ukey_s,
+                                tbl ? 2 * B : B, tbl ? q_sentinel : 0xFFFFFFFFu, tbl ? stageQ : stageU, D4, opt, long_len,
+                                nullptr, 0);
+        return;
+    }
     const int count = min((int)longs[0], longs_cap);
     if (count == 0) return;
     const int total = (int)longs[1];
     bool act[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
-    // consecutive slices go to different blocks (SMs): slice s is taken by warp (s / BLOCKS) % 8 of block s % BLOCKS
-    for (int s = (b - nwin) + DAISY_SMALL_SLICE_BLOCKS * wid; s < total; s += DAISY_SMALL_SLICE_BLOCKS * 8) {
+    // consecutive slices go to different blocks (SMs): slice s is taken by warp (s / NS) % 8 of block s % NS
+    for (int s = b + NS * wid; s < total; s += NS * 8) {
         int r = -1;
         for (int r0 = 0; r0 < count && r < 0; r0 += 32) {  // the row this slice belongs to
             bool hit = false;
             if (r0 + lane < count) {
                 const uint32_t *rec = longs + 2 + 5 * (size_t)(r0 + lane);
-                const int sl0 = (int)rec[4], nsl = (int)((rec[3] + DAISY_SMALL_SLICE - 1) / DAISY_SMALL_SLICE);
+                const int sl0 = (int)rec[4], nsl = (int)((rec[3] + SLICE - 1) / SLICE);
                 hit = s >= sl0 && s < sl0 + nsl;
             }
             const unsigned m = __ballot_sync(FULL, hit);
             if (m) r = r0 + __ffs(m) - 1;
         }
-        if (r < 0) continue;  // a record beyond longs_cap was dropped (cannot happen: the cap covers 3B / DAISY_SMALL_SLICE rows)
+        if (r < 0) continue;  // a record beyond longs_cap was dropped (cannot happen: the cap covers 3B / long_len rows)
         const uint32_t *rec = longs + 2 + 5 * (size_t)r;
         const int tbl = (int)rec[0];
         const uint32_t row = rec[1];
         const size_t q0 = rec[2];
         const int len = (int)rec[3], sl0 = (int)rec[4];
-        const int nsl = (len + DAISY_SMALL_SLICE - 1) / DAISY_SMALL_SLICE, j = s - sl0;
+        const int nsl = (len + SLICE - 1) / SLICE, j = s - sl0;
         float4 acc[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) acc[v] = f4_zero();
-        sum_staged<V>(tbl ? stageQ : stageU, q0 + (size_t)j * DAISY_SMALL_SLICE, min(DAISY_SMALL_SLICE, len - j * DAISY_SMALL_SLICE), D4,
-                      lane, act, acc);
+        sum_staged<V>(tbl ? stageQ : stageU, q0 + (size_t)j * SLICE, min(SLICE, len - j * SLICE), D4, lane, act, acc);
 #pragma unroll
         for (int v = 0; v < V; ++v)
             if (act[v]) __stcg(reinterpret_cast<float4 *>(stage2) + (size_t)s * D4 + lane + 32 * v, acc[v]);
@@ -1042,16 +1050,55 @@ __global__ void __launch_bounds__(256) k_small_seg(const float *__restrict__ P, 
         __threadfence();
         if (lane == 0) ticket[r] = 0;  // ready for the next step
         const float *table = tbl ? Q : P;
+        const float4 *s2 = reinterpret_cast<const float4 *>(stage2) + (size_t)sl0 * D4;
+        float4 tot[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) tot[v] = f4_zero();
+        for (int j0 = 0; j0 < nsl; j0 += 8) {  // fixed order: slice 0, 1, 2, ... (8 loads in flight)
+            float4 rr[8][V];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+                for (int v = 0; v < V; ++v)
+                    rr[jj][v] = (j0 + jj < nsl && act[v]) ? __ldcg(s2 + (size_t)(j0 + jj) * D4 + lane + 32 * v) : f4_zero();
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+                if (j0 + jj < nsl) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) tot[v] = f4_add(tot[v], rr[jj][v]);
+                }
+        }
 #pragma unroll
         for (int v = 0; v < V; ++v)
             if (act[v]) {
                 const int e = lane + 32 * v;
-                float4 tot = __ldcg(reinterpret_cast<const float4 *>(stage2) + (size_t)sl0 * D4 + e);
-                for (int jj = 1; jj < nsl; ++jj)  // fixed order: slice 0, 1, 2, ...
-                    tot = f4_add(tot, __ldcg(reinterpret_cast<const float4 *>(stage2) + (size_t)(sl0 + jj) * D4 + e));
                 const float4 old = (tbl == 0 || Opt::kNeedOldItem) ? ld_row(table, (size_t)row * D4 + e) : f4_zero();
-                opt.apply(tbl, (size_t)row, e, old, tot);
+                opt.apply(tbl, (size_t)row, e, old, tot[v]);
             }
+    }
+}
+
+// General path: list the rows with more than `long_len` contributions while the slots are assigned (bookkeeping
+// stream), so that k_seg_all's slice blocks can start on them at once.  Called by the thread at a row's FIRST sorted
+// position p; keys[p .. ] == row.
+__device__ __forceinline__ void list_long_row(const uint32_t *__restrict__ keys, int n, int p, uint32_t row, int tbl,
+                                              int long_len, int slice, uint32_t *longs, int longs_cap) {
+    if (p + long_len >= n || keys[p + long_len] != row) return;
+    int lo = p + long_len, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (int)(((long long)lo + hi + 1) >> 1);
+        if (keys[mid] == row) lo = mid; else hi = mid - 1;
+    }
+    const uint32_t len = (uint32_t)(lo - p + 1);
+    const uint32_t r = atomicAdd(&longs[0], 1u);
+    const uint32_t sl0 = atomicAdd(&longs[1], (len + slice - 1) / slice);
+    if ((int)r < longs_cap) {
+        uint32_t *rec = longs + 2 + 5 * (size_t)r;
+        rec[0] = (uint32_t)tbl;
+        rec[1] = row;
+        rec[2] = (uint32_t)p;
+        rec[3] = len;
+        rec[4] = sl0;
     }
 }
 
@@ -1164,7 +1211,7 @@ struct StepPlan {
     BookSet *k;
     int set;              // index of k in h->book
     const float *const *jsrc, *const *isrc;  // row-sharded step only (else null)
-    bool small;           // small-batch path: k_small_book / C = 1 / k_small_seg
+    bool small;           // small-batch path: k_small_book / C = 1 / k_seg_all
 };
 
 // Does a batch of B triples take the small-batch path?  Its refs must pack into 32 bits: row bits (of the VALUE U
@@ -1271,10 +1318,14 @@ static int book_phase(daisy_ctx *h, StepPlan &pl, const int32_t *triples, int64_
     h->launches += 4;
     phase_mark(h, PH_SORT_Q, s);
     // slots
-    k_slots_user<<<daisy_ceil_div(B, T), T, 0, bs>>>(k.ukey_s, h->uval_out, B, k.uslot);
+    // single GPU: the rows too long for one warp are listed here for k_seg_all (the sharded step finds them itself)
+    uint32_t *longs = sh ? nullptr : k.longs;
+    if (longs) DAISY_CUDA(cudaMemsetAsync(longs, 0, 2 * sizeof(uint32_t), bs));
+    k_slots_user<<<daisy_ceil_div(B, T), T, 0, bs>>>(k.ukey_s, h->uval_out, B, k.uslot, longs, h->longs_cap, h->heavy_len);
     DAISY_LAUNCH_CHECK(h);
     if (!sh) {
-        k_slots_item<<<daisy_ceil_div(2 * (int64_t)B, T), T, 0, bs>>>(k.qkey_s, h->val_out, 2 * B, B, I, k.jslot, k.islot);
+        k_slots_item<<<daisy_ceil_div(2 * (int64_t)B, T), T, 0, bs>>>(k.qkey_s, h->val_out, 2 * B, B, I, k.jslot, k.islot,
+                                                                      longs, h->longs_cap, h->heavy_len);
         DAISY_LAUNCH_CHECK(h);
     } else {
         const ShardSet &ss = sh->set[pl.set];
@@ -1313,7 +1364,7 @@ static int table_phase_v(daisy_ctx *h, const StepPlan &pl, const float *P, const
     const int D4 = h->D / 4;
     cudaStream_t s = pl.s;
     BookSet &k = *pl.k;
-    if (!pl.small) DAISY_CUDA(cudaMemsetAsync(h->heavy, 0, 2 * sizeof(uint32_t), s));
+    if (pl.jsrc) DAISY_CUDA(cudaMemsetAsync(h->heavy, 0, 2 * sizeof(uint32_t), s));
     MainArgs a;
     a.P = P; a.Q = Q; a.st = k.st; a.uslot = k.uslot; a.jslot = k.jslot; a.islot = k.islot;
     a.stageU = h->stageU; a.stageQ = h->stageQ; a.loss_part = h->loss_part;
@@ -1354,11 +1405,20 @@ static int table_phase_v(daisy_ctx *h, const StepPlan &pl, const float *P, const
         h->pool_used++;
     }
     phase_mark(h, PH_MAIN, s);
-    if (pl.small) {
-        const int blocksU = daisy_ceil_div(B, 8 * DAISY_SMALL_WIN), blocksQ = daisy_ceil_div(2 * B, 8 * DAISY_SMALL_WIN);
-        k_small_seg<V, Opt><<<blocksU + blocksQ + DAISY_SMALL_SLICE_BLOCKS + (loss_accum ? 1 : 0), 256, 0, s>>>(
-            P, Q, k.ukey_s, k.qkey_s, B, h->stageU, h->stageQ, h->stage2, D4, opt, blocksU, blocksQ, k.longs, h->longs_cap,
-            h->small_ticket, h->loss_part, warps, loss_accum);
+    if (!pl.jsrc) {  // single GPU: every multi-contribution row of both tables + the loss in one launch
+        const int NS = pl.small ? 64 : 2 * h->num_sms;
+        int blocksU, blocksQ;
+        if (pl.small) {
+            blocksU = daisy_ceil_div(B, 8 * DAISY_SMALL_WIN), blocksQ = daisy_ceil_div(2 * B, 8 * DAISY_SMALL_WIN);
+            k_seg_all<V, Opt, DAISY_SMALL_WIN, DAISY_SMALL_SLICE><<<NS + blocksU + blocksQ + (loss_accum ? 1 : 0), 256, 0, s>>>(
+                P, Q, k.ukey_s, k.qkey_s, B, 0xFFFFFFFFu, h->stageU, h->stageQ, h->stage2, D4, opt, NS, blocksU, blocksQ,
+                DAISY_SMALL_SLICE, k.longs, h->longs_cap, h->ticket, h->loss_part, warps, loss_accum);
+        } else {
+            blocksU = daisy_ceil_div(B, 8 * 32), blocksQ = daisy_ceil_div(2 * (int64_t)B, 8 * 32);
+            k_seg_all<V, Opt, 32, DAISY_SLICE><<<NS + blocksU + blocksQ + (loss_accum ? 1 : 0), 256, 0, s>>>(
+                P, Q, k.ukey_s, k.qkey_s, B, pl.I, h->stageU, h->stageQ, h->stage2, D4, opt, NS, blocksU, blocksQ,
+                h->heavy_len, k.longs, h->longs_cap, h->ticket, h->loss_part, warps, loss_accum);
+        }
         DAISY_LAUNCH_CHECK(h);
         for (int ph = PH_SEG_U; ph <= PH_LOSS; ++ph) phase_mark(h, ph, s);
         if (pl.piped) DAISY_CUDA(cudaEventRecord(k.freed, s));

@@ -61,7 +61,7 @@ struct ProbeOpt {  // the SGD functor of bpr_step.cu
     }
 };
 
-// the whole small-batch step (book, main, seg) on Zipf(1.0) positives, with per-block clocks of k_small_seg
+// the whole small-batch step (book, main, seg) on Zipf(1.0) positives, with per-block clocks of k_seg_all
 static void run_step(int B, uint32_t U, uint32_t I, int D) {
     std::vector<int32_t> t(3 * (size_t)B);
     uint32_t r = 777;
@@ -97,7 +97,7 @@ static void run_step(int B, uint32_t U, uint32_t I, int D) {
         cudaEventRecord(e[1]);
         k_bpr_main<1, ProbeOpt, false><<<daisy_ceil_div(B, 8), 256>>>(a, opt);
         cudaEventRecord(e[2]);
-        k_small_seg<1, ProbeOpt><<<blocksU + blocksQ + DAISY_SMALL_SLICE_BLOCKS + 1, 256>>>(P, Q, uk, qk, B, sU, sQ, st2, D / 4, opt, blocksU, blocksQ, longs, 4000, ticket, lp, B, loss);
+        k_seg_all<1, ProbeOpt, DAISY_SMALL_WIN, DAISY_SMALL_SLICE><<<64 + blocksU + blocksQ + 1, 256>>>(P, Q, uk, qk, B, 0xFFFFFFFFu, sU, sQ, st2, D / 4, opt, 64, blocksU, blocksQ, DAISY_SMALL_SLICE, longs, 4000, ticket, lp, B, loss);
         cudaEventRecord(e[3]);
         CK(cudaDeviceSynchronize());
         for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&ms[k], e[k], e[k + 1]);
