@@ -106,6 +106,8 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
     if (h->main_stages < 0) h->main_stages = 0;
     if (h->main_stages > 16) h->main_stages = 16;
     h->inputs_ready = 0;
+    h->graph_max_b = env_int("DAISY_GRAPH_MAX_B", 262144);
+    if (h->graph_max_b < 0) h->graph_max_b = 0;
     h->small_max = env_int("DAISY_SMALL_MAX", DAISY_SMALL_CAP);
     if (h->small_max < 0) h->small_max = 0;
     if (h->small_max > DAISY_SMALL_CAP) h->small_max = DAISY_SMALL_CAP;
@@ -198,6 +200,8 @@ extern "C" int daisy_destroy(daisy_handle_t h) {
         if (h->book[i].ready) cudaEventDestroy(h->book[i].ready);
         if (h->book[i].freed) cudaEventDestroy(h->book[i].freed);
     }
+    for (int i = 0; i < DAISY_MAX_BGRAPH; ++i)
+        if (h->bgraph[i].exec) cudaGraphExecDestroy(h->bgraph[i].exec);
     if (h->err_host) cudaFreeHost(h->err_host);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_call) cudaEventDestroy(h->ev_call);

@@ -87,6 +87,14 @@ struct daisy_shard {
     int64_t psteps;
 };
 
+// A captured bookkeeping chain (step_kernels.cuh: book_phase) of one bookkeeping set at one batch size.
+struct BookGraph {
+    cudaGraphExec_t exec;
+    int set, B, launches;
+    uint32_t U, I;
+};
+#define DAISY_MAX_BGRAPH 6
+
 struct daisy_ctx {
     int device;
     int num_sms;
@@ -139,6 +147,11 @@ struct daisy_ctx {
     int heavy_len;   // segments longer than this go to the block-per-row kernel
     int main_stages; // > 0: TMA-pipelined main kernel with this many stages (triples in flight) per warp; 0: register prefetch
     int small_max;   // batches up to this many triples take the 3-launch small-batch path (0 = never; <= DAISY_SMALL_CAP)
+
+    // --- CUDA-graph replay of the general bookkeeping chain for mid-size batches ---
+    int64_t graph_max_b;     // batches up to this size replay a captured graph (0 = never; DAISY_GRAPH_MAX_B)
+    BookGraph bgraph[DAISY_MAX_BGRAPH];
+    int n_bgraph, bgraph_next;
 
     // --- instrumentation ---
     int64_t launches;

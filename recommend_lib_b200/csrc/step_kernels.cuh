@@ -1225,6 +1225,64 @@ static bool small_path(const daisy_ctx *h, int64_t B, uint32_t U, uint32_t I, in
     return *vbU + *kbU <= 32 && *vbQ + *kbQ <= 32;
 }
 
+// The kernels of the general bookkeeping chain (prep .. slots) on stream bs; phase marks go to the caller's stream.
+static int book_kernels(daisy_ctx *h, BookSet &k, const StepPlan &pl, const int32_t *triples, int B, uint32_t U, uint32_t I,
+                        int C, cudaStream_t bs, cudaStream_t s, const daisy_shard *sh) {
+    const int T = 256;
+    // prep
+    k_prep<<<daisy_ceil_div(B, T), T, 0, bs>>>(triples, B, U, I, h->ikey_in, h->ival_in, h->err);
+    DAISY_LAUNCH_CHECK(h);
+    phase_mark(h, PH_PREP, s);
+    // sort by positive item
+    size_t tmp = h->cub_tmp_bytes;
+    DAISY_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->ikey_in, h->ikey_out, h->ival_in, h->ival_out, B, 0,
+                                               bits_for(I - 1), bs));
+    h->launches += 4;
+    phase_mark(h, PH_SORT_I, s);
+    // refs
+    k_refs<<<daisy_ceil_div(B, T), T, 0, bs>>>(triples, h->ival_out, h->ikey_out, B, U, I, C, k.st, h->ukey_in,
+                                               h->uval_in, h->key_in, h->val_in, k.islot);
+    DAISY_LAUNCH_CHECK(h);
+    phase_mark(h, PH_REFS, s);
+    tmp = h->cub_tmp_bytes;
+    DAISY_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->ukey_in, k.ukey_s, h->uval_in, h->uval_out, B, 0,
+                                               bits_for(U - 1), bs));
+    h->launches += 4;
+    phase_mark(h, PH_SORT_U, s);
+    tmp = h->cub_tmp_bytes;
+    DAISY_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->key_in, k.qkey_s, h->val_in, h->val_out, 2 * B, 0,
+                                               bits_for(I), bs));
+    h->launches += 4;
+    phase_mark(h, PH_SORT_Q, s);
+    // slots
+    // single GPU: the rows too long for one warp are listed here for k_seg_all (the sharded step finds them itself)
+    uint32_t *longs = sh ? nullptr : k.longs;
+    if (longs) DAISY_CUDA(cudaMemsetAsync(longs, 0, 2 * sizeof(uint32_t), bs));
+    k_slots_user<<<daisy_ceil_div(B, T), T, 0, bs>>>(k.ukey_s, h->uval_out, B, k.uslot, longs, h->longs_cap, h->heavy_len);
+    DAISY_LAUNCH_CHECK(h);
+    if (!sh) {
+        k_slots_item<<<daisy_ceil_div(2 * (int64_t)B, T), T, 0, bs>>>(k.qkey_s, h->val_out, 2 * B, B, I, k.jslot, k.islot,
+                                                                      longs, h->longs_cap, h->heavy_len);
+        DAISY_LAUNCH_CHECK(h);
+    } else {
+        const ShardSet &ss = sh->set[pl.set];
+        auto flags = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), StartFlag{k.qkey_s, I});
+        tmp = h->cub_tmp_bytes;
+        DAISY_CUDA(cub::DeviceScan::InclusiveSum(h->cub_tmp, tmp, flags, sh->cidx, 2 * B, bs));
+        h->launches += 2;
+        k_slots_item_shard<<<daisy_ceil_div(2 * (int64_t)B, T), T, 0, bs>>>(
+            k.qkey_s, h->val_out, sh->cidx, 2 * B, B, I, (uint32_t)sh->i_per, sh->world, k.jslot, k.islot, k.st,
+            ss.uniq_gid, ss.owner_off, sh->peers, sh->cache, h->D, ss.jsrc, ss.isrc, ss.multi);
+        DAISY_LAUNCH_CHECK(h);
+        k_shard_finish<<<daisy_ceil_div(2 * (int64_t)B, T), T, 0, bs>>>(k.qkey_s, sh->cidx, 2 * B, I, ss.uniq_gid,
+                                                                         ss.owner_off, sh->world, (uint32_t)sh->i_per,
+                                                                         sh->rank, (size_t)sh->cap, h->D, sh->peers,
+                                                                         ss.src, ss.dst);
+        DAISY_LAUNCH_CHECK(h);
+    }
+    return DAISY_OK;
+}
+
 // The integer bookkeeping of a step (prep .. slots) depends on the triples only, never on the tables.  It runs on
 // the handle's side stream into one of two bookkeeping sets, so that for step n+1 it overlaps the bandwidth-bound
 // kernels of step n on the caller's stream.  Per-phase timing (mode 2) serialises everything on the caller's
@@ -1292,56 +1350,53 @@ static int book_phase(daisy_ctx *h, StepPlan &pl, const int32_t *triples, int64_
         }
         return DAISY_OK;
     }
-    // prep
-    k_prep<<<daisy_ceil_div(B, T), T, 0, bs>>>(triples, B, U, I, h->ikey_in, h->ival_in, h->err);
-    DAISY_LAUNCH_CHECK(h);
-    phase_mark(h, PH_PREP, s);
-    // sort by positive item
-    size_t tmp = h->cub_tmp_bytes;
-    DAISY_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->ikey_in, h->ikey_out, h->ival_in, h->ival_out, B, 0,
-                                               bits_for(I - 1), bs));
-    h->launches += 4;
-    phase_mark(h, PH_SORT_I, s);
-    // refs
-    k_refs<<<daisy_ceil_div(B, T), T, 0, bs>>>(triples, h->ival_out, h->ikey_out, B, U, I, C, k.st, h->ukey_in,
-                                               h->uval_in, h->key_in, h->val_in, k.islot);
-    DAISY_LAUNCH_CHECK(h);
-    phase_mark(h, PH_REFS, s);
-    tmp = h->cub_tmp_bytes;
-    DAISY_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->ukey_in, k.ukey_s, h->uval_in, h->uval_out, B, 0,
-                                               bits_for(U - 1), bs));
-    h->launches += 4;
-    phase_mark(h, PH_SORT_U, s);
-    tmp = h->cub_tmp_bytes;
-    DAISY_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->key_in, k.qkey_s, h->val_in, h->val_out, 2 * B, 0,
-                                               bits_for(I), bs));
-    h->launches += 4;
-    phase_mark(h, PH_SORT_Q, s);
-    // slots
-    // single GPU: the rows too long for one warp are listed here for k_seg_all (the sharded step finds them itself)
-    uint32_t *longs = sh ? nullptr : k.longs;
-    if (longs) DAISY_CUDA(cudaMemsetAsync(longs, 0, 2 * sizeof(uint32_t), bs));
-    k_slots_user<<<daisy_ceil_div(B, T), T, 0, bs>>>(k.ukey_s, h->uval_out, B, k.uslot, longs, h->longs_cap, h->heavy_len);
-    DAISY_LAUNCH_CHECK(h);
-    if (!sh) {
-        k_slots_item<<<daisy_ceil_div(2 * (int64_t)B, T), T, 0, bs>>>(k.qkey_s, h->val_out, 2 * B, B, I, k.jslot, k.islot,
-                                                                      longs, h->longs_cap, h->heavy_len);
-        DAISY_LAUNCH_CHECK(h);
+    // Mid-size batches are bound by what the HOST spends on these ~15 launches (three CUB dispatches among them:
+    // 0.16 ms per step against 0.1 ms of device time at 65 536 triples), so the single-GPU bookkeeping chain of a
+    // (set, batch size) is captured once into a CUDA graph and replayed: one launch.  Nothing in it varies from step
+    // to step -- it reads the set's landing buffer and writes the set's arrays.
+    const int32_t *landing = h->triples + (size_t)pl.set * 3 * (size_t)h->maxB;
+    const bool graphed = piped && !sh && !tr && B64 <= h->graph_max_b;
+    if (graphed && triples != landing) {  // device-resident triples: bring them to the fixed address the graph reads
+        DAISY_CUDA(cudaMemcpyAsync((void *)landing, triples, (size_t)B * 3 * sizeof(int32_t), cudaMemcpyDeviceToDevice, bs));
+        triples = landing;
+    }
+    if (graphed) {
+        BookGraph *g = nullptr;
+        for (int i = 0; i < h->n_bgraph; ++i)
+            if (h->bgraph[i].set == pl.set && h->bgraph[i].B == B && h->bgraph[i].U == U && h->bgraph[i].I == I) g = &h->bgraph[i];
+        if (!g) {
+            const int64_t l0 = h->launches;
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            bool ok = cudaStreamBeginCapture(bs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                const int rc = book_kernels(h, k, pl, triples, B, U, I, C, bs, s, sh);
+                ok = (cudaStreamEndCapture(bs, &graph) == cudaSuccess) && rc == DAISY_OK && graph != nullptr;
+                if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+                if (graph) cudaGraphDestroy(graph);
+            }
+            if (ok) {
+                int slot = h->n_bgraph < DAISY_MAX_BGRAPH ? h->n_bgraph++ : (h->bgraph_next++ % DAISY_MAX_BGRAPH);
+                if (h->bgraph[slot].exec) cudaGraphExecDestroy(h->bgraph[slot].exec);
+                g = &h->bgraph[slot];
+                g->exec = exec; g->set = pl.set; g->B = B; g->U = U; g->I = I;
+                g->launches = (int)(h->launches - l0);
+            } else {  // capture is not available here: never try again, launch directly
+                cudaGetLastError();
+                h->graph_max_b = 0;
+            }
+            h->launches = l0;
+        }
+        if (g) {
+            DAISY_CUDA(cudaGraphLaunch(g->exec, bs));
+            h->launches += g->launches;
+        } else {
+            const int rc = book_kernels(h, k, pl, triples, B, U, I, C, bs, s, sh);
+            if (rc) return rc;
+        }
     } else {
-        const ShardSet &ss = sh->set[pl.set];
-        auto flags = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), StartFlag{k.qkey_s, I});
-        tmp = h->cub_tmp_bytes;
-        DAISY_CUDA(cub::DeviceScan::InclusiveSum(h->cub_tmp, tmp, flags, sh->cidx, 2 * B, bs));
-        h->launches += 2;
-        k_slots_item_shard<<<daisy_ceil_div(2 * (int64_t)B, T), T, 0, bs>>>(
-            k.qkey_s, h->val_out, sh->cidx, 2 * B, B, I, (uint32_t)sh->i_per, sh->world, k.jslot, k.islot, k.st,
-            ss.uniq_gid, ss.owner_off, sh->peers, sh->cache, h->D, ss.jsrc, ss.isrc, ss.multi);
-        DAISY_LAUNCH_CHECK(h);
-        k_shard_finish<<<daisy_ceil_div(2 * (int64_t)B, T), T, 0, bs>>>(k.qkey_s, sh->cidx, 2 * B, I, ss.uniq_gid,
-                                                                         ss.owner_off, sh->world, (uint32_t)sh->i_per,
-                                                                         sh->rank, (size_t)sh->cap, h->D, sh->peers,
-                                                                         ss.src, ss.dst);
-        DAISY_LAUNCH_CHECK(h);
+        const int rc = book_kernels(h, k, pl, triples, B, U, I, C, bs, s, sh);
+        if (rc) return rc;
     }
     phase_mark(h, PH_SLOTS, s);
     if (piped) {
