@@ -131,7 +131,6 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
         A(stageQ, 2 * B * dim);
         A(stage2, (size_t)h->slice_cap * dim);
         A(loss_part, B);
-        A(heavy, 2 + 5 * (size_t)h->heavy_cap);
         A(ticket, (size_t)h->longs_cap);
     }
 #undef A
@@ -153,7 +152,6 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
     if (!rc) {
         if (B > 0) {
             for (int i = 0; i < 2; ++i) cudaMemset(h->book[i].islot, 0xFF, B * sizeof(uint32_t));
-            cudaMemset(h->heavy, 0, 2 * sizeof(uint32_t));
             cudaMemset(h->ticket, 0, (size_t)h->longs_cap * sizeof(uint32_t));
         }
         k_err_reset<<<1, 1>>>(h->err);
@@ -187,7 +185,7 @@ extern "C" int daisy_destroy(daisy_handle_t h) {
     cudaDeviceSynchronize();
     daisy_shard_free(h);
     void *ptrs[] = {h->triples, h->key_in, h->val_in, h->val_out, h->ukey_in, h->uval_in, h->uval_out, h->ikey_in,
-                    h->ikey_out, h->ival_in, h->ival_out, h->stageU, h->stageQ, h->stage2, h->loss_part, h->heavy,
+                    h->ikey_out, h->ival_in, h->ival_out, h->stageU, h->stageQ, h->stage2, h->loss_part,
                     h->err, h->cub_tmp, h->ticket, h->scores, h->sel_hist, h->own_key, h->own_key_s, h->own_val, h->own_val_s,
                     h->own_tmp};
     for (void *p : ptrs)

@@ -124,7 +124,6 @@ struct daisy_ctx {
     float *stageQ;          // [2*maxB, D] staged item-row contributions (by sorted item-ref position)
     float *stage2;          // [slice_cap, D] level-1 partial sums of very hot rows
     float *loss_part;       // [maxB] per-warp loss partials
-    uint32_t *heavy;        // [0] = #hot rows, [1] = #slices, then 5 words per hot row: table, row, first pos, len, first slice
     int heavy_cap, slice_cap, longs_cap;
     uint32_t *ticket;       // [longs_cap] finished-slice counters of k_seg_all's long rows (zero between steps)
     int *err;               // [2]: flag, first bad position

@@ -188,10 +188,10 @@ extern "C" int daisy_owner_apply(daisy_handle_t h, float *Q_local, const int32_t
 //                counts of what this rank will push are WRITTEN into the owners' recv_ids / recv_cnt
 //   compute      the fused step kernels against (P_local, cache); a finished item-row sum is stored straight into the
 //                owner's memory by the kernel that completes it (PushOpt: k_bpr_main for rows referenced once,
-//                k_seg_reduce / k_heavy_final for repeated rows) -- the transfer overlaps the arithmetic
+//                k_seg_all for repeated rows) -- the transfer overlaps the arithmetic
 //   barrier      k_shard_barrier: arrival flags written into every peer's arena, acquire-spin on the own flags
-//   apply        k_owner_merge: per owned row, the senders' sums are added in sender-rank order (each sender's id list
-//                is ascending, so membership is a binary search) and the row is updated once -> deterministic
+//   apply        k_owner_add, one pass per sender in sender-rank order (a sender's id list is duplicate-free, so a pass
+//                is a plain streaming read-modify-write of distinct rows) -> deterministic
 //   barrier      owners are done: peers may fetch the next step's rows and overwrite the receive regions
 // =====================================================================================================================
 namespace {
@@ -442,13 +442,85 @@ static void launch_fetch(daisy_ctx *h, const ShardSet &ss, cudaStream_t s) {
     k_shard_fetch<V, 4><<<h->num_sms * 4, 256, 0, s>>>(ss.src, ss.multi, ss.owner_off, sh->world, sh->cache, h->D / 4);
 }
 
+// Owner side, default: ONE PASS PER SENDER, in sender-rank order.  A sender's id list is duplicate-free, so the
+// entries of one region touch distinct rows and a pass is a plain streaming read-modify-write (R entries in flight per
+// warp); passes follow each other on the stream, which fixes the order in which a row shared by several senders
+// receives their sums => deterministic, no membership searches at all.  (k_owner_merge, the single-pass variant that
+// finds every row's senders by binary search, cost 0.57 ms at 8 ranks -- 7 x 17 dependent L2 loads per entry; it is
+// kept behind DAISY_OWNER_MERGE=1.)
+template <int V, int R>
+__global__ void __launch_bounds__(256) k_owner_add(float *__restrict__ Q, const float *__restrict__ recv_g,
+                                                    const int32_t *__restrict__ recv_ids,
+                                                    const uint32_t *__restrict__ recv_cnt_s, size_t cap, int D4, float alpha,
+                                                    uint32_t rows_local, int *err) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const uint32_t nwarps = (uint32_t)((gridDim.x * (size_t)blockDim.x) >> 5);
+    uint32_t n = *recv_cnt_s;
+    if (n > cap) {  // cannot happen (a sender has at most 2*maxB = cap distinct rows); never read out of bounds
+        if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(&err[0], 32);
+        n = (uint32_t)cap;
+    }
+    bool act[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
+    for (uint32_t k0 = warp * R; k0 < n; k0 += nwarps * R) {
+        float4 g[R][V], old[R][V];
+        uint32_t row[R];
+#pragma unroll
+        for (int jj = 0; jj < R; ++jj) {
+            row[jj] = 0xFFFFFFFFu;
+            if (k0 + jj < n) {
+                row[jj] = (uint32_t)recv_ids[k0 + jj];
+                if (row[jj] >= rows_local) {
+                    if (lane == 0) atomicOr(&err[0], 1);
+                    row[jj] = 0xFFFFFFFFu;
+                }
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < R; ++jj)
+            if (row[jj] != 0xFFFFFFFFu) {
+#pragma unroll
+                for (int v = 0; v < V; ++v)
+                    if (act[v]) {
+                        g[jj][v] = ld_stream(recv_g, (size_t)(k0 + jj) * D4 + lane + 32 * v);
+                        old[jj][v] = ld_row(Q, (size_t)row[jj] * D4 + lane + 32 * v);
+                    }
+            }
+#pragma unroll
+        for (int jj = 0; jj < R; ++jj)
+            if (row[jj] != 0xFFFFFFFFu) {
+#pragma unroll
+                for (int v = 0; v < V; ++v)
+                    if (act[v])
+                        st_row(Q, (size_t)row[jj] * D4 + lane + 32 * v,
+                               make_float4(fmaf(alpha, g[jj][v].x, old[jj][v].x), fmaf(alpha, g[jj][v].y, old[jj][v].y),
+                                           fmaf(alpha, g[jj][v].z, old[jj][v].z), fmaf(alpha, g[jj][v].w, old[jj][v].w)));
+            }
+    }
+}
+
 template <int V>
 static void launch_merge(daisy_ctx *h, float alpha, cudaStream_t s) {
     daisy_shard *sh = h->sh;
     const int me = sh->rank;
-    k_owner_merge<V><<<h->num_sms * 8, 256, 0, s>>>(sh->peers.q[me], sh->peers.recv_g[me], sh->peers.recv_ids[me],
-                                                    sh->peers.recv_cnt[me], sh->world, (size_t)sh->cap, h->D / 4, alpha,
-                                                    (uint32_t)h->I, h->err);
+    static const int single_pass = getenv("DAISY_OWNER_MERGE") && atoi(getenv("DAISY_OWNER_MERGE")) == 1;
+    if (single_pass) {
+        k_owner_merge<V><<<h->num_sms * 8, 256, 0, s>>>(sh->peers.q[me], sh->peers.recv_g[me], sh->peers.recv_ids[me],
+                                                        sh->peers.recv_cnt[me], sh->world, (size_t)sh->cap, h->D / 4, alpha,
+                                                        (uint32_t)h->I, h->err);
+        return;
+    }
+    constexpr int R = V == 1 ? 4 : 2;
+    const size_t cap = (size_t)sh->cap;
+    for (int snd = 0; snd < sh->world; ++snd) {
+        k_owner_add<V, R><<<h->num_sms * 8, 256, 0, s>>>(sh->peers.q[me], sh->peers.recv_g[me] + (size_t)snd * cap * h->D,
+                                                         sh->peers.recv_ids[me] + (size_t)snd * cap,
+                                                         sh->peers.recv_cnt[me] + snd, cap, h->D / 4, alpha, (uint32_t)h->I,
+                                                         h->err);
+        if (snd + 1 < sh->world) h->launches++;
+    }
 }
 
 static int shard_compute(daisy_ctx *h, float *P_local, const int32_t *triples_dev, const int32_t *host_src, int64_t B,

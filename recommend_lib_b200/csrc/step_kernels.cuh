@@ -472,8 +472,7 @@ __device__ __forceinline__ void sum_staged(const float *__restrict__ stage, size
 template <int V, class Opt, int WIN = 32>
 __device__ __forceinline__ void seg_window(long long w, int tbl, const float *__restrict__ table,
                                            const uint32_t *__restrict__ keys, int n, uint32_t sentinel,
-                                           const float *__restrict__ stage, int D4, const Opt &opt, int heavy_len,
-                                           uint32_t *heavy, int heavy_cap) {
+                                           const float *__restrict__ stage, int D4, const Opt &opt, int heavy_len) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const long long base = w * WIN;
@@ -514,37 +513,7 @@ __device__ __forceinline__ void seg_window(long long w, int tbl, const float *__
             }
         }
         const size_t q0 = (size_t)(base + b);
-        if (len > heavy_len) {  // very hot row: reduced in two levels by k_heavy_slices / k_heavy_final
-            if (!heavy) continue;  // small-batch path: k_small_book listed it already, the slice blocks take it
-            // exact length by a 32-ary search over the sorted keys: keys[q] == row for q in [q0, q0 + len)
-            long long lo = (long long)q0 + len, hi = n;
-            while (lo < hi) {
-                const long long step = (hi - lo + 31) / 32;
-                const long long probe = lo + lane * step;
-                const bool ok = (probe < hi) && (keys[probe] == row);
-                const unsigned m = __ballot_sync(FULL, ok);
-                const int c = (m == FULL) ? 32 : (__ffs(~m) - 1);
-                if (c == 0) break;
-                const long long nhi = lo + c * step;
-                lo = lo + (c - 1) * step + 1;
-                hi = nhi < hi ? nhi : hi;
-            }
-            const uint32_t full = (uint32_t)(lo - (long long)q0);
-            if (lane == 0) {
-                const uint32_t nsl = (full + DAISY_SLICE - 1) / DAISY_SLICE;
-                const uint32_t idx = atomicAdd(&heavy[0], 1u);
-                const uint32_t sl0 = atomicAdd(&heavy[1], nsl);
-                if ((int)idx < heavy_cap) {
-                    uint32_t *rec = heavy + 2 + 5 * (size_t)idx;
-                    rec[0] = (uint32_t)tbl;
-                    rec[1] = row;
-                    rec[2] = (uint32_t)q0;
-                    rec[3] = full;
-                    rec[4] = sl0;
-                }
-            }
-            continue;
-        }
+        if (len > heavy_len) continue;  // a long row: the bookkeeping listed it, k_seg_all's slice blocks take it
         float4 old[V], acc[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
@@ -555,109 +524,6 @@ __device__ __forceinline__ void seg_window(long long w, int tbl, const float *__
 #pragma unroll
         for (int v = 0; v < V; ++v)
             if (act[v]) opt.apply(tbl, (size_t)row, lane + 32 * v, old[v], acc[v]);
-    }
-}
-
-template <int V, class Opt>
-__global__ void __launch_bounds__(256) k_seg_reduce(int tbl, const float *__restrict__ table,
-                                                     const uint32_t *__restrict__ keys, int n, uint32_t sentinel,
-                                                     const float *__restrict__ stage, int D4, Opt opt, int heavy_len,
-                                                     uint32_t *heavy, int heavy_cap) {
-    const long long w = (long long)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
-    seg_window<V, Opt>(w, tbl, table, keys, n, sentinel, stage, D4, opt, heavy_len, heavy, heavy_cap);
-}
-
-// Level 1: every slice of DAISY_SLICE consecutive staged contributions of a hot row is summed by one warp into
-// stage2[first_slice + j].  SPLIT blocks share one hot row so that even the hottest row is spread over
-// SPLIT * 8 warps.
-template <int V>
-__global__ void __launch_bounds__(256) k_heavy_slices(const float *__restrict__ stageU, const float *__restrict__ stageQ,
-                                                       float *__restrict__ stage2, int D4,
-                                                       const uint32_t *__restrict__ heavy, int heavy_cap, int split) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int count = min((int)heavy[0], heavy_cap);
-    bool act[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
-    for (int w = blockIdx.x; w < count * split; w += gridDim.x) {
-        const uint32_t *rec = heavy + 2 + 5 * (size_t)(w / split);
-        const int part = w % split;
-        const float *stage = rec[0] ? stageQ : stageU;
-        const size_t q0 = rec[2];
-        const int len = (int)rec[3];
-        const size_t sl0 = rec[4];
-        const int nsl = (len + DAISY_SLICE - 1) / DAISY_SLICE;
-        for (int j = part + split * wid; j < nsl; j += split * 8) {
-            const int c0 = j * DAISY_SLICE;
-            const int cn = min(DAISY_SLICE, len - c0);
-            float4 acc[V];
-#pragma unroll
-            for (int v = 0; v < V; ++v) acc[v] = f4_zero();
-            sum_staged<V>(stage, q0 + c0, cn, D4, lane, act, acc);
-#pragma unroll
-            for (int v = 0; v < V; ++v)
-                if (act[v]) st_stream(stage2, (sl0 + j) * D4 + lane + 32 * v, acc[v]);
-        }
-    }
-}
-
-// Level 2: one block per hot row sums the row's slice partials (fixed split over 8 warps, fixed combine order)
-// and applies the update.
-template <int V, class Opt>
-__global__ void __launch_bounds__(256) k_heavy_final(const float *__restrict__ P, const float *__restrict__ Q,
-                                                      const float *__restrict__ stage2, int D4, Opt opt,
-                                                      const uint32_t *__restrict__ heavy, int heavy_cap) {
-    __shared__ float4 part[8][32 * V];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int count = min((int)heavy[0], heavy_cap);
-    bool act[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
-    for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
-        const uint32_t *rec = heavy + 2 + 5 * (size_t)idx;
-        const int tbl = (int)rec[0];
-        const uint32_t row = rec[1];
-        const int nsl = ((int)rec[3] + DAISY_SLICE - 1) / DAISY_SLICE;
-        const size_t sl0 = rec[4];
-        const float *table = tbl ? Q : P;
-        const int per = (nsl + 7) / 8;
-        const int c0 = min(nsl, wid * per), c1 = min(nsl, c0 + per);
-        float4 acc[V];
-#pragma unroll
-        for (int v = 0; v < V; ++v) acc[v] = f4_zero();
-        sum_staged<V>(stage2, sl0 + c0, c1 - c0, D4, lane, act, acc);
-#pragma unroll
-        for (int v = 0; v < V; ++v) part[wid][lane + 32 * v] = acc[v];
-        __syncthreads();
-        if (wid == 0) {
-#pragma unroll
-            for (int v = 0; v < V; ++v)
-                if (act[v]) {
-                    float4 tot = part[0][lane + 32 * v];
-                    for (int ww = 1; ww < 8; ++ww) tot = f4_add(tot, part[ww][lane + 32 * v]);  // fixed order
-                    const int e = lane + 32 * v;
-                    const float4 old = (tbl == 0 || Opt::kNeedOldItem) ? ld_row(table, (size_t)row * D4 + e) : f4_zero();
-                    opt.apply(tbl, (size_t)row, e, old, tot);
-                }
-        }
-        __syncthreads();
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// loss: fixed-order reduction of per-warp partials (double accumulation), added to *loss_accum
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_loss(const float *__restrict__ part, int n, double *loss_accum) {
-    __shared__ double sh[32];
-    double s = 0.0;
-    for (int i = threadIdx.x; i < n; i += 1024) s += (double)part[i];
-    s = warp_sum_d(s);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        double t = sh[threadIdx.x];
-        t = warp_sum_d(t);
-        if (threadIdx.x == 0) *loss_accum += t;
     }
 }
 
@@ -914,7 +780,7 @@ __global__ void __launch_bounds__(1024) k_small_book(const int32_t *__restrict__
         key_out[p] = row;
         if (first && p + DAISY_SMALL_SLICE < n_c && (sk[p + DAISY_SMALL_SLICE] >> vb) == row) {
             // a row with more than DAISY_SMALL_SLICE contributions: too much for one warp (and for the L2 port of one SM).
-            // List it -- (table, row, first sorted position, length, first slice) like the general path's heavy
+            // List it -- (table, row, first sorted position, length, first slice) like the general path's
             // list -- for the slice blocks of k_seg_all.
             uint32_t lo = p + DAISY_SMALL_SLICE, hi = n_c - 1;
             while (lo < hi) {
@@ -961,8 +827,8 @@ static int launch_small_book(daisy_ctx *h, cudaStream_t bs, const int32_t *tripl
 }
 
 // ------------------------------------------------------------------------------------------------
-// Every row with several contributions, both tables, ONE launch (small-batch path and single-GPU general path; the
-// row-sharded step keeps k_seg_reduce / k_heavy_*, whose rows are finished by PushOpt over NVLink).
+// Every row with several contributions, both tables, ONE launch (all paths; in the row-sharded step `opt` is PushOpt,
+// which stores a finished item-row sum into its owner's memory over NVLink).
 //   blocks [0, NS)                  slice blocks: the rows the bookkeeping listed as longer than `long_len`.  One SM
 //        draws ~40 B/clk from L2 however many loads it has in flight (tools/small_book_probe.cu), so a hot row's
 //        staged contributions are spread over the SMs slice by slice: a warp sums one slice of SLICE contributions
@@ -984,7 +850,7 @@ __global__ void __launch_bounds__(256) k_seg_all(const float *__restrict__ P, co
                                                   int n_part, double *loss_accum) {
     const int b = blockIdx.x, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-    if (b >= NS + blocksU + blocksQ) {  // fixed-order reduction of the per-warp loss partials (cf. k_loss)
+    if (b >= NS + blocksU + blocksQ) {  // fixed-order reduction of the per-warp loss partials (double accumulation)
         if (!loss_accum) return;
         __shared__ double sh[8];
         double s = 0.0;
@@ -1003,8 +869,7 @@ __global__ void __launch_bounds__(256) k_seg_all(const float *__restrict__ P, co
         const int wb = b - NS;
         const int tbl = wb < blocksU ? 0 : 1;
         seg_window<V, Opt, WIN>((long long)(tbl ? wb - blocksU : wb) * 8 + wid, tbl, tbl ? Q : P, tbl ? qkey_s : ukey_s,
-                                tbl ? 2 * B : B, tbl ? q_sentinel : 0xFFFFFFFFu, tbl ? stageQ : stageU, D4, opt, long_len,
-                                nullptr, 0);
+                                tbl ? 2 * B : B, tbl ? q_sentinel : 0xFFFFFFFFu, tbl ? stageQ : stageU, D4, opt, long_len);
         return;
     }
     const int count = min((int)longs[0], longs_cap);
@@ -1100,6 +965,15 @@ __device__ __forceinline__ void list_long_row(const uint32_t *__restrict__ keys,
         rec[3] = len;
         rec[4] = sl0;
     }
+}
+
+__global__ void k_list_long_items(const uint32_t *__restrict__ key, int n, uint32_t sentinel, uint32_t *longs,
+                                  int longs_cap, int long_len) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t r = key[p];
+    if (r == sentinel) return;
+    if (p == 0 || key[p - 1] != r) list_long_row(key, n, p, r, 1, long_len, DAISY_SLICE, longs, longs_cap);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1255,9 +1129,9 @@ static int book_kernels(daisy_ctx *h, BookSet &k, const StepPlan &pl, const int3
     h->launches += 4;
     phase_mark(h, PH_SORT_Q, s);
     // slots
-    // single GPU: the rows too long for one warp are listed here for k_seg_all (the sharded step finds them itself)
-    uint32_t *longs = sh ? nullptr : k.longs;
-    if (longs) DAISY_CUDA(cudaMemsetAsync(longs, 0, 2 * sizeof(uint32_t), bs));
+    // the rows too long for one warp are listed here for k_seg_all's slice blocks
+    uint32_t *longs = k.longs;
+    DAISY_CUDA(cudaMemsetAsync(longs, 0, 2 * sizeof(uint32_t), bs));
     k_slots_user<<<daisy_ceil_div(B, T), T, 0, bs>>>(k.ukey_s, h->uval_out, B, k.uslot, longs, h->longs_cap, h->heavy_len);
     DAISY_LAUNCH_CHECK(h);
     if (!sh) {
@@ -1279,6 +1153,10 @@ static int book_kernels(daisy_ctx *h, BookSet &k, const StepPlan &pl, const int3
                                                                          sh->rank, (size_t)sh->cap, h->D, sh->peers,
                                                                          ss.src, ss.dst);
         DAISY_LAUNCH_CHECK(h);
+        // the sorted item-ref keys now hold cache rows (same grouping): list the long ones
+        k_list_long_items<<<daisy_ceil_div(2 * (int64_t)B, T), T, 0, bs>>>(k.qkey_s, 2 * B, I, longs, h->longs_cap,
+                                                                           h->heavy_len);
+        DAISY_LAUNCH_CHECK(h);
     }
     return DAISY_OK;
 }
@@ -1293,7 +1171,6 @@ static int book_phase(daisy_ctx *h, StepPlan &pl, const int32_t *triples, int64_
     int vbU = 0, kbU = 0, vbQ = 0, kbQ = 0;
     const bool small = !sh && small_path(h, B64, U, I, &vbU, &kbU, &vbQ, &kbQ);
     const int C = small ? 1 : auto_chunk(h, B);
-    const int T = 256;
     const bool piped = h->pipeline && h->timing != 2;
     cudaStream_t bs = piped ? h->side_stream : s;
     pl.B = B; pl.C = C; pl.U = U; pl.I = I; pl.piped = piped; pl.bs = bs; pl.s = s;
@@ -1419,7 +1296,6 @@ static int table_phase_v(daisy_ctx *h, const StepPlan &pl, const float *P, const
     const int D4 = h->D / 4;
     cudaStream_t s = pl.s;
     BookSet &k = *pl.k;
-    if (pl.jsrc) DAISY_CUDA(cudaMemsetAsync(h->heavy, 0, 2 * sizeof(uint32_t), s));
     MainArgs a;
     a.P = P; a.Q = Q; a.st = k.st; a.uslot = k.uslot; a.jslot = k.jslot; a.islot = k.islot;
     a.stageU = h->stageU; a.stageQ = h->stageQ; a.loss_part = h->loss_part;
@@ -1460,7 +1336,7 @@ static int table_phase_v(daisy_ctx *h, const StepPlan &pl, const float *P, const
         h->pool_used++;
     }
     phase_mark(h, PH_MAIN, s);
-    if (!pl.jsrc) {  // single GPU: every multi-contribution row of both tables + the loss in one launch
+    {   // every multi-contribution row of both tables + the loss in one launch
         const int NS = pl.small ? 64 : 2 * h->num_sms;
         int blocksU, blocksQ;
         if (pl.small) {
@@ -1476,37 +1352,7 @@ static int table_phase_v(daisy_ctx *h, const StepPlan &pl, const float *P, const
         }
         DAISY_LAUNCH_CHECK(h);
         for (int ph = PH_SEG_U; ph <= PH_LOSS; ++ph) phase_mark(h, ph, s);
-        if (pl.piped) DAISY_CUDA(cudaEventRecord(k.freed, s));
-        if (h->trace && h->tr_n < DAISY_TRACE_STEPS) {
-            cudaEventRecord(h->tr_ev[4 * h->tr_n + 3], s);
-            h->tr_n++;
-        }
-        if (h->timing == 2) {
-            h->ev_pending = 1;
-            h->ev_stream = s;
-        }
-        return DAISY_OK;
     }
-    // segmented reduces
-    k_seg_reduce<V, Opt><<<daisy_ceil_div(daisy_ceil_div(B, 32), 8), 256, 0, s>>>(
-        0, P, k.ukey_s, B, 0xFFFFFFFFu, h->stageU, D4, opt, h->heavy_len, h->heavy, h->heavy_cap);
-    DAISY_LAUNCH_CHECK(h);
-    phase_mark(h, PH_SEG_U, s);
-    k_seg_reduce<V, Opt><<<daisy_ceil_div(daisy_ceil_div(2 * (int64_t)B, 32), 8), 256, 0, s>>>(
-        1, Q, k.qkey_s, 2 * B, pl.I, h->stageQ, D4, opt, h->heavy_len, h->heavy, h->heavy_cap);
-    DAISY_LAUNCH_CHECK(h);
-    phase_mark(h, PH_SEG_Q, s);
-    const int split = 8;
-    k_heavy_slices<V><<<h->num_sms * 4, 256, 0, s>>>(h->stageU, h->stageQ, h->stage2, D4, h->heavy, h->heavy_cap, split);
-    DAISY_LAUNCH_CHECK(h);
-    k_heavy_final<V, Opt><<<h->num_sms, 256, 0, s>>>(P, Q, h->stage2, D4, opt, h->heavy, h->heavy_cap);
-    DAISY_LAUNCH_CHECK(h);
-    phase_mark(h, PH_HEAVY, s);
-    if (loss_accum) {
-        k_loss<<<1, 1024, 0, s>>>(h->loss_part, warps, loss_accum);
-        DAISY_LAUNCH_CHECK(h);
-    }
-    phase_mark(h, PH_LOSS, s);
     if (pl.piped) DAISY_CUDA(cudaEventRecord(k.freed, s));
     if (h->trace && h->tr_n < DAISY_TRACE_STEPS) {
         cudaEventRecord(h->tr_ev[4 * h->tr_n + 3], s);
