@@ -505,12 +505,11 @@ def bench_sharded(args, cfg, metric, unit):
         model.wire_rows = 0
     launches0 = handle.launches
     clocks = None
-    if rank == 0:
-        try:
-            import bench as _bench
-            clocks = _bench.ClockSampler(local)     # NVML initialisation takes tens of ms: before the barrier
-        except Exception:
-            clocks = None
+    try:                                            # every rank samples its own GPU (rank 0's goes into `clocks`)
+        import bench as _bench
+        clocks = _bench.ClockSampler(local)         # NVML initialisation takes tens of ms: before the barrier
+    except Exception:
+        clocks = None
     torch.cuda.synchronize()
     dist.barrier()                                  # all ranks enter the timed region together
     if clocks is not None:
@@ -579,6 +578,13 @@ def bench_sharded(args, cfg, metric, unit):
             if r == rank:
                 print(f"rank {rank} trace_ms(book_begin, book_end, kernels_begin, compute_end):", rows, flush=True)
             dist.barrier()
+    by_rank = None
+    if args.phases and peer:                        # which rank waits for which: the phases of every rank, side by side
+        mine = {"rank": rank, "sm_mhz": (clocks.summary()["sm_mhz"] if clocks is not None else None)}
+        mine.update({k: round(v, 4) for k, v in phases.items() if k != "compute_push_detail"})
+        mine["main"] = phases["compute_push_detail"].get("main")
+        by_rank = [None] * world
+        dist.all_gather_object(by_rank, mine)
     if rank == 0:
         ms_total, ms_e2e = float(ms), float(ms2)
         value = B * world * K / (ms_total * 1e-3)
@@ -613,5 +619,7 @@ def bench_sharded(args, cfg, metric, unit):
                              "hbm_whole_step_frac": (B * (24 * D + 12) / step_s / 1e9) / 6461.8}}
         if phases:
             line["phase_ms(device,host)"] = phases
+        if by_rank:
+            line["phase_ms_by_rank"] = by_rank
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()
