@@ -94,8 +94,9 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
     if (h->heavy_len < 8) h->heavy_len = 8;
     // a row is "very hot" above heavy_len contributions; at most 3B contributions exist per step
     h->heavy_cap = (int)(3 * max_batch / h->heavy_len) + 4;
+    h->mid_cap = max_batch < 131072 ? max_batch : 131072;
     {   // small-batch path: rows with more than 16 (DAISY_SMALL_SLICE, step_kernels.cuh) contributions, slices of 16
-        const int64_t sb = max_batch < DAISY_SMALL_CAP ? max_batch : DAISY_SMALL_CAP;
+        const int64_t sb = h->mid_cap;
         h->longs_cap = (int)(3 * sb / 16) + 4;
         if (h->longs_cap < h->heavy_cap) h->longs_cap = h->heavy_cap;  // the general path lists rows longer than heavy_len
         h->slice_cap = (int)(3 * max_batch / DAISY_SLICE) + h->heavy_cap + 4;
@@ -106,6 +107,9 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
     if (h->main_stages < 0) h->main_stages = 0;
     if (h->main_stages > 16) h->main_stages = 16;
     h->inputs_ready = 0;
+    h->mid_max = env_int("DAISY_MID_MAX", 65536);  // measured: above ~100 k triples the general pipeline (graph-replayed) is faster
+    if (h->mid_max < 0) h->mid_max = 0;
+    if (h->mid_max > h->mid_cap) h->mid_max = h->mid_cap;
     h->graph_max_b = env_int("DAISY_GRAPH_MAX_B", 262144);
     if (h->graph_max_b < 0) h->graph_max_b = 0;
     h->small_max = env_int("DAISY_SMALL_MAX", DAISY_SMALL_CAP);
@@ -132,6 +136,7 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
         A(stage2, (size_t)h->slice_cap * dim);
         A(loss_part, B);
         A(ticket, (size_t)h->longs_cap);
+        A(mid_buf, 4 * 3 * (size_t)h->mid_cap);
     }
 #undef A
     if (!rc && B > 0) {
@@ -186,7 +191,7 @@ extern "C" int daisy_destroy(daisy_handle_t h) {
     daisy_shard_free(h);
     void *ptrs[] = {h->triples, h->key_in, h->val_in, h->val_out, h->ukey_in, h->uval_in, h->uval_out, h->ikey_in,
                     h->ikey_out, h->ival_in, h->ival_out, h->stageU, h->stageQ, h->stage2, h->loss_part,
-                    h->err, h->cub_tmp, h->ticket, h->scores, h->sel_hist, h->own_key, h->own_key_s, h->own_val, h->own_val_s,
+                    h->err, h->cub_tmp, h->ticket, h->mid_buf, h->scores, h->sel_hist, h->own_key, h->own_key_s, h->own_val, h->own_val_s,
                     h->own_tmp};
     for (void *p : ptrs)
         if (p) cudaFree(p);

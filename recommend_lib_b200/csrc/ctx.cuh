@@ -146,6 +146,9 @@ struct daisy_ctx {
     int heavy_len;   // segments longer than this go to the block-per-row kernel
     int main_stages; // > 0: TMA-pipelined main kernel with this many stages (triples in flight) per warp; 0: register prefetch
     int small_max;   // batches up to this many triples take the 3-launch small-batch path (0 = never; <= DAISY_SMALL_CAP)
+    int64_t mid_max; // ... and up to this many the same path with k_mid_book (0 = never; <= mid_cap)
+    int64_t mid_cap; // min(maxB, 131072): what mid_buf is sized for
+    uint32_t *mid_buf;  // [4][3 * mid_cap] k_mid_book's two (key, value) scratch buffers
 
     // --- CUDA-graph replay of the general bookkeeping chain for mid-size batches ---
     int64_t graph_max_b;     // batches up to this size replay a captured graph (0 = never; DAISY_GRAPH_MAX_B)

@@ -544,7 +544,7 @@ __device__ __forceinline__ void seg_window(long long w, int tbl, const float *__
 // the general path's order (which groups triples by positive item first), so the two paths agree to rounding only.
 // ------------------------------------------------------------------------------------------------
 #ifdef DAISY_SMALL_PROBE  // tools/small_book_probe.cu: clock stamps of thread 0 of each block
-__device__ long long g_small_probe[32][32];
+__device__ long long g_small_probe[256][32];
 #define SMALL_PROBE(n) do { if (threadIdx.x == 0) g_small_probe[blockIdx.x][n] = clock64(); } while (0)
 #else
 #define SMALL_PROBE(n) do { } while (0)
@@ -809,6 +809,330 @@ __global__ void __launch_bounds__(1024) k_small_book(const int32_t *__restrict__
     SMALL_PROBE(31);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Mid-size batches (DAISY_SMALL_CAP < B <= DAISY_MID_CAP): the same class-split bookkeeping, generalised.
+// At these sizes the CUB chain of the general path is a latency chain of ~15 kernels (~140 us whatever B is), while
+// the table kernels need 20-80 us.  k_mid_book does the whole bookkeeping in ONE launch of 2 * 2^cb blocks: block c of
+// a table sweeps ALL refs of its table twice (count, then compact its class -- rows with low bits c -- as (row >> cb,
+// ref index) pairs into its slice [base_c, base_c + n_c) of a global scratch array; base_c = refs of lower classes),
+// sorts its slice on the remaining row bits with the LSD passes of block_sort_words -- here between two global
+// (L2-resident) buffers, so a class may have any size: a warp owns a contiguous range of the slice, counts its digits
+// in one sweep and recomputes the lane matches in the scatter sweep instead of keeping ranks in registers -- and
+// assigns the slots.  Refs are pairs, so there is no 32-bit packing limit.  No block waits for another one.
+// ------------------------------------------------------------------------------------------------
+static int bits_for(uint64_t max_value);
+#define DAISY_MID_CAP 131072
+#define DAISY_MID_TILE 8192  // refs per sweep tile: 1024 threads x 8
+struct MidScratch {
+    uint32_t *ak, *av, *bk, *bv;  // [3 * mid cap] each: user refs at [0, B), item refs at [B, 3B)
+};
+
+// Item sweep slots 2t and 2t + 1 are the negative and the positive item of triple t (adjacent words: a warp's loads
+// cover contiguous bytes); mid_ref gives the ref index a slot is filed under (negatives [0, B), positives [B, 2B)).
+__device__ __forceinline__ uint32_t mid_ref(int s, int B, bool items) {
+    return items ? (uint32_t)((s & 1) ? B + (s >> 1) : (s >> 1)) : (uint32_t)s;
+}
+
+__global__ void __launch_bounds__(1024) k_mid_book(const int32_t *__restrict__ triples, int B, uint32_t U, uint32_t I, int cb,
+                                                    int kbU, int kbQ, MidScratch ms, int32_t *__restrict__ st,
+                                                    uint32_t *__restrict__ ukey_s, uint32_t *__restrict__ qkey_s,
+                                                    uint32_t *__restrict__ uslot, uint32_t *__restrict__ jslot,
+                                                    uint32_t *__restrict__ islot, uint32_t *longs, int longs_cap,
+                                                    int *err) {
+    extern __shared__ __align__(16) unsigned char mid_dsm[];
+    uint32_t *hist = reinterpret_cast<uint32_t *>(mid_dsm);  // [32 * 513]
+    __shared__ uint32_t scan_tmp[33], tw_off[32 * 32 + 1], s_low;
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t NC = 1u << cb;
+    const bool items = blockIdx.x >= NC;
+    const uint32_t cls = blockIdx.x & (NC - 1);
+    const int n = items ? 2 * B : B;
+    const int kb = items ? kbQ : kbU;
+    const uint32_t bound = items ? I : U;
+    const size_t tbl_off = items ? (size_t)B : 0;  // this table's part of the scratch arrays
+    const int tiles = (n + DAISY_MID_TILE - 1) / DAISY_MID_TILE;  // <= 32
+    if (tid == 0) s_low = 0;
+    for (int i = tid; i < 32 * 32 + 1; i += 1024) tw_off[i] = 0;
+    __syncthreads();
+    SMALL_PROBE(0);
+    // ---- sweep 1: how many refs of this class every (tile, warp) holds; how many refs belong to lower classes ----
+    uint32_t low = 0;
+    const bool checker = !items && cls == 0;  // this block also validates the triples and writes the clamped copy
+    // slot s = tile base + w*256 + k*32 + lane.  Its word in the packed triples: users 3s; items 3(s>>1) + 2 - (s&1)
+    // (slots 2t, 2t+1 = negative, positive item of triple t) -- both advance by a constant per k, so a full tile is 8
+    // loads at immediate offsets from one base; the sweeps are bound by the instruction count of one SM.
+    const int wstep = items ? 48 : 96;
+    auto load_tile = [&](int tl, uint32_t (&rows)[8]) {
+        const int s0 = tl * DAISY_MID_TILE + w * 256 + lane;
+        const int32_t *p0 = triples + (items ? 3 * (s0 >> 1) + 2 - (s0 & 1) : 3 * s0);
+        if (tl * DAISY_MID_TILE + DAISY_MID_TILE <= n) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t r = (uint32_t)__ldg(p0 + k * wstep);
+                rows[k] = r < bound ? r : 0u;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                rows[k] = 0xFFFFFFFFu;
+                if (s0 + k * 32 < n) {
+                    const uint32_t r = (uint32_t)__ldg(p0 + k * wstep);
+                    rows[k] = r < bound ? r : 0u;
+                }
+            }
+        }
+    };
+    uint32_t nxt[8];
+    load_tile(0, nxt);
+    for (int tl = 0; tl < tiles; ++tl) {
+        uint32_t rows[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rows[k] = nxt[k];
+        if (tl + 1 < tiles) load_tile(tl + 1, nxt);  // the next tile's loads fly while this one is counted
+        if (checker) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int t = tl * DAISY_MID_TILE + w * 256 + k * 32 + lane;
+                if (t < n) {
+                    uint32_t u, i, j;
+                    bool bad;
+                    load_triple(triples, t, U, I, u, i, j, bad);
+                    st[3 * (size_t)t] = (int32_t)u;
+                    st[3 * (size_t)t + 1] = (int32_t)i;
+                    st[3 * (size_t)t + 2] = (int32_t)j;
+                    if (bad) {
+                        atomicOr(&err[0], 1);
+                        atomicMin(&err[1], t);
+                    }
+                }
+            }
+        }
+        uint32_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const bool in = rows[k] != 0xFFFFFFFFu;
+            const uint32_t c = rows[k] & (NC - 1);
+            mine += (in && c == cls) ? 1u : 0u;
+            low += (in && c < cls) ? 1u : 0u;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(FULL, mine, o);
+        if (lane == 0) tw_off[tl * 32 + w] = mine;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) low += __shfl_xor_sync(FULL, low, o);
+    if (lane == 0 && low) atomicAdd(&s_low, low);
+    __syncthreads();
+    SMALL_PROBE(1);
+    // exclusive scan of the 1024 (tile, warp) counts: thread t owns cell t
+    uint32_t n_c;
+    {
+        const uint32_t c = tw_off[tid];
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) scan_tmp[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            const uint32_t tot = scan_tmp[lane];
+            uint32_t inc2 = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL, inc2, o);
+                if (lane >= o) inc2 += v;
+            }
+            scan_tmp[lane] = inc2 - tot;
+            if (lane == 31) scan_tmp[32] = inc2;
+        }
+        __syncthreads();
+        tw_off[tid] = scan_tmp[w] + incl - c;
+        n_c = scan_tmp[32];
+    }
+    const uint32_t base_c = s_low;
+    __syncthreads();
+    uint32_t *ak = ms.ak + tbl_off + base_c, *av = ms.av + tbl_off + base_c;
+    uint32_t *bk = ms.bk + tbl_off + base_c, *bv = ms.bv + tbl_off + base_c;
+    SMALL_PROBE(2);
+    // ---- sweep 2: compact this class's refs, in ref order, as (row >> cb, ref index) ----
+    load_tile(0, nxt);
+    for (int tl = 0; tl < tiles; ++tl) {
+        uint32_t rows[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rows[k] = nxt[k];
+        if (tl + 1 < tiles) load_tile(tl + 1, nxt);
+        uint32_t run = tw_off[tl * 32 + w];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const bool mine = rows[k] != 0xFFFFFFFFu && (rows[k] & (NC - 1)) == cls;
+            const unsigned m = __ballot_sync(FULL, mine);
+            if (mine) {
+                const uint32_t pos = run + __popc(m & lt);
+                ak[pos] = rows[k] >> cb;
+                av[pos] = mid_ref(tl * DAISY_MID_TILE + w * 256 + k * 32 + lane, B, items);
+            }
+            run += __popc(m);
+        }
+    }
+    __syncthreads();  // (block-scope visibility of the global stores above)
+    SMALL_PROBE(3);
+    // ---- LSD passes between (ak, av) and (bk, bv): warp w owns [w * len_w, (w + 1) * len_w) of the slice ----
+    const uint32_t len_w = (((n_c + 31u) / 32u) + 31u) & ~31u;
+    const uint32_t r0 = (uint32_t)w * len_w, r1 = min(r0 + len_w, n_c);
+    int nbits = kb - cb;
+    if (nbits < 1) nbits = 1;
+    const int passes = (nbits + 8) / 9;
+    int done = 0;
+    for (int p = 0; p < passes && n_c > 0; ++p) {
+        int db = (nbits - done + (passes - p) - 1) / (passes - p);
+        if (db < 5) db = 5;
+        const int NB = 1 << db, HS = NB + 1;
+        const uint32_t dmask = (uint32_t)NB - 1u;
+        uint32_t *wh = hist + (size_t)w * HS;
+        for (int i = lane; i < NB; i += 32) wh[i] = 0;
+        __syncwarp();
+        for (uint32_t q = r0 + lane; q - lane < r1; q += 32) {  // count
+            const bool valid = q < r1;
+            const uint32_t d = valid ? ((ak[q] >> done) & dmask) : 0u;
+            const unsigned vm = __ballot_sync(FULL, valid);
+            unsigned m = vm;
+            for (int bb = 0; bb < db; ++bb) {
+                const bool bit = (d >> bb) & 1u;
+                const unsigned v = __ballot_sync(FULL, valid && bit);
+                m &= bit ? v : (vm & ~v);
+            }
+            if (valid && lane == __ffs(m) - 1) wh[d] += __popc(m);
+            __syncwarp();
+        }
+        __syncthreads();
+        {   // exclusive scan of the cells in (digit, warp) order: thread t owns E consecutive cells
+            const int E = NB / 32;
+            uint32_t sum = 0;
+            for (int e = 0; e < E; ++e) {
+                const int L = tid * E + e;
+                sum += hist[(size_t)(L & 31) * HS + (L >> 5)];
+            }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) scan_tmp[w] = incl;
+            __syncthreads();
+            if (w == 0) {
+                const uint32_t tot = scan_tmp[lane];
+                uint32_t inc2 = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(FULL, inc2, o);
+                    if (lane >= o) inc2 += v;
+                }
+                scan_tmp[lane] = inc2 - tot;
+            }
+            __syncthreads();
+            uint32_t run = scan_tmp[w] + incl - sum;
+            for (int e = 0; e < E; ++e) {
+                const int L = tid * E + e;
+                uint32_t *cell = hist + (size_t)(L & 31) * HS + (L >> 5);
+                const uint32_t c = *cell;
+                *cell = run;
+                run += c;
+            }
+        }
+        __syncthreads();
+        for (uint32_t q = r0 + lane; q - lane < r1; q += 32) {  // scatter: the matches again, offsets advance as we go
+            const bool valid = q < r1;
+            const uint32_t key = valid ? ak[q] : 0u, val = valid ? av[q] : 0u;
+            const uint32_t d = (key >> done) & dmask;
+            const unsigned vm = __ballot_sync(FULL, valid);
+            unsigned m = vm;
+            for (int bb = 0; bb < db; ++bb) {
+                const bool bit = (d >> bb) & 1u;
+                const unsigned v = __ballot_sync(FULL, valid && bit);
+                m &= bit ? v : (vm & ~v);
+            }
+            const int leader = valid ? __ffs(m) - 1 : 0;
+            uint32_t base = 0;
+            if (valid && lane == leader) {
+                base = wh[d];
+                wh[d] = base + __popc(m);
+            }
+            base = __shfl_sync(FULL, base, leader);
+            if (valid) {
+                const uint32_t pos = base + __popc(m & lt);
+                bk[pos] = key;
+                bv[pos] = val;
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        uint32_t *t;
+        t = ak; ak = bk; bk = t;
+        t = av; av = bv; bv = t;
+        done += db;
+    }
+    SMALL_PROBE(4);
+    // ---- slots: (ak, av) is the class's slice, sorted by row, refs of a row in ref order ----
+    uint32_t *key_out = (items ? qkey_s : ukey_s) + base_c;
+    for (uint32_t p = tid; p < n_c; p += 1024) {
+        const uint32_t key = ak[p], idx = av[p];
+        const bool first = (p == 0) || (ak[p - 1] != key);
+        const bool last = (p == n_c - 1) || (ak[p + 1] != key);
+        const uint32_t slot = (first && last) ? DAISY_DIRECT : base_c + p;
+        const uint32_t row = (key << cb) | cls;
+        key_out[p] = row;
+        if (!items)
+            uslot[idx] = slot;
+        else if (idx < (uint32_t)B)
+            jslot[idx] = slot;
+        else
+            islot[idx - B] = slot;
+        if (first && p + DAISY_SMALL_SLICE < n_c && ak[p + DAISY_SMALL_SLICE] == key) {  // a long row (cf. k_small_book)
+            uint32_t lo = p + DAISY_SMALL_SLICE, hi = n_c - 1;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (ak[mid] == key) lo = mid; else hi = mid - 1;
+            }
+            const uint32_t len = lo - p + 1;
+            const uint32_t r = atomicAdd(&longs[0], 1u);
+            const uint32_t sl0 = atomicAdd(&longs[1], (len + DAISY_SMALL_SLICE - 1) / DAISY_SMALL_SLICE);
+            if ((int)r < longs_cap) {
+                uint32_t *rec = longs + 2 + 5 * (size_t)r;
+                rec[0] = items ? 1u : 0u;
+                rec[1] = row;
+                rec[2] = base_c + p;
+                rec[3] = len;
+                rec[4] = sl0;
+            }
+        }
+    }
+    SMALL_PROBE(5);
+}
+
+static int launch_mid_book(daisy_ctx *h, cudaStream_t bs, const int32_t *triples, int B, uint32_t U, uint32_t I, BookSet &k) {
+    const size_t smem = sizeof(uint32_t) * DAISY_SMALL_HIST_WORDS;
+    static bool granted[64];
+    if (!granted[h->device & 63]) {
+        DAISY_CUDA(cudaFuncSetAttribute(k_mid_book, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        granted[h->device & 63] = true;
+    }
+    // classes: enough blocks to fill the GPU, few enough that a class still holds a few thousand refs
+    const int cb = B <= 16384 ? 4 : (B <= 65536 ? 5 : 6);
+    MidScratch ms;
+    const size_t cap3 = 3 * (size_t)h->mid_cap;
+    ms.ak = h->mid_buf; ms.av = ms.ak + cap3; ms.bk = ms.av + cap3; ms.bv = ms.bk + cap3;
+    DAISY_CUDA(cudaMemsetAsync(k.longs, 0, 2 * sizeof(uint32_t), bs));
+    k_mid_book<<<2 << cb, 1024, smem, bs>>>(triples, B, U, I, cb, bits_for(U), bits_for(I), ms, k.st, k.ukey_s, k.qkey_s,
+                                            k.uslot, k.jslot, k.islot, k.longs, h->longs_cap, h->err);
+    DAISY_LAUNCH_CHECK(h);
+    return DAISY_OK;
+}
+
 template <int IPT>
 static int launch_small_book(daisy_ctx *h, cudaStream_t bs, const int32_t *triples, int B, uint32_t U, uint32_t I, int vbU,
                              int kbU, int vbQ, int kbQ, BookSet &k) {
@@ -919,19 +1243,29 @@ __global__ void __launch_bounds__(256) k_seg_all(const float *__restrict__ P, co
         float4 tot[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) tot[v] = f4_zero();
-        for (int j0 = 0; j0 < nsl; j0 += 8) {  // fixed order: slice 0, 1, 2, ... (8 loads in flight)
-            float4 rr[8][V];
+        // fixed order: groups of 64 slices (group sums added in group order), slices of a group in slice order, 8
+        // loads in flight -- two levels so that the rounding error of a very long row does not grow with its length
+        for (int g0 = 0; g0 < nsl; g0 += 64) {
+            float4 grp[V];
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj)
+            for (int v = 0; v < V; ++v) grp[v] = f4_zero();
+            const int g1 = min(nsl, g0 + 64);
+            for (int j0 = g0; j0 < g1; j0 += 8) {
+                float4 rr[8][V];
 #pragma unroll
-                for (int v = 0; v < V; ++v)
-                    rr[jj][v] = (j0 + jj < nsl && act[v]) ? __ldcg(s2 + (size_t)(j0 + jj) * D4 + lane + 32 * v) : f4_zero();
+                for (int jj = 0; jj < 8; ++jj)
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj)
-                if (j0 + jj < nsl) {
+                    for (int v = 0; v < V; ++v)
+                        rr[jj][v] = (j0 + jj < g1 && act[v]) ? __ldcg(s2 + (size_t)(j0 + jj) * D4 + lane + 32 * v) : f4_zero();
 #pragma unroll
-                    for (int v = 0; v < V; ++v) tot[v] = f4_add(tot[v], rr[jj][v]);
-                }
+                for (int jj = 0; jj < 8; ++jj)
+                    if (j0 + jj < g1) {
+#pragma unroll
+                        for (int v = 0; v < V; ++v) grp[v] = f4_add(grp[v], rr[jj][v]);
+                    }
+            }
+#pragma unroll
+            for (int v = 0; v < V; ++v) tot[v] = f4_add(tot[v], grp[v]);
         }
 #pragma unroll
         for (int v = 0; v < V; ++v)
@@ -1169,7 +1503,9 @@ static int book_phase(daisy_ctx *h, StepPlan &pl, const int32_t *triples, int64_
                       cudaStream_t s, const int32_t *host_src, bool inputs_ready, const daisy_shard *sh) {
     const int B = (int)B64;
     int vbU = 0, kbU = 0, vbQ = 0, kbQ = 0;
-    const bool small = !sh && small_path(h, B64, U, I, &vbU, &kbU, &vbQ, &kbQ);
+    const bool tiny = !sh && small_path(h, B64, U, I, &vbU, &kbU, &vbQ, &kbQ);
+    const bool mid = !sh && !tiny && B64 > 0 && B64 <= h->mid_max;   // also small batches whose refs do not pack
+    const bool small = tiny || mid;  // C = 1, one-launch bookkeeping, k_seg_all with short windows and slices
     const int C = small ? 1 : auto_chunk(h, B);
     const bool piped = h->pipeline && h->timing != 2;
     cudaStream_t bs = piped ? h->side_stream : s;
@@ -1209,7 +1545,9 @@ static int book_phase(daisy_ctx *h, StepPlan &pl, const int32_t *triples, int64_
     if (small) {
         for (int ph = PH_PREP; ph < PH_SLOTS; ++ph) phase_mark(h, ph, s);
         int rc;
-        if (2 * B <= 4096)
+        if (mid)
+            rc = launch_mid_book(h, bs, triples, B, U, I, k);
+        else if (2 * B <= 4096)
             rc = launch_small_book<4>(h, bs, triples, B, U, I, vbU, kbU, vbQ, kbQ, k);
         else if (2 * B <= 8192)
             rc = launch_small_book<8>(h, bs, triples, B, U, I, vbU, kbU, vbQ, kbQ, k);
@@ -1337,7 +1675,7 @@ static int table_phase_v(daisy_ctx *h, const StepPlan &pl, const float *P, const
     }
     phase_mark(h, PH_MAIN, s);
     {   // every multi-contribution row of both tables + the loss in one launch
-        const int NS = pl.small ? 64 : 2 * h->num_sms;
+        const int NS = (pl.small && B <= DAISY_SMALL_CAP) ? 64 : 2 * h->num_sms;
         int blocksU, blocksQ;
         if (pl.small) {
             blocksU = daisy_ceil_div(B, 8 * DAISY_SMALL_WIN), blocksQ = daisy_ceil_div(2 * B, 8 * DAISY_SMALL_WIN);
