@@ -107,6 +107,7 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
     if (h->main_stages < 0) h->main_stages = 0;
     if (h->main_stages > 16) h->main_stages = 16;
     h->inputs_ready = 0;
+    h->seg_win = env_int("DAISY_SEG_WIN", 32) == 16 ? 16 : 32;
     h->mid_max = env_int("DAISY_MID_MAX", 65536);  // measured: above ~100 k triples the general pipeline (graph-replayed) is faster
     if (h->mid_max < 0) h->mid_max = 0;
     if (h->mid_max > h->mid_cap) h->mid_max = h->mid_cap;

@@ -1682,6 +1682,11 @@ static int table_phase_v(daisy_ctx *h, const StepPlan &pl, const float *P, const
             k_seg_all<V, Opt, DAISY_SMALL_WIN, DAISY_SMALL_SLICE><<<NS + blocksU + blocksQ + (loss_accum ? 1 : 0), 256, 0, s>>>(
                 P, Q, k.ukey_s, k.qkey_s, B, 0xFFFFFFFFu, h->stageU, h->stageQ, h->stage2, D4, opt, NS, blocksU, blocksQ,
                 DAISY_SMALL_SLICE, k.longs, h->longs_cap, h->ticket, h->loss_part, warps, loss_accum);
+        } else if (h->seg_win == 16) {  // DAISY_SEG_WIN: sorted refs per warp of the window blocks (general path)
+            blocksU = daisy_ceil_div(B, 8 * 16), blocksQ = daisy_ceil_div(2 * (int64_t)B, 8 * 16);
+            k_seg_all<V, Opt, 16, DAISY_SLICE><<<NS + blocksU + blocksQ + (loss_accum ? 1 : 0), 256, 0, s>>>(
+                P, Q, k.ukey_s, k.qkey_s, B, pl.I, h->stageU, h->stageQ, h->stage2, D4, opt, NS, blocksU, blocksQ,
+                h->heavy_len, k.longs, h->longs_cap, h->ticket, h->loss_part, warps, loss_accum);
         } else {
             blocksU = daisy_ceil_div(B, 8 * 32), blocksQ = daisy_ceil_div(2 * (int64_t)B, 8 * 32);
             k_seg_all<V, Opt, 32, DAISY_SLICE><<<NS + blocksU + blocksQ + (loss_accum ? 1 : 0), 256, 0, s>>>(
