@@ -1324,7 +1324,7 @@ static int auto_chunk(const daisy_ctx *h, int64_t B) {
     // keep >= ~4 waves of 32 resident warps per SM before growing the chunk
     const int64_t want_warps = (int64_t)h->num_sms * 32 * 4;
     int c = 1;
-    while (c < 16 && B / (2 * c) >= want_warps) c *= 2;
+    while (c < 32 && B / (2 * c) >= want_warps) c *= 2;  // 32 at 1 M triples: main kernel 0.43 ms vs 0.45 at 16
     return c;
 }
 
