@@ -18,6 +18,15 @@ One step = one pass of the hot path (daisy_bpr_step) over one batch of synthetic
   cpu_baseline : the reference's CPU path (oracle TorchPort: nn.Embedding-equivalent tables + autograd +
           optim.SGD, the calls of BPRMFRecommender.py:172-176) timed on this box's host cores, bounded sample
 --impl reference : the reference arm -- the same CPU path timed alone, same metric / config.
+
+Secondary lines (not the driver's metric; `profiles/` holds one of each):
+  --workload config3 [--batch B] [--epoch-api]   ml-20m shape (L2-resident), B = 65 536 by default; --epoch-api runs the K
+                     timed steps through ONE daisy_bpr_epoch call (what BPRMFRecommender.fit does)
+  --workload config1   ml-100k, 20 epochs + HR@10 / NDCG@10 through BPRMFRecommender.fit, reference loop beside it
+  --workload config2   funk-SVD (daisy_mf_fit) on the ml-1m shape
+  --workload eval      full-catalogue top-100 for 16 384 users x 2 M items
+  --workload sampler   device-side negative sampler on the ml-20m shape
+  --phases / --trace   per-phase device times (serialised) / timeline of bookkeeping vs table kernels
 """
 from __future__ import annotations
 
