@@ -185,3 +185,26 @@ def test_sampler_rule_semantics():
     big = sample_epoch(np.array([[0, 1], [0, 2]] * 1), 10, 4000, 5, 0, shuffle=False)
     c = np.bincount(big[:, 2], minlength=10)
     assert c[1] == 0 and c[2] == 0 and c[[0, 3, 4, 5, 6, 7, 8, 9]].min() > 0.8 * 8000 / 8
+
+
+# ------------------------------------------------------------------------------------------------
+# next row (NCF-GMF): the oracle is pinned before any kernel is built on it
+# ------------------------------------------------------------------------------------------------
+def test_gmf_oracle_matches_reference_ncf_with_adam(golden):
+    """oracle/gmf_oracle.py (closed-form forward / BCE / dense gradients / torch-default Adam over EVERY row) against
+    5 steps of the unmodified reference NCF(model='GMF') + nn.BCEWithLogitsLoss + optim.Adam
+    (tests/golden/make_ncf_golden.py).  float64 closed form vs the reference's fp32: 2e-6 relative on the tables."""
+    from oracle import gmf_oracle
+    g = golden("gmf_small.npz")
+    st = gmf_oracle.GMFAdam(g["P0"], g["Q0"], g["w0"], g["b0"], lr=float(g["lr"]))
+    for k in range(len(g["losses"])):
+        loss = st.step(g["users"][k], g["items"][k], g["labels"][k])
+        assert abs(loss - g["losses"][k]) < 2e-6 * abs(g["losses"][k]) + 1e-7, (k, loss, g["losses"][k])
+        for got, want in ((st.P, g["P"][k]), (st.Q, g["Q"][k]), (st.w, g["w"][k]), (st.b, g["b"][k])):
+            assert rel_err(got, want) <= 2e-6, (k, rel_err(got, want))
+    # untouched rows keep moving under dense Adam: users >= U/2 get no gradient on odd steps, yet step 1 -> 2 moves them
+    U = g["P0"].shape[0]
+    quiet = np.setdiff1d(np.arange(U // 2, U), g["users"][1])
+    assert quiet.size > 0 and np.abs(g["P"][1][quiet] - g["P"][0][quiet]).max() > 0
+    fwd = gmf_oracle.gmf_forward(st.P, st.Q, st.w, st.b[0], g["users"][0], g["items"][0])
+    assert np.allclose(fwd, g["fwd_last"], rtol=1e-5, atol=1e-6)
