@@ -26,6 +26,7 @@ Secondary lines (not the driver's metric; `profiles/` holds one of each):
   --workload config2   funk-SVD (daisy_mf_fit) on the ml-1m shape
   --workload eval      full-catalogue top-100 for 16 384 users x 2 M items
   --workload sampler   device-side negative sampler on the ml-20m shape
+  --workload gmf       NCF-GMF training step (daisy_gmf_step) on the ml-100k shape, batch 256
   --phases / --trace   per-phase device times (serialised) / timeline of bookkeeping vs table kernels
 """
 from __future__ import annotations
@@ -435,6 +436,80 @@ def run_config1(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# NCF-GMF (secondary line)
+# ------------------------------------------------------------------------------------------------
+def run_gmf(args):
+    """samples/s of the fused GMF step (daisy_gmf_step: gather, BCE, deterministic row sums, dense Adam) at the
+    reference script's defaults on the ml-100k shape (943 x 1 682, factor_num 32, batch 256, lr 0.001;
+    NCFRecommender.py:140-160), 1 positive + 4 sampled negatives per interaction, next to the closed-form restatement
+    of the reference loop (oracle/gmf_oracle.py, numpy) on the host."""
+    import torch
+    from recommend_lib_b200.ncf import NCF, GMFAdam
+    U, I, D, B = 943, 1682, 32, args.batch or 256
+    K, W = max(args.steps, 200), max(args.warmup, 20)
+    rng = np.random.default_rng(2019)
+    n = (K + W) * B
+    users = rng.integers(0, U, n).astype(np.int64)
+    items = rng.integers(0, I, n).astype(np.int64)
+    labels = (np.arange(n) % 5 == 0).astype(np.float32)
+    dev = torch.device("cuda:0")
+    torch.manual_seed(2019)
+    model = NCF(U, I, D, 3, 0.0, "GMF", max_batch=B).to(dev)
+    opt = GMFAdam(model, lr=0.001)
+    packed = torch.from_numpy(np.stack([users, items, labels.astype(np.int64)], 1).astype(np.int32)).reshape(K + W, B, 3)
+    host = packed.pin_memory()
+    devs = packed.to(dev)
+
+    run = lambda first, count, src: [opt.step(src[s]) for s in range(first, first + count)]
+    run(0, W, devs)
+    model.check()
+    torch.cuda.synchronize()
+    l0 = model.handle(B).launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    run(W, K, devs)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    launches = model.handle(B).launches - l0
+    loss_host = torch.zeros(K + W, dtype=torch.float64).pin_memory()
+    ev0.record()
+    for s in range(W, W + K):                       # e2e: pinned host samples in, the step's loss read back
+        opt.step(host[s])
+        loss_host[s:s + 1].copy_(opt._loss, non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms2 = ev0.elapsed_time(ev1)
+    loss = float(loss_host[W + K - 1])
+    model.check()
+    from oracle import gmf_oracle
+    st = gmf_oracle.GMFAdam(np.random.default_rng(1).normal(0, 0.01, (U, D)), np.random.default_rng(2).normal(0, 0.01, (I, D)),
+                            np.random.default_rng(3).normal(0, 0.3, D), np.zeros(1), lr=0.001, dtype=np.float32)
+    nc = 200
+    t0 = time.time()
+    for s in range(nc):
+        st.step(users[s * B:(s + 1) * B], items[s * B:(s + 1) * B], labels[s * B:(s + 1) * B])
+    cpu_dt = time.time() - t0
+    bytes_step = B * (2 * 4 * D * 3) + 8 * 4 * D * (U + I)      # gather + stage + grad rows, dense Adam pass
+    line = {"metric": "gmf_train_samples_per_s", "value": B * K / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "NCF-GMF training step on the ml-100k shape (943 x 1682, factor_num 32, batch 256, Adam lr 0.001)",
+                       "user_num": U, "item_num": I, "dim": D, "batch": B,
+                       "l2": "tables + Adam moments (1 MB) are L2-resident; the step is launch-latency-bound (5 launches)"},
+            "e2e": {"value": B * K / (ms2 * 1e-3), "unit": "samples/s", "ms_per_step": ms2 / K,
+                    "h2d_bytes_per_step": B * 12, "d2h_bytes_per_step": 8},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": bytes_step / (ms / K * 1e-3) / 1e9, "peak": measured_peaks()[0],
+                         "unit": "GB/s", "frac": bytes_step / (ms / K * 1e-3) / 1e9 / measured_peaks()[0], "traffic": None,
+                         "note": "latency-bound at this size; bytes = per-sample rows + the dense Adam pass over both tables"},
+            "cpu_baseline": {"value": B * nc / cpu_dt, "unit": "samples/s", "cores": 1, "kind": "port",
+                             "sample": f"{nc} steps of the closed-form restatement (numpy, float32) of the reference loop"},
+            "final_loss": loss}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
 # config 2: funk-SVD (secondary line, not the driver's metric)
 # ------------------------------------------------------------------------------------------------
 def run_mf(args):
@@ -622,7 +697,7 @@ def main():
     ap.add_argument("--phases", action="store_true", help="also print the per-phase breakdown of the step")
     ap.add_argument("--trace", action="store_true", help="also print a timeline of bookkeeping vs table kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="config4", choices=["config4", "config3", "config2", "config1", "sampler", "eval"],
+    ap.add_argument("--workload", default="config4", choices=["config4", "config3", "config2", "config1", "sampler", "eval", "gmf"],
                     help="N = 1 only: config4 is the driver's metric; config3 (L2-resident ml-20m shape) and config2 "
                          "(funk-SVD) are secondary lines kept under profiles/")
     ap.add_argument("--eval-users", type=int, default=16384)
@@ -644,6 +719,8 @@ def main():
         return bench_sharded(args, CFG5, METRIC, UNIT)
     if args.workload == "config1":
         return run_config1(args)
+    if args.workload == "gmf":
+        return run_gmf(args)
     if args.workload == "config2":
         return run_mf(args)
     if args.workload == "sampler":

@@ -191,6 +191,27 @@ DAISY_API int daisy_bpr_adam_step(daisy_handle_t h, float *P, float *Q, float *m
                         const int32_t *triples, int64_t B, float lr, float beta1, float beta2, float eps,
                         int64_t step_no, double *loss_accum, daisy_stream_t stream);
 
+/* ---- NCF, GMF variant -----------------------------------------------
+ * NCF.forward with model == 'GMF' (NCFRecommender.py:105-125): pred[t] = w . (P[u_t] * Q[i_t]) + b.
+ * samples: device int32 [B,3] packed (user, item, label); the label column is ignored here.
+ * P = embed_user_GMF.weight [user_num, dim], Q = embed_item_GMF.weight [item_num, dim], w = predict_layer.weight
+ * [dim] (16-byte aligned), b = predict_layer.bias [1]. */
+DAISY_API int daisy_gmf_forward(daisy_handle_t h, const float *P, const float *Q, const float *w, const float *b,
+                      const int32_t *samples, int64_t B, float *pred, daisy_stream_t stream);
+
+/* One training step of the script's loop (NCFRecommender.py:283-287 with :255, :260):
+ *   model.zero_grad(); prediction = model(user, item); loss = nn.BCEWithLogitsLoss()(prediction, label);
+ *   loss.backward(); optim.Adam(lr).step()
+ * fused: gradients at the pre-step parameters, repeated rows accumulate deterministically (sort-by-row segmented
+ * reduction, no float atomics), then torch-default Adam over EVERY element of both tables and of the predict layer
+ * (dense Adam: a row without a gradient still moves while its first moment decays).
+ * mP,vP [user_num,dim], mQ,vQ [item_num,dim]: Adam moments of the tables; mwb [2*(dim+1)]: moments of (w.., b):
+ * first moments, then second moments.  step_no is 1-based.  loss_accum (device double, may be NULL): the batch's
+ * MEAN loss is added to it.  B <= 8192 (the reference's batch is 256); labels are 0 / 1 in column 2 of samples. */
+DAISY_API int daisy_gmf_step(daisy_handle_t h, float *P, float *Q, float *w, float *b, float *mP, float *vP, float *mQ,
+                   float *vQ, float *mwb, const int32_t *samples, int64_t B, float lr, float beta1, float beta2,
+                   float eps, int64_t step_no, double *loss_accum, daisy_stream_t stream);
+
 /* metric_eval / _bpr_topk (util/metrics.py:46-66,88-94), all groups in one launch:
  * for n < N: score[c] = <P[users[n]], Q[cand[n,c]]>, c < C; the K best in (score desc, position asc) order.
  * out_pos [N,K] int32 = candidate positions (the `indices` of torch.topk), out_item [N,K] = cand ids

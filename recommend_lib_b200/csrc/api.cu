@@ -192,7 +192,7 @@ extern "C" int daisy_destroy(daisy_handle_t h) {
     daisy_shard_free(h);
     void *ptrs[] = {h->triples, h->key_in, h->val_in, h->val_out, h->ukey_in, h->uval_in, h->uval_out, h->ikey_in,
                     h->ikey_out, h->ival_in, h->ival_out, h->stageU, h->stageQ, h->stage2, h->loss_part,
-                    h->err, h->cub_tmp, h->ticket, h->mid_buf, h->scores, h->sel_hist, h->own_key, h->own_key_s, h->own_val, h->own_val_s,
+                    h->err, h->cub_tmp, h->ticket, h->mid_buf, h->gradP, h->gradQ, h->wpart, h->scores, h->sel_hist, h->own_key, h->own_key_s, h->own_val, h->own_val_s,
                     h->own_tmp};
     for (void *p : ptrs)
         if (p) cudaFree(p);

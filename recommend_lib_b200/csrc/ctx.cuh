@@ -145,6 +145,9 @@ struct daisy_ctx {
     int chunk;       // max positive-item run length handled by one warp in the main kernel (0 = auto)
     int heavy_len;   // segments longer than this go to the block-per-row kernel
     int main_stages; // > 0: TMA-pipelined main kernel with this many stages (triples in flight) per warp; 0: register prefetch
+    int pairs_mode;  // set by csrc/gmf.cu around book_phase: the batch holds (user, item, label) samples
+    float *gradP, *gradQ;  // [U, D], [I, D] dense gradient buffers of the GMF step (allocated on first use, kept zero between steps)
+    float *wpart;    // [maxB, D + 1] per-sample contributions to the predict layer's gradient (GMF step)
     int seg_win;     // sorted refs per warp of k_seg_all's window blocks in the general path: 32 (default) or 16
     int small_max;   // batches up to this many triples take the 3-launch small-batch path (0 = never; <= DAISY_SMALL_CAP)
     int64_t mid_max; // ... and up to this many the same path with k_mid_book (0 = never; <= mid_cap)

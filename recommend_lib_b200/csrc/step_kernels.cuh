@@ -671,7 +671,9 @@ __global__ void __launch_bounds__(1024) k_small_book(const int32_t *__restrict__
                                                       uint32_t *__restrict__ ukey_s, uint32_t *__restrict__ qkey_s,
                                                       uint32_t *__restrict__ uslot, uint32_t *__restrict__ jslot,
                                                       uint32_t *__restrict__ islot, uint32_t *longs, int longs_cap,
-                                                      int *err) {
+                                                      int *err, int pairs) {
+    // pairs != 0 (csrc/gmf.cu): the batch holds (user, item, label) samples -- ONE item ref per sample (column 1, filed
+    // under jslot), column 2 is a label and is neither a row nor range-checked
     extern __shared__ __align__(16) unsigned char small_dsm[];
     uint32_t *hist = reinterpret_cast<uint32_t *>(small_dsm);
     uint32_t *sk = hist + DAISY_SMALL_HIST_WORDS;  // [1024 * IPT] compacted, then sorted words
@@ -682,7 +684,7 @@ __global__ void __launch_bounds__(1024) k_small_book(const int32_t *__restrict__
     constexpr uint32_t NC = 1u << DAISY_SMALL_CB;
     const bool items = blockIdx.x >= NC;
     const uint32_t cls = blockIdx.x & (NC - 1);
-    const int n = items ? 2 * B : B;
+    const int n = items ? (pairs ? B : 2 * B) : B;
     const int vb = items ? vbQ : vbU, kb = items ? kbQ : kbU;
     const uint32_t bound = items ? I : U;
     uint32_t keys[IPT];
@@ -698,7 +700,11 @@ __global__ void __launch_bounds__(1024) k_small_book(const int32_t *__restrict__
             if (checker) {
                 uint32_t u, i, j;
                 bool bad;
-                load_triple(triples, t, U, I, u, i, j, bad);
+                load_triple(triples, t, U, pairs ? 0xFFFFFFFFu : I, u, i, j, bad);
+                if (pairs && i >= I) {  // (the label column was let through by the unbounded check above)
+                    bad = true;
+                    i = 0;
+                }
                 st[3 * (size_t)t] = (int32_t)u;
                 st[3 * (size_t)t + 1] = (int32_t)i;
                 st[3 * (size_t)t + 2] = (int32_t)j;
@@ -708,7 +714,7 @@ __global__ void __launch_bounds__(1024) k_small_book(const int32_t *__restrict__
                 }
                 row = u;
             } else {
-                row = (uint32_t)__ldg(triples + 3 * (size_t)t + (items ? (idx < B ? 2 : 1) : 0));
+                row = (uint32_t)__ldg(triples + 3 * (size_t)t + (items ? ((idx < B && !pairs) ? 2 : 1) : 0));
             }
         }
         keys[k] = row;
@@ -1135,7 +1141,7 @@ static int launch_mid_book(daisy_ctx *h, cudaStream_t bs, const int32_t *triples
 
 template <int IPT>
 static int launch_small_book(daisy_ctx *h, cudaStream_t bs, const int32_t *triples, int B, uint32_t U, uint32_t I, int vbU,
-                             int kbU, int vbQ, int kbQ, BookSet &k) {
+                             int kbU, int vbQ, int kbQ, BookSet &k, int pairs = 0) {
     const size_t smem = sizeof(uint32_t) * (DAISY_SMALL_HIST_WORDS + 1024 * IPT);
     static bool granted[64];
     if (!granted[h->device & 63]) {
@@ -1145,7 +1151,7 @@ static int launch_small_book(daisy_ctx *h, cudaStream_t bs, const int32_t *tripl
     DAISY_CUDA(cudaMemsetAsync(k.longs, 0, 2 * sizeof(uint32_t), bs));
     k_small_book<IPT><<<2 << DAISY_SMALL_CB, 1024, smem, bs>>>(triples, B, U, I, vbU, kbU, vbQ, kbQ, k.st, k.ukey_s,
                                                              k.qkey_s, k.uslot, k.jslot, k.islot, k.longs,
-                                                             h->longs_cap, h->err);
+                                                             h->longs_cap, h->err, pairs);
     DAISY_LAUNCH_CHECK(h);
     return DAISY_OK;
 }
@@ -1166,7 +1172,7 @@ static int launch_small_book(daisy_ctx *h, cudaStream_t bs, const int32_t *tripl
 template <int V, class Opt, int WIN, int SLICE>
 __global__ void __launch_bounds__(256) k_seg_all(const float *__restrict__ P, const float *__restrict__ Q,
                                                   const uint32_t *__restrict__ ukey_s,
-                                                  const uint32_t *__restrict__ qkey_s, int B, uint32_t q_sentinel,
+                                                  const uint32_t *__restrict__ qkey_s, int B, int nQ, uint32_t q_sentinel,
                                                   const float *__restrict__ stageU, const float *__restrict__ stageQ,
                                                   float *__restrict__ stage2, int D4, Opt opt, int NS, int blocksU,
                                                   int blocksQ, int long_len, const uint32_t *__restrict__ longs,
@@ -1193,7 +1199,7 @@ __global__ void __launch_bounds__(256) k_seg_all(const float *__restrict__ P, co
         const int wb = b - NS;
         const int tbl = wb < blocksU ? 0 : 1;
         seg_window<V, Opt, WIN>((long long)(tbl ? wb - blocksU : wb) * 8 + wid, tbl, tbl ? Q : P, tbl ? qkey_s : ukey_s,
-                                tbl ? 2 * B : B, tbl ? q_sentinel : 0xFFFFFFFFu, tbl ? stageQ : stageU, D4, opt, long_len);
+                                tbl ? nQ : B, tbl ? q_sentinel : 0xFFFFFFFFu, tbl ? stageQ : stageU, D4, opt, long_len);
         return;
     }
     const int count = min((int)longs[0], longs_cap);
@@ -1503,7 +1509,14 @@ static int book_phase(daisy_ctx *h, StepPlan &pl, const int32_t *triples, int64_
                       cudaStream_t s, const int32_t *host_src, bool inputs_ready, const daisy_shard *sh) {
     const int B = (int)B64;
     int vbU = 0, kbU = 0, vbQ = 0, kbQ = 0;
-    const bool tiny = !sh && small_path(h, B64, U, I, &vbU, &kbU, &vbQ, &kbQ);
+    const int pairs = h->pairs_mode;  // csrc/gmf.cu: (user, item, label) samples, one item ref each
+    bool tiny = !sh && small_path(h, B64, U, I, &vbU, &kbU, &vbQ, &kbQ);
+    if (pairs) {
+        vbQ = bits_for((uint64_t)(B64 > 1 ? B64 - 1 : 1));
+        tiny = B64 > 0 && B64 <= DAISY_SMALL_CAP && vbU + kbU <= 32 && vbQ + kbQ <= 32 && h->small_max > 0 && B64 <= h->small_max;
+        DAISY_REQUIRE(tiny, DAISY_EUNSUPPORTED, "the (user, item, label) step takes batches of 1..%d samples whose row and "
+                      "sample indices pack into 32 bits (batch %lld, %u users, %u items)", h->small_max, (long long)B64, U, I);
+    }
     const bool mid = !sh && !tiny && B64 > 0 && B64 <= h->mid_max;   // also small batches whose refs do not pack
     const bool small = tiny || mid;  // C = 1, one-launch bookkeeping, k_seg_all with short windows and slices
     const int C = small ? 1 : auto_chunk(h, B);
@@ -1548,11 +1561,11 @@ static int book_phase(daisy_ctx *h, StepPlan &pl, const int32_t *triples, int64_
         if (mid)
             rc = launch_mid_book(h, bs, triples, B, U, I, k);
         else if (2 * B <= 4096)
-            rc = launch_small_book<4>(h, bs, triples, B, U, I, vbU, kbU, vbQ, kbQ, k);
+            rc = launch_small_book<4>(h, bs, triples, B, U, I, vbU, kbU, vbQ, kbQ, k, pairs);
         else if (2 * B <= 8192)
-            rc = launch_small_book<8>(h, bs, triples, B, U, I, vbU, kbU, vbQ, kbQ, k);
+            rc = launch_small_book<8>(h, bs, triples, B, U, I, vbU, kbU, vbQ, kbQ, k, pairs);
         else
-            rc = launch_small_book<16>(h, bs, triples, B, U, I, vbU, kbU, vbQ, kbQ, k);
+            rc = launch_small_book<16>(h, bs, triples, B, U, I, vbU, kbU, vbQ, kbQ, k, pairs);
         if (rc) return rc;
         phase_mark(h, PH_SLOTS, s);
         if (piped) {
@@ -1680,17 +1693,17 @@ static int table_phase_v(daisy_ctx *h, const StepPlan &pl, const float *P, const
         if (pl.small) {
             blocksU = daisy_ceil_div(B, 8 * DAISY_SMALL_WIN), blocksQ = daisy_ceil_div(2 * B, 8 * DAISY_SMALL_WIN);
             k_seg_all<V, Opt, DAISY_SMALL_WIN, DAISY_SMALL_SLICE><<<NS + blocksU + blocksQ + (loss_accum ? 1 : 0), 256, 0, s>>>(
-                P, Q, k.ukey_s, k.qkey_s, B, 0xFFFFFFFFu, h->stageU, h->stageQ, h->stage2, D4, opt, NS, blocksU, blocksQ,
+                P, Q, k.ukey_s, k.qkey_s, B, 2 * B, 0xFFFFFFFFu, h->stageU, h->stageQ, h->stage2, D4, opt, NS, blocksU, blocksQ,
                 DAISY_SMALL_SLICE, k.longs, h->longs_cap, h->ticket, h->loss_part, warps, loss_accum);
         } else if (h->seg_win == 16) {  // DAISY_SEG_WIN: sorted refs per warp of the window blocks (general path)
             blocksU = daisy_ceil_div(B, 8 * 16), blocksQ = daisy_ceil_div(2 * (int64_t)B, 8 * 16);
             k_seg_all<V, Opt, 16, DAISY_SLICE><<<NS + blocksU + blocksQ + (loss_accum ? 1 : 0), 256, 0, s>>>(
-                P, Q, k.ukey_s, k.qkey_s, B, pl.I, h->stageU, h->stageQ, h->stage2, D4, opt, NS, blocksU, blocksQ,
+                P, Q, k.ukey_s, k.qkey_s, B, 2 * B, pl.I, h->stageU, h->stageQ, h->stage2, D4, opt, NS, blocksU, blocksQ,
                 h->heavy_len, k.longs, h->longs_cap, h->ticket, h->loss_part, warps, loss_accum);
         } else {
             blocksU = daisy_ceil_div(B, 8 * 32), blocksQ = daisy_ceil_div(2 * (int64_t)B, 8 * 32);
             k_seg_all<V, Opt, 32, DAISY_SLICE><<<NS + blocksU + blocksQ + (loss_accum ? 1 : 0), 256, 0, s>>>(
-                P, Q, k.ukey_s, k.qkey_s, B, pl.I, h->stageU, h->stageQ, h->stage2, D4, opt, NS, blocksU, blocksQ,
+                P, Q, k.ukey_s, k.qkey_s, B, 2 * B, pl.I, h->stageU, h->stageQ, h->stage2, D4, opt, NS, blocksU, blocksQ,
                 h->heavy_len, k.longs, h->longs_cap, h->ticket, h->loss_part, warps, loss_accum);
         }
         DAISY_LAUNCH_CHECK(h);

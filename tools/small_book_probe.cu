@@ -30,7 +30,7 @@ static void run(int B, uint32_t U, uint32_t I) {
     for (int it = 0; it < 5; ++it) {
         cudaEventRecord(e0);
         CK(cudaMemset(longs, 0, 8));
-        k_small_book<IPT><<<2 << DAISY_SMALL_CB, 1024, smem>>>(tri, B, U, I, vbU, kbU, vbQ, kbQ, st, uk, qk, us, js, is, longs, 4000, err);
+        k_small_book<IPT><<<2 << DAISY_SMALL_CB, 1024, smem>>>(tri, B, U, I, vbU, kbU, vbQ, kbQ, st, uk, qk, us, js, is, longs, 4000, err, 0);
         cudaEventRecord(e1);
         CK(cudaDeviceSynchronize());
         cudaEventElapsedTime(&ms, e0, e1);
@@ -93,11 +93,11 @@ static void run_step(int B, uint32_t U, uint32_t I, int D) {
     for (int it = 0; it < 5; ++it) {
         cudaEventRecord(e[0]);
         cudaMemsetAsync(longs, 0, 8);
-        k_small_book<16><<<2 << DAISY_SMALL_CB, 1024, smem>>>(tri, B, U, I, vbU, kbU, vbQ, kbQ, st, uk, qk, us, js, is, longs, 4000, err);
+        k_small_book<16><<<2 << DAISY_SMALL_CB, 1024, smem>>>(tri, B, U, I, vbU, kbU, vbQ, kbQ, st, uk, qk, us, js, is, longs, 4000, err, 0);
         cudaEventRecord(e[1]);
         k_bpr_main<1, ProbeOpt, false><<<daisy_ceil_div(B, 8), 256>>>(a, opt);
         cudaEventRecord(e[2]);
-        k_seg_all<1, ProbeOpt, DAISY_SMALL_WIN, DAISY_SMALL_SLICE><<<64 + blocksU + blocksQ + 1, 256>>>(P, Q, uk, qk, B, 0xFFFFFFFFu, sU, sQ, st2, D / 4, opt, 64, blocksU, blocksQ, DAISY_SMALL_SLICE, longs, 4000, ticket, lp, B, loss);
+        k_seg_all<1, ProbeOpt, DAISY_SMALL_WIN, DAISY_SMALL_SLICE><<<64 + blocksU + blocksQ + 1, 256>>>(P, Q, uk, qk, B, 2 * B, 0xFFFFFFFFu, sU, sQ, st2, D / 4, opt, 64, blocksU, blocksQ, DAISY_SMALL_SLICE, longs, 4000, ticket, lp, B, loss);
         cudaEventRecord(e[3]);
         CK(cudaDeviceSynchronize());
         for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&ms[k], e[k], e[k + 1]);
@@ -248,7 +248,7 @@ static void check_step(int B, uint32_t U, uint32_t I, int D, int cb, int NS) {
     a.B = B; a.D4 = D / 4; a.C = 1; a.c2 = 1.f; a.jsrc = nullptr; a.isrc = nullptr;
     const int blocksU = daisy_ceil_div(B, 8 * DAISY_SMALL_WIN), blocksQ = daisy_ceil_div(2 * B, 8 * DAISY_SMALL_WIN);
     k_bpr_main<1, ProbeOpt, false><<<daisy_ceil_div(B, 8), 256>>>(a, opt);
-    k_seg_all<1, ProbeOpt, DAISY_SMALL_WIN, DAISY_SMALL_SLICE><<<NS + blocksU + blocksQ + 1, 256>>>(P, Q, uk, qk, B, 0xFFFFFFFFu, sU, sQ, st2, D / 4, opt, NS, blocksU, blocksQ, DAISY_SMALL_SLICE, longs, 30000, ticket, lp, B, loss);
+    k_seg_all<1, ProbeOpt, DAISY_SMALL_WIN, DAISY_SMALL_SLICE><<<NS + blocksU + blocksQ + 1, 256>>>(P, Q, uk, qk, B, 2 * B, 0xFFFFFFFFu, sU, sQ, st2, D / 4, opt, NS, blocksU, blocksQ, DAISY_SMALL_SLICE, longs, 30000, ticket, lp, B, loss);
     CK(cudaDeviceSynchronize());
     std::vector<float> gP(hP.size()), gQ(hQ.size());
     CK(cudaMemcpy(gP.data(), P, gP.size() * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(gQ.data(), Q, gQ.size() * 4, cudaMemcpyDeviceToHost));
