@@ -212,6 +212,15 @@ DAISY_API int daisy_gmf_step(daisy_handle_t h, float *P, float *Q, float *w, flo
                    float *vQ, float *mwb, const int32_t *samples, int64_t B, float lr, float beta1, float beta2,
                    float eps, int64_t step_no, double *loss_accum, daisy_stream_t stream);
 
+/* The loop `for user, item, label in train_loader:` of one epoch (NCFRecommender.py:268-288) inside the library:
+ * samples int32 [n,3] (already shuffled), consumed in consecutive batches of `batch`, step numbers
+ * first_step_no, first_step_no + 1, ...; on_host = 1: (pinned) host memory, copied in batch by batch.
+ * loss_accum receives the SUM of the batches' mean losses. */
+DAISY_API int daisy_gmf_epoch(daisy_handle_t h, float *P, float *Q, float *w, float *b, float *mP, float *vP, float *mQ,
+                    float *vQ, float *mwb, const int32_t *samples, int64_t n, int64_t batch, int on_host, float lr,
+                    float beta1, float beta2, float eps, int64_t first_step_no, double *loss_accum,
+                    daisy_stream_t stream);
+
 /* metric_eval / _bpr_topk (util/metrics.py:46-66,88-94), all groups in one launch:
  * for n < N: score[c] = <P[users[n]], Q[cand[n,c]]>, c < C; the K best in (score desc, position asc) order.
  * out_pos [N,K] int32 = candidate positions (the `indices` of torch.topk), out_item [N,K] = cand ids

@@ -202,19 +202,25 @@ static int gmf_table_phase(daisy_ctx *h, const StepPlan &pl, float *P, float *Q,
 
 }  // namespace
 
-extern "C" int daisy_gmf_step(daisy_handle_t h, float *P, float *Q, float *w, float *b, float *mP, float *vP, float *mQ,
-                              float *vQ, float *mwb, const int32_t *samples, int64_t B, float lr, float beta1, float beta2,
-                              float eps, int64_t step_no, double *loss_accum, daisy_stream_t stream) {
-    int rc = check_step_args(h, P, Q, samples, B);
+namespace {
+struct GmfParams {
+    float *P, *Q, *w, *b, *mP, *vP, *mQ, *vQ, *mwb;
+    float lr, beta1, beta2, eps;
+};
+
+static int gmf_check(daisy_ctx *h, const GmfParams &p, const void *samples, int64_t B, int64_t step_no) {
+    int rc = check_step_args(h, p.P, p.Q, samples, B);
     if (rc) return rc;
-    DAISY_REQUIRE(w && b && mP && vP && mQ && vQ && mwb, DAISY_EINVAL, "null predict-layer or Adam moment pointer");
-    DAISY_REQUIRE(((uintptr_t)w % 16 == 0), DAISY_EINVAL, "predict-layer weight must be 16-byte aligned");
+    DAISY_REQUIRE(p.w && p.b && p.mP && p.vP && p.mQ && p.vQ && p.mwb, DAISY_EINVAL, "null predict-layer or Adam moment pointer");
+    DAISY_REQUIRE(((uintptr_t)p.w % 16 == 0), DAISY_EINVAL, "predict-layer weight must be 16-byte aligned");
     DAISY_REQUIRE(step_no >= 1, DAISY_EINVAL, "step_no is 1-based");
     DAISY_REQUIRE(h->scale == 1.0, DAISY_EINVAL, "lazy L2 scale is %g: call daisy_materialize before a GMF step", h->scale);
-    DAISY_REQUIRE(h->D <= 512, DAISY_EUNSUPPORTED, "dim %d unsupported", h->D);
-    DeviceGuard g(h->device);
-    DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
-    cudaStream_t s = (cudaStream_t)stream;
+    return DAISY_OK;
+}
+
+// one step; samples_dev is what the kernels read (for host_src != null: the landing buffer the copy fills)
+static int gmf_step_impl(daisy_ctx *h, const GmfParams &p, const int32_t *samples_dev, const int32_t *host_src, int64_t B,
+                         int64_t step_no, double *loss_accum, cudaStream_t s, bool inputs_ready) {
     if (!h->gradP) {  // dense gradient buffers: zero once, k_dense_adam keeps them zero
         const size_t nP = (size_t)h->U * h->D, nQ = (size_t)h->I * h->D;
         DAISY_CUDA(cudaMalloc((void **)&h->gradP, nP * sizeof(float)));
@@ -223,25 +229,66 @@ extern "C" int daisy_gmf_step(daisy_handle_t h, float *P, float *Q, float *w, fl
         DAISY_CUDA(cudaMemsetAsync(h->gradP, 0, nP * sizeof(float), s));
         DAISY_CUDA(cudaMemsetAsync(h->gradQ, 0, nQ * sizeof(float), s));
     }
+    if (B == 0) return DAISY_OK;  // optimizer.step() without gradients: Adam skips parameters whose .grad is None
     AdamScalars a;
-    a.b1 = beta1;
-    a.b2 = beta2;
-    a.eps = eps;
-    a.step_size = (float)((double)lr / (1.0 - pow((double)beta1, (double)step_no)));
-    a.inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)beta2, (double)step_no)));
-    if (B == 0) {  // optimizer.step() with no gradients: Adam skips parameters whose .grad is None -- nothing moves
-        return DAISY_OK;
-    }
+    a.b1 = p.beta1;
+    a.b2 = p.beta2;
+    a.eps = p.eps;
+    a.step_size = (float)((double)p.lr / (1.0 - pow((double)p.beta1, (double)step_no)));
+    a.inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)p.beta2, (double)step_no)));
     StepPlan pl;
     h->pairs_mode = 1;
-    rc = book_phase(h, pl, samples, B, (uint32_t)h->U, (uint32_t)h->I, s, nullptr, h->inputs_ready != 0, nullptr);
+    int rc = book_phase(h, pl, samples_dev, B, (uint32_t)h->U, (uint32_t)h->I, s, host_src, host_src != nullptr || inputs_ready,
+                        nullptr);
     h->pairs_mode = 0;
     if (rc) return rc;
     const int D4 = h->D / 4;
-    if (D4 <= 32) return gmf_table_phase<1>(h, pl, P, Q, w, b, mP, vP, mQ, vQ, mwb, a, loss_accum);
-    if (D4 <= 64) return gmf_table_phase<2>(h, pl, P, Q, w, b, mP, vP, mQ, vQ, mwb, a, loss_accum);
-    if (D4 <= 96) return gmf_table_phase<3>(h, pl, P, Q, w, b, mP, vP, mQ, vQ, mwb, a, loss_accum);
-    return gmf_table_phase<4>(h, pl, P, Q, w, b, mP, vP, mQ, vQ, mwb, a, loss_accum);
+    if (D4 <= 32) return gmf_table_phase<1>(h, pl, p.P, p.Q, p.w, p.b, p.mP, p.vP, p.mQ, p.vQ, p.mwb, a, loss_accum);
+    if (D4 <= 64) return gmf_table_phase<2>(h, pl, p.P, p.Q, p.w, p.b, p.mP, p.vP, p.mQ, p.vQ, p.mwb, a, loss_accum);
+    if (D4 <= 96) return gmf_table_phase<3>(h, pl, p.P, p.Q, p.w, p.b, p.mP, p.vP, p.mQ, p.vQ, p.mwb, a, loss_accum);
+    return gmf_table_phase<4>(h, pl, p.P, p.Q, p.w, p.b, p.mP, p.vP, p.mQ, p.vQ, p.mwb, a, loss_accum);
+}
+}  // namespace
+
+extern "C" int daisy_gmf_step(daisy_handle_t h, float *P, float *Q, float *w, float *b, float *mP, float *vP, float *mQ,
+                              float *vQ, float *mwb, const int32_t *samples, int64_t B, float lr, float beta1, float beta2,
+                              float eps, int64_t step_no, double *loss_accum, daisy_stream_t stream) {
+    const GmfParams p = {P, Q, w, b, mP, vP, mQ, vQ, mwb, lr, beta1, beta2, eps};
+    int rc = gmf_check(h, p, samples, B, step_no);
+    if (rc) return rc;
+    DeviceGuard g(h->device);
+    DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
+    return gmf_step_impl(h, p, samples, nullptr, B, step_no, loss_accum, (cudaStream_t)stream, h->inputs_ready != 0);
+}
+
+extern "C" int daisy_gmf_epoch(daisy_handle_t h, float *P, float *Q, float *w, float *b, float *mP, float *vP, float *mQ,
+                               float *vQ, float *mwb, const int32_t *samples, int64_t n, int64_t batch, int on_host, float lr,
+                               float beta1, float beta2, float eps, int64_t first_step_no, double *loss_accum,
+                               daisy_stream_t stream) {
+    DAISY_REQUIRE(n >= 0 && batch > 0, DAISY_EINVAL, "epoch of %lld samples in batches of %lld", (long long)n, (long long)batch);
+    const GmfParams p = {P, Q, w, b, mP, vP, mQ, vQ, mwb, lr, beta1, beta2, eps};
+    int rc = gmf_check(h, p, samples, batch < n ? batch : n, first_step_no);
+    if (rc) return rc;
+    DeviceGuard g(h->device);
+    DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!on_host && n > 0 && h->pipeline && !h->inputs_ready) {  // cf. daisy_bpr_epoch
+        DAISY_CUDA(cudaEventRecord(h->ev_call, s));
+        DAISY_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_call, 0));
+    }
+    int64_t step_no = first_step_no;
+    for (int64_t at = 0; at < n; at += batch, ++step_no) {
+        const int64_t B = n - at < batch ? n - at : batch;
+        const int32_t *src = samples + 3 * at;
+        if (on_host) {
+            int32_t *dst = h->triples + (size_t)h->book_idx * 3 * (size_t)h->maxB;
+            rc = gmf_step_impl(h, p, dst, src, B, step_no, loss_accum, s, true);
+        } else {
+            rc = gmf_step_impl(h, p, src, nullptr, B, step_no, loss_accum, s, true);
+        }
+        if (rc) return rc;
+    }
+    return DAISY_OK;
 }
 
 extern "C" int daisy_gmf_forward(daisy_handle_t h, const float *P, const float *Q, const float *w, const float *b,

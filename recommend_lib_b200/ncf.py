@@ -148,6 +148,33 @@ class GMFAdam:
                                       c_vp(mwb.data_ptr()), c_vp(s.data_ptr()), B, self.lr, self.betas[0], self.betas[1],
                                       self.eps, self.t, c_vp(self._loss.data_ptr()), _lib.stream_ptr(torch, P.device)))
 
+    def epoch(self, samples, batch_size):
+        """All steps of one epoch in ONE library call (``daisy_gmf_epoch``): ``samples`` is the epoch's packed int32
+        [n,3] tensor (device or pinned host), consumed in consecutive batches -- the loop of NCFRecommender.py:268-288.
+        ``last_loss()`` then returns the SUM of the batches' mean losses."""
+        m = self.model
+        P, Q, w, b = m._tensors()
+        s = samples
+        if s.dtype != torch.int32 or s.dim() != 2 or s.shape[1] != 3 or not s.is_contiguous():
+            raise ValueError("packed samples must be a contiguous int32 [n, 3] tensor")
+        n, batch = s.shape[0], int(batch_size)
+        if self.state is None:
+            D = m.factor_num
+            self.state = [torch.zeros_like(P), torch.zeros_like(P), torch.zeros_like(Q), torch.zeros_like(Q),
+                          torch.zeros(2 * (D + 1), dtype=torch.float32, device=P.device)]
+            self._loss = torch.zeros(1, dtype=torch.float64, device=P.device)
+        if n == 0:
+            return
+        self._loss.zero_()
+        h = m.handle(min(batch, n))
+        mP, vP, mQ, vQ, mwb = self.state
+        _lib.check(h.L.daisy_gmf_epoch(h.ptr, c_vp(P.data_ptr()), c_vp(Q.data_ptr()), c_vp(w.data_ptr()), c_vp(b.data_ptr()),
+                                       c_vp(mP.data_ptr()), c_vp(vP.data_ptr()), c_vp(mQ.data_ptr()), c_vp(vQ.data_ptr()),
+                                       c_vp(mwb.data_ptr()), c_vp(s.data_ptr()), n, batch, 0 if s.is_cuda else 1, self.lr,
+                                       self.betas[0], self.betas[1], self.eps, self.t + 1, c_vp(self._loss.data_ptr()),
+                                       _lib.stream_ptr(torch, P.device)))
+        self.t += (n + batch - 1) // batch
+
     def last_loss(self):
         return float(self._loss.item()) if self._loss is not None else 0.0
 
