@@ -50,9 +50,11 @@ def hr_ndcg(pos):
 
 
 def metric_eval(model, test_loader, top_k, algo="bpr"):
-    """Drop-in for ``metric_eval`` (util/metrics.py:88-94); returns (HR, NDCG)."""
-    if algo != "bpr":
-        raise ValueError("only algo='bpr' is on the accelerated path")
+    """Drop-in for ``metric_eval`` (util/metrics.py:88-94); returns (HR, NDCG).  ``algo='bpr'`` (``_bpr_topk``) with a
+    ``BPR`` model, ``algo='ncf'`` (``_ncf_topk``, :68-86) with an ``NCF(model='GMF')`` model: both loaders yield
+    (user, candidates, _) groups whose first candidate is the ground truth."""
+    if algo not in ("bpr", "ncf"):
+        raise ValueError("algo must be 'bpr' or 'ncf'")
     groups = {}
     order = []
     for user, item_i, _ in test_loader:

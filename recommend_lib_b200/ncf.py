@@ -66,6 +66,12 @@ class NCF(nn.Module):
             raise _lib.DaisyError("NCF tables are on the CPU: call model.cuda() first (no CPU fallback)")
         return P, Q, self.predict_layer.weight, self.predict_layer.bias
 
+    def _tables(self):
+        """(P * w, Q): what the candidate top-K kernel ranks with -- <P[u] * w, Q[i]> = logit - b, and the bias does not
+        change a ranking (metrics.metric_eval(..., algo='ncf'), util/metrics.py:68-86)."""
+        P, Q, w, _ = self._tensors()
+        return (P * w.reshape(1, -1)).contiguous(), Q
+
     def handle(self, batch=None):
         P = self._tensors()[0]
         dev = P.device.index if P.device.index is not None else torch.cuda.current_device()
