@@ -124,6 +124,26 @@ class DeviceTripleSampler:
         self._lib.check(self.h.L.daisy_check(self.h.ptr, self._lib.stream_ptr(self._torch, self.device)))
 
 
+class SampleSampler(TripleSampler):
+    """``(user, item, label)`` samples for pointwise training -- the deterministic stand-in for ``NCFData.ng_sample`` +
+    ``DataLoader(shuffle=True)`` (util/data_loader.py:945-960, NCFRecommender.py:240-241): every training pair once
+    with label 1, ``num_ng`` negatives per pair with label 0 (uniform items, re-drawn while ``(u, j)`` is a training
+    pair), one epoch-keyed permutation.  Fed identically to the reference loop and to the CUDA path."""
+
+    def __len__(self):
+        return (self.num_ng + 1) * len(self.users)
+
+    def sample_epoch(self, epoch, shuffle=True):
+        tri = super().sample_epoch(epoch, shuffle=False)                       # (u, i, j), positive-major
+        n_pos = len(self.users)
+        out = np.empty(((self.num_ng + 1) * n_pos, 3), dtype=np.int32)
+        out[:n_pos, 0], out[:n_pos, 1], out[:n_pos, 2] = self.users, self.items, 1      # features_ps, labels_ps
+        out[n_pos:, 0], out[n_pos:, 1], out[n_pos:, 2] = tri[:, 0], tri[:, 2], 0        # features_ng, labels_ng
+        if shuffle:
+            out = out[_rng(self.seed, 4, epoch).permutation(out.shape[0])]
+        return np.ascontiguousarray(out)
+
+
 # --------------------------------------------------------------------------
 # synthetic workloads of BASELINE.json configs 2-5 (SURVEY.md section 8d)
 # --------------------------------------------------------------------------
