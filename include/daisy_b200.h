@@ -191,6 +191,17 @@ DAISY_API int daisy_bpr_adam_step(daisy_handle_t h, float *P, float *Q, float *m
                         const int32_t *triples, int64_t B, float lr, float beta1, float beta2, float eps,
                         int64_t step_no, double *loss_accum, daisy_stream_t stream);
 
+/* ---- BPR-FM with two one-hot features per example ------------------
+ * BPRFM (BPRFMRecommender.py:29-80) with batch_norm = False and drop_prob = [0, 0], features [user, user_num + item],
+ * values [1, 1]:  pred = <e_u, e_i> + b_u + b_i + bias_,  loss = -(pred_i - pred_j).sigmoid().log().sum()  (:214-219),
+ * optimiser torch.optim.Adagrad(lr, initial_accumulator_value) (:191-193), which moves only elements with a gradient.
+ * The handle is created with dim = num_factors + 4.  E [user_num + item_num, dim]: AUGMENTED rows
+ * [e_0 .. e_{F-1}, x, 0, 0, 0] with x = 1 for user rows (constant) and x = b_i for item rows; acc: Adagrad state_sum,
+ * same layout, initialised to initial_accumulator_value.  triples: device int32 [B,3] (user, item_i, item_j) with
+ * item ids relative to the item block.  The user bias and bias_ cancel in pred_i - pred_j and never move. */
+DAISY_API int daisy_bprfm_adagrad_step(daisy_handle_t h, float *E, float *acc, const int32_t *triples, int64_t B, float lr,
+                             float eps, double *loss_accum, daisy_stream_t stream);
+
 /* ---- NCF, GMF variant -----------------------------------------------
  * NCF.forward with model == 'GMF' (NCFRecommender.py:105-125): pred[t] = w . (P[u_t] * Q[i_t]) + b.
  * samples: device int32 [B,3] packed (user, item, label); the label column is ignored here.

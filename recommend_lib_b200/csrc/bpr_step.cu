@@ -76,6 +76,35 @@ struct AdamOpt {
     }
 };
 
+// torch.optim.Adagrad (lr_decay 0) on the rows present in the batch: state_sum += g^2; w -= lr * g / (sqrt(state_sum) +
+// eps).  An element with zero gradient does not move under Adagrad, so the reference's dense optimiser and this sparse
+// one are the same function.  BPR-FM (daisy_bprfm_adagrad_step) runs on AUGMENTED rows [e_0 .. e_{F-1}, x, 0, 0, 0]:
+// x = 1 for a user row (a constant, not a parameter: float4 `const_e` of table 0 is never written), x = b_i for an item
+// row, so that <user row, item_i row - item_j row> = <e_u, e_i - e_j> + b_i - b_j and the bias gradient falls out of
+// the same kernels.  g = -d.
+struct AdagradOpt {
+    static constexpr bool kNeedOldItem = true;
+    float *P, *Q, *aP, *aQ;
+    float lr, eps;
+    int D4, const_e;
+    __device__ __forceinline__ float one(float w, float g, float &acc) const {
+        acc = fmaf(g, g, acc);
+        return w - lr * g / (sqrtf(acc) + eps);
+    }
+    __device__ __forceinline__ void apply(int tbl, size_t row, int e, float4 old, float4 d) const {
+        if (tbl == 0 && e == const_e) return;
+        const size_t idx = row * D4 + e;
+        float *A = tbl ? aQ : aP;
+        float4 acc = ld_row(A, idx), r;
+        r.x = one(old.x, -d.x, acc.x);
+        r.y = one(old.y, -d.y, acc.y);
+        r.z = one(old.z, -d.z, acc.z);
+        r.w = one(old.w, -d.w, acc.w);
+        st_row(A, idx, acc);
+        st_row(tbl ? Q : P, idx, r);
+    }
+};
+
 // shared body of daisy_bpr_step / daisy_bpr_step_host
 static int sgd_step(daisy_ctx *h, float *P, float *Q, const int32_t *triples_dev, const int32_t *host_src, int64_t B,
                     float lr, float wd, double *loss_accum, daisy_stream_t stream, bool inputs_ready) {
@@ -172,4 +201,26 @@ extern "C" int daisy_bpr_adam_step(daisy_handle_t h, float *P, float *Q, float *
     opt.D4 = h->D / 4;
     return run_step<AdamOpt>(h, P, Q, triples, B, opt, 1.0f, loss_accum, (cudaStream_t)stream, nullptr,
                              h->inputs_ready != 0);
+}
+
+extern "C" int daisy_bprfm_adagrad_step(daisy_handle_t h, float *E, float *acc, const int32_t *triples, int64_t B, float lr,
+                                        float eps, double *loss_accum, daisy_stream_t stream) {
+    DAISY_REQUIRE(h != nullptr && E && acc, DAISY_EINVAL, "null argument");
+    float *P = E, *Q = E + (size_t)h->U * h->D;            // users first, then items, in ONE feature table
+    int rc = check_step_args(h, P, Q, triples, B);
+    if (rc) return rc;
+    DAISY_REQUIRE(h->D >= 8, DAISY_EINVAL, "augmented row width %d: need num_factors + 4", h->D);
+    DAISY_REQUIRE(h->scale == 1.0, DAISY_EINVAL, "lazy L2 scale is %g: call daisy_materialize first", h->scale);
+    if (B == 0) return DAISY_OK;
+    DeviceGuard g(h->device);
+    DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
+    AdagradOpt opt;
+    opt.P = P; opt.Q = Q;
+    opt.aP = acc; opt.aQ = acc + (size_t)h->U * h->D;
+    opt.lr = lr;
+    opt.eps = eps;
+    opt.D4 = h->D / 4;
+    opt.const_e = h->D / 4 - 1;                             // the last float4 of a row: [x, 0, 0, 0]
+    return run_step<AdagradOpt>(h, P, Q, triples, B, opt, 1.0f, loss_accum, (cudaStream_t)stream, nullptr,
+                                h->inputs_ready != 0);
 }

@@ -208,3 +208,23 @@ def test_gmf_oracle_matches_reference_ncf_with_adam(golden):
     assert quiet.size > 0 and np.abs(g["P"][1][quiet] - g["P"][0][quiet]).max() > 0
     fwd = gmf_oracle.gmf_forward(st.P, st.Q, st.w, st.b[0], g["users"][0], g["items"][0])
     assert np.allclose(fwd, g["fwd_last"], rtol=1e-5, atol=1e-6)
+
+
+def test_bprfm_oracle_matches_reference_with_adagrad(golden):
+    """oracle/bprfm_oracle.py against 4 steps of the unmodified reference BPRFM(batch_norm=False, drop_prob=[0, 0]) +
+    optim.Adagrad(lr=0.05, initial_accumulator_value=1e-8) (tests/golden/make_bprfm_golden.py).  Biases within 1e-6;
+    embeddings within 5e-5: with state_sum starting at 1e-8, an element whose gradient nearly cancels to |g| ~ 1e-4 turns
+    the fp32 rounding of the reference's own gradient (1e-8 absolute) into 2e-5 of its value -- the float64 closed
+    form and the reference differ by that much, on exactly such an element."""
+    from oracle import bprfm_oracle
+    g = golden("bprfm_small.npz")
+    E, b = g["E0"].astype(np.float64), g["b0"].astype(np.float64)
+    aE, ab = np.full_like(E, 1e-8), np.full_like(b, 1e-8)
+    for k in range(len(g["losses"])):
+        loss = bprfm_oracle.bprfm_adagrad_step(E, b, float(g["bias_"]), aE, ab, g["feats_i"][k], g["feats_j"][k], lr=float(g["lr"]))
+        assert abs(loss - g["losses"][k]) <= 1e-6 * g["losses"][k], k
+        assert rel_err(E, g["E"][k]) <= 5e-5 and rel_err(b, g["b"][k]) <= 1e-6, (k, rel_err(E, g["E"][k]), rel_err(b, g["b"][k]))
+    U = int(g["user_num"])
+    assert np.array_equal(g["b"][-1][:U], g["b0"][:U])          # user biases never move (their gradient is +g - g)
+    pi = bprfm_oracle.pred(E, b, float(g["bias_"]), g["feats_i"][0])
+    assert np.allclose(pi, g["fwd_i"], rtol=1e-4, atol=1e-5)
