@@ -27,6 +27,7 @@ Secondary lines (not the driver's metric; `profiles/` holds one of each):
   --workload eval      full-catalogue top-100 for 16 384 users x 2 M items
   --workload sampler   device-side negative sampler on the ml-20m shape
   --workload gmf       NCF-GMF training step (daisy_gmf_step) on the ml-100k shape, batch 256
+  --workload bprfm     BPR-FM training step (daisy_bprfm_adagrad_step) on the ml-100k shape, batch 4 096
   --phases / --trace   per-phase device times (serialised) / timeline of bookkeeping vs table kernels
 """
 from __future__ import annotations
@@ -510,6 +511,80 @@ def run_gmf(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# BPR-FM (secondary line)
+# ------------------------------------------------------------------------------------------------
+def run_bprfm(args):
+    """triples/s of the fused BPR-FM step (daisy_bprfm_adagrad_step: the BPR kernels on augmented rows + Adagrad) at the
+    reference script's defaults on the ml-100k shape (943 + 1 682 features, hidden_factor 64, batch 4 096, Adagrad lr
+    0.05; BPRFMRecommender.py:122-150) with batch_norm off / dropout 0, next to the closed-form restatement of the
+    reference loop (oracle/bprfm_oracle.py, numpy) on the host."""
+    import torch
+    from recommend_lib_b200.bprfm import BPRFM, FMAdagrad
+    from recommend_lib_b200.sampler import synthetic_triples
+    U, I, F, B = 943, 1682, 64, args.batch or 4096
+    K, W = max(args.steps, 200), max(args.warmup, 20)
+    tri = synthetic_triples((K + W) * B, U, I, seed=2019, zipf=1.0).reshape(K + W, B, 3)
+    dev = torch.device("cuda:0")
+    torch.manual_seed(2019)
+    model = BPRFM(U + I, F, False, [0.0, 0.0], user_num=U, max_batch=B).to(dev)
+    opt = FMAdagrad(model, lr=0.05)
+    devt = torch.from_numpy(tri).to(dev)
+    for s in range(W):
+        opt.step(devt[s])
+    model.check()
+    torch.cuda.synchronize()
+    l0 = model.handle(B).launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for s in range(W, W + K):
+        opt.step(devt[s])
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    launches = model.handle(B).launches - l0
+    host = torch.from_numpy(tri).pin_memory()
+    loss_host = torch.zeros(K + W, dtype=torch.float64).pin_memory()
+    opt.loss_sum()
+    ev0.record()
+    for s in range(W, W + K):                       # e2e: pinned host triples in, loss read back every step
+        opt.step(host[s].to(dev, non_blocking=True))
+        loss_host[s:s + 1].copy_(opt._loss, non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms2 = ev0.elapsed_time(ev1)
+    model.check()
+    from oracle import bprfm_oracle
+    rng = np.random.default_rng(1)
+    E = rng.normal(0, 0.01, (U + I, F)).astype(np.float32)
+    b = np.zeros(U + I, np.float32)
+    aE, ab = np.full_like(E, 1e-8), np.full_like(b, 1e-8)
+    nc = 20
+    t0 = time.time()
+    for s in range(nc):
+        fi = np.stack([tri[s, :, 0], U + tri[s, :, 1]], 1)
+        fj = np.stack([tri[s, :, 0], U + tri[s, :, 2]], 1)
+        bprfm_oracle.bprfm_adagrad_step(E, b, 0.0, aE, ab, fi, fj, lr=0.05)
+    cpu_dt = time.time() - t0
+    line = {"metric": "bprfm_train_triples_per_s", "value": B * K / (ms * 1e-3), "unit": "triples/s", "n_gpus": 1, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BPR-FM training step on the ml-100k shape (943 + 1682 features, hidden_factor 64, batch "
+                                   "4096, Adagrad lr 0.05, batch_norm off, dropout 0)", "user_num": U, "item_num": I,
+                       "dim": F, "batch": B, "l2": "tables (0.7 MB) are L2-resident; launch-latency-bound (3 launches)"},
+            "e2e": {"value": B * K / (ms2 * 1e-3), "unit": "triples/s", "ms_per_step": ms2 / K,
+                    "h2d_bytes_per_step": B * 12, "d2h_bytes_per_step": 8},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": B * (24 * (F + 4) + 12) / (ms / K * 1e-3) / 1e9,
+                         "peak": measured_peaks()[0], "unit": "GB/s",
+                         "frac": B * (24 * (F + 4) + 12) / (ms / K * 1e-3) / 1e9 / measured_peaks()[0], "traffic": None,
+                         "note": "latency-bound at this size"},
+            "cpu_baseline": {"value": B * nc / cpu_dt, "unit": "triples/s", "cores": 1, "kind": "port",
+                             "sample": f"{nc} steps of the closed-form restatement (numpy, float32) of the reference loop"},
+            "mean_loss_per_triple": float(loss_host[W + K - 1]) / (B * K)}      # the loss accumulates over the K e2e steps
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
 # config 2: funk-SVD (secondary line, not the driver's metric)
 # ------------------------------------------------------------------------------------------------
 def run_mf(args):
@@ -697,7 +772,7 @@ def main():
     ap.add_argument("--phases", action="store_true", help="also print the per-phase breakdown of the step")
     ap.add_argument("--trace", action="store_true", help="also print a timeline of bookkeeping vs table kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="config4", choices=["config4", "config3", "config2", "config1", "sampler", "eval", "gmf"],
+    ap.add_argument("--workload", default="config4", choices=["config4", "config3", "config2", "config1", "sampler", "eval", "gmf", "bprfm"],
                     help="N = 1 only: config4 is the driver's metric; config3 (L2-resident ml-20m shape) and config2 "
                          "(funk-SVD) are secondary lines kept under profiles/")
     ap.add_argument("--eval-users", type=int, default=16384)
@@ -721,6 +796,8 @@ def main():
         return run_config1(args)
     if args.workload == "gmf":
         return run_gmf(args)
+    if args.workload == "bprfm":
+        return run_bprfm(args)
     if args.workload == "config2":
         return run_mf(args)
     if args.workload == "sampler":

@@ -168,7 +168,12 @@ class FMAdagrad:
         if self.acc is None or self.acc.shape != m._aug.shape or self.acc.device != m._aug.device:
             self.acc = torch.full_like(m._aug, self.init_acc)
             self._loss = torch.zeros(1, dtype=torch.float64, device=dev)
-        tri = m.triples(features_i, feature_values_i, features_j, feature_values_j)
+        if features_j is None and torch.is_tensor(features_i) and features_i.dtype == torch.int32 and features_i.is_cuda:
+            tri = features_i                          # packed (user, item_i, item_j) int32 [B,3], item ids relative
+            if tri.dim() != 2 or tri.shape[1] != 3 or not tri.is_contiguous():
+                raise ValueError("packed triples must be a contiguous int32 [B, 3] device tensor")
+        else:
+            tri = m.triples(features_i, feature_values_i, features_j, feature_values_j)
         B = tri.shape[0]
         h = m.handle(B)
         _lib.check(h.L.daisy_bprfm_adagrad_step(h.ptr, c_vp(m._aug.data_ptr()), c_vp(self.acc.data_ptr()),
