@@ -81,6 +81,7 @@ struct daisy_shard {
     uint32_t *cidx;   // [2*maxB] scan scratch (bookkeeping stream only)
     float *cache;     // [2*maxB, D] fetched pre-step item rows of the current batch
     uint32_t epoch;   // barrier epoch (same sequence on every rank)
+    int ilv;          // chunk interleave of the main kernel = world (DAISY_SHARD_INTERLEAVE; 0 / 1 = sorted order)
     // phase profile (daisy_set_timing(h, 2)): bookkeeping, fetch, compute+push, barrier, apply, barrier
     cudaEvent_t pev[7];
     double pms[6];

@@ -246,7 +246,7 @@ template <int V, int R>
 __global__ void __launch_bounds__(256) k_shard_fetch(const float *const *__restrict__ src,
                                                       const uint8_t *__restrict__ multi,
                                                       const uint32_t *__restrict__ owner_off, int G,
-                                                      float *__restrict__ cache, int D4) {
+                                                      float *__restrict__ cache, int D4, int ilv) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
     const uint32_t nwarps = (uint32_t)((gridDim.x * (size_t)blockDim.x) >> 5);
@@ -254,7 +254,14 @@ __global__ void __launch_bounds__(256) k_shard_fetch(const float *const *__restr
     bool act[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
-    for (uint32_t c0 = warp * R; c0 < nuniq; c0 += nwarps * R) {
+    // groups of R cache rows (ascending = grouped by owner) are dealt round-robin over `ilv` ranges of the list, so the
+    // loads in flight are spread over all owners (MainArgs::ilv has the reason)
+    const int ngroups = (int)((nuniq + R - 1) / R);
+    const uint32_t nraw = ilv > 1 ? (uint32_t)ilv * (uint32_t)((ngroups + ilv - 1) / ilv) : (uint32_t)ngroups;
+    for (uint32_t raw = warp; raw < nraw; raw += nwarps) {
+        const int grp = interleaved_chunk((int)raw, ngroups, ilv);
+        if (grp < 0) continue;
+        const uint32_t c0 = (uint32_t)grp * R;
         float4 r[R][V];
         bool take[R];  // rows referenced once are read by the main kernel straight from their owner
 #pragma unroll
@@ -439,7 +446,7 @@ static void launch_fetch(daisy_ctx *h, const ShardSet &ss, cudaStream_t s) {
     k_shard_push_ids<<<h->num_sms * 2, 256, 0, s>>>(ss.owner_off, sh->world, ss.uniq_gid, (uint32_t)sh->i_per, sh->rank,
                                                     (size_t)sh->cap, sh->peers);
     h->launches++;
-    k_shard_fetch<V, 4><<<h->num_sms * 4, 256, 0, s>>>(ss.src, ss.multi, ss.owner_off, sh->world, sh->cache, h->D / 4);
+    k_shard_fetch<V, 4><<<h->num_sms * 4, 256, 0, s>>>(ss.src, ss.multi, ss.owner_off, sh->world, sh->cache, h->D / 4, sh->ilv);
 }
 
 // Owner side, default: ONE PASS PER SENDER, in sender-rank order.  A sender's id list is duplicate-free, so the
@@ -648,6 +655,11 @@ extern "C" int daisy_shard_init(daisy_handle_t h, int rank, int world, int64_t i
     DAISY_REQUIRE(sh != nullptr, DAISY_ENOMEM, "host allocation failed");
     sh->rank = rank;
     shard_layout(sh, h->D, h->maxB, world, item_num_global);
+    {   // schedule of the main kernel: chunks dealt round-robin over `world` ranges of the owner-grouped order
+        const char *v = getenv("DAISY_SHARD_INTERLEAVE");
+        sh->ilv = (v && *v) ? atoi(v) : world;
+        if (sh->ilv < 0 || sh->ilv > 1024) sh->ilv = world;
+    }
     const size_t D = (size_t)h->D, cap = (size_t)sh->cap;
     h->sh = sh;
     bool ok = true;

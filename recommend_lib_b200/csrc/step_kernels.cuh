@@ -120,14 +120,33 @@ struct MainArgs {
     // PTR mode (row-sharded step): where to read the item rows of sorted triple k from -- the owner's memory (peer
     // or local address) for rows referenced once, the fetched-row cache otherwise.  st then holds cache rows.
     const float *const *jsrc, *const *isrc;
+    // PTR mode: the chunks (sorted by positive item = grouped by OWNER) are dealt to the warps round-robin over `ilv`
+    // equal ranges of the sorted order, so that at any moment a rank's loads and stores are spread over all owners
+    // instead of every rank walking the owners 0, 1, 2, ... at the same time (incast on one owner's links).
+    // 0 / 1 = sorted order.  Scheduling only: which warp takes which chunk never changes a result.
+    int ilv;
 };
+
+// warp -> chunk in PTR mode (see MainArgs::ilv); -1 = no chunk for this warp
+__device__ __forceinline__ int interleaved_chunk(int raw, int nchunks, int ilv) {
+    if (ilv <= 1) return raw < nchunks ? raw : -1;
+    const int per = (nchunks + ilv - 1) / ilv;
+    const int q = raw / ilv, r = raw - q * ilv;
+    if (q >= per) return -1;
+    const int c = r * per + q;
+    return c < nchunks ? c : -1;
+}
 
 template <int V, class Opt, bool PTR>
 __global__ void __launch_bounds__(256) k_bpr_main(MainArgs a, Opt opt) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int warp = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    int warp = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
     const int C = a.C;
+    if (PTR) {
+        warp = interleaved_chunk(warp, (a.B + C - 1) / C, a.ilv);
+        if (warp < 0) return;
+    }
     const long long k0 = (long long)warp * C;  // (k0 + lane fits size_t below: k0 < B)
     if (k0 >= a.B) return;  // warp-uniform
     const int n = (int)min((long long)C, (long long)a.B - k0);
@@ -300,8 +319,12 @@ __global__ void __launch_bounds__(256) k_bpr_main_tma(MainArgs a, Opt opt, int S
     extern __shared__ __align__(128) unsigned char dsm[];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int warp = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    int warp = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
     const int C = a.C;
+    if (PTR) {
+        warp = interleaved_chunk(warp, (a.B + C - 1) / C, a.ilv);
+        if (warp < 0) return;
+    }
     const long long k0 = (long long)warp * C;
     if (k0 >= a.B) return;  // warp-uniform; no block-wide barrier is used below
     const int n = (int)min((long long)C, (long long)a.B - k0);
@@ -1426,6 +1449,7 @@ struct StepPlan {
     int set;              // index of k in h->book
     const float *const *jsrc, *const *isrc;  // row-sharded step only (else null)
     bool small;           // small-batch path: k_small_book / C = 1 / k_seg_all
+    int ilv;              // row-sharded step: chunk interleave of the main kernel (MainArgs::ilv), else 0
 };
 
 // Does a batch of B triples take the small-batch path?  Its refs must pack into 32 bits: row bits (of the VALUE U
@@ -1527,6 +1551,7 @@ static int book_phase(daisy_ctx *h, StepPlan &pl, const int32_t *triples, int64_
     pl.small = small;
     pl.jsrc = sh ? sh->set[pl.set].jsrc : nullptr;
     pl.isrc = sh ? sh->set[pl.set].isrc : nullptr;
+    pl.ilv = sh ? sh->ilv : 0;
     BookSet &k = h->book[h->book_idx];
     pl.k = &k;
     h->book_idx ^= 1;
@@ -1652,10 +1677,13 @@ static int table_phase_v(daisy_ctx *h, const StepPlan &pl, const float *P, const
     a.stageU = h->stageU; a.stageQ = h->stageQ; a.loss_part = h->loss_part;
     a.B = B; a.D4 = D4; a.C = C; a.c2 = c2;
     a.jsrc = pl.jsrc; a.isrc = pl.isrc;
+    a.ilv = pl.jsrc ? pl.ilv : 0;
     const int warps = daisy_ceil_div(B, C);
     const bool pool = (h->timing == 1 && h->pool_used < DAISY_EVPOOL);
     if (pool) cudaEventRecord(h->evpool[2 * h->pool_used], s);
-    const int blocks = daisy_ceil_div(warps, 8);
+    // interleaved (row-sharded step): ilv ranges of ceil(warps / ilv) chunks each, dealt round-robin
+    const int warps_launched = a.ilv > 1 ? a.ilv * daisy_ceil_div(warps, a.ilv) : warps;
+    const int blocks = daisy_ceil_div(warps_launched, 8);
     // TMA-pipelined variant: S stages of 3 rows per warp in shared memory, at most ~56 KB per block so that four
     // blocks stay resident per SM; rows too long for two stages fall back to the register-prefetch kernel
     const size_t stage_bytes = (size_t)8 * 3 * D4 * 16;

@@ -67,6 +67,8 @@ int main(int argc, char **argv) {
     std::vector<float4 *> table(G), pulled(G), recv(G);
     std::vector<const float4 **> src(G);
     std::vector<float4 **> dstp(G);
+    std::vector<const float4 **> src_i(G);
+    std::vector<float4 **> dstp_i(G);
     std::vector<cudaStream_t> s1(G), s2(G);
     std::vector<cudaEvent_t> e0(G), e1(G);
     for (int d = 0; d < G; ++d) {
@@ -93,6 +95,17 @@ int main(int argc, char **argv) {
         }
         CK(cudaSetDevice(d));
         CK(cudaMemcpy(src[d], hs.data(), (size_t)n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dstp[d], hd.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+        // the same rows, dealt round-robin over G ranges of the owner-grouped list in groups of 32 rows (what
+        // MainArgs::ilv / k_shard_fetch do): at any moment a GPU's accesses are spread over all owners
+        const int grp = 32, ng = (n + grp - 1) / grp, per = (ng + G - 1) / G;
+        std::vector<const float4 *> is; std::vector<float4 *> id;
+        for (int raw = 0; raw < G * per; ++raw) {
+            const int c = (raw % G) * per + raw / G;
+            if (c >= ng) continue;
+            for (int x = c * grp; x < std::min(n, (c + 1) * grp); ++x) { is.push_back(hs[x]); id.push_back(hd[x]); }
+        }
+        CK(cudaMalloc(&src_i[d], (size_t)n * 8)); CK(cudaMalloc(&dstp_i[d], (size_t)n * 8));
+        CK(cudaMemcpy(src_i[d], is.data(), (size_t)n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dstp_i[d], id.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
     }
     auto run = [&](const char *name, int mode, double bytes_each_way) {
         for (int it = 0; it < 4; ++it) {
@@ -100,10 +113,12 @@ int main(int argc, char **argv) {
             for (int d = 0; d < G; ++d) {
                 CK(cudaSetDevice(d));
                 CK(cudaEventRecord(e0[d], s1[d]));
-                if (mode == 0) k_pull<4><<<148 * 8, 256, 0, s1[d]>>>(src[d], n, pulled[d]);
-                if (mode == 1) k_push<4><<<148 * 8, 256, 0, s1[d]>>>(dstp[d], n, pulled[d]);
-                if (mode == 2) k_pull_push<4><<<148 * 8, 256, 0, s1[d]>>>(src[d], dstp[d], n);
-                if (mode == 3) k_pull_push<8><<<148 * 8, 256, 0, s1[d]>>>(src[d], dstp[d], n);
+                const float4 **sp = mode >= 4 ? src_i[d] : src[d];
+                float4 **dp = mode >= 4 ? dstp_i[d] : dstp[d];
+                if (mode % 4 == 0) k_pull<4><<<148 * 8, 256, 0, s1[d]>>>(sp, n, pulled[d]);
+                if (mode % 4 == 1) k_push<4><<<148 * 8, 256, 0, s1[d]>>>(dp, n, pulled[d]);
+                if (mode % 4 == 2) k_pull_push<4><<<148 * 8, 256, 0, s1[d]>>>(sp, dp, n);
+                if (mode % 4 == 3) k_pull_push<8><<<148 * 8, 256, 0, s1[d]>>>(sp, dp, n);
                 CK(cudaEventRecord(e1[d], s1[d]));
             }
             if (it == 3) {
@@ -118,5 +133,10 @@ int main(int argc, char **argv) {
     run("all GPUs push to all peers", 1, b);
     run("pull + push per row (4 rows in flight/warp)", 2, 2 * b);  // every GPU also serves the same volume: 2 x b each way
     run("pull + push per row (8 rows in flight/warp)", 3, 2 * b);
+    printf("-- the same rows, interleaved over the owners --\n");
+    run("all GPUs pull from all peers", 4, b);
+    run("all GPUs push to all peers", 5, b);
+    run("pull + push per row (4 rows in flight/warp)", 6, 2 * b);
+    run("pull + push per row (8 rows in flight/warp)", 7, 2 * b);
     return 0;
 }
