@@ -605,6 +605,9 @@ def bench_sharded(args, cfg, metric, unit):
                                        ("block rows, triples routed to the user's owner, item rows + row gradients "
                                         "exchanged by NCCL all-to-all"),
                            "exchange": args.exchange, "peer_mapping": args.mapping if peer else None,
+                           "main_schedule": (f"chunks dealt round-robin over "
+                                             f"{os.environ.get('DAISY_SHARD_INTERLEAVE') or world} owner ranges "
+                                             f"(DAISY_SHARD_INTERLEAVE; 0 = sorted order)") if peer else None,
                            "l2": "inputs larger than L2", "lazy_decay_materialized_in_timed_region": True},
                 "clocks": clocks.summary() if clocks is not None else None,
                 "e2e": {"value": B * world * K / (ms_e2e * 1e-3), "unit": unit, "ms_per_step": ms_e2e / K,
