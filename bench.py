@@ -770,6 +770,8 @@ def main():
                     help="also fold the lazy L2 scale into the tables every N steps (0: only once, at the end of the "
                          "timed region -- what an epoch end does; the library itself only needs it when c < 1e-4)")
     ap.add_argument("--phases", action="store_true", help="also print the per-phase breakdown of the step")
+    ap.add_argument("--no-phases", action="store_true", dest="no_phases",
+                    help="N > 1: leave out the per-rank phase profile the fused peer path adds after the timed regions")
     ap.add_argument("--trace", action="store_true", help="also print a timeline of bookkeeping vs table kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="config4", choices=["config4", "config3", "config2", "config1", "sampler", "eval", "gmf", "bprfm"],

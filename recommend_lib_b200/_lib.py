@@ -57,6 +57,7 @@ SIGNATURES = {
     "daisy_shard_barrier": [c_vp, c_vp],
     "daisy_shard_apply": [c_vp, c_f32, c_f32, c_vp],
     "daisy_shard_materialize": [c_vp, c_vp, c_vp],
+    "daisy_shard_schedule": [c_i32, c_i32, c_i32, ctypes.POINTER(c_i32)],
     "daisy_shard_last_counts": [c_vp, c_vp, c_vp],
     "daisy_shard_peer_q": [c_vp, c_i32, ctypes.POINTER(c_vp)],
     "daisy_gather_rows": [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp],

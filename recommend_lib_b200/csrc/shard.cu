@@ -622,6 +622,12 @@ void daisy_shard_free(daisy_ctx *h) {
     h->sh = nullptr;
 }
 
+extern "C" int daisy_shard_schedule(int warp, int nchunks, int interleave, int *chunk) {
+    DAISY_REQUIRE(chunk != nullptr && warp >= 0 && nchunks >= 0 && interleave >= 0, DAISY_EINVAL, "bad schedule query");
+    *chunk = interleaved_chunk(warp, nchunks, interleave);
+    return DAISY_OK;
+}
+
 extern "C" int daisy_shard_arena_size(int dim, int64_t max_batch, int world, int64_t item_num_global, int64_t *bytes) {
     DAISY_REQUIRE(bytes != nullptr, DAISY_EINVAL, "null argument");
     DAISY_REQUIRE(dim > 0 && dim % 4 == 0 && dim <= 512 && max_batch > 0 && world >= 1 && world <= DAISY_MAX_RANKS &&

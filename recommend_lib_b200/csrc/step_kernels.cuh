@@ -128,7 +128,7 @@ struct MainArgs {
 };
 
 // warp -> chunk in PTR mode (see MainArgs::ilv); -1 = no chunk for this warp
-__device__ __forceinline__ int interleaved_chunk(int raw, int nchunks, int ilv) {
+__host__ __device__ __forceinline__ int interleaved_chunk(int raw, int nchunks, int ilv) {
     if (ilv <= 1) return raw < nchunks ? raw : -1;
     const int per = (nchunks + ilv - 1) / ilv;
     const int q = raw / ilv, r = raw - q * ilv;

@@ -556,12 +556,15 @@ def bench_sharded(args, cfg, metric, unit):
     dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     check()
     phases = None
+    # the fused peer path always adds its per-rank phase profile (10 serialised steps AFTER both timed regions): it is
+    # what says which rank the others wait for at the barrier; --no-phases drops it
+    want_phases = args.phases or (peer and not getattr(args, "no_phases", False))
     if args.phases and not peer:
         model.profile = []
         run(0, min(nb, 10), devtri)
         phases = model.profile_summary()
         model.profile = None
-    elif args.phases:
+    elif want_phases:
         handle.set_timing(2)
         run(0, min(nb, 10), devtri)
         phases, _ = model.phase_ms()
@@ -579,7 +582,7 @@ def bench_sharded(args, cfg, metric, unit):
                 print(f"rank {rank} trace_ms(book_begin, book_end, kernels_begin, compute_end):", rows, flush=True)
             dist.barrier()
     by_rank = None
-    if args.phases and peer:                        # which rank waits for which: the phases of every rank, side by side
+    if want_phases and peer:                        # which rank waits for which: the phases of every rank, side by side
         mine = {"rank": rank, "sm_mhz": (clocks.summary()["sm_mhz"] if clocks is not None else None)}
         mine.update({k: round(v, 4) for k, v in phases.items() if k != "compute_push_detail"})
         mine["main"] = phases["compute_push_detail"].get("main")

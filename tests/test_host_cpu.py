@@ -151,3 +151,29 @@ def test_rank_metrics_match_the_reference_functions(golden):
             assert got[name] == pytest.approx(want[name], rel=1e-12, abs=1e-15), (c, name)
     with pytest.raises(ValueError):
         rank_metrics(np.zeros((3, 4)), np.ones(3), top_k=5)              # 'Relevance score length < k'
+
+
+def test_shard_schedule_deals_every_chunk_to_exactly_one_warp():
+    """The owner-interleaved schedule of the row-sharded step kernel: the library's own mapping
+    (host instance of the __host__ __device__ function the kernels call) is a bijection onto the chunks, and
+    consecutive warps address consecutive owner ranges."""
+    import ctypes
+    from recommend_lib_b200 import _lib
+    L = _lib.load()
+    out = ctypes.c_int32()
+
+    def chunk(w, n, g):
+        _lib.check(L.daisy_shard_schedule(w, n, g, ctypes.byref(out)))
+        return out.value
+
+    for n in (0, 1, 2, 7, 8, 9, 37, 1000, 31250, 31251):
+        for g in (0, 1, 2, 3, 4, 8):
+            launched = n if g <= 1 else g * ((n + g - 1) // g)
+            warps = (launched + 7) // 8 * 8                       # whole blocks of 8 warps are launched
+            got = [chunk(w, n, g) for w in range(warps)]
+            assert sorted(c for c in got if c >= 0) == list(range(n)), (n, g)
+    n, g = 31250, 8                                               # config 5: 1 M triples in chunks of 32, 8 ranks
+    per = (n + g - 1) // g
+    assert [chunk(w, n, g) // per for w in range(16)] == [0, 1, 2, 3, 4, 5, 6, 7] * 2
+    assert [chunk(w, n, 0) for w in range(4)] == [0, 1, 2, 3]
+    assert L.daisy_shard_schedule(0, 10, 2, None) != 0            # null output pointer is an error, not a crash
