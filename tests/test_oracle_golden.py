@@ -228,3 +228,23 @@ def test_bprfm_oracle_matches_reference_with_adagrad(golden):
     assert np.array_equal(g["b"][-1][:U], g["b0"][:U])          # user biases never move (their gradient is +g - g)
     pi = bprfm_oracle.pred(E, b, float(g["bias_"]), g["feats_i"][0])
     assert np.allclose(pi, g["fwd_i"], rtol=1e-4, atol=1e-5)
+
+
+# ---------------------------------------------------------------- next row N4: Item2Vec / SGNS
+@pytest.mark.parametrize("branch", ["w", "u"])       # negatives from the unigram^0.75 table / uniform (:86-91)
+def test_sgns_oracle_matches_reference_item2vec_with_adam(golden, branch):
+    """oracle/sgns_oracle.py (closed-form SGNS loss for given negatives, dense gradients with the padding row masked,
+    torch-default Adam over EVERY row) against 5 steps of the reference's own Item2Vec + SGNS classes and
+    torch.optim.Adam (tests/golden/make_sgns_golden.py)."""
+    from oracle import sgns_oracle
+    g = golden("sgns_small.npz")
+    k = lambda name: g[f"{branch}_{name}"]
+    st = sgns_oracle.SGNSAdam(k("iv0"), k("ov0"))
+    for s in range(len(k("losses"))):
+        loss = st.step(k("iword")[s], k("owords")[s], k("nwords")[s])
+        assert loss == pytest.approx(float(k("losses")[s]), rel=1e-6), s
+        assert rel_err(st.iv, k("iv")[s]) < 1e-6, s
+        assert rel_err(st.ov, k("ov")[s]) < 1e-6, s
+        assert np.abs(st.iv[0]).max() == 0 and np.abs(st.ov[0]).max() == 0        # the padding row never moves
+    # rows without a gradient in a step still move under dense Adam once they have a first moment
+    assert rel_err(st.iv, k("iv0")) > 1e-3
