@@ -248,3 +248,47 @@ def test_sgns_oracle_matches_reference_item2vec_with_adam(golden, branch):
         assert np.abs(st.iv[0]).max() == 0 and np.abs(st.ov[0]).max() == 0        # the padding row never moves
     # rows without a gradient in a step still move under dense Adam once they have a first moment
     assert rel_err(st.iv, k("iv0")) > 1e-3
+
+
+# ---------------------------------------------------------------- row N3, the script's defaults: batch norm + dropout
+@pytest.mark.parametrize("branch,tol_b,tol_fwd", [("cond", 1e-6, 1e-6), ("script", 2e-4, 2e-5)])
+def test_bprfm_full_oracle_matches_reference_with_batch_norm_and_dropout(golden, branch, tol_b, tol_fwd):
+    """oracle/bprfm_oracle.py: BPRFMFull (bi-interaction, BatchNorm1d in training mode incl. running statistics,
+    dropout with the RECORDED masks, Adagrad over every parameter) against 4 steps of the unmodified reference
+    BPRFM(batch_norm=True, drop_prob=[0.5, 0.2]) (tests/golden/make_bprfm_bn_golden.py).  'cond': accumulator 0.1,
+    everything within 1e-6.  'script': the script's 1e-8 -- the user bias gradient is +g - g = rounding noise, which an
+    accumulator of 1e-8 turns into 5e-5 of the bias scale (same effect as in the batch_norm=False fixture)."""
+    from oracle import bprfm_oracle
+    g = golden("bprfm_bn_small.npz")
+    k = lambda name: g[f"{branch}_{name}"]
+    st = bprfm_oracle.BPRFMFull(k("E0"), k("b0"), float(k("g0")), True, lr=float(k("lr")),
+                                initial_accumulator_value=float(k("acc0")))
+    ones = np.ones((k("fi").shape[1], 2))
+    for s in range(len(k("loss"))):
+        loss = st.step(k("fi")[s], ones, k("fj")[s], ones, k("mi")[s], k("mj")[s])
+        assert loss == pytest.approx(float(k("loss")[s]), rel=1e-6), s
+        assert rel_err(st.E, k("E")[s]) < 1e-6, s
+        assert rel_err(st.bias, k("b")[s]) < tol_b, s
+        assert abs(st.bias_[0] - float(k("g")[s])) < 1e-6, s
+        assert rel_err(st.gamma, k("gamma")[s]) < 1e-6 and rel_err(st.beta, k("beta")[s]) < 2e-6, s
+        assert rel_err(st.running_mean, k("rm")[s]) < 1e-6 and rel_err(st.running_var, k("rv")[s]) < 1e-6, s
+    pi, pj = st.forward(k("fi")[0], ones, k("fj")[0], ones)          # eval mode: running statistics, no dropout
+    assert rel_err(pi, k("fwd_i")) < tol_fwd and rel_err(pj, k("fwd_j")) < tol_fwd
+    assert (k("mi")[0] == 0).mean() == pytest.approx(float(k("p")), abs=0.1)        # the recorded masks are masks
+
+
+def test_bprfm_full_oracle_reduces_to_the_two_feature_closed_form(golden):
+    """With batch_norm off and no mask BPRFMFull is the oracle the CUDA path is checked against (bprfm_adagrad_step)."""
+    from oracle import bprfm_oracle
+    g = golden("bprfm_small.npz")
+    E, b = g["E0"].astype(np.float64), g["b0"].astype(np.float64)
+    aE, ab = np.full_like(E, 1e-8), np.full_like(b, 1e-8)
+    full = bprfm_oracle.BPRFMFull(g["E0"], g["b0"], float(g["bias_"]), False, lr=float(g["lr"]))
+    ones = np.ones((g["feats_i"].shape[1], 2))
+    for s in range(len(g["losses"])):
+        l0 = bprfm_oracle.bprfm_adagrad_step(E, b, float(g["bias_"]), aE, ab, g["feats_i"][s], g["feats_j"][s], lr=float(g["lr"]))
+        l1 = full.step(g["feats_i"][s], ones, g["feats_j"][s], ones)
+        assert l1 == pytest.approx(l0, rel=1e-12)
+        # the general form gives the user bias a gradient of -s + s that is zero only up to rounding; with the script's
+        # 1e-8 accumulator that is visible on the biases, not on the embeddings
+        assert rel_err(full.E, E) < 1e-9 and rel_err(full.bias, b) < 2e-4
