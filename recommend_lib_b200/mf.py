@@ -38,7 +38,7 @@ def _device_fit(user_num, item_num, n_factors, n_epochs, prm, users, items, rati
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     h = _lib.Handle(idx, user_num, item_num, n_factors, 0)
     try:
-        t = lambda a: torch.from_numpy(a).to(dev)
+        t = lambda a: torch.from_numpy(a if a.flags.writeable else a.copy()).to(dev)   # read-only views (np.load) warn
         dA, dB, dba, dbb = t(A), t(Bm), t(ba), t(bb)
         du, di, dr = t(users), t(items), t(ratings)
         sse = torch.zeros(max(n_epochs, 1), dtype=torch.float64, device=dev) if want_sse else None
