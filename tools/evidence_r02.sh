@@ -1,0 +1,22 @@
+# Round 2, first GPU calls: what round 1 could not measure after its GPU budget ended.
+#   1 GPU :  gpurun --timeout 600 -- 'bash tools/evidence_r02.sh one'
+#   N GPUs:  gpurun --gpus 8 --timeout 400 -- 'bash tools/evidence_r02.sh many 8'     (then 4, 2)
+set -x
+mode=${1:-one}
+if [ "$mode" = one ]; then
+  python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/r02_gpu_tests.log
+  python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1
+  python bench.py > gpurun_out/r02_bench_n1_default.json 2> gpurun_out/r02_bench_n1_default.err
+  tail -3 gpurun_out/r02_gpu_tests.log; tail -1 gpurun_out/r02_smoke.log; cut -c1-300 gpurun_out/r02_bench_n1_default.json
+else
+  N=${2:-8}
+  run() {  # $1 = tag, rest = environment
+    tag=$1; shift
+    env "$@" python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+      bench.py --gpus $N --steps 50 --warmup 5 > gpurun_out/r02_bench_n${N}_${tag}.json 2> gpurun_out/r02_bench_n${N}_${tag}.err
+    cut -c1-200 gpurun_out/r02_bench_n${N}_${tag}.json
+  }
+  run interleaved DAISY_SHARD_INTERLEAVE=$N     # the default since r01e: chunks dealt round-robin over the owners
+  run sorted DAISY_SHARD_INTERLEAVE=0           # the schedule of every r01b-r01d multi-GPU line
+  timeout 60 ./tools/peer_a2a_bw $N > gpurun_out/r02_peer_a2a_bw_${N}gpu.log 2>&1; cat gpurun_out/r02_peer_a2a_bw_${N}gpu.log
+fi
