@@ -1192,11 +1192,13 @@ static int launch_small_book(daisy_ctx *h, cudaStream_t bs, const int32_t *tripl
 //        `long_len` contributions that start in its window
 //   the last block                  the loss reduction
 // ------------------------------------------------------------------------------------------------
-#ifndef DAISY_SEG_MIN_BLOCKS  // experiment knob (compile time): 2 caps k_seg_all at 128 registers -> two blocks per SM
-#define DAISY_SEG_MIN_BLOCKS 1
+#ifdef DAISY_SEG_MIN_BLOCKS  // experiment knob (compile time): 2 caps k_seg_all at 128 registers -> two blocks per SM
+#define DAISY_SEG_BOUNDS __launch_bounds__(256, DAISY_SEG_MIN_BLOCKS)
+#else
+#define DAISY_SEG_BOUNDS __launch_bounds__(256)
 #endif
 template <int V, class Opt, int WIN, int SLICE>
-__global__ void __launch_bounds__(256, DAISY_SEG_MIN_BLOCKS) k_seg_all(const float *__restrict__ P, const float *__restrict__ Q,
+__global__ void DAISY_SEG_BOUNDS k_seg_all(const float *__restrict__ P, const float *__restrict__ Q,
                                                   const uint32_t *__restrict__ ukey_s,
                                                   const uint32_t *__restrict__ qkey_s, int B, int nQ, uint32_t q_sentinel,
                                                   const float *__restrict__ stageU, const float *__restrict__ stageQ,
