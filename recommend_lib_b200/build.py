@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import glob
 import os
+import shlex
 import shutil
 import subprocess
 import sys
@@ -52,13 +53,17 @@ def build(force=False, verbose=False):
     """Compile every csrc/*.cu to an object (only the stale ones) and link the shared library."""
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
+    # experiments: DAISY_NVCC_EXTRA="-DDAISY_SEG_MIN_BLOCKS=2 -DDAISY_SEG_COMBINE_TILE=4" rebuilds everything with the
+    # extra flags (DESIGN.md section 11); an ordinary build afterwards needs --force to get the default library back
+    extra = shlex.split(os.environ.get("DAISY_NVCC_EXTRA", ""))
+    force = force or bool(extra)
     headers = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
     objs, procs = [], []
     for src in sources():
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or _stale(obj, [src, *headers]):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+            cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), flush=True)

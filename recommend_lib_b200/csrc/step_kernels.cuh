@@ -1284,15 +1284,19 @@ __global__ void DAISY_SEG_BOUNDS k_seg_all(const float *__restrict__ P, const fl
 #pragma unroll
             for (int v = 0; v < V; ++v) grp[v] = f4_zero();
             const int g1 = min(nsl, g0 + 64);
-            for (int j0 = g0; j0 < g1; j0 += 8) {
-                float4 rr[8][V];
+#ifndef DAISY_SEG_COMBINE_TILE  // slice sums in flight per warp of the combine tail (any value: same order of additions)
+#define DAISY_SEG_COMBINE_TILE 8
+#endif
+            constexpr int CT = DAISY_SEG_COMBINE_TILE;
+            for (int j0 = g0; j0 < g1; j0 += CT) {
+                float4 rr[CT][V];
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj)
+                for (int jj = 0; jj < CT; ++jj)
 #pragma unroll
                     for (int v = 0; v < V; ++v)
                         rr[jj][v] = (j0 + jj < g1 && act[v]) ? __ldcg(s2 + (size_t)(j0 + jj) * D4 + lane + 32 * v) : f4_zero();
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj)
+                for (int jj = 0; jj < CT; ++jj)
                     if (j0 + jj < g1) {
 #pragma unroll
                         for (int v = 0; v < V; ++v) grp[v] = f4_add(grp[v], rr[jj][v]);
