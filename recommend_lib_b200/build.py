@@ -50,17 +50,25 @@ def _stale(target, deps):
 
 
 def build(force=False, verbose=False):
-    """Compile every csrc/*.cu to an object (only the stale ones) and link the shared library."""
+    """Compile every csrc/*.cu to an object (only the stale ones) and link the shared library.
+
+    Experiments: DAISY_NVCC_EXTRA="-DDAISY_SEG_MIN_BLOCKS=2 -DDAISY_SEG_COMBINE_TILE=4" with
+    DAISY_LIB_VARIANT=seg2 builds libdaisy_b200_seg2.so from objects under csrc/_obj_seg2/ next to the default library,
+    which is left alone; a process started with DAISY_LIB_VARIANT=seg2 loads that one (_lib.py), so both travel to the
+    GPU box in one snapshot and one call can measure them side by side."""
     nvcc = _nvcc()
-    os.makedirs(OBJ, exist_ok=True)
-    # experiments: DAISY_NVCC_EXTRA="-DDAISY_SEG_MIN_BLOCKS=2 -DDAISY_SEG_COMBINE_TILE=4" rebuilds everything with the
-    # extra flags (DESIGN.md section 11); an ordinary build afterwards needs --force to get the default library back
     extra = shlex.split(os.environ.get("DAISY_NVCC_EXTRA", ""))
-    force = force or bool(extra)
+    variant = os.environ.get("DAISY_LIB_VARIANT", "")
+    if extra and not variant:
+        raise RuntimeError("DAISY_NVCC_EXTRA needs DAISY_LIB_VARIANT=<name>: the default library is never built with "
+                           "experimental flags")
+    obj_dir = OBJ + ("_" + variant if variant else "")
+    lib = LIB[:-3] + ("_" + variant if variant else "") + ".so"
+    os.makedirs(obj_dir, exist_ok=True)
     headers = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
     objs, procs = [], []
     for src in sources():
-        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or _stale(obj, [src, *headers]):
             cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj]
@@ -71,14 +79,14 @@ def build(force=False, verbose=False):
     failed = [src for src, p in procs if p.wait() != 0]
     if failed:
         raise RuntimeError("nvcc failed for: " + ", ".join(failed))
-    if force or procs or _stale(LIB, objs):
+    if force or procs or _stale(lib, objs):
         # shared cudart: inside a PyTorch process the library binds to the libcudart.so.12 torch already loaded, so
         # both see ONE runtime (same current-device state, streams and events interoperate by construction)
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared", "-o", LIB, *objs]
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared", "-o", lib, *objs]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

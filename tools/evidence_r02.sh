@@ -8,6 +8,14 @@ if [ "$mode" = one ]; then
   python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1
   python bench.py > gpurun_out/r02_bench_n1_default.json 2> gpurun_out/r02_bench_n1_default.err
   tail -3 gpurun_out/r02_gpu_tests.log; tail -1 gpurun_out/r02_smoke.log; cut -c1-300 gpurun_out/r02_bench_n1_default.json
+  # k_seg_all at two blocks per SM (lead 3).  Build the variant HERE before the call:
+  #   DAISY_LIB_VARIANT=seg2 DAISY_NVCC_EXTRA="-DDAISY_SEG_MIN_BLOCKS=2 -DDAISY_SEG_COMBINE_TILE=4" python -m recommend_lib_b200.build
+  if [ -f recommend_lib_b200/libdaisy_b200_seg2.so ]; then
+    DAISY_LIB_VARIANT=seg2 python -m pytest tests/test_bpr_gpu.py -m gpu -q 2>&1 | tail -3 > gpurun_out/r02_gpu_tests_seg2.log
+    DAISY_LIB_VARIANT=seg2 python bench.py --no-cpu-baseline --phases > gpurun_out/r02_bench_n1_seg2.json 2>/dev/null
+    python bench.py --no-cpu-baseline --phases > gpurun_out/r02_bench_n1_phases.json 2>/dev/null
+    tail -1 gpurun_out/r02_gpu_tests_seg2.log; cut -c1-200 gpurun_out/r02_bench_n1_seg2.json; cut -c1-200 gpurun_out/r02_bench_n1_phases.json
+  fi
 else
   N=${2:-8}
   run() {  # $1 = tag, rest = environment
