@@ -295,6 +295,41 @@ DAISY_API int daisy_mf_predict(daisy_handle_t h, const double *pu, const double 
                      const int32_t *users, const int32_t *items, int64_t n, int with_bias, double mu,
                      double *est, daisy_stream_t stream);
 
+/* ---- BPR-FM at the reference script's defaults: batch norm + dropout ---------------------
+ * EXPERIMENTAL: compiled for sm_100a, not yet run on a GPU (csrc/fmbn.cu has the status); the verified BPR-FM path is
+ * daisy_bprfm_adagrad_step (batch_norm off, dropout 0).
+ * Replaces, for features = [user, user_num + item] with values 1 (util/data_loader.py:159-172, 595-614):
+ *   BPRFM._out with nn.BatchNorm1d(num_factors) + nn.Dropout(drop_prob[0])   BPRFMRecommender.py:45-80
+ *   the training step + optim.Adagrad over every parameter                    BPRFMRecommender.py:191-193, 214-219
+ * All pointers are device pointers owned by the caller (the module's parameter / buffer tensors and the optimizer's
+ * state_sum tensors), fp32, contiguous. */
+typedef struct {
+    float *E;            /* [num_features, F]  embeddings.weight */
+    float *bias;         /* [num_features]     biases.weight */
+    float *accE, *accb;  /* Adagrad state_sum of the two tables (step only) */
+    float *gamma, *beta; /* [F]  FM_layers[0].weight / .bias */
+    float *acc_gamma, *acc_beta;        /* their Adagrad state_sum (step only) */
+    float *running_mean, *running_var;  /* [F]  FM_layers[0] buffers */
+    float lr, eps;       /* Adagrad: lr, eps (torch default 1e-10) */
+    float bn_eps, momentum; /* BatchNorm1d: 1e-5, 0.1 */
+    int64_t user_num, num_features;     /* features [0, user_num) are users, the rest items */
+    int F;               /* num_factors, 1..255 */
+} daisy_fmbn_params;
+
+/* Bytes of device scratch daisy_fmbn_step needs for batches of up to B triples (no device call). */
+DAISY_API int daisy_fmbn_scratch_bytes(int64_t B, int F, int64_t *bytes);
+/* One training step on B >= 2 triples (user, item_i, item_j; item ids relative to user_num).  mask_i / mask_j [B, F]:
+ * the dropout masks of the positive / negative _out call, kept elements already scaled by 1 / (1 - p); NULL = no
+ * dropout.  loss_accum += -sum log sigmoid(pred_i - pred_j).  Batch statistics, running statistics (updated once per
+ * _out call, positive first) and every reduction are computed in a fixed order: bit-reproducible.  Asynchronous. */
+DAISY_API int daisy_fmbn_step(daisy_handle_t h, const daisy_fmbn_params *p, const int32_t *triples, int64_t B,
+                    const float *mask_i, const float *mask_j, void *scratch, int64_t scratch_bytes,
+                    double *loss_accum, daisy_stream_t stream);
+/* Evaluation-mode forward (running statistics, no dropout): pred = sum_f BN(e_u * e_item)_f + b_item; the caller adds
+ * the user bias and bias_ (equal for every item of a user). */
+DAISY_API int daisy_fmbn_forward(daisy_handle_t h, const daisy_fmbn_params *p, const int32_t *triples, int64_t B,
+                       float *pred_i, float *pred_j, daisy_stream_t stream);
+
 /* ---- introspection for tests / bench ------------------------------------------------------------- */
 /* Number of kernels launched by this handle since creation (the bench's gpu_launches claim). */
 DAISY_API int daisy_launch_count(daisy_handle_t h, int64_t *n);

@@ -8,6 +8,8 @@ Public surface (mirrors the reference):
 * ``SVD`` / ``RSVD`` (ctor kwargs, ``fit``, ``predict``)  -- util/matrix_factorization.pyx:5-167
 * ``NCF(..., model='GMF')`` + ``GMFAdam``           -- NCFRecommender.py:28-125, 255-287 (next row)
 * ``BPRFM(..., batch_norm=False, drop_prob=[0, 0])`` + ``FMAdagrad``  -- BPRFMRecommender.py:29-80, 191-219 (N3)
+* ``BPRFMBN(..., batch_norm=True, drop_prob)`` + ``FMBNAdagrad``     -- the same script at its defaults; EXPERIMENTAL,
+  compiled but not yet run on a GPU (bprfm_bn.py)
 
 All compute goes through the C-ABI library ``libdaisy_b200.so`` (``include/daisy_b200.h``);
 there is no CPU fallback: using any of the above without the built library or without
@@ -22,7 +24,7 @@ _LAZY = {
     "BPR": ".bpr", "BPRMFRecommender": ".bpr", "BPRSGD": ".bpr", "BPRAdam": ".bpr",
     "metric_eval": ".metrics", "topk_candidates": ".metrics", "topk_full": ".metrics", "rank_metrics": ".metrics", "final_kpi": ".metrics",
     "SVD": ".mf", "RSVD": ".mf", "MFRecommender": ".mf",
-    "NCF": ".ncf", "GMFAdam": ".ncf", "BPRFM": ".bprfm", "FMAdagrad": ".bprfm",
+    "NCF": ".ncf", "GMFAdam": ".ncf", "BPRFM": ".bprfm", "FMAdagrad": ".bprfm", "BPRFMBN": ".bprfm_bn", "FMBNAdagrad": ".bprfm_bn",
     "TripleSampler": ".sampler", "DeviceTripleSampler": ".sampler",
     "ShardedBPR": ".sharded", "PeerShardedBPR": ".sharded",
     "lib": "._lib",

@@ -25,6 +25,14 @@ class MFParams(ctypes.Structure):
                 ("reg2", c_f64), ("global_mean", c_f64)]
 
 
+class FMBNParams(ctypes.Structure):
+    """daisy_fmbn_params"""
+    _fields_ = [("E", c_vp), ("bias", c_vp), ("accE", c_vp), ("accb", c_vp), ("gamma", c_vp), ("beta", c_vp),
+                ("acc_gamma", c_vp), ("acc_beta", c_vp), ("running_mean", c_vp), ("running_var", c_vp),
+                ("lr", c_f32), ("eps", c_f32), ("bn_eps", c_f32), ("momentum", c_f32),
+                ("user_num", c_i64), ("num_features", c_i64), ("F", c_i32)]
+
+
 # name -> argtypes; every entry returns int except daisy_last_error.  Kept in one table so that the CPU test
 # can check it against the prototypes of include/daisy_b200.h.
 SIGNATURES = {
@@ -72,6 +80,9 @@ SIGNATURES = {
     "daisy_mf_fit": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, ctypes.POINTER(MFParams),
                      c_vp, c_vp],
     "daisy_mf_predict": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_f64, c_vp, c_vp],
+    "daisy_fmbn_scratch_bytes": [c_i64, c_i32, ctypes.POINTER(c_i64)],
+    "daisy_fmbn_step": [c_vp, ctypes.POINTER(FMBNParams), c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp],
+    "daisy_fmbn_forward": [c_vp, ctypes.POINTER(FMBNParams), c_vp, c_i64, c_vp, c_vp, c_vp],
     "daisy_launch_count": [c_vp, ctypes.POINTER(c_i64)],
     "daisy_set_timing": [c_vp, c_i32],
     "daisy_last_step_timing": [c_vp, ctypes.POINTER(c_f32), ctypes.POINTER(c_f32)],

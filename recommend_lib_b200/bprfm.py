@@ -33,8 +33,8 @@ class BPRFM(nn.Module):
     def __init__(self, num_features, num_factors, batch_norm=False, drop_prob=(0.0, 0.0), user_num=None, max_batch=4096):
         super().__init__()
         if batch_norm or any(float(p) != 0.0 for p in drop_prob):
-            raise NotImplementedError("only batch_norm=False, drop_prob=[0, 0] is on the accelerated path (dropout draws "
-                                      "from torch's global generator inside forward: no reproducible reference output)")
+            raise NotImplementedError("only batch_norm=False, drop_prob=[0, 0] is on this (GPU-verified) path; the batch-norm "
+                                      "+ dropout step is bprfm_bn.BPRFMBN / FMBNAdagrad (experimental: not yet run on a GPU)")
         if user_num is None or not (0 < int(user_num) < int(num_features)):
             raise ValueError("user_num (features [0, user_num) are users, the rest items) is required")
         if num_factors % 4:

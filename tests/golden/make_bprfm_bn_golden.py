@@ -70,7 +70,7 @@ def run(acc0, batch_norm=True, p=0.5, U=50, I=40, F=8, B=96, steps=4):
     with torch.no_grad():
         ones = torch.ones(B, 2)
         pi, pj = model(torch.from_numpy(rec["fi"][0]).long(), ones, torch.from_numpy(rec["fj"][0]).long(), ones)
-    out = dict(E0=s0["E"], b0=s0["b"], g0=s0["g"], fwd_i=pi.numpy(), fwd_j=pj.numpy(), acc0=acc0, p=p, lr=0.05)
+    out = dict(E0=s0["E"], b0=s0["b"], g0=s0["g"], fwd_i=pi.numpy(), fwd_j=pj.numpy(), acc0=acc0, p=p, lr=0.05, user_num=U)
     out.update({k: np.stack(v) for k, v in rec.items() if v})
     return out
 

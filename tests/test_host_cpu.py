@@ -177,3 +177,29 @@ def test_shard_schedule_deals_every_chunk_to_exactly_one_warp():
     assert [chunk(w, n, g) // per for w in range(16)] == [0, 1, 2, 3, 4, 5, 6, 7] * 2
     assert [chunk(w, n, 0) for w in range(4)] == [0, 1, 2, 3]
     assert L.daisy_shard_schedule(0, 10, 2, None) != 0            # null output pointer is an error, not a crash
+
+
+def test_bprfm_bn_module_is_a_drop_in_and_has_no_cpu_path():
+    """BPRFMBN (experimental batch-norm path of BPR-FM) keeps the reference class's module structure -- the state_dict
+    keys and shapes of BPRFM(num_features, num_factors, True, [0.5, 0.2]) (BPRFMRecommender.py:45-55) -- and refuses to
+    compute without a CUDA device."""
+    import torch
+    from recommend_lib_b200 import _lib
+    from recommend_lib_b200.bprfm_bn import BPRFMBN, FMBNAdagrad
+    m = BPRFMBN(90, 8, True, [0.5, 0.2], user_num=50)
+    sd = m.state_dict()
+    assert list(sd.keys()) == ["bias_", "embeddings.weight", "biases.weight", "FM_layers.0.weight", "FM_layers.0.bias",
+                               "FM_layers.0.running_mean", "FM_layers.0.running_var", "FM_layers.0.num_batches_tracked"]
+    assert tuple(sd["embeddings.weight"].shape) == (90, 8) and tuple(sd["biases.weight"].shape) == (90, 1)
+    assert float(sd["biases.weight"].abs().max()) == 0.0 and 0.005 < float(sd["embeddings.weight"].std()) < 0.02
+    with pytest.raises(NotImplementedError):
+        BPRFMBN(90, 8, False, [0.0, 0.0], user_num=50)
+    with pytest.raises(ValueError):
+        BPRFMBN(90, 8, True, [0.5, 0.2])                      # user_num is required
+    if not torch.cuda.is_available():
+        m.eval()
+        f = torch.zeros(2, 2, dtype=torch.long)
+        with pytest.raises(_lib.DaisyError):
+            m(f, None, f, None)
+        with pytest.raises(_lib.DaisyError):
+            FMBNAdagrad(m).step(f, None, f, None)
