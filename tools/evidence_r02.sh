@@ -16,6 +16,9 @@ if [ "$mode" = one ]; then
     python bench.py --no-cpu-baseline --phases > gpurun_out/r02_bench_n1_phases.json 2>/dev/null
     tail -1 gpurun_out/r02_gpu_tests_seg2.log; cut -c1-200 gpurun_out/r02_bench_n1_seg2.json; cut -c1-200 gpurun_out/r02_bench_n1_phases.json
   fi
+  # experimental kernels that have never run on a GPU (last: a crash here must not cost the evidence above)
+  DAISY_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_bprfm_bn_gpu.py -m gpu -q -x 2>&1 | tail -30 > gpurun_out/r02_experimental_fmbn.log
+  tail -5 gpurun_out/r02_experimental_fmbn.log
 else
   N=${2:-8}
   run() {  # $1 = tag, rest = environment
