@@ -330,6 +330,28 @@ DAISY_API int daisy_fmbn_step(daisy_handle_t h, const daisy_fmbn_params *p, cons
 DAISY_API int daisy_fmbn_forward(daisy_handle_t h, const daisy_fmbn_params *p, const int32_t *triples, int64_t B,
                        float *pred_i, float *pred_j, daisy_stream_t stream);
 
+/* ---- Item2Vec / skip-gram with negative sampling ---------------------------------------
+ * EXPERIMENTAL: compiled for sm_100a, not yet run on a GPU (csrc/sgns.cu has the status).
+ * Replaces Item2Vec.forward_i / forward_o + SGNS.forward (Item2VecRecommender.py:60-97) with the negatives given, and
+ * loss.backward() + optim.Adam(sgns.parameters()).step() (:266, 274-277; torch's Adam is dense: every row of both
+ * tables is stepped).  Device pointers owned by the caller, fp32, contiguous. */
+typedef struct {
+    float *iv, *ov;                  /* [vocab, D]  embedding.ivectors.weight / embedding.ovectors.weight */
+    float *m_iv, *v_iv, *m_ov, *v_ov; /* Adam exp_avg / exp_avg_sq of the two tables */
+    float lr, beta1, beta2, eps;     /* torch defaults: 1e-3, 0.9, 0.999, 1e-8 */
+    int64_t vocab;
+    int D;                           /* embedding size, 1..512 */
+    int padding_idx;                 /* row that receives no gradient (nn.Embedding(padding_idx=0)); -1 = none */
+} daisy_sgns_params;
+
+/* Bytes of device scratch daisy_sgns_step needs (no device call). */
+DAISY_API int daisy_sgns_scratch_bytes(int64_t B, int C, int n_negs, int64_t vocab, int D, int64_t *bytes);
+/* One training step: iword [B], owords [B, C], nwords [B, C * n_negs] (the layout of :86-87), step_no 1-based (Adam's
+ * bias correction).  loss_accum += the batch loss of :97 (mean form).  Fixed-order reductions: bit-reproducible. */
+DAISY_API int daisy_sgns_step(daisy_handle_t h, const daisy_sgns_params *p, const int32_t *iword, const int32_t *owords,
+                    const int32_t *nwords, int64_t B, int C, int n_negs, int64_t step_no, void *scratch,
+                    int64_t scratch_bytes, double *loss_accum, daisy_stream_t stream);
+
 /* ---- introspection for tests / bench ------------------------------------------------------------- */
 /* Number of kernels launched by this handle since creation (the bench's gpu_launches claim). */
 DAISY_API int daisy_launch_count(daisy_handle_t h, int64_t *n);

@@ -33,6 +33,13 @@ class FMBNParams(ctypes.Structure):
                 ("user_num", c_i64), ("num_features", c_i64), ("F", c_i32)]
 
 
+class SGNSParams(ctypes.Structure):
+    """daisy_sgns_params"""
+    _fields_ = [("iv", c_vp), ("ov", c_vp), ("m_iv", c_vp), ("v_iv", c_vp), ("m_ov", c_vp), ("v_ov", c_vp),
+                ("lr", c_f32), ("beta1", c_f32), ("beta2", c_f32), ("eps", c_f32),
+                ("vocab", c_i64), ("D", c_i32), ("padding_idx", c_i32)]
+
+
 # name -> argtypes; every entry returns int except daisy_last_error.  Kept in one table so that the CPU test
 # can check it against the prototypes of include/daisy_b200.h.
 SIGNATURES = {
@@ -83,6 +90,9 @@ SIGNATURES = {
     "daisy_fmbn_scratch_bytes": [c_i64, c_i32, ctypes.POINTER(c_i64)],
     "daisy_fmbn_step": [c_vp, ctypes.POINTER(FMBNParams), c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp],
     "daisy_fmbn_forward": [c_vp, ctypes.POINTER(FMBNParams), c_vp, c_i64, c_vp, c_vp, c_vp],
+    "daisy_sgns_scratch_bytes": [c_i64, c_i32, c_i32, c_i64, c_i32, ctypes.POINTER(c_i64)],
+    "daisy_sgns_step": [c_vp, ctypes.POINTER(SGNSParams), c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i64, c_vp, c_i64, c_vp,
+                        c_vp],
     "daisy_launch_count": [c_vp, ctypes.POINTER(c_i64)],
     "daisy_set_timing": [c_vp, c_i32],
     "daisy_last_step_timing": [c_vp, ctypes.POINTER(c_f32), ctypes.POINTER(c_f32)],

@@ -203,3 +203,27 @@ def test_bprfm_bn_module_is_a_drop_in_and_has_no_cpu_path():
             m(f, None, f, None)
         with pytest.raises(_lib.DaisyError):
             FMBNAdagrad(m).step(f, None, f, None)
+
+
+def test_item2vec_modules_are_drop_ins_and_have_no_cpu_path():
+    """Item2Vec / SGNS (experimental N4 path) keep the reference's module structure (state_dict keys of
+    SGNS(Item2Vec(V, D), ...), Item2VecRecommender.py:37-80), its initialisation (padding row zero, U(-0.5/D, 0.5/D)) and
+    its negative-sampling table (unigram^0.75); computing without a CUDA device raises."""
+    import torch
+    from recommend_lib_b200 import _lib
+    from recommend_lib_b200.item2vec import Item2Vec, SGNS, SGNSAdam
+    counts = np.arange(1, 41, dtype=np.float64)
+    sgns = SGNS(Item2Vec(40, 12), vocab_size=40, n_negs=5, weights=counts)
+    assert list(sgns.state_dict().keys()) == ["embedding.ivectors.weight", "embedding.ovectors.weight"]
+    W = sgns.embedding.ivectors.weight
+    assert float(W[0].abs().max()) == 0.0 and float(W.abs().max()) <= 0.5 / 12 and float(W[1:].abs().min()) > 0
+    wf = counts ** 0.75
+    assert np.allclose(sgns.weights.numpy(), wf / wf.sum(), rtol=1e-6)
+    assert tuple(sgns.draw_negatives(3, 2, "cpu").shape) == (3, 10)
+    uni = SGNS(Item2Vec(40, 12), vocab_size=40, n_negs=5).draw_negatives(500, 2, "cpu")
+    assert int(uni.min()) >= 0 and int(uni.max()) <= 38          # uniform_(0, V - 1).long(): V - 1 is never drawn (:90-91)
+    with pytest.raises(RuntimeError):
+        sgns(torch.zeros(3, dtype=torch.long), torch.zeros(3, 2, dtype=torch.long))
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.DaisyError):
+            SGNSAdam(sgns).step(np.arange(3), np.zeros((3, 2), dtype=np.int64))

@@ -19,6 +19,8 @@ if [ "$mode" = one ]; then
   # experimental kernels that have never run on a GPU (last: a crash here must not cost the evidence above)
   DAISY_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_bprfm_bn_gpu.py -m gpu -q -x 2>&1 | tail -30 > gpurun_out/r02_experimental_fmbn.log
   tail -5 gpurun_out/r02_experimental_fmbn.log
+  DAISY_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_sgns_gpu.py -m gpu -q -x 2>&1 | tail -30 > gpurun_out/r02_experimental_sgns.log
+  tail -5 gpurun_out/r02_experimental_sgns.log
 else
   N=${2:-8}
   run() {  # $1 = tag, rest = environment
