@@ -3,6 +3,7 @@
 //
 // STATUS: compiled for sm_100a, NOT YET RUN ON A GPU (written after the GPU budget of round 1 was spent); the GPU tests
 // (tests/test_bprfm_bn_gpu.py) are excluded from the default run until it has been (DAISY_EXPERIMENTAL=1 runs them).
+// Executed so far only under the host emulation of tests/emu (tests/test_kernel_emulation.py: golden run + oracle green).
 // The checker exists and is pinned to the unmodified reference: oracle/bprfm_oracle.py: BPRFMFull.
 //
 // With features = [user, user_num + item] and values 1 the bi-interaction vector is x = e_u (.) e_i.  BatchNorm1d in

@@ -1,0 +1,57 @@
+"""TEST INFRASTRUCTURE ONLY: compile product translation units (csrc/fmbn.cu, csrc/sgns.cu) for the HOST against the
+emulation shim of tests/emu/emu.h, so that kernels which have not run on a GPU yet can at least be executed and checked
+against the oracle.  The only rewrite of the source is the launch syntax:
+    kernel<<<grid, block, smem, stream>>>(args);   ->   emu::launch(emu::Cfg(grid, block, smem, stream), [&] { kernel(args); });
+"""
+import os
+import re
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "recommend_lib_b200", "csrc")
+OUT = os.path.join(HERE, "_build")
+
+GLUE = r'''
+#include <stdarg.h>
+static thread_local char g_err[512];
+void daisy_set_error(const char *fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); }
+extern "C" const char *emu_last_error() { return g_err; }
+extern "C" daisy_ctx *emu_handle() {
+    daisy_ctx *h = (daisy_ctx *)calloc(1, sizeof(daisy_ctx));
+    h->num_sms = 4;
+    h->err = (int *)calloc(2, sizeof(int));
+    h->err[1] = 0x7fffffff;
+    return h;
+}
+extern "C" int emu_err_flag(daisy_ctx *h) { return h->err[0]; }
+extern "C" int emu_err_pos(daisy_ctx *h) { return h->err[1]; }
+'''
+
+
+def rewrite(src):
+    pat = re.compile(r"(\b\w+)<<<(.+?)>>>\((.*?)\);", re.S)
+    out, n = pat.subn(lambda m: f"emu::launch(emu::Cfg({m.group(2)}), [&] {{ {m.group(1)}({m.group(3)}); }});", src)
+    assert n > 0
+    return out
+
+
+def build(unit):
+    """unit: 'fmbn' or 'sgns' -> path of the host shared library executing that unit's kernels."""
+    os.makedirs(OUT, exist_ok=True)
+    src_path = os.path.join(CSRC, unit + ".cu")
+    so = os.path.join(OUT, f"lib{unit}_emu.so")
+    deps = [src_path, os.path.join(CSRC, "ctx.cuh"), os.path.join(HERE, "emu.h"), os.path.join(HERE, "cub", "cub.cuh"), __file__]
+    if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
+        return so
+    cpp = os.path.join(OUT, unit + "_emu.cpp")
+    with open(cpp, "w") as f:
+        f.write(rewrite(open(src_path).read()) + GLUE)
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-w",
+                           "-I", HERE, "-I", CSRC, "-o", so, cpp])
+    return so
+
+
+if __name__ == "__main__":
+    for u in ("fmbn", "sgns"):
+        print(build(u))

@@ -1,0 +1,129 @@
+// TEST INFRASTRUCTURE ONLY.  A functional emulation of the CUDA execution model on host threads, just wide enough for
+// the plain kernels of csrc/fmbn.cu and csrc/sgns.cu: blocks run one after the other, every thread of a block is an
+// OS thread, __syncthreads is a block barrier, warp shuffles exchange through a per-warp buffer between two warp
+// barriers, atomics are host atomics, a thread that returns drops out of its barriers.  tests/emu/build_emu.py rewrites
+// `kernel<<<grid, block, smem, stream>>>(args);` into emu::launch(...) and compiles the unit with g++ -std=c++20.
+// It checks indexing and arithmetic of kernels that could not be run on a GPU yet; it says nothing about performance
+// or about memory-model subtleties of the real hardware.
+#pragma once
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+typedef int cudaError_t;
+typedef void *cudaStream_t;
+typedef void *cudaEvent_t;
+typedef void *cudaGraphExec_t;
+#define cudaSuccess 0
+inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+inline cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n); return *p ? cudaSuccess : 1; }
+
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__ static
+
+namespace emu {
+struct Block {
+    std::unique_ptr<std::barrier<>> bar;
+    std::vector<std::unique_ptr<std::barrier<>>> wbar;
+    std::vector<uint64_t> xbuf;  // [warps][32]
+};
+inline Block *&cur() { static Block *b = nullptr; return b; }
+inline thread_local int t_lin = 0;
+}  // namespace emu
+inline thread_local dim3 threadIdx, blockIdx;
+inline dim3 blockDim, gridDim;
+
+inline void __syncthreads() { emu::cur()->bar->arrive_and_wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::cur()->wbar[emu::t_lin >> 5]->arrive_and_wait(); }
+
+template <class T>
+inline T emu_exchange(T v, int src_lane) {
+    static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+    emu::Block *b = emu::cur();
+    const int w = emu::t_lin >> 5, lane = emu::t_lin & 31;
+    uint64_t bits = 0;
+    memcpy(&bits, &v, sizeof(T));
+    b->xbuf[(size_t)w * 32 + lane] = bits;
+    b->wbar[w]->arrive_and_wait();
+    const uint64_t got = b->xbuf[(size_t)w * 32 + (src_lane & 31)];
+    b->wbar[w]->arrive_and_wait();
+    T r;
+    memcpy(&r, &got, sizeof(T));
+    return r;
+}
+template <class T> inline T __shfl_sync(unsigned, T v, int src) { return emu_exchange(v, src); }
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_exchange(v, (emu::t_lin & 31) ^ m); }
+
+inline int atomicOr(int *p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicMin(int *p, int v) {
+    int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+template <class T> inline T min(T a, T b) { return a < b ? a : b; }
+
+// ctx.cuh keeps its device helpers behind __CUDACC__ (some are inline PTX); the two the plain kernels use:
+inline float warp_sum(float v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+inline double warp_sum_d(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+namespace emu {
+struct Cfg {
+    dim3 grid, block;
+    Cfg(dim3 g, dim3 b, size_t = 0, cudaStream_t = nullptr) : grid(g), block(b) {}
+};
+inline void launch(const Cfg &c, const std::function<void()> &body) {
+    const int T = (int)(c.block.x * c.block.y * c.block.z);
+    if (T % 32) { fprintf(stderr, "emu: block of %d threads is not a multiple of 32\n", T); abort(); }
+    blockDim = c.block;
+    gridDim = c.grid;
+    for (unsigned bz = 0; bz < c.grid.z; ++bz)
+        for (unsigned by = 0; by < c.grid.y; ++by)
+            for (unsigned bx = 0; bx < c.grid.x; ++bx) {
+                Block blk;
+                blk.bar = std::make_unique<std::barrier<>>(T);
+                for (int w = 0; w < T / 32; ++w) blk.wbar.push_back(std::make_unique<std::barrier<>>(32));
+                blk.xbuf.assign((size_t)T, 0);
+                cur() = &blk;
+                std::vector<std::thread> th;
+                th.reserve(T);
+                for (int t = 0; t < T; ++t)
+                    th.emplace_back([&, t] {
+                        t_lin = t;
+                        threadIdx = dim3(t % c.block.x, (t / c.block.x) % c.block.y, t / (c.block.x * c.block.y));
+                        blockIdx = dim3(bx, by, bz);
+                        body();
+                        blk.wbar[t >> 5]->arrive_and_drop();  // a finished thread no longer takes part in barriers
+                        blk.bar->arrive_and_drop();
+                    });
+                for (auto &x : th) x.join();
+                cur() = nullptr;
+            }
+}
+}  // namespace emu

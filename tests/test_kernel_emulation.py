@@ -1,0 +1,199 @@
+"""CPU execution of kernels that have NOT run on a GPU yet (csrc/fmbn.cu, csrc/sgns.cu).
+
+tests/emu compiles the product's own translation units for the host against a functional emulation of the CUDA
+execution model (OS threads, block / warp barriers, shuffle exchange buffers) and this file drives the SAME extern "C"
+entry points the GPU path exports, against the golden runs of the unmodified reference and the oracle.  It checks
+indexing, reductions and arithmetic; it is not a product path (nothing in recommend_lib_b200 can reach it), not a
+performance statement, and not a substitute for tests/test_bprfm_bn_gpu.py / tests/test_sgns_gpu.py on the B200."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, rel_err
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+import build_emu  # noqa: E402
+
+from recommend_lib_b200 import _lib  # noqa: E402  (only the ctypes structure definitions are used here)
+
+c_vp, c_i64, c_i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+
+
+def _load(unit):
+    L = ctypes.CDLL(build_emu.build(unit))
+    L.emu_handle.restype = c_vp
+    L.emu_last_error.restype = ctypes.c_char_p
+    L.emu_err_flag.argtypes = [c_vp]
+    L.emu_err_pos.argtypes = [c_vp]
+    return L
+
+
+def _p(a):
+    return c_vp(a.ctypes.data) if a is not None else None
+
+
+def _scratch(nbytes):
+    raw = np.zeros(nbytes + 256, dtype=np.uint8)
+    off = (-raw.ctypes.data) % 256
+    return raw, c_vp(raw.ctypes.data + off)
+
+
+# ------------------------------------------------------------------------------------------------ BPR-FM, batch norm
+class FmEmu:
+    def __init__(self, E0, b0, U, lr, acc0):
+        self.L = _load("fmbn")
+        self.L.daisy_fmbn_scratch_bytes.argtypes = [c_i64, c_i32, ctypes.POINTER(c_i64)]
+        self.L.daisy_fmbn_step.argtypes = [c_vp, ctypes.POINTER(_lib.FMBNParams), c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]
+        self.L.daisy_fmbn_forward.argtypes = [c_vp, ctypes.POINTER(_lib.FMBNParams), c_vp, c_i64, c_vp, c_vp, c_vp]
+        self.h = c_vp(self.L.emu_handle())
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32).copy()
+        self.E, self.b = f32(E0), f32(b0)
+        N, F = self.E.shape
+        self.accE, self.accb = np.full_like(self.E, acc0), np.full_like(self.b, acc0)
+        self.gamma, self.beta = np.ones(F, np.float32), np.zeros(F, np.float32)
+        self.accg, self.accbt = np.full(F, acc0, np.float32), np.full(F, acc0, np.float32)
+        self.rm, self.rv = np.zeros(F, np.float32), np.ones(F, np.float32)
+        self.prm = _lib.FMBNParams(_p(self.E), _p(self.b), _p(self.accE), _p(self.accb), _p(self.gamma), _p(self.beta),
+                                   _p(self.accg), _p(self.accbt), _p(self.rm), _p(self.rv), lr, 1e-10, 1e-5, 0.1, U, N, F)
+        self.loss = np.zeros(1, np.float64)
+
+    def step(self, tri, mi, mj):
+        tri = np.ascontiguousarray(tri, dtype=np.int32)
+        mi = None if mi is None else np.ascontiguousarray(mi, dtype=np.float32)
+        mj = None if mj is None else np.ascontiguousarray(mj, dtype=np.float32)
+        need = c_i64()
+        assert self.L.daisy_fmbn_scratch_bytes(len(tri), self.E.shape[1], ctypes.byref(need)) == 0
+        raw, sp = _scratch(need.value)
+        self.loss[0] = 0
+        rc = self.L.daisy_fmbn_step(self.h, ctypes.byref(self.prm), _p(tri), len(tri), _p(mi), _p(mj), sp, need.value,
+                                    _p(self.loss), None)
+        assert rc == 0, self.L.emu_last_error()
+        return float(self.loss[0])
+
+    def forward(self, tri):
+        tri = np.ascontiguousarray(tri, dtype=np.int32)
+        pi, pj = np.zeros(len(tri), np.float32), np.zeros(len(tri), np.float32)
+        assert self.L.daisy_fmbn_forward(self.h, ctypes.byref(self.prm), _p(tri), len(tri), _p(pi), _p(pj), None) == 0
+        return pi, pj
+
+
+@pytest.mark.parametrize("branch,tol_E,tol_b", [("cond", 1e-5, 1e-5), ("script", 1e-4, 2e-4)])
+def test_fmbn_kernels_emulated_match_the_reference_golden_run(golden, branch, tol_E, tol_b):
+    g = golden("bprfm_bn_small.npz")
+    k = lambda name: g[f"{branch}_{name}"]
+    U = int(k("user_num"))
+    m = FmEmu(k("E0"), k("b0"), U, float(k("lr")), float(k("acc0")))
+    for s in range(2):                                           # two of the four recorded steps keep the test short
+        tri = np.stack([k("fi")[s][:, 0], k("fi")[s][:, 1] - U, k("fj")[s][:, 1] - U], 1)
+        loss = m.step(tri, k("mi")[s], k("mj")[s])
+        assert abs(loss - k("loss")[s]) <= 1e-5 * k("loss")[s], s
+        assert rel_err(m.E, k("E")[s]) <= tol_E, (s, rel_err(m.E, k("E")[s]))
+        assert rel_err(m.b, k("b")[s]) <= tol_b, (s, rel_err(m.b, k("b")[s]))
+        assert rel_err(m.gamma, k("gamma")[s]) <= 1e-5 and rel_err(m.beta, k("beta")[s]) <= 2e-5, s
+        assert rel_err(m.rm, k("rm")[s]) <= 1e-5 and rel_err(m.rv, k("rv")[s]) <= 1e-5, s
+
+
+def test_fmbn_kernels_emulated_match_the_oracle_and_flag_bad_ids():
+    from oracle import bprfm_oracle
+    rng = np.random.default_rng(4)
+    U, I, F, B, p = 30, 25, 40, 70, 0.5                          # F > 32: two lane-strided passes; ragged last block
+    E0 = (rng.standard_normal((U + I, F)) * 0.4).astype(np.float32)
+    b0 = (rng.standard_normal(U + I) * 0.05).astype(np.float32)
+    tri = np.stack([rng.integers(0, U, B), rng.integers(0, I, B), rng.integers(0, I, B)], 1).astype(np.int32)
+    tri[:20, 0] = 3
+    tri[30:45, 1] = 5
+    tri[-9:, 2] = 5
+    tri[0, 2] = tri[0, 1]                                        # i == j
+    keep = lambda: ((rng.random((B, F)) >= p) / (1 - p)).astype(np.float32)
+    m = FmEmu(E0, b0, U, 0.05, 0.1)
+    ora = bprfm_oracle.BPRFMFull(E0, b0, 0.0, True, lr=0.05, initial_accumulator_value=0.1)
+    fi, fj = np.stack([tri[:, 0], U + tri[:, 1]], 1), np.stack([tri[:, 0], U + tri[:, 2]], 1)
+    ones = np.ones((B, 2))
+    for s, masks in enumerate([(keep(), keep()), (None, None)]):
+        loss = m.step(tri, *masks)
+        lo = ora.step(fi, ones, fj, ones, *masks)
+        assert abs(loss - lo) <= 1e-5 * lo, s
+        assert rel_err(m.E, ora.E) <= 1e-5 and rel_err(m.b, ora.bias) <= 1e-5, (s, rel_err(m.E, ora.E), rel_err(m.b, ora.bias))
+        assert rel_err(m.gamma, ora.gamma) <= 1e-5 and rel_err(m.beta, ora.beta) <= 2e-5, s
+        assert rel_err(m.rm, ora.running_mean) <= 1e-5 and rel_err(m.rv, ora.running_var) <= 1e-5, s
+    pi, pj = m.forward(tri)
+    oi, oj = ora.forward(fi, ones, fj, ones)
+    ub = ora.bias[tri[:, 0]]                                     # the library leaves the user bias + bias_ to the caller
+    assert np.allclose(pi + ub, oi, rtol=1e-4, atol=1e-5) and np.allclose(pj + ub, oj, rtol=1e-4, atol=1e-5)
+    assert m.L.emu_err_flag(m.h) == 0
+    bad = tri.copy()
+    bad[17, 2] = I
+    m.step(bad, None, None)
+    assert m.L.emu_err_flag(m.h) == 1 and m.L.emu_err_pos(m.h) == 17
+
+
+# ------------------------------------------------------------------------------------------------ Item2Vec / SGNS
+class SgEmu:
+    def __init__(self, iv0, ov0):
+        self.L = _load("sgns")
+        self.L.daisy_sgns_scratch_bytes.argtypes = [c_i64, c_i32, c_i32, c_i64, c_i32, ctypes.POINTER(c_i64)]
+        self.L.daisy_sgns_step.argtypes = [c_vp, ctypes.POINTER(_lib.SGNSParams), c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i64,
+                                           c_vp, c_i64, c_vp, c_vp]
+        self.h = c_vp(self.L.emu_handle())
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32).copy()
+        self.iv, self.ov = f32(iv0), f32(ov0)
+        self.mom = [np.zeros_like(self.iv) for _ in range(4)]
+        V, D = self.iv.shape
+        self.prm = _lib.SGNSParams(_p(self.iv), _p(self.ov), _p(self.mom[0]), _p(self.mom[1]), _p(self.mom[2]), _p(self.mom[3]),
+                                   1e-3, 0.9, 0.999, 1e-8, V, D, 0)
+        self.t = 0
+        self.loss = np.zeros(1, np.float64)
+
+    def step(self, iw, ow, nw):
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        iw, ow, nw = i32(iw), i32(ow), i32(nw)
+        B, C = ow.shape
+        N = nw.shape[1] // C
+        V, D = self.iv.shape
+        need = c_i64()
+        assert self.L.daisy_sgns_scratch_bytes(B, C, N, V, D, ctypes.byref(need)) == 0
+        raw, sp = _scratch(need.value)
+        self.t += 1
+        self.loss[0] = 0
+        rc = self.L.daisy_sgns_step(self.h, ctypes.byref(self.prm), _p(iw), _p(ow), _p(nw) if N else None, B, C, N, self.t, sp,
+                                    need.value, _p(self.loss), None)
+        assert rc == 0, self.L.emu_last_error()
+        return float(self.loss[0])
+
+
+@pytest.mark.parametrize("branch", ["w", "u"])
+def test_sgns_kernels_emulated_match_the_reference_golden_run(golden, branch):
+    g = golden("sgns_small.npz")
+    k = lambda name: g[f"{branch}_{name}"]
+    m = SgEmu(k("iv0"), k("ov0"))
+    for s in range(2):
+        loss = m.step(k("iword")[s], k("owords")[s], k("nwords")[s])
+        assert abs(loss - k("losses")[s]) <= 1e-5 * k("losses")[s], s
+        assert rel_err(m.iv, k("iv")[s]) <= 1e-5 and rel_err(m.ov, k("ov")[s]) <= 1e-5, (s, rel_err(m.iv, k("iv")[s]))
+        assert np.abs(m.iv[0]).max() == 0 and np.abs(m.ov[0]).max() == 0
+
+
+def test_sgns_kernels_emulated_match_the_oracle_and_flag_bad_ids():
+    from oracle import sgns_oracle
+    rng = np.random.default_rng(8)
+    V, D, B, C, N = 23, 44, 19, 3, 2                             # D > 32, ragged block, rows without any ref
+    iv0 = (rng.standard_normal((V, D)) * 0.3).astype(np.float32)
+    ov0 = (rng.standard_normal((V, D)) * 0.3).astype(np.float32)
+    iv0[0] = 0
+    ov0[0] = 0
+    m, ora = SgEmu(iv0, ov0), sgns_oracle.SGNSAdam(iv0, ov0)
+    for s in range(2):
+        iw, ow, nw = rng.integers(1, V - 3, B), rng.integers(0, V - 3, (B, C)), rng.integers(0, V - 3, (B, C * N))
+        iw[:6] = 3
+        nw[:, 0] = 5                                             # a hot output row: several slices in k_sgns_rows
+        loss = m.step(iw, ow, nw)
+        lo = ora.step(iw, ow, nw)
+        assert abs(loss - lo) <= 1e-5 * lo, s
+        assert rel_err(m.iv, ora.iv) <= 1e-5 and rel_err(m.ov, ora.ov) <= 1e-5, (s, rel_err(m.iv, ora.iv), rel_err(m.ov, ora.ov))
+    assert m.L.emu_err_flag(m.h) == 0
+    nw[5, 2] = V
+    m.step(iw, ow, nw)
+    assert m.L.emu_err_flag(m.h) == 1 and m.L.emu_err_pos(m.h) == 5
