@@ -22,6 +22,7 @@ One step = one pass of the hot path (daisy_bpr_step) over one batch of synthetic
 Secondary lines (not the driver's metric; `profiles/` holds one of each):
   --workload config3 [--batch B] [--epoch-api]   ml-20m shape (L2-resident), B = 65 536 by default; --epoch-api runs the K
                      timed steps through ONE daisy_bpr_epoch call (what BPRMFRecommender.fit does)
+  --workload bprfm_bn / sgns   the two experimental next-row paths (BPR-FM with batch norm + dropout, Item2Vec / SGNS)
   --workload config1   ml-100k, 20 epochs + HR@10 / NDCG@10 through BPRMFRecommender.fit, reference loop beside it
   --workload config2   funk-SVD (daisy_mf_fit) on the ml-1m shape
   --workload eval      full-catalogue top-100 for 16 384 users x 2 M items
@@ -584,6 +585,104 @@ def run_bprfm(args):
     print(json.dumps(line), flush=True)
 
 
+def run_experimental(args):
+    """Secondary lines of the two EXPERIMENTAL next-row paths (not yet run on a GPU when this was written; DESIGN.md
+    section 9): `--workload bprfm_bn` = BPR-FM at the script's defaults (batch norm + dropout 0.5, ml-100k shape,
+    hidden_factor 64, batch 4 096, Adagrad) through FMBNAdagrad.step; `--workload sgns` = Item2Vec / SGNS at the script's
+    defaults (window 5 -> 10 context items, 20 negatives, e_dim 300, batch 4 096, Adam; ml-100k vocabulary) through
+    SGNSAdam.step.  Device-timed steps with resident inputs, then the same steps from pinned host inputs with the loss
+    read back; the closed-form oracle on one host core beside them."""
+    import torch
+    dev = torch.device("cuda:0")
+    torch.manual_seed(2019)
+    rng = np.random.default_rng(2019)
+    K, W = max(args.steps, 50), max(args.warmup, 5)
+    if args.workload == "bprfm_bn":
+        from recommend_lib_b200.bprfm_bn import BPRFMBN, FMBNAdagrad
+        from recommend_lib_b200.sampler import synthetic_triples
+        from oracle import bprfm_oracle
+        U, I, F, B = 943, 1682, 64, args.batch or 4096
+        tri = synthetic_triples((K + W) * B, U, I, seed=2019, zipf=1.0).reshape(K + W, B, 3)
+        model = BPRFMBN(U + I, F, True, [0.5, 0.2], user_num=U).to(dev)
+        model.train()
+        opt = FMBNAdagrad(model, lr=0.05)
+        inputs = [(torch.from_numpy(tri[s]),) for s in range(K + W)]
+        units, unit, metric = B, "triples/s", "bprfm_bn_train_triples_per_s"
+        handle = model.handle
+        ora = bprfm_oracle.BPRFMFull(rng.normal(0, 0.01, (U + I, F)), np.zeros(U + I), 0.0, True, lr=0.05)
+        ones = np.ones((B, 2))
+
+        def cpu_step(s):
+            keep = lambda: (rng.random((B, F)) >= 0.5) * 2.0
+            ora.step(np.stack([tri[s, :, 0], U + tri[s, :, 1]], 1), ones, np.stack([tri[s, :, 0], U + tri[s, :, 2]], 1), ones,
+                     keep(), keep())
+        workload = ("BPR-FM training step at the script's defaults on the ml-100k shape (943 + 1682 features, hidden_factor "
+                    "64, batch 4096, batch norm, dropout 0.5 drawn on the device, Adagrad lr 0.05)")
+        h2d = B * 12
+    else:
+        from recommend_lib_b200.item2vec import Item2Vec, SGNS, SGNSAdam
+        from oracle import sgns_oracle
+        V, D, B, C, N = 1683, 300, args.batch or 4096, 10, 20
+        counts = 1.0 / np.arange(1, V + 1)
+        model = Item2Vec(vocab_size=V, embedding_size=D)
+        sgns = SGNS(embedding=model, vocab_size=V, n_negs=N, weights=counts).to(dev)
+        opt = SGNSAdam(sgns)
+        pw = counts / counts.sum()
+        iw = rng.choice(V - 1, size=(K + W, B), p=pw[1:] / pw[1:].sum()) + 1
+        ow = rng.choice(V, size=(K + W, B, C), p=pw)
+        inputs = [(torch.from_numpy(iw[s]).int(), torch.from_numpy(ow[s]).int()) for s in range(K + W)]
+        units, unit, metric = B, "examples/s", "sgns_train_examples_per_s"
+        handle = opt.handle
+        ora = sgns_oracle.SGNSAdam(model.ivectors.weight.detach().cpu().numpy(), model.ovectors.weight.detach().cpu().numpy())
+        wneg = pw ** 0.75 / (pw ** 0.75).sum()
+
+        def cpu_step(s):
+            ora.step(iw[s], ow[s], rng.choice(V, size=(B, C * N), p=wneg))
+        workload = ("Item2Vec / SGNS training step at the script's defaults (ml-100k vocabulary of 1683, e_dim 300, batch "
+                    "4096, 10 context items, 20 negatives each drawn on the device from unigram^0.75, dense Adam)")
+        h2d = B * 4 * (1 + C)
+    devin = [tuple(t.to(dev) for t in x) for x in inputs]
+    for s in range(W):
+        opt.step(*devin[s])
+    torch.cuda.synchronize()
+    opt.loss_sum()
+    l0 = handle().launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for s in range(W, W + K):
+        opt.step(*devin[s])
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    launches = handle().launches - l0
+    loss_dev = opt.loss_sum() / K
+    host = [tuple(t.pin_memory() for t in x) for x in inputs]
+    loss_host = torch.zeros(K + W, dtype=torch.float64).pin_memory()
+    ev0.record()
+    for s in range(W, W + K):                       # e2e: pinned host ids in, loss read back every step
+        opt.step(*(t.to(dev, non_blocking=True) for t in host[s]))
+        loss_host[s:s + 1].copy_(opt._loss, non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms2 = ev0.elapsed_time(ev1)
+    nc = 3
+    t0 = time.time()
+    for s in range(nc):
+        cpu_step(s)
+    cpu_dt = time.time() - t0
+    line = {"metric": metric, "value": units * K / (ms * 1e-3), "unit": unit, "n_gpus": 1, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": workload, "batch": B, "status": "experimental path, first version",
+                                            "l2": "tables are L2-resident at this size"},
+            "e2e": {"value": units * K / (ms2 * 1e-3), "unit": unit, "ms_per_step": ms2 / K, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 8},
+            "gpu_launches": int(launches), "roofline": None,
+            "cpu_baseline": {"value": units * nc / cpu_dt, "unit": unit, "cores": 1, "kind": "port",
+                             "sample": f"{nc} steps of the closed-form restatement (numpy, float64) of the reference loop"},
+            "mean_loss_per_step": loss_dev}
+    print(json.dumps(line), flush=True)
+
+
 # ------------------------------------------------------------------------------------------------
 # config 2: funk-SVD (secondary line, not the driver's metric)
 # ------------------------------------------------------------------------------------------------
@@ -774,7 +873,7 @@ def main():
                     help="N > 1: leave out the per-rank phase profile the fused peer path adds after the timed regions")
     ap.add_argument("--trace", action="store_true", help="also print a timeline of bookkeeping vs table kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="config4", choices=["config4", "config3", "config2", "config1", "sampler", "eval", "gmf", "bprfm"],
+    ap.add_argument("--workload", default="config4", choices=["config4", "config3", "config2", "config1", "sampler", "eval", "gmf", "bprfm", "bprfm_bn", "sgns"],
                     help="N = 1 only: config4 is the driver's metric; config3 (L2-resident ml-20m shape) and config2 "
                          "(funk-SVD) are secondary lines kept under profiles/")
     ap.add_argument("--eval-users", type=int, default=16384)
@@ -798,6 +897,8 @@ def main():
         return run_config1(args)
     if args.workload == "gmf":
         return run_gmf(args)
+    if args.workload in ("bprfm_bn", "sgns"):
+        return run_experimental(args)
     if args.workload == "bprfm":
         return run_bprfm(args)
     if args.workload == "config2":
