@@ -97,10 +97,13 @@ __global__ void __launch_bounds__(256) k_sgns_main(const float *__restrict__ iv,
     }
     float loss = 0.f;
     const int NR = R - C;  // negatives per example
+    uint32_t ids = 0;  // lane l holds the (validated) row of ref r0 + l of the current group of 32 refs
     for (int r = 0; r < R; ++r) {
-        uint32_t row = 0;
-        if (lane == 0) row = sg_row(r < C ? owords[(size_t)b * C + r] : nwords[(size_t)b * NR + (r - C)], V, b, err);
-        row = __shfl_sync(0xffffffffu, row, 0);
+        if ((r & 31) == 0) {  // one coalesced id load per 32 refs instead of a dependent scalar load per ref
+            const int rr = r + lane;
+            ids = rr < R ? sg_row(rr < C ? owords[(size_t)b * C + rr] : nwords[(size_t)b * NR + (rr - C)], V, b, err) : 0u;
+        }
+        const uint32_t row = __shfl_sync(0xffffffffu, ids, r & 31);
         const float *o = ov + (size_t)row * D;
         float orow[SG_K];
         float dot = 0.f;

@@ -182,10 +182,11 @@ def test_sgns_kernels_emulated_match_the_reference_golden_run(golden, branch):
         assert np.abs(m.iv[0]).max() == 0 and np.abs(m.ov[0]).max() == 0
 
 
-def test_sgns_kernels_emulated_match_the_oracle_and_flag_bad_ids():
+@pytest.mark.parametrize("V,D,B,C,N", [(23, 44, 19, 3, 2),       # D > 32, ragged block, rows without any ref
+                                        (17, 8, 9, 5, 8)])        # 45 refs per example: two groups of coalesced id loads
+def test_sgns_kernels_emulated_match_the_oracle_and_flag_bad_ids(V, D, B, C, N):
     from oracle import sgns_oracle
     rng = np.random.default_rng(8)
-    V, D, B, C, N = 23, 44, 19, 3, 2                             # D > 32, ragged block, rows without any ref
     iv0 = (rng.standard_normal((V, D)) * 0.3).astype(np.float32)
     ov0 = (rng.standard_normal((V, D)) * 0.3).astype(np.float32)
     iv0[0] = 0
