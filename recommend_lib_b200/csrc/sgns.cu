@@ -74,7 +74,9 @@ __device__ __forceinline__ uint32_t sg_row(int32_t id, uint32_t V, int pos, int 
 
 __device__ __forceinline__ float sg_softplus(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
 
-// one warp per example
+// one warp per example; K = lane-strided values per lane (D <= 32 K), so that a short row does not pay for 16 registers
+// per row held
+template <int K>
 __global__ void __launch_bounds__(256) k_sgns_main(const float *__restrict__ iv, const float *__restrict__ ov,
                                                     const int32_t *__restrict__ iword, const int32_t *__restrict__ owords,
                                                     const int32_t *__restrict__ nwords, int B, int C, int R, uint32_t V, int D,
@@ -88,9 +90,9 @@ __global__ void __launch_bounds__(256) k_sgns_main(const float *__restrict__ iv,
     uint32_t w = 0;
     if (lane == 0) w = sg_row(iword[b], V, b, err);
     w = __shfl_sync(0xffffffffu, w, 0);
-    float ir[SG_K], gi[SG_K];
+    float ir[K], gi[K];
 #pragma unroll
-    for (int k = 0; k < SG_K; ++k) {
+    for (int k = 0; k < K; ++k) {
         const int f = lane + 32 * k;
         ir[k] = f < D ? iv[(size_t)w * D + f] : 0.f;
         gi[k] = 0.f;
@@ -105,10 +107,10 @@ __global__ void __launch_bounds__(256) k_sgns_main(const float *__restrict__ iv,
         }
         const uint32_t row = __shfl_sync(0xffffffffu, ids, r & 31);
         const float *o = ov + (size_t)row * D;
-        float orow[SG_K];
+        float orow[K];
         float dot = 0.f;
 #pragma unroll
-        for (int k = 0; k < SG_K; ++k) {
+        for (int k = 0; k < K; ++k) {
             const int f = lane + 32 * k;
             orow[k] = f < D ? o[f] : 0.f;
             dot += ir[k] * orow[k];
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(256) k_sgns_main(const float *__restrict__ iv,
             loss += sg_softplus(dot);
         }
 #pragma unroll
-        for (int k = 0; k < SG_K; ++k) gi[k] += c * orow[k];
+        for (int k = 0; k < K; ++k) gi[k] += c * orow[k];
         if (lane == 0) {
             const size_t p = (size_t)b * R + r;
             coef[p] = c;
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(256) k_sgns_main(const float *__restrict__ iv,
         }
     }
 #pragma unroll
-    for (int k = 0; k < SG_K; ++k) {
+    for (int k = 0; k < K; ++k) {
         const int f = lane + 32 * k;
         if (f < D) ci[(size_t)b * D + f] = gi[k];
     }
@@ -154,12 +156,13 @@ __device__ __forceinline__ int sg_lower_bound(const uint32_t *__restrict__ a, in
 
 // grid (V, 2): blockIdx.y = 0: gradient of ovectors[row] = sum over its refs of coef * ivectors[iword_b] (pre-step);
 //              blockIdx.y = 1: gradient of ivectors[row] = sum over the examples centred on it of their ci rows.
+template <int K>
 __global__ void __launch_bounds__(256) k_sgns_rows(const uint32_t *__restrict__ kout, const uint32_t *__restrict__ vout, int n,
                                                     const uint32_t *__restrict__ ikout, const uint32_t *__restrict__ ivout, int B,
                                                     int R, const float *__restrict__ coef, const float *__restrict__ ci,
                                                     const float *__restrict__ iv, const uint32_t *__restrict__ ikin, int D,
                                                     int padding_idx, float *__restrict__ gO, float *__restrict__ gI) {
-    __shared__ float part[8][SG_MAX_D];
+    __shared__ float part[8][32 * K];
     __shared__ int seg[2];
     const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
     const uint32_t row = blockIdx.x;
@@ -172,30 +175,30 @@ __global__ void __launch_bounds__(256) k_sgns_rows(const uint32_t *__restrict__ 
     const int lo = seg[0], hi = seg[1], len = hi - lo;
     const int per = (len + 7) / 8;
     const int q0 = lo + wv * per, q1 = min(hi, q0 + per);
-    float acc[SG_K];
+    float acc[K];
 #pragma unroll
-    for (int k = 0; k < SG_K; ++k) acc[k] = 0.f;
+    for (int k = 0; k < K; ++k) acc[k] = 0.f;
     for (int q = q0; q < q1; ++q) {
         if (otab) {
             const uint32_t p = vout[q];
             const float c = coef[p];
             const float *src = iv + (size_t)ikin[p / (uint32_t)R] * D;  // ikin[b] = validated centre row of example b
 #pragma unroll
-            for (int k = 0; k < SG_K; ++k) {
+            for (int k = 0; k < K; ++k) {
                 const int f = lane + 32 * k;
                 if (f < D) acc[k] += c * src[f];
             }
         } else {
             const float *src = ci + (size_t)ivout[q] * D;
 #pragma unroll
-            for (int k = 0; k < SG_K; ++k) {
+            for (int k = 0; k < K; ++k) {
                 const int f = lane + 32 * k;
                 if (f < D) acc[k] += src[f];
             }
         }
     }
 #pragma unroll
-    for (int k = 0; k < SG_K; ++k) {
+    for (int k = 0; k < K; ++k) {
         const int f = lane + 32 * k;
         if (f < D) part[wv][f] = acc[k];
     }
@@ -286,9 +289,17 @@ extern "C" int daisy_sgns_step(daisy_handle_t h, const daisy_sgns_params *p, con
     const uint32_t V = (uint32_t)p->vocab;
     const size_t nvd = (size_t)p->vocab * D;
     if (B > 0) {
-        k_sgns_main<<<daisy_ceil_div(B, 8), 256, 0, s>>>(p->iv, p->ov, iword, owords, nwords, Bi, C, (int)R, V, D,
-                                                         1.0f / ((float)B * (float)C), w.coef, w.ci, w.lossp, w.kin, w.vin,
-                                                         w.ikin, w.ivin, h->err);
+        const float inv_bc = 1.0f / ((float)B * (float)C);
+        const int mblocks = daisy_ceil_div(B, 8);
+        if (D <= 128)
+            k_sgns_main<4><<<mblocks, 256, 0, s>>>(p->iv, p->ov, iword, owords, nwords, Bi, C, (int)R, V, D, inv_bc, w.coef, w.ci,
+                                                   w.lossp, w.kin, w.vin, w.ikin, w.ivin, h->err);
+        else if (D <= 320)
+            k_sgns_main<10><<<mblocks, 256, 0, s>>>(p->iv, p->ov, iword, owords, nwords, Bi, C, (int)R, V, D, inv_bc, w.coef, w.ci,
+                                                    w.lossp, w.kin, w.vin, w.ikin, w.ivin, h->err);
+        else
+            k_sgns_main<SG_K><<<mblocks, 256, 0, s>>>(p->iv, p->ov, iword, owords, nwords, Bi, C, (int)R, V, D, inv_bc, w.coef,
+                                                      w.ci, w.lossp, w.kin, w.vin, w.ikin, w.ivin, h->err);
         DAISY_LAUNCH_CHECK(h);
         const int bits = sg_bits(p->vocab);
         size_t cub_bytes = w.cub_bytes;
@@ -296,8 +307,15 @@ extern "C" int daisy_sgns_step(daisy_handle_t h, const daisy_sgns_params *p, con
         cub_bytes = w.cub_bytes;
         DAISY_CUDA(cub::DeviceRadixSort::SortPairs(w.cub, cub_bytes, w.ikin, w.ikout, w.ivin, w.ivout, Bi, 0, bits, s));
         h->launches += 6;
-        k_sgns_rows<<<dim3(V, 2), 256, 0, s>>>(w.kout, w.vout, n, w.ikout, w.ivout, Bi, (int)R, w.coef, w.ci, p->iv, w.ikin, D,
-                                               p->padding_idx, w.gO, w.gI);
+        if (D <= 128)
+            k_sgns_rows<4><<<dim3(V, 2), 256, 0, s>>>(w.kout, w.vout, n, w.ikout, w.ivout, Bi, (int)R, w.coef, w.ci, p->iv, w.ikin,
+                                                      D, p->padding_idx, w.gO, w.gI);
+        else if (D <= 320)
+            k_sgns_rows<10><<<dim3(V, 2), 256, 0, s>>>(w.kout, w.vout, n, w.ikout, w.ivout, Bi, (int)R, w.coef, w.ci, p->iv, w.ikin,
+                                                       D, p->padding_idx, w.gO, w.gI);
+        else
+            k_sgns_rows<SG_K><<<dim3(V, 2), 256, 0, s>>>(w.kout, w.vout, n, w.ikout, w.ivout, Bi, (int)R, w.coef, w.ci, p->iv,
+                                                         w.ikin, D, p->padding_idx, w.gO, w.gI);
         DAISY_LAUNCH_CHECK(h);
     } else {  // optimizer.step() on an empty batch: zero gradients, the moments still decay
         DAISY_CUDA(cudaMemsetAsync(w.gI, 0, nvd * sizeof(float), s));

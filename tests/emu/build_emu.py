@@ -32,9 +32,9 @@ extern "C" int emu_err_pos(daisy_ctx *h) { return h->err[1]; }
 
 
 def rewrite(src):
-    pat = re.compile(r"(\b\w+)<<<(.+?)>>>\((.*?)\);", re.S)
+    pat = re.compile(r"(\b\w+(?:<[\w\s,]+>)?)<<<(.+?)>>>\((.*?)\);", re.S)   # kernel or kernel<template args>
     out, n = pat.subn(lambda m: f"emu::launch(emu::Cfg({m.group(2)}), [&] {{ {m.group(1)}({m.group(3)}); }});", src)
-    assert n > 0
+    assert n > 0 and '<<<' not in out, 'a launch was not rewritten'
     return out
 
 

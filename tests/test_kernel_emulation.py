@@ -183,7 +183,9 @@ def test_sgns_kernels_emulated_match_the_reference_golden_run(golden, branch):
 
 
 @pytest.mark.parametrize("V,D,B,C,N", [(23, 44, 19, 3, 2),       # D > 32, ragged block, rows without any ref
-                                        (17, 8, 9, 5, 8)])        # 45 refs per example: two groups of coalesced id loads
+                                        (17, 8, 9, 5, 8),         # 45 refs per example: two groups of coalesced id loads
+                                        (9, 300, 5, 2, 1),        # the script's e_dim: the 10-values-per-lane kernels
+                                        (9, 420, 4, 1, 2)])       # ... and the 16-values-per-lane ones
 def test_sgns_kernels_emulated_match_the_oracle_and_flag_bad_ids(V, D, B, C, N):
     from oracle import sgns_oracle
     rng = np.random.default_rng(8)
@@ -201,6 +203,6 @@ def test_sgns_kernels_emulated_match_the_oracle_and_flag_bad_ids(V, D, B, C, N):
         assert abs(loss - lo) <= 1e-5 * lo, s
         assert rel_err(m.iv, ora.iv) <= 1e-5 and rel_err(m.ov, ora.ov) <= 1e-5, (s, rel_err(m.iv, ora.iv), rel_err(m.ov, ora.ov))
     assert m.L.emu_err_flag(m.h) == 0
-    nw[5, 2] = V
+    nw[B - 2, -1] = V
     m.step(iw, ow, nw)
-    assert m.L.emu_err_flag(m.h) == 1 and m.L.emu_err_pos(m.h) == 5
+    assert m.L.emu_err_flag(m.h) == 1 and m.L.emu_err_pos(m.h) == B - 2
