@@ -292,3 +292,31 @@ def test_bprfm_full_oracle_reduces_to_the_two_feature_closed_form(golden):
         # the general form gives the user bias a gradient of -s + s that is zero only up to rounding; with the script's
         # 1e-8 accumulator that is visible on the biases, not on the embeddings
         assert rel_err(full.E, E) < 1e-9 and rel_err(full.bias, b) < 2e-4
+
+
+# ---------------------------------------------------------------- row N3: NCF with an MLP tower (MLP, NeuMF-end)
+def _neumf_oracle(g, tag, name):
+    from oracle import neumf_oracle
+    k = lambda n: g[f"{tag}_{n}"]
+    L = int(k("num_layers"))
+    return k, L, neumf_oracle.NeuMFAdam(name, k("Pg_0"), k("Qg_0"), k("Pm_0"), k("Qm_0"), [k(f"W{l}_0") for l in range(L)],
+                                        [k(f"b{l}_0") for l in range(L)], k("wp_0"), k("bp_0"), lr=float(k("lr")))
+
+
+@pytest.mark.parametrize("tag,name", [("mlp", "MLP"), ("neumf", "NeuMF-end")])
+def test_neumf_oracle_matches_reference_ncf_with_adam(golden, tag, name):
+    """oracle/neumf_oracle.py (closed-form MLP tower + GMF branch, BCE, dense gradients, torch-default Adam over every
+    parameter that has a gradient) against 4 steps of the reference's own NCF class with model 'MLP' and the script's
+    default 'NeuMF-end', dropout 0 (tests/golden/make_neumf_golden.py)."""
+    k, L, st = _neumf_oracle(golden("neumf_small.npz"), tag, name)
+    for s in range(len(k("loss"))):
+        loss = st.step(k("users")[s], k("items")[s], k("labels")[s])
+        assert loss == pytest.approx(float(k("loss")[s]), rel=1e-6), s
+        for mine, key in ((st.Pg, "Pg"), (st.Qg, "Qg"), (st.Pm, "Pm"), (st.Qm, "Qm"), (st.wp, "wp")):
+            assert rel_err(mine, k(key)[s]) < 1e-6, (s, key)
+        assert abs(st.bp[0] - float(k("bp")[s][0])) < 1e-8
+        for l in range(L):
+            assert rel_err(st.Ws[l], k(f"W{l}")[s]) < 1e-6 and rel_err(st.bs[l], k(f"b{l}")[s]) < 2e-6, (s, l)
+    assert rel_err(st.forward(k("users")[0], k("items")[0]), k("fwd_last")) < 2e-6
+    if tag == "mlp":                                       # no gradient ever reaches the GMF tables: torch's Adam skips them
+        assert np.array_equal(st.Pg, k("Pg_0").astype(np.float64))
