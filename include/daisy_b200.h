@@ -352,6 +352,38 @@ DAISY_API int daisy_sgns_step(daisy_handle_t h, const daisy_sgns_params *p, cons
                     const int32_t *nwords, int64_t B, int C, int n_negs, int64_t step_no, void *scratch,
                     int64_t scratch_bytes, double *loss_accum, daisy_stream_t stream);
 
+/* ---- NCF with an MLP tower: model 'MLP' and the script's default 'NeuMF-end'  ----------
+ * EXPERIMENTAL: compiled for sm_100a, not yet run on a GPU (csrc/neumf.cu has the status); the verified NCF path is the
+ * GMF variant (daisy_gmf_step).
+ * Replaces NCF.forward (NCFRecommender.py:105-125) with dropout 0 and the training step :283-287 with
+ * nn.BCEWithLogitsLoss() (:255) and optim.Adam(model.parameters(), lr) (:260).  Device pointers owned by the caller (the
+ * module's parameter tensors and the optimizer's exp_avg / exp_avg_sq), fp32, contiguous; torch's Linear layout
+ * W_l [out_l, in_l] with in_0 = 2 * factor * 2^(num_layers - 1), out_l = in_l / 2. */
+#define DAISY_NEUMF_MAX_LAYERS 6
+typedef struct {
+    int neumf;               /* 0: model 'MLP' (the GMF tables are not touched), 1: 'NeuMF-end' */
+    int num_layers, factor;  /* factor * 2^num_layers <= 1024 */
+    int64_t user_num, item_num;
+    float *Pg, *Qg;          /* embed_user_GMF / embed_item_GMF  [n, factor]                     (neumf only) */
+    float *Pm, *Qm;          /* embed_user_MLP / embed_item_MLP  [n, factor * 2^(num_layers-1)] */
+    float *W[DAISY_NEUMF_MAX_LAYERS], *b[DAISY_NEUMF_MAX_LAYERS];   /* MLP_layers Linear weights / biases */
+    float *wp, *bp;          /* predict_layer weight [factor or 2 * factor: GMF part first], bias [1] */
+    float *m_Pg, *v_Pg, *m_Qg, *v_Qg, *m_Pm, *v_Pm, *m_Qm, *v_Qm;   /* Adam moments (step only) */
+    float *m_W[DAISY_NEUMF_MAX_LAYERS], *v_W[DAISY_NEUMF_MAX_LAYERS], *m_b[DAISY_NEUMF_MAX_LAYERS], *v_b[DAISY_NEUMF_MAX_LAYERS];
+    float *m_wp, *v_wp, *m_bp, *v_bp;
+    float lr, beta1, beta2, eps;
+} daisy_neumf_params;
+
+/* Bytes of device scratch daisy_neumf_step needs for batches of up to B samples (no device call). */
+DAISY_API int daisy_neumf_scratch_bytes(const daisy_neumf_params *p, int64_t B, int64_t *bytes);
+/* logits[B] of (user, item, label) int32 samples (the label column is ignored). */
+DAISY_API int daisy_neumf_forward(daisy_handle_t h, const daisy_neumf_params *p, const int32_t *samples, int64_t B,
+                        float *logits, daisy_stream_t stream);
+/* One training step on B (user, item, label) samples; step_no is 1-based (Adam's bias correction);
+ * loss_accum += the batch's mean BCE.  Fixed-order reductions: bit-reproducible. */
+DAISY_API int daisy_neumf_step(daisy_handle_t h, const daisy_neumf_params *p, const int32_t *samples, int64_t B,
+                     int64_t step_no, void *scratch, int64_t scratch_bytes, double *loss_accum, daisy_stream_t stream);
+
 /* ---- introspection for tests / bench ------------------------------------------------------------- */
 /* Number of kernels launched by this handle since creation (the bench's gpu_launches claim). */
 DAISY_API int daisy_launch_count(daisy_handle_t h, int64_t *n);

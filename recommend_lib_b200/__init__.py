@@ -10,6 +10,8 @@ Public surface (mirrors the reference):
 * ``BPRFM(..., batch_norm=False, drop_prob=[0, 0])`` + ``FMAdagrad``  -- BPRFMRecommender.py:29-80, 191-219 (N3)
 * ``BPRFMBN(..., batch_norm=True, drop_prob)`` + ``FMBNAdagrad``     -- the same script at its defaults; EXPERIMENTAL,
   compiled but not yet run on a GPU (bprfm_bn.py)
+* ``NeuMF(..., model in ('MLP', 'NeuMF-end'))`` + ``NeuMFAdam``  -- NCFRecommender.py:28-125, 255-287 with the MLP tower
+  (the script's default model); EXPERIMENTAL, compiled but not yet run on a GPU (ncf_mlp.py)
 * ``Item2Vec`` / ``SGNS`` + ``SGNSAdam``                        -- Item2VecRecommender.py:37-97, 266-277 (N4); EXPERIMENTAL,
   compiled but not yet run on a GPU (item2vec.py)
 
@@ -27,7 +29,7 @@ _LAZY = {
     "metric_eval": ".metrics", "topk_candidates": ".metrics", "topk_full": ".metrics", "rank_metrics": ".metrics", "final_kpi": ".metrics",
     "SVD": ".mf", "RSVD": ".mf", "MFRecommender": ".mf",
     "NCF": ".ncf", "GMFAdam": ".ncf", "BPRFM": ".bprfm", "FMAdagrad": ".bprfm", "BPRFMBN": ".bprfm_bn", "FMBNAdagrad": ".bprfm_bn",
-    "Item2Vec": ".item2vec", "SGNS": ".item2vec", "SGNSAdam": ".item2vec",
+    "NeuMF": ".ncf_mlp", "NeuMFAdam": ".ncf_mlp", "Item2Vec": ".item2vec", "SGNS": ".item2vec", "SGNSAdam": ".item2vec",
     "TripleSampler": ".sampler", "DeviceTripleSampler": ".sampler",
     "ShardedBPR": ".sharded", "PeerShardedBPR": ".sharded",
     "lib": "._lib",

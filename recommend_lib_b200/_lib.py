@@ -40,6 +40,20 @@ class SGNSParams(ctypes.Structure):
                 ("vocab", c_i64), ("D", c_i32), ("padding_idx", c_i32)]
 
 
+NEUMF_MAX_LAYERS = 6
+_vp6 = c_vp * NEUMF_MAX_LAYERS
+
+
+class NeuMFParams(ctypes.Structure):
+    """daisy_neumf_params"""
+    _fields_ = [("neumf", c_i32), ("num_layers", c_i32), ("factor", c_i32), ("user_num", c_i64), ("item_num", c_i64),
+                ("Pg", c_vp), ("Qg", c_vp), ("Pm", c_vp), ("Qm", c_vp), ("W", _vp6), ("b", _vp6), ("wp", c_vp), ("bp", c_vp),
+                ("m_Pg", c_vp), ("v_Pg", c_vp), ("m_Qg", c_vp), ("v_Qg", c_vp), ("m_Pm", c_vp), ("v_Pm", c_vp),
+                ("m_Qm", c_vp), ("v_Qm", c_vp), ("m_W", _vp6), ("v_W", _vp6), ("m_b", _vp6), ("v_b", _vp6),
+                ("m_wp", c_vp), ("v_wp", c_vp), ("m_bp", c_vp), ("v_bp", c_vp),
+                ("lr", c_f32), ("beta1", c_f32), ("beta2", c_f32), ("eps", c_f32)]
+
+
 # name -> argtypes; every entry returns int except daisy_last_error.  Kept in one table so that the CPU test
 # can check it against the prototypes of include/daisy_b200.h.
 SIGNATURES = {
@@ -93,6 +107,9 @@ SIGNATURES = {
     "daisy_sgns_scratch_bytes": [c_i64, c_i32, c_i32, c_i64, c_i32, ctypes.POINTER(c_i64)],
     "daisy_sgns_step": [c_vp, ctypes.POINTER(SGNSParams), c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i64, c_vp, c_i64, c_vp,
                         c_vp],
+    "daisy_neumf_scratch_bytes": [ctypes.POINTER(NeuMFParams), c_i64, ctypes.POINTER(c_i64)],
+    "daisy_neumf_forward": [c_vp, ctypes.POINTER(NeuMFParams), c_vp, c_i64, c_vp, c_vp],
+    "daisy_neumf_step": [c_vp, ctypes.POINTER(NeuMFParams), c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp],
     "daisy_launch_count": [c_vp, ctypes.POINTER(c_i64)],
     "daisy_set_timing": [c_vp, c_i32],
     "daisy_last_step_timing": [c_vp, ctypes.POINTER(c_f32), ctypes.POINTER(c_f32)],

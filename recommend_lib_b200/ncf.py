@@ -41,8 +41,8 @@ class NCF(nn.Module):
                  MLP_model=None, max_batch=256):
         super().__init__()
         if model != "GMF":
-            raise NotImplementedError("only model='GMF' is on the accelerated path (the MLP towers are dense layers "
-                                      "outside the gather/score/scatter hot path)")
+            raise NotImplementedError("only model='GMF' is on this (GPU-verified) path; 'MLP' / 'NeuMF-end' are "
+                                      "ncf_mlp.NeuMF / NeuMFAdam (experimental: not yet run on a GPU)")
         if factor_num % 4:
             raise ValueError("factor_num must be a multiple of 4 (rows move as 128-bit vectors)")
         self.dropout, self.model = dropout, model

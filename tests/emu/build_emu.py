@@ -56,5 +56,5 @@ def build(unit):
 
 
 if __name__ == "__main__":
-    for u in ("fmbn", "sgns"):
+    for u in ("fmbn", "sgns", "neumf"):
         print(build(u))

@@ -227,3 +227,33 @@ def test_item2vec_modules_are_drop_ins_and_have_no_cpu_path():
     if not torch.cuda.is_available():
         with pytest.raises(_lib.DaisyError):
             SGNSAdam(sgns).step(np.arange(3), np.zeros((3, 2), dtype=np.int64))
+
+
+def test_neumf_module_is_a_drop_in_and_has_no_cpu_path():
+    """NeuMF (experimental MLP / NeuMF-end path of NCF) keeps the reference class's module structure: the 12 state_dict
+    entries of NCF(U, I, F, 3, 0.0, model) (NCFRecommender.py:45-66) with their shapes; computing without a CUDA device
+    raises."""
+    import torch
+    from recommend_lib_b200 import _lib
+    from recommend_lib_b200.ncf_mlp import NeuMF, NeuMFAdam
+    U, I, F, L = 40, 30, 8, 3
+    for name, P in (("MLP", F), ("NeuMF-end", 2 * F)):
+        m = NeuMF(U, I, F, L, 0.0, name)
+        sd = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        assert sd == {"embed_user_GMF.weight": (U, F), "embed_item_GMF.weight": (I, F),
+                      "embed_user_MLP.weight": (U, 4 * F), "embed_item_MLP.weight": (I, 4 * F),
+                      "MLP_layers.1.weight": (4 * F, 8 * F), "MLP_layers.1.bias": (4 * F,),
+                      "MLP_layers.4.weight": (2 * F, 4 * F), "MLP_layers.4.bias": (2 * F,),
+                      "MLP_layers.7.weight": (F, 2 * F), "MLP_layers.7.bias": (F,),
+                      "predict_layer.weight": (1, P), "predict_layer.bias": (1,)}
+        assert float(m.predict_layer.bias.abs().max()) == 0.0
+    with pytest.raises(NotImplementedError):
+        NeuMF(U, I, F, L, 0.5, "NeuMF-end")                      # dropout is not on the accelerated path
+    with pytest.raises(NotImplementedError):
+        NeuMF(U, I, F, L, 0.0, "GMF")
+    if not torch.cuda.is_available():
+        z = torch.zeros(2, dtype=torch.long)
+        with pytest.raises(_lib.DaisyError):
+            m(z, z)
+        with pytest.raises(_lib.DaisyError):
+            NeuMFAdam(m).step(z, z, torch.zeros(2))

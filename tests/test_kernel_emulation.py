@@ -206,3 +206,101 @@ def test_sgns_kernels_emulated_match_the_oracle_and_flag_bad_ids(V, D, B, C, N):
     nw[B - 2, -1] = V
     m.step(iw, ow, nw)
     assert m.L.emu_err_flag(m.h) == 1 and m.L.emu_err_pos(m.h) == B - 2
+
+
+# ------------------------------------------------------------------------------------------------ NCF: MLP / NeuMF-end
+class NmEmu:
+    def __init__(self, name, Pg, Qg, Pm, Qm, Ws, bs, wp, bp, lr):
+        self.L = _load("neumf")
+        PP = ctypes.POINTER(_lib.NeuMFParams)
+        self.L.daisy_neumf_scratch_bytes.argtypes = [PP, c_i64, ctypes.POINTER(c_i64)]
+        self.L.daisy_neumf_forward.argtypes = [c_vp, PP, c_vp, c_i64, c_vp, c_vp]
+        self.L.daisy_neumf_step.argtypes = [c_vp, PP, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp]
+        self.h = c_vp(self.L.emu_handle())
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32).copy()
+        self.T = dict(Pg=f32(Pg), Qg=f32(Qg), Pm=f32(Pm), Qm=f32(Qm), wp=f32(wp).reshape(-1), bp=f32(bp).reshape(-1))
+        self.W, self.b = [f32(W) for W in Ws], [f32(b) for b in bs]
+        z = np.zeros_like
+        self.M = {k: (z(v), z(v)) for k, v in self.T.items()}
+        self.MW = [(z(W), z(W)) for W in self.W]
+        self.Mb = [(z(b), z(b)) for b in self.b]
+        nl = len(Ws)
+        arr = lambda xs: (c_vp * 6)(*[x.ctypes.data for x in xs], *([None] * (6 - nl)))
+        T, M = self.T, self.M
+        self.prm = _lib.NeuMFParams(
+            int(name != "MLP"), nl, T["Pg"].shape[1], T["Pm"].shape[0], T["Qm"].shape[0],
+            _p(T["Pg"]), _p(T["Qg"]), _p(T["Pm"]), _p(T["Qm"]), arr(self.W), arr(self.b), _p(T["wp"]), _p(T["bp"]),
+            _p(M["Pg"][0]), _p(M["Pg"][1]), _p(M["Qg"][0]), _p(M["Qg"][1]), _p(M["Pm"][0]), _p(M["Pm"][1]),
+            _p(M["Qm"][0]), _p(M["Qm"][1]), arr([m for m, _ in self.MW]), arr([v for _, v in self.MW]),
+            arr([m for m, _ in self.Mb]), arr([v for _, v in self.Mb]), _p(M["wp"][0]), _p(M["wp"][1]),
+            _p(M["bp"][0]), _p(M["bp"][1]), lr, 0.9, 0.999, 1e-8)
+        self.t = 0
+        self.loss = np.zeros(1, np.float64)
+
+    def step(self, users, items, labels):
+        smp = np.ascontiguousarray(np.stack([users, items, np.asarray(labels).astype(np.int64)], 1), dtype=np.int32)
+        need = c_i64()
+        assert self.L.daisy_neumf_scratch_bytes(ctypes.byref(self.prm), len(smp), ctypes.byref(need)) == 0
+        raw, sp = _scratch(need.value)
+        self.t += 1
+        self.loss[0] = 0
+        rc = self.L.daisy_neumf_step(self.h, ctypes.byref(self.prm), _p(smp), len(smp), self.t, sp, need.value, _p(self.loss), None)
+        assert rc == 0, self.L.emu_last_error()
+        return float(self.loss[0])
+
+    def forward(self, users, items):
+        smp = np.ascontiguousarray(np.stack([users, items, np.zeros_like(users)], 1), dtype=np.int32)
+        out = np.zeros(len(smp), np.float32)
+        assert self.L.daisy_neumf_forward(self.h, ctypes.byref(self.prm), _p(smp), len(smp), _p(out), None) == 0
+        return out
+
+
+@pytest.mark.parametrize("tag,name", [("mlp", "MLP"), ("neumf", "NeuMF-end")])
+def test_neumf_kernels_emulated_match_the_reference_golden_run(golden, tag, name):
+    g = golden("neumf_small.npz")
+    k = lambda n: g[f"{tag}_{n}"]
+    L = int(k("num_layers"))
+    m = NmEmu(name, k("Pg_0"), k("Qg_0"), k("Pm_0"), k("Qm_0"), [k(f"W{l}_0") for l in range(L)],
+              [k(f"b{l}_0") for l in range(L)], k("wp_0"), k("bp_0"), float(k("lr")))
+    for s in range(2):                                           # two of the four recorded steps keep the test short
+        loss = m.step(k("users")[s], k("items")[s], k("labels")[s])
+        assert abs(loss - k("loss")[s]) <= 1e-5 * k("loss")[s], s
+        for key in ("Pg", "Qg", "Pm", "Qm", "wp"):
+            assert rel_err(m.T[key], k(key)[s]) <= 1e-5, (s, key, rel_err(m.T[key], k(key)[s]))
+        assert abs(m.T["bp"][0] - k("bp")[s][0]) <= 1e-6
+        for l in range(L):
+            assert rel_err(m.W[l], k(f"W{l}")[s]) <= 1e-5 and rel_err(m.b[l], k(f"b{l}")[s]) <= 2e-5, (s, l)
+    if tag == "mlp":
+        assert np.array_equal(m.T["Pg"], k("Pg_0")) and np.array_equal(m.T["Qg"], k("Qg_0"))
+
+
+def test_neumf_kernels_emulated_match_the_oracle_and_flag_bad_ids():
+    from oracle import neumf_oracle
+    rng = np.random.default_rng(12)
+    U, I, F, L, B = 21, 33, 12, 2, 37                           # F not a multiple of 32, ragged, items > users
+    Dm = F << (L - 1)
+    init = lambda *sh: (rng.standard_normal(sh) * 0.3).astype(np.float32)
+    Pg, Qg, Pm, Qm = init(U, F), init(I, F), init(U, Dm), init(I, Dm)
+    Ws, bs, n_in = [], [], 2 * Dm
+    for l in range(L):
+        Ws.append(init(n_in // 2, n_in))
+        bs.append(init(n_in // 2) * 0.1)
+        n_in //= 2
+    wp, bp = init(2 * F), init(1)
+    m = NmEmu("NeuMF-end", Pg, Qg, Pm, Qm, Ws, bs, wp, bp, 1e-3)
+    ora = neumf_oracle.NeuMFAdam("NeuMF-end", Pg, Qg, Pm, Qm, Ws, bs, wp, bp, lr=1e-3)
+    for s in range(2):
+        u, i, y = rng.integers(0, U, B), rng.integers(0, I, B), (rng.random(B) < 0.3).astype(np.int64)
+        u[:9] = 3
+        i[10:18] = 5
+        loss, lo = m.step(u, i, y), ora.step(u, i, y)
+        assert abs(loss - lo) <= 1e-5 * lo, s
+        for key, ref in (("Pg", ora.Pg), ("Qg", ora.Qg), ("Pm", ora.Pm), ("Qm", ora.Qm), ("wp", ora.wp), ("bp", ora.bp)):
+            assert rel_err(m.T[key], ref) <= 1e-5, (s, key, rel_err(m.T[key], ref))
+        for l in range(L):
+            assert rel_err(m.W[l], ora.Ws[l]) <= 1e-5 and rel_err(m.b[l], ora.bs[l]) <= 1e-5, (s, l)
+    assert np.allclose(m.forward(u, i), ora.forward(u, i), rtol=1e-4, atol=1e-5)
+    assert m.L.emu_err_flag(m.h) == 0
+    u[4] = U
+    m.step(u, i, y)
+    assert m.L.emu_err_flag(m.h) == 1 and m.L.emu_err_pos(m.h) == 4
