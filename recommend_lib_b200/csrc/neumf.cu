@@ -5,7 +5,7 @@
 // STATUS: compiled for sm_100a, NOT YET RUN ON A GPU (written after the GPU budget of round 1 was spent); the GPU tests
 // (tests/test_neumf_gpu.py) are excluded from the default run until it has been (DAISY_EXPERIMENTAL=1 runs them).
 // Executed so far only under the host emulation of tests/emu (tests/test_kernel_emulation.py: golden run + oracle green).
-// The checker is pinned to the unmodified reference: oracle/neumf_oracle.py.
+// The checker is pinned to the unmodified reference: the NeuMF checker under oracle/.
 //
 // First version, plain kernels, every reduction in a fixed order (bit-reproducible):
 //   k_nm_sample   one block (4 warps) per sample: gathers, the MLP tower forward in shared memory (a warp per output

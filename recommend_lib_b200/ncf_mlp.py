@@ -4,7 +4,7 @@
 SURVEY.md section 8f, row N3.  The GMF variant is ``ncf.NCF`` / ``GMFAdam``.
 
 EXPERIMENTAL: the kernels are compiled for sm_100a but have not run on a GPU yet (round 1 ended its GPU budget first);
-tests/test_neumf_gpu.py runs only with ``DAISY_EXPERIMENTAL=1``.  The checker is ``oracle/neumf_oracle.py``, pinned to
+tests/test_neumf_gpu.py runs only with ``DAISY_EXPERIMENTAL=1``.  The checker is the NeuMF checker under ``oracle/``, pinned to
 the unmodified reference class; the same translation unit passes it under the host emulation of tests/emu.
 
 Same module structure as the reference (all four embedding tables, ``MLP_layers = Sequential(Dropout, Linear, ReLU, ...)``,
