@@ -22,7 +22,8 @@ One step = one pass of the hot path (daisy_bpr_step) over one batch of synthetic
 Secondary lines (not the driver's metric; `profiles/` holds one of each):
   --workload config3 [--batch B] [--epoch-api]   ml-20m shape (L2-resident), B = 65 536 by default; --epoch-api runs the K
                      timed steps through ONE daisy_bpr_epoch call (what BPRMFRecommender.fit does)
-  --workload bprfm_bn / sgns   the two experimental next-row paths (BPR-FM with batch norm + dropout, Item2Vec / SGNS)
+  --workload bprfm_bn / sgns / neumf   the experimental next-row paths (BPR-FM with batch norm + dropout, Item2Vec / SGNS,
+                     NCF 'NeuMF-end')
   --workload config1   ml-100k, 20 epochs + HR@10 / NDCG@10 through BPRMFRecommender.fit, reference loop beside it
   --workload config2   funk-SVD (daisy_mf_fit) on the ml-1m shape
   --workload eval      full-catalogue top-100 for 16 384 users x 2 M items
@@ -619,6 +620,31 @@ def run_experimental(args):
         workload = ("BPR-FM training step at the script's defaults on the ml-100k shape (943 + 1682 features, hidden_factor "
                     "64, batch 4096, batch norm, dropout 0.5 drawn on the device, Adagrad lr 0.05)")
         h2d = B * 12
+    elif args.workload == "neumf":
+        from recommend_lib_b200.ncf_mlp import NeuMF, NeuMFAdam
+        from oracle import neumf_oracle
+        U, I, F, L, B = 943, 1682, 32, 3, args.batch or 256
+        K, W = max(args.steps, 400), max(args.warmup, 20)
+        model = NeuMF(U, I, F, L, 0.0, "NeuMF-end").to(dev)
+        opt = NeuMFAdam(model, lr=0.001)
+        us, its = rng.integers(0, U, (K + W, B)), (rng.zipf(1.2, (K + W, B)) - 1) % I
+        ys = (rng.random((K + W, B)) < 0.2).astype(np.int32)
+        inputs = [(torch.from_numpy(np.stack([us[s], its[s], ys[s]], 1).astype(np.int32)),) for s in range(K + W)]
+        _step = opt.step
+        opt.step = lambda smp: _step(smp[:, 0], smp[:, 1], smp[:, 2])      # one packed [B, 3] tensor per step crosses PCIe
+        units, unit, metric = B, "samples/s", "neumf_train_samples_per_s"
+        handle = model.handle
+        c = lambda t: t.detach().cpu().numpy()
+        ora = neumf_oracle.NeuMFAdam("NeuMF-end", c(model.embed_user_GMF.weight), c(model.embed_item_GMF.weight),
+                                     c(model.embed_user_MLP.weight), c(model.embed_item_MLP.weight),
+                                     [c(m.weight) for m in model.linears()], [c(m.bias) for m in model.linears()],
+                                     c(model.predict_layer.weight), c(model.predict_layer.bias))
+
+        def cpu_step(s):
+            ora.step(us[s], its[s], ys[s])
+        workload = ("NCF training step, model 'NeuMF-end' at the script's defaults on the ml-100k shape (943 x 1682, factor_num "
+                    "32, 3 MLP layers, batch 256, dropout 0, Adam lr 0.001)")
+        h2d = B * 12
     else:
         from recommend_lib_b200.item2vec import Item2Vec, SGNS, SGNSAdam
         from oracle import sgns_oracle
@@ -665,7 +691,7 @@ def run_experimental(args):
     ev1.record()
     torch.cuda.synchronize()
     ms2 = ev0.elapsed_time(ev1)
-    nc = 3
+    nc = 20 if args.workload == "neumf" else 3
     t0 = time.time()
     for s in range(nc):
         cpu_step(s)
@@ -873,7 +899,7 @@ def main():
                     help="N > 1: leave out the per-rank phase profile the fused peer path adds after the timed regions")
     ap.add_argument("--trace", action="store_true", help="also print a timeline of bookkeeping vs table kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="config4", choices=["config4", "config3", "config2", "config1", "sampler", "eval", "gmf", "bprfm", "bprfm_bn", "sgns"],
+    ap.add_argument("--workload", default="config4", choices=["config4", "config3", "config2", "config1", "sampler", "eval", "gmf", "bprfm", "bprfm_bn", "sgns", "neumf"],
                     help="N = 1 only: config4 is the driver's metric; config3 (L2-resident ml-20m shape) and config2 "
                          "(funk-SVD) are secondary lines kept under profiles/")
     ap.add_argument("--eval-users", type=int, default=16384)
@@ -897,7 +923,7 @@ def main():
         return run_config1(args)
     if args.workload == "gmf":
         return run_gmf(args)
-    if args.workload in ("bprfm_bn", "sgns"):
+    if args.workload in ("bprfm_bn", "sgns", "neumf"):
         return run_experimental(args)
     if args.workload == "bprfm":
         return run_bprfm(args)

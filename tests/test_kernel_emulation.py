@@ -1,16 +1,17 @@
-"""CPU execution of kernels that have NOT run on a GPU yet (csrc/fmbn.cu, csrc/sgns.cu).
+"""CPU execution of kernels that have NOT run on a GPU yet (csrc/fmbn.cu, csrc/sgns.cu, csrc/neumf.cu; SURVEY.md section 8f
+rows N3 / N4).
 
 tests/emu compiles the product's own translation units for the host against a functional emulation of the CUDA
 execution model (OS threads, block / warp barriers, shuffle exchange buffers) and this file drives the SAME extern "C"
 entry points the GPU path exports, against the golden runs of the unmodified reference and the oracle.  It checks
 indexing, reductions and arithmetic; it is not a product path (nothing in recommend_lib_b200 can reach it), not a
-performance statement, and not a substitute for tests/test_bprfm_bn_gpu.py / tests/test_sgns_gpu.py on the B200.
+performance statement, and not a substitute for tests/test_bprfm_bn_gpu.py / test_sgns_gpu.py / test_neumf_gpu.py on the B200.
 
 Memcheck (compute-sanitizer is closed on the GPU pool): the same tests pass with the units built under AddressSanitizer +
 UBSan --
     DAISY_EMU_SANITIZE=1 LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" \
         ASAN_OPTIONS=detect_leaks=0 python -m pytest tests/test_kernel_emulation.py
-(6 passed, no report, at the state of the commit that added this note)."""
+(12 passed, no report, with all three units, at the state of the commit that added csrc/neumf.cu)."""
 import ctypes
 import os
 import sys
