@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY: compile product translation units (csrc/fmbn.cu, csrc/sgns.cu) for the HOST against the
 emulation shim of tests/emu/emu.h, so that kernels which have not run on a GPU yet can at least be executed and checked
 against the oracle.  DAISY_EMU_SANITIZE=1 builds with AddressSanitizer + UBSan (run pytest with LD_PRELOAD=$(gcc -print-file-name=libasan.so)
-ASAN_OPTIONS=detect_leaks=0): the memcheck that compute-sanitizer would do on the GPU pool, where it is closed.
+ASAN_OPTIONS=detect_leaks=0): the memcheck that compute-sanitizer would do on the GPU pool, where it is closed;
+DAISY_EMU_SANITIZE=thread builds with ThreadSanitizer (LD_PRELOAD libtsan.so): its racecheck.
 The only rewrite of the source is the launch syntax:
     kernel<<<grid, block, smem, stream>>>(args);   ->   emu::launch(emu::Cfg(grid, block, smem, stream), [&] { kernel(args); });
 """
@@ -42,14 +43,16 @@ def build(unit):
     """unit: 'fmbn' or 'sgns' -> path of the host shared library executing that unit's kernels."""
     os.makedirs(OUT, exist_ok=True)
     src_path = os.path.join(CSRC, unit + ".cu")
-    so = os.path.join(OUT, f"lib{unit}_emu{'_san' if os.environ.get('DAISY_EMU_SANITIZE') else ''}.so")
+    so = os.path.join(OUT, f"lib{unit}_emu{'_' + os.environ['DAISY_EMU_SANITIZE'] if os.environ.get('DAISY_EMU_SANITIZE') else ''}.so")
     deps = [src_path, os.path.join(CSRC, "ctx.cuh"), os.path.join(HERE, "emu.h"), os.path.join(HERE, "cub", "cub.cuh"), __file__]
     if os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
         return so
     cpp = os.path.join(OUT, unit + "_emu.cpp")
     with open(cpp, "w") as f:
         f.write(rewrite(open(src_path).read()) + GLUE)
-    san = ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-g"] if os.environ.get("DAISY_EMU_SANITIZE") else []
+    mode = os.environ.get("DAISY_EMU_SANITIZE", "")
+    san = {"": [], "1": ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-g"],
+           "thread": ["-fsanitize=thread", "-fno-omit-frame-pointer", "-g"]}[mode]
     subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-w", *san,
                            "-I", HERE, "-I", CSRC, "-o", so, cpp])
     return so

@@ -11,7 +11,12 @@ Memcheck (compute-sanitizer is closed on the GPU pool): the same tests pass with
 UBSan --
     DAISY_EMU_SANITIZE=1 LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" \
         ASAN_OPTIONS=detect_leaks=0 python -m pytest tests/test_kernel_emulation.py
-(12 passed, no report, with all three units, at the state of the commit that added csrc/neumf.cu)."""
+(12 passed, no report, with all three units, at the state of the commit that added csrc/neumf.cu).
+Race check: every emulated CUDA thread is an OS thread, so ThreadSanitizer sees a missing __syncthreads or two threads
+writing one location (validated on a kernel with its barrier removed: one report; with it: none) --
+    DAISY_EMU_SANITIZE=thread LD_PRELOAD="$(gcc -print-file-name=libtsan.so)" TSAN_OPTIONS=report_signal_unsafe=0 \
+        python -m pytest tests/test_kernel_emulation.py
+(12 passed, no data-race report)."""
 import ctypes
 import os
 import sys
