@@ -20,9 +20,13 @@ GLUE = r'''
 static thread_local char g_err[512];
 void daisy_set_error(const char *fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); }
 extern "C" const char *emu_last_error() { return g_err; }
-extern "C" daisy_ctx *emu_handle() {
+extern "C" daisy_ctx *emu_handle_dims(long long U, long long I, int D);
+extern "C" daisy_ctx *emu_handle() { return emu_handle_dims(0, 0, 4); }
+extern "C" daisy_ctx *emu_handle_dims(long long U, long long I, int D) {
     daisy_ctx *h = (daisy_ctx *)calloc(1, sizeof(daisy_ctx));
     h->num_sms = 4;
+    h->U = U; h->I = I; h->D = D;
+    h->scale = 1.0;
     h->err = (int *)calloc(2, sizeof(int));
     h->err[1] = 0x7fffffff;
     return h;
@@ -36,6 +40,7 @@ def rewrite(src):
     pat = re.compile(r"(\b\w+(?:<[\w\s,]+>)?)<<<(.+?)>>>\((.*?)\);", re.S)   # kernel or kernel<template args>
     out, n = pat.subn(lambda m: f"emu::launch(emu::Cfg({m.group(2)}), [&] {{ {m.group(1)}({m.group(3)}); }});", src)
     assert n > 0 and '<<<' not in out, 'a launch was not rewritten'
+    out = re.sub(r"extern\s+__shared__\s+(\w+)\s+(\w+)\[\];", r"\1 *\2 = (\1 *)emu::dyn_smem();", out)   # dynamic shared memory
     return out
 
 
@@ -59,5 +64,5 @@ def build(unit):
 
 
 if __name__ == "__main__":
-    for u in ("fmbn", "sgns", "neumf"):
+    for u in ("fmbn", "sgns", "neumf", "bpr_eval", "sampler"):
         print(build(u))

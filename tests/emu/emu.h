@@ -28,6 +28,13 @@ inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 inline cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n); return *p ? cudaSuccess : 1; }
+inline cudaError_t cudaMallocAsync(void **p, size_t n, cudaStream_t) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : 1; }
+inline cudaError_t cudaFreeAsync(void *p, cudaStream_t) { free(p); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+typedef void *cudaMemPool_t;
+enum { cudaMemPoolAttrReleaseThreshold = 0 };
+inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t *, int) { return 1; }  // "no pool": the caller skips its tuning
+inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, int, void *) { return cudaSuccess; }
 
 struct dim3 {
     unsigned x, y, z;
@@ -47,9 +54,11 @@ struct Block {
     std::unique_ptr<std::barrier<>> bar;
     std::vector<std::unique_ptr<std::barrier<>>> wbar;
     std::vector<uint64_t> xbuf;  // [warps][32]
+    std::vector<uint64_t> dyn;   // dynamic shared memory of the launch (8-byte aligned)
 };
 inline Block *&cur() { static Block *b = nullptr; return b; }
 inline thread_local int t_lin = 0;
+inline void *dyn_smem() { return cur()->dyn.data(); }  // `extern __shared__ T name[];` is rewritten to use this
 }  // namespace emu
 inline thread_local dim3 threadIdx, blockIdx;
 inline dim3 blockDim, gridDim;
@@ -83,7 +92,34 @@ inline int atomicMin(int *p, int v) {
 }
 template <class T> inline T min(T a, T b) { return a < b ? a : b; }
 
-// ctx.cuh keeps its device helpers behind __CUDACC__ (some are inline PTX); the two the plain kernels use:
+// ctx.cuh keeps its device helpers behind __CUDACC__ (some are inline PTX): plain equivalents of the ones the emulated
+// units use (cache hints have no meaning here)
+struct float4 { float x, y, z, w; };
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float4 ld_row(const float *base, size_t i) { return reinterpret_cast<const float4 *>(base)[i]; }
+inline void st_row(float *base, size_t i, float4 v) { reinterpret_cast<float4 *>(base)[i] = v; }
+inline float4 ld_stream(const float *base, size_t i) { return ld_row(base, i); }
+inline void st_stream(float *base, size_t i, float4 v) { st_row(base, i, v); }
+inline float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+inline float4 f4_sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+inline float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+inline float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+inline float f4_dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+inline unsigned __ballot_sync(unsigned, int pred) {
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l) m |= (unsigned)(emu_exchange(pred ? 1 : 0, l) != 0) << l;
+    return m;
+}
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+template <class T> inline T max(T a, T b) { return a < b ? b : a; }
+// the two warp reductions the plain kernels use:
 inline float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
@@ -96,7 +132,8 @@ inline double warp_sum_d(double v) {
 namespace emu {
 struct Cfg {
     dim3 grid, block;
-    Cfg(dim3 g, dim3 b, size_t = 0, cudaStream_t = nullptr) : grid(g), block(b) {}
+    size_t smem;
+    Cfg(dim3 g, dim3 b, size_t sm = 0, cudaStream_t = nullptr) : grid(g), block(b), smem(sm) {}
 };
 inline void launch(const Cfg &c, const std::function<void()> &body) {
     const int T = (int)(c.block.x * c.block.y * c.block.z);
@@ -110,6 +147,7 @@ inline void launch(const Cfg &c, const std::function<void()> &body) {
                 blk.bar = std::make_unique<std::barrier<>>(T);
                 for (int w = 0; w < T / 32; ++w) blk.wbar.push_back(std::make_unique<std::barrier<>>(32));
                 blk.xbuf.assign((size_t)T, 0);
+                blk.dyn.assign(c.smem / 8 + 1, 0);
                 cur() = &blk;
                 std::vector<std::thread> th;
                 th.reserve(T);

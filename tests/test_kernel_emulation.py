@@ -310,3 +310,65 @@ def test_neumf_kernels_emulated_match_the_oracle_and_flag_bad_ids():
     u[4] = U
     m.step(u, i, y)
     assert m.L.emu_err_flag(m.h) == 1 and m.L.emu_err_pos(m.h) == 4
+
+
+# ------------------------------------------------------------------------------------------------ units that DO run on the GPU
+# csrc/bpr_eval.cu and csrc/sampler.cu (8f row N1) are GPU-verified product code
+# (tests/test_bpr_gpu.py, tests/test_sampler_gpu.py).  They are plain CUDA, so the same emulation gives them what the
+# closed compute-sanitizer cannot on this pool: a memcheck / racecheck run (DAISY_EMU_SANITIZE=1 / thread, see above).
+def _dims_handle(L, U, I, D):
+    L.emu_handle_dims.restype = c_vp
+    L.emu_handle_dims.argtypes = [ctypes.c_longlong, ctypes.c_longlong, c_i32]
+    return c_vp(L.emu_handle_dims(U, I, D))
+
+
+def test_eval_kernels_emulated_forward_and_candidate_topk():
+    from oracle import bpr_oracle
+    L = _load("bpr_eval")
+    rng = np.random.default_rng(21)
+    U, I, D, B, N, C, K = 37, 131, 24, 45, 11, 100, 10             # D / 4 = 6 lanes active; ragged B; C > 3 x 32
+    P = (rng.standard_normal((U, D)) * 0.3).astype(np.float32)
+    Q = (rng.standard_normal((I, D)) * 0.3).astype(np.float32)
+    h = _dims_handle(L, U, I, D)
+    tri = np.stack([rng.integers(0, U, B), rng.integers(0, I, B), rng.integers(0, I, B)], 1).astype(np.int32)
+    pi, pj = np.zeros(B, np.float32), np.zeros(B, np.float32)
+    L.daisy_bpr_forward.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]
+    assert L.daisy_bpr_forward(h, _p(P), _p(Q), _p(tri), B, _p(pi), _p(pj), None) == 0, L.emu_last_error()
+    ri, rj = bpr_oracle.bpr_scores(P, Q, tri[:, 0], tri[:, 1], tri[:, 2])
+    assert np.allclose(pi, ri, rtol=1e-5, atol=1e-6) and np.allclose(pj, rj, rtol=1e-5, atol=1e-6)
+    users = rng.integers(0, U, N).astype(np.int32)
+    cands = np.stack([rng.permutation(I)[:C - 1] for _ in range(N)]).astype(np.int32)
+    cands = np.concatenate([cands, cands[:, :1]], 1)               # a duplicated candidate: an exact score tie
+    cands = np.ascontiguousarray(cands[:, :C])
+    assert cands.shape == (N, C)
+    pos, item, score = np.zeros((N, K), np.int32), np.zeros((N, K), np.int32), np.zeros((N, K), np.float32)
+    L.daisy_topk_candidates.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]
+    assert L.daisy_topk_candidates(h, _p(P), _p(Q), _p(users), _p(cands), N, C, K, _p(pos), _p(item), _p(score), None) == 0
+    for g in range(N):
+        sc = bpr_oracle.candidate_scores(P, Q, users[g], cands[g])
+        assert np.array_equal(item[g], cands[g][pos[g]])
+        assert np.allclose(score[g], sc[pos[g]], rtol=1e-5, atol=1e-6)
+        assert np.all(np.diff(score[g]) <= 0)                                       # descending
+        kth = np.sort(sc)[::-1][K - 1]
+        assert score[g][-1] >= kth - 1e-5                                           # nothing better was left out
+        ties = [a for a in range(K - 1) if score[g][a] == score[g][a + 1]]
+        assert all(pos[g][a] < pos[g][a + 1] for a in ties)                         # ties: position ascending
+    assert L.emu_err_flag(h) == 0
+
+
+@pytest.mark.parametrize("shuffle", [0, 1])
+def test_sampler_kernels_emulated_match_the_oracle_bit_for_bit(shuffle):
+    from oracle import sampler_oracle
+    L = _load("sampler")
+    rng = np.random.default_rng(31)
+    U, I, n_pairs, num_ng = 40, 23, 150, 3                        # dense positives: many rejected draws
+    pairs = np.unique(np.stack([rng.integers(0, U, n_pairs), rng.integers(0, I, n_pairs)], 1), axis=0).astype(np.int32)
+    keys = np.unique(pairs[:, 0].astype(np.int64) * I + pairs[:, 1]).astype(np.int64)
+    h = _dims_handle(L, U, I, 4)
+    out = np.zeros((len(pairs) * num_ng, 3), np.int32)
+    L.daisy_sample_triples.argtypes = [c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, ctypes.c_uint64, ctypes.c_uint32, c_i32, c_vp, c_vp]
+    rc = L.daisy_sample_triples(h, _p(pairs), len(pairs), num_ng, _p(keys), len(keys), 2019, 5, shuffle, _p(out), None)
+    assert rc == 0, L.emu_last_error()
+    want = sampler_oracle.sample_epoch(pairs, I, num_ng, 2019, 5, bool(shuffle))
+    assert np.array_equal(out, want)
+    assert L.emu_err_flag(h) == 0
