@@ -1,4 +1,5 @@
-"""TEST INFRASTRUCTURE ONLY: compile product translation units (csrc/fmbn.cu, csrc/sgns.cu) for the HOST against the
+"""TEST INFRASTRUCTURE ONLY: compile plain-CUDA product translation units (csrc/fmbn.cu, sgns.cu, neumf.cu, bpr_eval.cu,
+sampler.cu, topk_full.cu) for the HOST against the
 emulation shim of tests/emu/emu.h, so that kernels which have not run on a GPU yet can at least be executed and checked
 against the oracle.  DAISY_EMU_SANITIZE=1 builds with AddressSanitizer + UBSan (run pytest with LD_PRELOAD=$(gcc -print-file-name=libasan.so)
 ASAN_OPTIONS=detect_leaks=0): the memcheck that compute-sanitizer would do on the GPU pool, where it is closed;
@@ -40,7 +41,7 @@ def rewrite(src):
     pat = re.compile(r"(\b\w+(?:<[\w\s,]+>)?)<<<(.+?)>>>\((.*?)\);", re.S)   # kernel or kernel<template args>
     out, n = pat.subn(lambda m: f"emu::launch(emu::Cfg({m.group(2)}), [&] {{ {m.group(1)}({m.group(3)}); }});", src)
     assert n > 0 and '<<<' not in out, 'a launch was not rewritten'
-    out = re.sub(r"extern\s+__shared__\s+(\w+)\s+(\w+)\[\];", r"\1 *\2 = (\1 *)emu::dyn_smem();", out)   # dynamic shared memory
+    out = re.sub(r"extern\s+__shared__\s+([\w ]+?)\s+(\w+)\[\];", r"\1 *\2 = (\1 *)emu::dyn_smem();", out)   # dynamic shared memory
     return out
 
 
@@ -64,5 +65,5 @@ def build(unit):
 
 
 if __name__ == "__main__":
-    for u in ("fmbn", "sgns", "neumf", "bpr_eval", "sampler"):
+    for u in ("fmbn", "sgns", "neumf", "bpr_eval", "sampler", "topk_full"):
         print(build(u))

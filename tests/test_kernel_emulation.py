@@ -372,3 +372,44 @@ def test_sampler_kernels_emulated_match_the_oracle_bit_for_bit(shuffle):
     want = sampler_oracle.sample_epoch(pairs, I, num_ng, 2019, 5, bool(shuffle))
     assert np.array_equal(out, want)
     assert L.emu_err_flag(h) == 0
+
+
+@pytest.mark.parametrize("I,D,N,K,paths", [(300, 16, 5, 10, ("exact",)), (33000, 8, 3, 10, ("exact", "filter"))])
+def test_full_catalogue_topk_emulated(monkeypatch, I, D, N, K, paths):
+    """csrc/topk_full.cu (row A9, GPU-verified): both selection strategies under the emulation; the filtered path must
+    return exactly what the materialise-and-select path returns."""
+    L = _load("topk_full")
+    L.daisy_topk_full.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]
+    rng = np.random.default_rng(I + N)
+    U = 20
+    P = rng.standard_normal((U, D)).astype(np.float32)
+    Q = rng.standard_normal((I, D)).astype(np.float32)
+    Q[rng.integers(0, I, I // 20)] = Q[rng.integers(0, I, I // 20)]                # exactly tied scores
+    users = rng.integers(0, U, N).astype(np.int32)
+    excl = [np.sort(rng.choice(I, size=rng.integers(0, 30), replace=False)) for _ in range(N)]
+    ptr = np.zeros(N + 1, np.int64)
+    ptr[1:] = np.cumsum([len(e) for e in excl])
+    idx = (np.concatenate(excl) if ptr[-1] else np.zeros(0)).astype(np.int32)
+    ref = P[users].astype(np.float64) @ Q.astype(np.float64).T
+    out = {}
+    for path in paths:
+        monkeypatch.setenv("DAISY_TOPK_PATH", path)
+        h = _dims_handle(L, U, I, D)
+        items, scores = np.zeros((N, K), np.int32), np.zeros((N, K), np.float32)
+        rc = L.daisy_topk_full(h, _p(P), _p(Q), _p(users), N, K, _p(ptr), _p(idx) if len(idx) else None, _p(items), _p(scores), None)
+        assert rc == 0, L.emu_last_error()
+        assert L.emu_err_flag(h) == 0
+        out[path] = (items, scores)
+        for n in range(N):
+            r = ref[n].copy()
+            r[excl[n]] = -np.inf
+            got = items[n]
+            assert len(set(got.tolist())) == K and not (set(got.tolist()) & set(excl[n].tolist()))
+            assert np.allclose(scores[n], r[got], rtol=1e-4, atol=1e-4)
+            assert (np.diff(scores[n]) <= 0).all()
+            tie = np.diff(scores[n]) == 0
+            assert (np.diff(got)[tie] > 0).all()
+            kth = np.sort(r)[-K]
+            assert set(np.nonzero(r > kth + 1e-3)[0].tolist()) <= set(got.tolist()) and r[got].min() >= kth - 1e-3
+    if len(paths) == 2:
+        assert np.array_equal(out["exact"][0], out["filter"][0]) and np.array_equal(out["exact"][1], out["filter"][1])
