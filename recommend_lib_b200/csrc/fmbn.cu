@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(256) k_fm_apply(const uint32_t *__restrict__ k
     float acc[(FM_MAX_F + 1 + 31) / 32];
 #pragma unroll
     for (int k = 0; k < (FM_MAX_F + 1 + 31) / 32; ++k) acc[k] = 0.f;
+#pragma unroll 4  // independent index -> row chains: let the scheduler put several rows in flight
     for (int q = p; q < n && kout[q] == row; ++q) {
         const float *g = contrib + (size_t)vout[q] * W;
 #pragma unroll

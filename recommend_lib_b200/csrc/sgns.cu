@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(256) k_sgns_rows(const uint32_t *__restrict__ 
     float acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = 0.f;
+#pragma unroll 4  // independent index -> row chains: let the scheduler put several rows in flight
     for (int q = q0; q < q1; ++q) {
         if (otab) {
             const uint32_t p = vout[q];
