@@ -105,3 +105,49 @@ int mf_oracle_predict(int64_t u, int64_t i, int64_t U, int64_t I, int D, int wit
     *est = with_bias ? mu + bu[u] + bi[i] + dot : dot;
     return 0;
 }
+
+/* SVDpp.fit -- util/matrix_factorization.pyx:193-271 (loop body :238-263).  Strictly sequential: every rating of user u
+ * updates pu[u], qi[i], both biases AND the implicit-feedback row yj[j] of EVERY item j the user rated (:259-263), so
+ * two ratings of different users conflict whenever the users share an item.
+ * ur_ptr [U+1], ur_idx: the items each user rated, in the order of their first appearance in the training frame
+ * (`ur[u].append((i, r))`, :231-234 -- list order is what the sums below follow).  Operation order as in the .pyx:
+ * u_impl_fdb[f] accumulates yj[j, f] / sqrt_Iu over j in list order (:245-247); the factor loop reads puf, qif BEFORE
+ * updating (:254-258); yj[j, f] uses the OLD qif (:261-263).  Returns the last epoch's sum of squared errors. */
+double mf_oracle_svdpp_fit(int64_t n, const int32_t *users, const int32_t *items, const double *ratings,
+                           int D, int n_epochs,
+                           double lr_bu, double lr_bi, double lr_pu, double lr_qi, double lr_yj,
+                           double reg_bu, double reg_bi, double reg_pu, double reg_qi, double reg_yj,
+                           double global_mean, const int64_t *ur_ptr, const int32_t *ur_idx,
+                           double *pu, double *qi, double *yj, double *bu, double *bi, double *u_impl_fdb)
+{
+    double sse = 0.0;
+    for (int epoch = 0; epoch < n_epochs; ++epoch) {
+        sse = 0.0;
+        for (int64_t t = 0; t < n; ++t) {
+            const int32_t u = users[t], i = items[t];
+            const int32_t *Iu = ur_idx + ur_ptr[u];
+            const int64_t nI = ur_ptr[u + 1] - ur_ptr[u];
+            const double sqrt_Iu = __builtin_sqrt((double)nI);                    /* :241 */
+            for (int f = 0; f < D; ++f) u_impl_fdb[f] = 0.0;                      /* :243 */
+            for (int64_t k = 0; k < nI; ++k)                                      /* :244-246 */
+                for (int f = 0; f < D; ++f) u_impl_fdb[f] += yj[(size_t)Iu[k] * D + f] / sqrt_Iu;
+            double dot = 0.0;                                                     /* :248-250 */
+            for (int f = 0; f < D; ++f) dot += qi[(size_t)i * D + f] * (pu[(size_t)u * D + f] + u_impl_fdb[f]);
+            const double err = ratings[t] - (global_mean + bu[u] + bi[i] + dot);  /* :252 */
+            sse += err * err;
+            bu[u] += lr_bu * (err - reg_bu * bu[u]);                              /* :255-256 */
+            bi[i] += lr_bi * (err - reg_bi * bi[i]);
+            for (int f = 0; f < D; ++f) {                                         /* :259-265 */
+                const double puf = pu[(size_t)u * D + f], qif = qi[(size_t)i * D + f];
+                pu[(size_t)u * D + f] += lr_pu * (err * qif - reg_pu * puf);
+                qi[(size_t)i * D + f] += lr_qi * (err * (puf + u_impl_fdb[f]) - reg_qi * qif);
+                for (int64_t k = 0; k < nI; ++k) {
+                    double *y = yj + (size_t)Iu[k] * D + f;
+                    *y += lr_yj * (err * qif / sqrt_Iu - reg_yj * *y);
+                }
+            }
+        }
+    }
+    return sse;
+}
+

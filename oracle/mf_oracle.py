@@ -39,6 +39,9 @@ def lib():
         L.mf_oracle_svd_fit.argtypes = [i64, ip, ip, dp, i32, i32, i32, d, d, d, d, d, d, d, d, d, dp, dp, dp, dp]
         L.mf_oracle_rsvd_fit.restype = d
         L.mf_oracle_rsvd_fit.argtypes = [i64, ip, ip, dp, i32, i32, i32, d, d, d, d, dp, dp, dp, dp]
+        L.mf_oracle_svdpp_fit.restype = d
+        L.mf_oracle_svdpp_fit.argtypes = [i64, ip, ip, dp, i32, i32, d, d, d, d, d, d, d, d, d, d, d,
+                                          ctypes.POINTER(ctypes.c_int64), ip, dp, dp, dp, dp, dp, dp]
         L.mf_oracle_predict.restype = i32
         L.mf_oracle_predict.argtypes = [i64, i64, i64, i64, i32, i32, d, dp, dp, dp, dp, dp]
         _lib = L
@@ -106,3 +109,43 @@ def predict(u, i, pu, qi, bu, bi, with_bias, mu=0.0):
     if rc == -2:
         raise ValueError('Invalid item code')
     return est.value
+
+
+
+def user_item_lists(users, items, user_num):
+    """``ur`` of SVDpp.fit (util/matrix_factorization.pyx:231-234) in CSR form: per user the items of its ratings in
+    frame order (a repeated (user, item) rating appears twice, as in the reference's list)."""
+    users = np.asarray(users, dtype=np.int64)
+    order = np.argsort(users, kind="stable")
+    ptr = np.zeros(user_num + 1, dtype=np.int64)
+    np.add.at(ptr, users + 1, 1)
+    return np.cumsum(ptr), np.ascontiguousarray(np.asarray(items)[order], dtype=np.int32)
+
+
+def svdpp_fit(users, items, ratings, pu, qi, yj, n_epochs=20, lr_all=.007, reg_all=.02):
+    """SVDpp.fit (util/matrix_factorization.pyx:193-271).  Returns dict(pu, qi, yj, bu, bi, global_mean, sse)."""
+    users = np.ascontiguousarray(users, dtype=np.int32)
+    items = np.ascontiguousarray(items, dtype=np.int32)
+    ratings = np.ascontiguousarray(ratings, dtype=np.float64)
+    pu, qi, yj = (np.array(a, dtype=np.float64, order="C") for a in (pu, qi, yj))
+    bu, bi = np.zeros(pu.shape[0]), np.zeros(qi.shape[0])
+    ptr, idx = user_item_lists(users, items, pu.shape[0])
+    mu = float(ratings.mean())
+    scratch = np.zeros(pu.shape[1])
+    sse = lib().mf_oracle_svdpp_fit(len(ratings), _ip(users), _ip(items), _dp(ratings), pu.shape[1], n_epochs,
+                                    lr_all, lr_all, lr_all, lr_all, lr_all, reg_all, reg_all, reg_all, reg_all, reg_all, mu,
+                                    ptr.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _ip(idx), _dp(pu), _dp(qi), _dp(yj),
+                                    _dp(bu), _dp(bi), _dp(scratch))
+    return dict(pu=pu, qi=qi, yj=yj, bu=bu, bi=bi, global_mean=mu, sse=sse, ur_ptr=ptr, ur_idx=idx)
+
+
+def svdpp_predict(u, i, fit):
+    """SVDpp.predict (util/matrix_factorization.pyx:273-288)."""
+    pu, qi, yj = fit["pu"], fit["qi"], fit["yj"]
+    if u >= pu.shape[0]:
+        raise ValueError('Invalid user code')
+    if i >= qi.shape[0]:
+        raise ValueError('Invalid item code')
+    Iu = fit["ur_idx"][fit["ur_ptr"][u]:fit["ur_ptr"][u + 1]]
+    impl = 0 if len(Iu) == 0 else sum(yj[j] for j in Iu) / np.sqrt(len(Iu))
+    return fit["global_mean"] + fit["bu"][u] + fit["bi"][i] + np.dot(qi[i], pu[u] + impl)

@@ -320,3 +320,21 @@ def test_neumf_oracle_matches_reference_ncf_with_adam(golden, tag, name):
     assert rel_err(st.forward(k("users")[0], k("items")[0]), k("fwd_last")) < 2e-6
     if tag == "mlp":                                       # no gradient ever reaches the GMF tables: torch's Adam skips them
         assert np.array_equal(st.Pg, k("Pg_0").astype(np.float64))
+
+
+# ---------------------------------------------------------------- row N4: SVD++
+def test_svdpp_c_oracle_is_bit_identical_to_the_reference_extension(golden):
+    """oracle/mf_oracle.c: mf_oracle_svdpp_fit against the reference's own compiled SVDpp
+    (util/matrix_factorization.pyx:169-288; tests/golden/make_svdpp_golden.py): all five arrays bit for bit, predictions
+    to the last ulp (the reference sums the implicit rows with Python's sum, the oracle in the same order)."""
+    g = golden("svdpp_small.npz")
+    o = mf_oracle.svdpp_fit(g["users"], g["items"], g["ratings"], g["pu0"], g["qi0"], g["yj0"], n_epochs=int(g["E"]))
+    for k in ("pu", "qi", "yj", "bu", "bi"):
+        assert np.array_equal(o[k], g[k]), k
+    assert o["global_mean"] == float(g["mu"])
+    pred = np.array([mf_oracle.svdpp_predict(int(u), int(i), o) for u, i in zip(g["users"][:15], g["items"][:15])])
+    assert np.allclose(pred, g["pred"], rtol=0, atol=1e-14)
+    with pytest.raises(ValueError, match="Invalid user code"):
+        mf_oracle.svdpp_predict(int(g["U"]), 0, o)
+    with pytest.raises(ValueError, match="Invalid item code"):
+        mf_oracle.svdpp_predict(0, int(g["I"]), o)
