@@ -24,6 +24,7 @@ Secondary lines (not the driver's metric; `profiles/` holds one of each):
                      timed steps through ONE daisy_bpr_epoch call (what BPRMFRecommender.fit does)
   --workload bprfm_bn / sgns / neumf   the experimental next-row paths (BPR-FM with batch norm + dropout, Item2Vec / SGNS,
                      NCF 'NeuMF-end')
+  --workload svdpp     SVD++ (daisy_svdpp_fit, experimental) on the ml-1m shape at the script's defaults (n_factors 20)
   --workload config1   ml-100k, 20 epochs + HR@10 / NDCG@10 through BPRMFRecommender.fit, reference loop beside it
   --workload config2   funk-SVD (daisy_mf_fit) on the ml-1m shape
   --workload eval      full-catalogue top-100 for 16 384 users x 2 M items
@@ -775,6 +776,77 @@ def run_mf(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# SVD++ (secondary line of an experimental path)
+# ------------------------------------------------------------------------------------------------
+def run_svdpp(args):
+    """ratings/s of SVDpp.fit (daisy_svdpp_fit: one thread block walking the ratings in order, float64) on the
+    ml-1m-shaped synthetic ratings of config 2 at the script's defaults (n_factors 20, lr 0.007, reg 0.02, SVDppRecommender.py:30-44),
+    next to the C restatement of the reference loop on a bounded sample.  EXPERIMENTAL path (csrc/svdpp.cu)."""
+    import ctypes
+    import torch
+    from recommend_lib_b200 import _lib
+    from recommend_lib_b200._lib import SVDppParams, c_vp
+    from recommend_lib_b200.sampler import synthetic_ratings
+    from recommend_lib_b200.svdpp import user_histories
+    cfg = CFG2
+    U, I, D, N = cfg["user_num"], cfg["item_num"], 20, cfg["n"]
+    users, items, ratings = synthetic_ratings(N, U, I, seed=2019)
+    ratings = ratings.astype(np.float64)
+    ptr, idx, mult = user_histories(users, items, U)
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(0)
+    pu, qi, yj = rng.normal(0, 0.1, (U, D)), rng.normal(0, 0.1, (I, D)), rng.normal(0, 0.1, (I, D))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    dpu, dqi, dyj, dbu, dbi = t(pu), t(qi), t(yj), t(np.zeros(U)), t(np.zeros(I))
+    du, di, dr = t(users.astype(np.int32)), t(items.astype(np.int32)), t(ratings)
+    dptr, didx = t(ptr), t(idx)
+    dmult = t(mult) if mult is not None else None
+    prm = SVDppParams(.007, .007, .007, .007, .007, .02, .02, .02, .02, .02, float(ratings.mean()))
+    h = _lib.Handle(0, U, I, D, 0)
+    s = _lib.stream_ptr(torch, dev)
+    fit = lambda ep: _lib.check(h.L.daisy_svdpp_fit(
+        h.ptr, c_vp(dpu.data_ptr()), c_vp(dqi.data_ptr()), c_vp(dyj.data_ptr()), c_vp(dbu.data_ptr()), c_vp(dbi.data_ptr()),
+        c_vp(du.data_ptr()), c_vp(di.data_ptr()), c_vp(dr.data_ptr()), N, ep, c_vp(dptr.data_ptr()), c_vp(didx.data_ptr()),
+        c_vp(dmult.data_ptr()) if dmult is not None else None, ctypes.byref(prm), None, s))
+    fit(1)
+    torch.cuda.synchronize()
+    K = max(1, min(args.steps, 2))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    fit(K)
+    ev1.record()
+    torch.cuda.synchronize()
+    _lib.check(h.L.daisy_check(h.ptr, s))
+    ms = ev0.elapsed_time(ev1)
+    from oracle import mf_oracle
+    n_cpu = 100_000
+    t0 = time.time()
+    mf_oracle.svdpp_fit(users[:n_cpu], items[:n_cpu], ratings[:n_cpu], pu, qi, yj, n_epochs=1, lists=(ptr, idx),
+                        global_mean=float(ratings.mean()))
+    cpu_dt = time.time() - t0
+    rows = float(np.diff(ptr)[users].mean())                     # history rows gathered and rewritten per rating
+    byts = N * K * (2 * rows * 8 * D + 4 * 8 * D + 12) / (ms * 1e-3) / 1e9
+    line = {"metric": "svdpp_train_ratings_per_s", "value": N * K / (ms * 1e-3), "unit": "ratings/s", "n_gpus": 1, "steps": K,
+            "warmup": 1, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"SVD++ (SVDpp.fit) on ml-1m-shaped synthetic ratings (config 2's set), n_factors {D}",
+                       "status": "experimental path, first version", "user_num": U, "item_num": I, "ratings": N, "dim": D,
+                       "history_rows_per_rating": rows,
+                       "step": "one epoch (a pass over the ratings in the given order, strictly sequential semantics)",
+                       "l2": "tables are L2-resident; one thread block: the bound is one SM's L2 bandwidth and the barrier chain"},
+            "roofline": {"bound": "hbm", "achieved": byts, "peak": measured_peaks()[0], "unit": "GB/s",
+                         "frac": byts / measured_peaks()[0], "traffic": None,
+                         "note": "2 x history rows x 8 D + 4 x 8 D + 12 B per rating; one SM, L2-resident: not an HBM-bound kernel"},
+            "cpu_baseline": {"value": n_cpu / cpu_dt, "unit": "ratings/s", "cores": 1, "kind": "port",
+                             "sample": f"C restatement of the Cython loop (bit-identical to the compiled reference class, "
+                                       f"tests/test_oracle_golden.py), the first {n_cpu} ratings of the epoch with the full histories, single thread "
+                                       "(the loop is serial); the reference's own fit adds DataFrame.iterrows and a Python "
+                                       "list comprehension per rating"},
+            "gpu_launches": int(h.launches)}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
 # device-side negative sampler (SURVEY 8f N1; secondary line)
 # ------------------------------------------------------------------------------------------------
 def run_sampler(args):
@@ -899,7 +971,7 @@ def main():
                     help="N > 1: leave out the per-rank phase profile the fused peer path adds after the timed regions")
     ap.add_argument("--trace", action="store_true", help="also print a timeline of bookkeeping vs table kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="config4", choices=["config4", "config3", "config2", "config1", "sampler", "eval", "gmf", "bprfm", "bprfm_bn", "sgns", "neumf"],
+    ap.add_argument("--workload", default="config4", choices=["config4", "config3", "config2", "config1", "sampler", "eval", "gmf", "bprfm", "bprfm_bn", "sgns", "neumf", "svdpp"],
                     help="N = 1 only: config4 is the driver's metric; config3 (L2-resident ml-20m shape) and config2 "
                          "(funk-SVD) are secondary lines kept under profiles/")
     ap.add_argument("--eval-users", type=int, default=16384)
@@ -929,6 +1001,8 @@ def main():
         return run_bprfm(args)
     if args.workload == "config2":
         return run_mf(args)
+    if args.workload == "svdpp":
+        return run_svdpp(args)
     if args.workload == "sampler":
         return run_sampler(args)
     if args.workload == "eval":

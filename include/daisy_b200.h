@@ -295,6 +295,35 @@ DAISY_API int daisy_mf_predict(daisy_handle_t h, const double *pu, const double 
                      const int32_t *users, const int32_t *items, int64_t n, int with_bias, double mu,
                      double *est, daisy_stream_t stream);
 
+/* ---- SVD++: SVDpp.fit / SVDpp.predict, util/matrix_factorization.pyx:193-288 -----------
+ * EXPERIMENTAL: compiled for sm_100a, not yet run on a GPU (csrc/svdpp.cu has the status and the plan).
+ * daisy_svdpp_fit runs `n_epochs` passes over the n ratings IN THE GIVEN ORDER with the reference's strictly sequential
+ * semantics (loop body :238-263): every rating of user u updates bu[u], bi[i], pu[u], qi[i] and the implicit-feedback
+ * row yj[j] of EVERY item j in the user's history.  Tables are float64 like the reference's (pu [U,dim], qi [I,dim],
+ * yj [I,dim], bu [U], bi [I]; U, I, dim are the handle's); users/items int32, ratings float64, all on the device.
+ * The histories (`ur`, :231-234) come in CSR form: ur_ptr int64 [U+1], ur_idx int32 [ur_ptr[U]] = per user the items
+ * of its ratings in frame order.  ur_mult (int32, parallel to ur_idx, may be NULL when no history holds an item twice):
+ * the number of occurrences of ur_idx[k] in its user's list if k is the first occurrence, else 0 -- a repeated
+ * (user, item) rating makes the reference apply that row's update twice per rating, and so does the kernel.
+ * sse_out (device double[n_epochs], may be NULL) receives the sum of squared errors of each epoch.  Out-of-range ids
+ * raise DAISY_EINDEX at daisy_check and leave the tables untouched. */
+typedef struct {
+    double lr_bu, lr_bi, lr_pu, lr_qi, lr_yj;
+    double reg_bu, reg_bi, reg_pu, reg_qi, reg_yj;
+    double global_mean;
+} daisy_svdpp_params;
+
+DAISY_API int daisy_svdpp_fit(daisy_handle_t h, double *pu, double *qi, double *yj, double *bu, double *bi,
+                    const int32_t *users, const int32_t *items, const double *ratings, int64_t n, int n_epochs,
+                    const int64_t *ur_ptr, const int32_t *ur_idx, const int32_t *ur_mult,
+                    const daisy_svdpp_params *prm, double *sse_out, daisy_stream_t stream);
+
+/* The user side of SVDpp.predict (:281-286): z_out[u] = pu[u] + sum_{j in Iu} yj[j] / sqrt|Iu| for every user
+ * (a user without history keeps pu[u]); est = global_mean + bu[u] + bi[i] + <qi[i], z[u]> is then
+ * daisy_mf_predict(z, qi, bu, bi, ..., with_bias = 1, mu = global_mean). */
+DAISY_API int daisy_svdpp_user_factors(daisy_handle_t h, const double *pu, const double *yj, const int64_t *ur_ptr,
+                             const int32_t *ur_idx, double *z_out, daisy_stream_t stream);
+
 /* ---- BPR-FM at the reference script's defaults: batch norm + dropout ---------------------
  * EXPERIMENTAL: compiled for sm_100a, not yet run on a GPU (csrc/fmbn.cu has the status); the verified BPR-FM path is
  * daisy_bprfm_adagrad_step (batch_norm off, dropout 0).

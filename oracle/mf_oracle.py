@@ -122,15 +122,17 @@ def user_item_lists(users, items, user_num):
     return np.cumsum(ptr), np.ascontiguousarray(np.asarray(items)[order], dtype=np.int32)
 
 
-def svdpp_fit(users, items, ratings, pu, qi, yj, n_epochs=20, lr_all=.007, reg_all=.02):
-    """SVDpp.fit (util/matrix_factorization.pyx:193-271).  Returns dict(pu, qi, yj, bu, bi, global_mean, sse)."""
+def svdpp_fit(users, items, ratings, pu, qi, yj, n_epochs=20, lr_all=.007, reg_all=.02, lists=None, global_mean=None):
+    """SVDpp.fit (util/matrix_factorization.pyx:193-271).  Returns dict(pu, qi, yj, bu, bi, global_mean, sse).
+    ``lists`` = (ptr, idx) and ``global_mean`` of a larger frame let a bounded PREFIX of that frame's ratings be walked with
+    the full frame's histories (bench.py's cpu_baseline sample); by default both come from the given ratings."""
     users = np.ascontiguousarray(users, dtype=np.int32)
     items = np.ascontiguousarray(items, dtype=np.int32)
     ratings = np.ascontiguousarray(ratings, dtype=np.float64)
     pu, qi, yj = (np.array(a, dtype=np.float64, order="C") for a in (pu, qi, yj))
     bu, bi = np.zeros(pu.shape[0]), np.zeros(qi.shape[0])
-    ptr, idx = user_item_lists(users, items, pu.shape[0])
-    mu = float(ratings.mean())
+    ptr, idx = user_item_lists(users, items, pu.shape[0]) if lists is None else lists
+    mu = float(ratings.mean()) if global_mean is None else float(global_mean)
     scratch = np.zeros(pu.shape[1])
     sse = lib().mf_oracle_svdpp_fit(len(ratings), _ip(users), _ip(items), _dp(ratings), pu.shape[1], n_epochs,
                                     lr_all, lr_all, lr_all, lr_all, lr_all, reg_all, reg_all, reg_all, reg_all, reg_all, mu,

@@ -14,6 +14,8 @@ Public surface (mirrors the reference):
   (the script's default model); EXPERIMENTAL, compiled but not yet run on a GPU (ncf_mlp.py)
 * ``Item2Vec`` / ``SGNS`` + ``SGNSAdam``                        -- Item2VecRecommender.py:37-97, 266-277 (N4); EXPERIMENTAL,
   compiled but not yet run on a GPU (item2vec.py)
+* ``SVDpp`` (ctor kwargs, ``fit``, ``predict``)                -- util/matrix_factorization.pyx:169-288 (N4); EXPERIMENTAL,
+  compiled but not yet run on a GPU (svdpp.py)
 
 All compute goes through the C-ABI library ``libdaisy_b200.so`` (``include/daisy_b200.h``);
 there is no CPU fallback: using any of the above without the built library or without
@@ -27,7 +29,7 @@ __all__ = ["BPR", "BPRMFRecommender", "metric_eval", "SVD", "RSVD", "MFRecommend
 _LAZY = {
     "BPR": ".bpr", "BPRMFRecommender": ".bpr", "BPRSGD": ".bpr", "BPRAdam": ".bpr",
     "metric_eval": ".metrics", "topk_candidates": ".metrics", "topk_full": ".metrics", "rank_metrics": ".metrics", "final_kpi": ".metrics",
-    "SVD": ".mf", "RSVD": ".mf", "MFRecommender": ".mf",
+    "SVD": ".mf", "RSVD": ".mf", "MFRecommender": ".mf", "SVDpp": ".svdpp",
     "NCF": ".ncf", "GMFAdam": ".ncf", "BPRFM": ".bprfm", "FMAdagrad": ".bprfm", "BPRFMBN": ".bprfm_bn", "FMBNAdagrad": ".bprfm_bn",
     "NeuMF": ".ncf_mlp", "NeuMFAdam": ".ncf_mlp", "Item2Vec": ".item2vec", "SGNS": ".item2vec", "SGNSAdam": ".item2vec",
     "TripleSampler": ".sampler", "DeviceTripleSampler": ".sampler",

@@ -25,6 +25,13 @@ class MFParams(ctypes.Structure):
                 ("reg2", c_f64), ("global_mean", c_f64)]
 
 
+class SVDppParams(ctypes.Structure):
+    """daisy_svdpp_params"""
+    _fields_ = [("lr_bu", c_f64), ("lr_bi", c_f64), ("lr_pu", c_f64), ("lr_qi", c_f64), ("lr_yj", c_f64),
+                ("reg_bu", c_f64), ("reg_bi", c_f64), ("reg_pu", c_f64), ("reg_qi", c_f64), ("reg_yj", c_f64),
+                ("global_mean", c_f64)]
+
+
 class FMBNParams(ctypes.Structure):
     """daisy_fmbn_params"""
     _fields_ = [("E", c_vp), ("bias", c_vp), ("accE", c_vp), ("accb", c_vp), ("gamma", c_vp), ("beta", c_vp),
@@ -101,6 +108,9 @@ SIGNATURES = {
     "daisy_mf_fit": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, ctypes.POINTER(MFParams),
                      c_vp, c_vp],
     "daisy_mf_predict": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_f64, c_vp, c_vp],
+    "daisy_svdpp_fit": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp,
+                        ctypes.POINTER(SVDppParams), c_vp, c_vp],
+    "daisy_svdpp_user_factors": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "daisy_fmbn_scratch_bytes": [c_i64, c_i32, ctypes.POINTER(c_i64)],
     "daisy_fmbn_step": [c_vp, ctypes.POINTER(FMBNParams), c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp],
     "daisy_fmbn_forward": [c_vp, ctypes.POINTER(FMBNParams), c_vp, c_i64, c_vp, c_vp, c_vp],

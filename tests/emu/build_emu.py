@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE ONLY: compile plain-CUDA product translation units (csrc/fmbn.cu, sgns.cu, neumf.cu, bpr_eval.cu,
+"""TEST INFRASTRUCTURE ONLY: compile plain-CUDA product translation units (csrc/fmbn.cu, sgns.cu, neumf.cu, svdpp.cu, bpr_eval.cu,
 sampler.cu, topk_full.cu) for the HOST against the
 emulation shim of tests/emu/emu.h, so that kernels which have not run on a GPU yet can at least be executed and checked
 against the oracle.  DAISY_EMU_SANITIZE=1 builds with AddressSanitizer + UBSan (run pytest with LD_PRELOAD=$(gcc -print-file-name=libasan.so)
@@ -65,5 +65,5 @@ def build(unit):
 
 
 if __name__ == "__main__":
-    for u in ("fmbn", "sgns", "neumf", "bpr_eval", "sampler", "topk_full"):
+    for u in ("fmbn", "sgns", "neumf", "svdpp", "bpr_eval", "sampler", "topk_full"):
         print(build(u))

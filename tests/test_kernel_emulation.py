@@ -1,5 +1,5 @@
-"""CPU execution of kernels that have NOT run on a GPU yet (csrc/fmbn.cu, csrc/sgns.cu, csrc/neumf.cu; SURVEY.md section 8f
-rows N3 / N4).
+"""CPU execution of kernels that have NOT run on a GPU yet (csrc/fmbn.cu, csrc/sgns.cu, csrc/neumf.cu, csrc/svdpp.cu;
+SURVEY.md section 8f rows N3 / N4).
 
 tests/emu compiles the product's own translation units for the host against a functional emulation of the CUDA
 execution model (OS threads, block / warp barriers, shuffle exchange buffers) and this file drives the SAME extern "C"
@@ -310,6 +310,97 @@ def test_neumf_kernels_emulated_match_the_oracle_and_flag_bad_ids():
     u[4] = U
     m.step(u, i, y)
     assert m.L.emu_err_flag(m.h) == 1 and m.L.emu_err_pos(m.h) == 4
+
+
+# ------------------------------------------------------------------------------------------------ SVD++
+class SvdppEmu:
+    """daisy_svdpp_fit / daisy_svdpp_user_factors of csrc/svdpp.cu on host threads, fed by the product's own host logic
+    (recommend_lib_b200.svdpp.user_histories)."""
+
+    def __init__(self, U, I, D):
+        self.L = _load("svdpp")
+        self.L.daisy_svdpp_fit.argtypes = [c_vp] * 9 + [c_i64, c_i32, c_vp, c_vp, c_vp, ctypes.POINTER(_lib.SVDppParams), c_vp, c_vp]
+        self.L.daisy_svdpp_user_factors.argtypes = [c_vp] * 7
+        self.h = _dims_handle(self.L, U, I, D)
+        self.U, self.I, self.D = U, I, D
+
+    def fit(self, users, items, ratings, pu, qi, yj, epochs, lr=.007, reg=.02, mu=None):
+        from recommend_lib_b200.svdpp import user_histories
+        users = np.ascontiguousarray(users, dtype=np.int32)
+        items = np.ascontiguousarray(items, dtype=np.int32)
+        ratings = np.ascontiguousarray(ratings, dtype=np.float64)
+        ptr, idx, mult = user_histories(np.clip(users, 0, self.U - 1), items, self.U)
+        self.ptr, self.idx, self.mult = ptr, idx, mult
+        o = dict(pu=np.array(pu, dtype=np.float64), qi=np.array(qi, dtype=np.float64), yj=np.array(yj, dtype=np.float64),
+                 bu=np.zeros(self.U), bi=np.zeros(self.I), sse=np.zeros(max(epochs, 1)))
+        prm = _lib.SVDppParams(lr, lr, lr, lr, lr, reg, reg, reg, reg, reg, float(ratings.mean() if mu is None else mu))
+        rc = self.L.daisy_svdpp_fit(self.h, _p(o["pu"]), _p(o["qi"]), _p(o["yj"]), _p(o["bu"]), _p(o["bi"]), _p(users), _p(items),
+                                    _p(ratings), len(ratings), epochs, _p(ptr), _p(idx), _p(mult), ctypes.byref(prm),
+                                    _p(o["sse"]), None)
+        assert rc == 0, self.L.emu_last_error()
+        return o
+
+    def user_factors(self, pu, yj):
+        z = np.zeros_like(pu)
+        assert self.L.daisy_svdpp_user_factors(self.h, _p(pu), _p(yj), _p(self.ptr), _p(self.idx), _p(z), None) == 0
+        return z
+
+
+def test_svdpp_kernels_emulated_match_the_reference_golden_run(golden, monkeypatch):
+    """tests/golden/svdpp_small.npz: 3 epochs of the reference's own compiled SVDpp (repeated (user, item) ratings
+    included).  float64, sums re-associated over warps / lanes -> 1e-9 like the funk-SVD tests."""
+    monkeypatch.setenv("DAISY_SVDPP_THREADS", "64")                 # 2 warps: histories longer than the warp count
+    g = golden("svdpp_small.npz")
+    U, I, D, E = int(g["U"]), int(g["I"]), int(g["D"]), int(g["E"])
+    e = SvdppEmu(U, I, D)
+    o = e.fit(g["users"], g["items"], g["ratings"], g["pu0"], g["qi0"], g["yj0"], E)
+    assert e.mult is not None and e.mult.max() >= 2                 # the fixture does repeat a (user, item) pair
+    for k in ("pu", "qi", "yj", "bu", "bi"):
+        assert np.allclose(o[k], g[k], rtol=1e-9, atol=1e-12), k
+    z = e.user_factors(o["pu"], o["yj"])
+    pred = float(g["mu"]) + o["bu"][g["users"][:15]] + o["bi"][g["items"][:15]] + \
+        np.einsum("nd,nd->n", o["qi"][g["items"][:15]], z[g["users"][:15]])
+    assert np.allclose(pred, g["pred"], rtol=1e-9, atol=1e-12)
+    assert e.L.emu_err_flag(e.h) == 0
+
+
+@pytest.mark.parametrize("U,I,D,n,E,threads", [(17, 23, 44, 260, 2, 64),      # D > 32 (two values per lane), ragged
+                                               (9, 12, 130, 90, 1, 160),      # D > 128: five values per lane slot, 5 warps
+                                               (1, 40, 8, 2100, 1, 64)])      # one history longer than the shared-memory list
+def test_svdpp_kernels_emulated_match_the_oracle_and_flag_bad_ids(monkeypatch, U, I, D, n, E, threads):
+    from oracle import mf_oracle
+    monkeypatch.setenv("DAISY_SVDPP_THREADS", str(threads))
+    rng = np.random.default_rng(U * 1000 + D)
+    users = rng.integers(0, max(U - 2, 1), n)                       # the last users have no rating at all
+    items = rng.integers(0, I, n)
+    users[5], items[5] = users[4], items[4]                         # a repeated (user, item) pair for sure
+    ratings = rng.integers(1, 6, n).astype(np.float64)
+    pu0, qi0, yj0 = (rng.normal(0, .1, s) for s in ((U, D), (I, D), (I, D)))
+    ref = mf_oracle.svdpp_fit(users, items, ratings, pu0, qi0, yj0, n_epochs=E)
+    e = SvdppEmu(U, I, D)
+    o = e.fit(users, items, ratings, pu0, qi0, yj0, E)
+    rptr, ridx = mf_oracle.user_item_lists(users, items, U)
+    assert np.array_equal(e.ptr, rptr) and np.array_equal(e.idx, ridx)
+    for k in ("pu", "qi", "yj", "bu", "bi"):
+        assert np.allclose(o[k], ref[k], rtol=1e-9, atol=1e-12), k
+    assert np.isclose(o["sse"][E - 1], ref["sse"], rtol=1e-9)
+    z = e.user_factors(o["pu"], o["yj"])
+    for u in (0, U - 1):
+        Iu = ridx[rptr[u]:rptr[u + 1]]
+        want = o["pu"][u] + (o["yj"][Iu].sum(0) / np.sqrt(len(Iu)) if len(Iu) else 0)
+        assert np.allclose(z[u], want, rtol=1e-12, atol=1e-14)
+    assert e.L.emu_err_flag(e.h) == 0
+    # an out-of-range item: flagged, nothing written
+    bad = items.copy()
+    bad[n // 2] = I
+    e2 = SvdppEmu(U, I, D)
+    o2 = e2.fit(users, np.minimum(bad, I - 1), ratings, pu0, qi0, yj0, 0)      # lists built from valid ids
+    prm = _lib.SVDppParams(.007, .007, .007, .007, .007, .02, .02, .02, .02, .02, float(ratings.mean()))
+    bad32, u32 = bad.astype(np.int32), users.astype(np.int32)
+    assert e2.L.daisy_svdpp_fit(e2.h, _p(o2["pu"]), _p(o2["qi"]), _p(o2["yj"]), _p(o2["bu"]), _p(o2["bi"]), _p(u32), _p(bad32),
+                                _p(ratings), n, 1, _p(e2.ptr), _p(e2.idx), _p(e2.mult), ctypes.byref(prm), None, None) == 0
+    assert e2.L.emu_err_flag(e2.h) & 2 and e2.L.emu_err_pos(e2.h) == n // 2
+    assert np.array_equal(o2["pu"], pu0) and np.array_equal(o2["yj"], yj0) and not o2["bu"].any()
 
 
 # ------------------------------------------------------------------------------------------------ units that DO run on the GPU

@@ -23,7 +23,9 @@ if [ "$mode" = one ]; then
   tail -5 gpurun_out/r02_experimental_sgns.log
   DAISY_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_neumf_gpu.py -m gpu -q -x 2>&1 | tail -30 > gpurun_out/r02_experimental_neumf.log
   tail -5 gpurun_out/r02_experimental_neumf.log
-  for w in bprfm_bn sgns neumf; do timeout 300 python bench.py --workload $w > gpurun_out/r02_bench_$w.json 2> gpurun_out/r02_bench_$w.err; cut -c1-220 gpurun_out/r02_bench_$w.json; done
+  DAISY_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_svdpp_gpu.py -m gpu -q -x 2>&1 | tail -30 > gpurun_out/r02_experimental_svdpp.log
+  tail -5 gpurun_out/r02_experimental_svdpp.log
+  for w in bprfm_bn sgns neumf svdpp; do timeout 300 python bench.py --workload $w > gpurun_out/r02_bench_$w.json 2> gpurun_out/r02_bench_$w.err; cut -c1-220 gpurun_out/r02_bench_$w.json; done
 else
   N=${2:-8}
   run() {  # $1 = tag, rest = environment
