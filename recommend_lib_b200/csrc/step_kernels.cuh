@@ -514,6 +514,20 @@ __device__ __forceinline__ void seg_window(long long w, int tbl, const float *__
     bool act[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
+#ifdef DAISY_SEG_PREFETCH  // experiment knob: the warp walks its rows one after the other, each a DRAM round trip; ask L2 for the
+    // window's staged contributions (they sit at their sorted positions: one contiguous run) and table rows up front
+    {
+        const bool in_multi = valid && (prev == key || (next == key && p + 1 < n));
+        if (in_multi) {
+            const char *sp = reinterpret_cast<const char *>(stage + (size_t)p * D4 * 4);
+            for (int o = 0; o < D4 * 16; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + o));
+        }
+        if (multi && (tbl == 0 || Opt::kNeedOldItem)) {
+            const char *tp = reinterpret_cast<const char *>(table + (size_t)key * D4 * 4);
+            for (int o = 0; o < D4 * 16; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + o));
+        }
+    }
+#endif
 
     while (todo) {
         const int b = __ffs(todo) - 1;
@@ -1192,7 +1206,10 @@ static int launch_small_book(daisy_ctx *h, cudaStream_t bs, const int32_t *tripl
 //        `long_len` contributions that start in its window
 //   the last block                  the loss reduction
 // ------------------------------------------------------------------------------------------------
-#ifdef DAISY_SEG_MIN_BLOCKS  // experiment knob (compile time): 2 caps k_seg_all at 128 registers -> two blocks per SM
+#if defined(DAISY_SEG_MIN_BLOCKS_V1)  // experiment knob: only the one-float4-per-lane instantiation (D <= 128, what config 4 runs;
+// 52 registers = 4 blocks per SM by default): 5 / 6 / 8 blocks per SM cap it at 48 / 40 / 32 registers (4 / 16 / 24 bytes spilled)
+#define DAISY_SEG_BOUNDS __launch_bounds__(256, (V == 1 ? DAISY_SEG_MIN_BLOCKS_V1 : 1))
+#elif defined(DAISY_SEG_MIN_BLOCKS)  // experiment knob (compile time): 2 caps k_seg_all at 128 registers -> two blocks per SM
 #define DAISY_SEG_BOUNDS __launch_bounds__(256, DAISY_SEG_MIN_BLOCKS)
 #else
 #define DAISY_SEG_BOUNDS __launch_bounds__(256)

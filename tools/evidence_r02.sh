@@ -8,14 +8,16 @@ if [ "$mode" = one ]; then
   python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1
   python bench.py > gpurun_out/r02_bench_n1_default.json 2> gpurun_out/r02_bench_n1_default.err
   tail -3 gpurun_out/r02_gpu_tests.log; tail -1 gpurun_out/r02_smoke.log; cut -c1-300 gpurun_out/r02_bench_n1_default.json
-  # k_seg_all at two blocks per SM (lead 3).  Build the variant HERE before the call:
-  #   DAISY_LIB_VARIANT=seg2 DAISY_NVCC_EXTRA="-DDAISY_SEG_MIN_BLOCKS=2 -DDAISY_SEG_COMBINE_TILE=4" python -m recommend_lib_b200.build
-  if [ -f recommend_lib_b200/libdaisy_b200_seg2.so ]; then
-    DAISY_LIB_VARIANT=seg2 python -m pytest tests/test_bpr_gpu.py -m gpu -q 2>&1 | tail -3 > gpurun_out/r02_gpu_tests_seg2.log
-    DAISY_LIB_VARIANT=seg2 python bench.py --no-cpu-baseline --phases > gpurun_out/r02_bench_n1_seg2.json 2>/dev/null
-    python bench.py --no-cpu-baseline --phases > gpurun_out/r02_bench_n1_phases.json 2>/dev/null
-    tail -1 gpurun_out/r02_gpu_tests_seg2.log; cut -c1-200 gpurun_out/r02_bench_n1_seg2.json; cut -c1-200 gpurun_out/r02_bench_n1_phases.json
-  fi
+  # k_seg_all variants (lead 3).  Build them HERE before the call: bash tools/build_variants.sh
+  python bench.py --no-cpu-baseline --phases > gpurun_out/r02_bench_n1_phases.json 2>/dev/null
+  cut -c1-200 gpurun_out/r02_bench_n1_phases.json
+  for v in segmb6 segmb8 segpf segpf8; do
+    if [ -f recommend_lib_b200/libdaisy_b200_$v.so ]; then
+      DAISY_LIB_VARIANT=$v python -m pytest tests/test_bpr_gpu.py -m gpu -q 2>&1 | tail -3 > gpurun_out/r02_gpu_tests_$v.log
+      DAISY_LIB_VARIANT=$v python bench.py --no-cpu-baseline --phases > gpurun_out/r02_bench_n1_$v.json 2>/dev/null
+      tail -1 gpurun_out/r02_gpu_tests_$v.log; cut -c1-200 gpurun_out/r02_bench_n1_$v.json
+    fi
+  done
   # experimental kernels that have never run on a GPU (last: a crash here must not cost the evidence above)
   DAISY_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_bprfm_bn_gpu.py -m gpu -q -x 2>&1 | tail -30 > gpurun_out/r02_experimental_fmbn.log
   tail -5 gpurun_out/r02_experimental_fmbn.log
@@ -26,6 +28,8 @@ if [ "$mode" = one ]; then
   DAISY_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_svdpp_gpu.py -m gpu -q -x 2>&1 | tail -30 > gpurun_out/r02_experimental_svdpp.log
   tail -5 gpurun_out/r02_experimental_svdpp.log
   for w in bprfm_bn sgns neumf svdpp; do timeout 300 python bench.py --workload $w > gpurun_out/r02_bench_$w.json 2> gpurun_out/r02_bench_$w.err; cut -c1-220 gpurun_out/r02_bench_$w.json; done
+  # SVD++: block size of the one-block kernel (barrier cost against rows in flight)
+  for t in 128 256 512; do DAISY_SVDPP_THREADS=$t timeout 300 python bench.py --workload svdpp --steps 1 > gpurun_out/r02_bench_svdpp_t$t.json 2>/dev/null; cut -c1-120 gpurun_out/r02_bench_svdpp_t$t.json; done
 else
   N=${2:-8}
   run() {  # $1 = tag, rest = environment
