@@ -33,6 +33,7 @@ extern "C" daisy_ctx *emu_handle_dims(long long U, long long I, int D) {
     return h;
 }
 extern "C" int emu_err_flag(daisy_ctx *h) { return h->err[0]; }
+extern "C" int emu_check(daisy_ctx *h, void *) { return h->err[0] ? DAISY_EINDEX : DAISY_OK; }   // api.cu's daisy_check, minus the stream
 extern "C" int emu_err_pos(daisy_ctx *h) { return h->err[1]; }
 '''
 

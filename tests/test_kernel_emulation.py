@@ -403,6 +403,62 @@ def test_svdpp_kernels_emulated_match_the_oracle_and_flag_bad_ids(monkeypatch, U
     assert np.array_equal(o2["pu"], pu0) and np.array_equal(o2["yj"], yj0) and not o2["bu"].any()
 
 
+def test_svdpp_drop_in_class_host_logic_over_the_emulated_kernels(golden, monkeypatch):
+    """recommend_lib_b200.svdpp.SVDpp end to end (frame -> histories -> daisy_svdpp_fit -> attributes, predict, ur,
+    user_factors) with the library handle swapped for the host build of csrc/svdpp.cu: the Python around the C ABI is
+    exercised before it ever costs GPU time.  Only test scaffolding is patched; the product has no such switch."""
+    import torch
+    pd = pytest.importorskip("pandas")
+    from recommend_lib_b200 import svdpp as mod
+    L = _load("svdpp")
+    L.emu_check.argtypes = [c_vp, c_vp]
+
+    class EmuHandle:
+        def __init__(self, device_index, user_num, item_num, dim, max_batch, flags=0):
+            self.L = L
+            self.ptr = _dims_handle(L, user_num, item_num, dim)
+            L.daisy_check = L.emu_check
+
+        def close(self):
+            pass
+
+    monkeypatch.setenv("DAISY_SVDPP_THREADS", "64")
+    monkeypatch.setattr(mod._lib, "Handle", EmuHandle)
+    monkeypatch.setattr(mod._lib, "require_cuda", lambda: torch)
+    monkeypatch.setattr(mod._lib, "stream_ptr", lambda t, d: None)
+    L.daisy_svdpp_fit.argtypes = None       # the class passes c_void_p / byref objects itself
+    L.daisy_svdpp_user_factors.argtypes = None
+    g = golden("svdpp_small.npz")
+    U, I, D, E = int(g["U"]), int(g["I"]), int(g["D"]), int(g["E"])
+    a = mod.SVDpp(U, I, n_factors=D, n_epochs=E, verbose=False, device="cpu:0")
+    frame = pd.DataFrame({"user": g["users"], "item": g["items"], "rating": g["ratings"]})
+    state = np.random.get_state()
+    np.random.seed(3)
+    a.fit(frame)                                                   # draws pu, qi, yj from numpy's global RNG like the reference
+    np.random.seed(3)
+    pu0, qi0, yj0 = (np.random.normal(0, .1, size=s) for s in ((U, D), (I, D), (I, D)))
+    np.random.set_state(state)
+    from oracle import mf_oracle
+    ref = mf_oracle.svdpp_fit(g["users"], g["items"], g["ratings"], pu0, qi0, yj0, n_epochs=E)
+    for k in ("pu", "qi", "yj", "bu", "bi"):
+        assert np.allclose(getattr(a, k), ref[k], rtol=1e-9, atol=1e-12), k
+    assert np.isclose(a.global_mean, ref["global_mean"]) and np.isclose(a.sse_[E - 1], ref["sse"], rtol=1e-9)
+    for u, i in zip(g["users"][:10], g["items"][:10]):
+        assert np.isclose(a.predict(int(u), int(i)), mf_oracle.svdpp_predict(int(u), int(i), ref), rtol=1e-9)
+    u0 = int(g["users"][0])
+    sel = g["users"] == u0
+    assert a.ur[u0] == list(zip(g["items"][sel].tolist(), g["ratings"][sel].tolist()))      # the reference's self.ur
+    z = a.user_factors()
+    Iu = [j for j, _ in a.ur[u0]]
+    assert np.allclose(z[u0], a.pu[u0] + a.yj[Iu].sum(0) / np.sqrt(len(Iu)), rtol=1e-12)
+    with pytest.raises(ValueError, match="Invalid user code"):
+        a.predict(U, 0)
+    with pytest.raises(ValueError, match="Invalid item code"):
+        a.fit(pd.DataFrame({"user": [0, 1], "item": [0, I], "rating": [3.0, 4.0]}))
+    with pytest.raises(ValueError, match="Invalid user code"):
+        a.fit(pd.DataFrame({"user": [0, U], "item": [0, 1], "rating": [3.0, 4.0]}))
+
+
 # ------------------------------------------------------------------------------------------------ units that DO run on the GPU
 # csrc/bpr_eval.cu (SURVEY 8a rows A2 / A8) and csrc/sampler.cu (8f row N1) are GPU-verified product code
 # (tests/test_bpr_gpu.py, tests/test_sampler_gpu.py).  They are plain CUDA, so the same emulation gives them what the
