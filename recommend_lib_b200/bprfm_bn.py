@@ -164,7 +164,7 @@ class FMBNAdagrad:
     def step(self, features_i, feature_values_i=None, features_j=None, feature_values_j=None, mask_i=None, mask_j=None):
         m = self.model
         dev = m._device()
-        if features_j is None and torch.is_tensor(features_i) and features_i.dtype == torch.int32 and features_i.is_cuda:
+        if features_j is None and torch.is_tensor(features_i) and features_i.dtype == torch.int32 and features_i.device == dev:
             tri = features_i                          # packed (user, item_i, item_j) int32 [B,3], item ids relative
             if tri.dim() != 2 or tri.shape[1] != 3 or not tri.is_contiguous():
                 raise ValueError("packed triples must be a contiguous int32 [B, 3] device tensor")

@@ -426,8 +426,8 @@ def test_svdpp_drop_in_class_host_logic_over_the_emulated_kernels(golden, monkey
     monkeypatch.setattr(mod._lib, "Handle", EmuHandle)
     monkeypatch.setattr(mod._lib, "require_cuda", lambda: torch)
     monkeypatch.setattr(mod._lib, "stream_ptr", lambda t, d: None)
-    L.daisy_svdpp_fit.argtypes = None       # the class passes c_void_p / byref objects itself
-    L.daisy_svdpp_user_factors.argtypes = None
+    for name in ("daisy_svdpp_fit", "daisy_svdpp_user_factors"):      # what _lib.load() does for the real library
+        getattr(L, name).argtypes = _lib.SIGNATURES[name]
     g = golden("svdpp_small.npz")
     U, I, D, E = int(g["U"]), int(g["I"]), int(g["D"]), int(g["E"])
     a = mod.SVDpp(U, I, n_factors=D, n_epochs=E, verbose=False, device="cpu:0")
@@ -560,3 +560,116 @@ def test_full_catalogue_topk_emulated(monkeypatch, I, D, N, K, paths):
             assert set(np.nonzero(r > kth + 1e-3)[0].tolist()) <= set(got.tolist()) and r[got].min() >= kth - 1e-3
     if len(paths) == 2:
         assert np.array_equal(out["exact"][0], out["filter"][0]) and np.array_equal(out["exact"][1], out["filter"][1])
+
+
+# ------------------------------------------------------------------------------------------------ the gated GPU tests themselves
+# The functions of tests/test_*_gpu.py of the four experimental units are called here directly (their skip marks only act
+# under collection) with the product's library handle swapped for the host build of the unit and `dev` = the CPU: the
+# Python around the C ABI -- module structure, argument marshalling, scratch sizing, error mapping -- and the GPU tests'
+# own assertions run before they cost GPU time.  Only small parameter sets (every CUDA thread is an OS thread).
+class _EmuProduct:
+    """Swap recommend_lib_b200._lib's device plumbing for the host build of one unit (test scaffolding only)."""
+
+    def __init__(self, monkeypatch, unit):
+        import torch
+        from recommend_lib_b200 import _lib as plib
+        L = _load(unit)
+        L.emu_check.argtypes = [c_vp, c_vp]
+        L.daisy_check = L.emu_check
+        L.daisy_launch_count = lambda *a: 0
+        for name, argtypes in plib.SIGNATURES.items():      # what _lib.load() does for the real library
+            if name != "daisy_check" and hasattr(L, name):
+                getattr(L, name).argtypes = argtypes
+                getattr(L, name).restype = ctypes.c_int
+
+        class EmuHandle:
+            def __init__(self, device_index, user_num, item_num, dim, max_batch, flags=0):
+                self.L, self.device_index = L, device_index
+                self.ptr = _dims_handle(L, user_num, item_num, dim)
+
+            def close(self):
+                pass
+
+        real_empty = torch.empty
+
+        def aligned_empty(*size, **kw):         # scratch buffers must be 256-byte aligned (CUDA allocations are)
+            if kw.get("dtype") is torch.uint8 and len(size) == 1 and isinstance(size[0], int):
+                raw = real_empty(size[0] + 256, **kw)
+                off = (-raw.data_ptr()) % 256
+                out = raw[off:off + size[0]]
+                out._keepalive = raw
+                return out
+            return real_empty(*size, **kw)
+
+        monkeypatch.setattr(plib, "Handle", EmuHandle)
+        monkeypatch.setattr(plib, "require_cuda", lambda: torch)
+        monkeypatch.setattr(plib, "stream_ptr", lambda t, d: None)
+        monkeypatch.setattr(torch, "empty", aligned_empty)
+        monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+        self.L = L
+
+
+def test_sgns_gpu_tests_pass_over_the_emulated_kernels(golden, monkeypatch):
+    import torch
+    import test_sgns_gpu as G
+    from recommend_lib_b200 import item2vec
+    _EmuProduct(monkeypatch, "sgns")
+    monkeypatch.setattr(item2vec.SGNSAdam, "_device", lambda self: self.sgns.embedding.ivectors.weight.device)
+    cpu = torch.device("cpu")
+    G.test_sgns_golden_five_steps(golden, cpu, "u")
+    G.test_sgns_against_oracle(cpu, 64, 36, 7, 1, 0)
+    G.test_sgns_reports_bad_ids(cpu)
+    if os.environ.get("DAISY_EMU_FULL") == "1":                  # minutes on host threads
+        G.test_sgns_golden_five_steps(golden, cpu, "w")
+        G.test_sgns_against_oracle(cpu, 50, 16, 33, 3, 2)
+        G.test_sgns_is_bit_reproducible_and_draws_its_own_negatives(cpu)
+
+
+def test_fmbn_gpu_tests_pass_over_the_emulated_kernels(golden, monkeypatch):
+    import torch
+    import test_bprfm_bn_gpu as G
+    from recommend_lib_b200 import bprfm_bn
+    _EmuProduct(monkeypatch, "fmbn")
+    monkeypatch.setattr(bprfm_bn.BPRFMBN, "_device", lambda self: self.embeddings.weight.device)
+    cpu = torch.device("cpu")
+    G.test_fmbn_golden_four_steps(golden, cpu, "cond", 1e-5, 1e-5)
+    G.test_fmbn_against_oracle(cpu, 50, 40, 8, 96, 0.5)
+    G.test_fmbn_reports_bad_ids_and_refuses_training_mode_forward(cpu)
+    if os.environ.get("DAISY_EMU_FULL") == "1":
+        G.test_fmbn_golden_four_steps(golden, cpu, "script", 1e-4, 2e-4)
+        G.test_fmbn_is_bit_reproducible_and_draws_its_own_masks(cpu)
+
+
+def test_neumf_gpu_tests_pass_over_the_emulated_kernels(golden, monkeypatch):
+    import torch
+    import test_neumf_gpu as G
+    from recommend_lib_b200 import ncf_mlp
+    _EmuProduct(monkeypatch, "neumf")
+    monkeypatch.setattr(ncf_mlp.NeuMF, "_device", lambda self: self.embed_user_MLP.weight.device)
+    cpu = torch.device("cpu")
+    G.test_neumf_golden_four_steps(golden, cpu, "mlp", "MLP")
+    if os.environ.get("DAISY_EMU_FULL") == "1":
+        G.test_neumf_against_oracle(cpu, "MLP", 50, 70, 8, 1, 33)
+        G.test_neumf_golden_four_steps(golden, cpu, "neumf", "NeuMF-end")
+        G.test_neumf_is_bit_reproducible_and_reports_bad_ids(cpu)
+
+
+def test_svdpp_gpu_tests_pass_over_the_emulated_kernels(golden, monkeypatch):
+    import torch
+    import test_svdpp_gpu as G
+    from recommend_lib_b200 import svdpp as mod
+    _EmuProduct(monkeypatch, "svdpp")
+    d = list(mod.SVDpp.__init__.__defaults__)
+    assert d[-1] == "cuda"
+    monkeypatch.setattr(mod.SVDpp.__init__, "__defaults__", tuple(d[:-1] + ["cpu:0"]))
+
+    def predict_many(user_num, item_num, n_factors, A, Bm, ba, bb, users, items, with_bias, mu, device):
+        u, i = np.asarray(users), np.asarray(items)          # daisy_mf_predict lives in csrc/mf.cu (GPU-verified, not emulable)
+        return mu + ba[u] + bb[i] + np.einsum("nd,nd->n", Bm[i], A[u])
+
+    monkeypatch.setattr(mod, "_predict_many", predict_many)
+    G.test_svdpp_golden(golden, monkeypatch, "64")
+    G.test_svdpp_fit_seeds_like_the_reference(golden)
+    monkeypatch.setenv("DAISY_SVDPP_THREADS", "64")
+    G.test_svdpp_against_c_oracle(5, 30, 20, 200, 1)
+    G.test_svdpp_bad_item_raises_and_leaves_no_partial_state()
