@@ -16,9 +16,10 @@
 //                      factor.  Per rating: (1) warps sum their rows of yj, fixed-order cross-warp sum in shared
 //                      memory -> u_impl; (2) dot product <qi, pu + u_impl> by warp tree + fixed-order sum over warps
 //                      -> err; (3) biases, pu, qi (old values, :254-258), then every yj row of the history with the
-//                      OLD qi (:261-263).  The header (u, i, r, list range) and the item list of rating t + 1 are
-//                      prefetched into shared memory while rating t computes, so the dependent-load chain
-//                      users[t] -> ur_ptr[u] -> ur_idx[k] -> yj row is off the critical path.
+//                      OLD qi (:261-263).  The header (u, i, r, list range) of rating t + 2, the item list and the
+//                      rating's own rows of rating t + 1 are fetched while rating t computes, so the dependent-load
+//                      chain users[t] -> ur_ptr[u] -> ur_idx[k] -> yj row is off the critical path: no load issued
+//                      between two barriers of a rating is consumed before the next one, except the history rows.
 //                      A history that holds an item m times (a repeated (user, item) rating) applies that row's update
 //                      m times in a row from the thread owning its first occurrence (`ur_mult`), which is what the
 //                      reference's `for j in Iu` does.
@@ -76,17 +77,16 @@ __global__ void k_svdpp_validate(const int32_t *users, const int32_t *items, lon
 }
 
 template <int M>
-__global__ void __launch_bounds__(1024, 1) k_svdpp_seq(SpArgs a) {
+__global__ void __launch_bounds__(M >= 8 ? 512 : 1024, 1) k_svdpp_seq(SpArgs a) {   // D > 128: 512 threads, 128 registers
     extern __shared__ double sp_smem[];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, W = blockDim.x >> 5, T = blockDim.x;
     const int D = a.D;
     double *red = sp_smem;                  // [W][D]  per-warp partial sums of the history rows
-    double *uimpl = red + (size_t)W * D;    // [D]
-    double *qold = uimpl + D;               // [D]     qi[i] before this rating's update
+    double *qold = red + (size_t)W * D;     // [D]     qi[i] before this rating's update
     double *wsum = qold + D;                // [32]    per-warp partial dot products
-    double *nb = wsum + 32;                 // [2][2]  bu[u], bi[i] of the current / next rating
-    SpHdr *hdr = reinterpret_cast<SpHdr *>(nb + 4);              // [2]
-    int *list = reinterpret_cast<int *>(hdr + 2);                // [2][SP_CAP] item ids of the current / next history
+    double *nb = wsum + 32;                 // [2]     bu[u], bi[i] of the current rating
+    SpHdr *hdr = reinterpret_cast<SpHdr *>(nb + 2);              // [3]     ring: current, next, the one being fetched
+    int *list = reinterpret_cast<int *>(hdr + 3);                // [2][SP_CAP] item ids of the current / next history
     int *mlist = list + 2 * SP_CAP;                              // [2][SP_CAP] their multiplicities
     if (a.err[0] != 0) return;              // an id failed validation: touch nothing (block-uniform)
     const long long total = a.n * (long long)a.epochs;
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(1024, 1) k_svdpp_seq(SpArgs a) {
     const daisy_svdpp_params prm = a.prm;
     const int Dw = (D + 31) >> 5;           // warps holding factors in the dot product
 
-    auto load_hdr = [&](long long t, SpHdr *h) {   // one thread; a dependent chain, hidden behind the previous rating
+    auto load_hdr = [&](long long t, SpHdr *h) {   // prologue only: one thread, two dependent loads
         const int u = a.users[t], i = a.items[t];
         h->u = u;
         h->i = i;
@@ -111,36 +111,52 @@ __global__ void __launch_bounds__(1024, 1) k_svdpp_seq(SpArgs a) {
         }
     };
 
-    if (tid == 0) load_hdr(0, &hdr[0]);
+    // Everything a rating needs besides the history rows travels ahead of it, so that no dependent load sits between two
+    // of its barriers: the header (u, i, r, list range) two ratings ahead -- ids fetched at the top of a rating, the list
+    // range after its second barrier, written to the ring before its third; the item list and the rating's own rows
+    // pu[u], qi[i], bu[u], bi[i] one rating ahead, the latter fetched by the very thread that wrote them last, so a
+    // rating that repeats the user or the item reads its predecessor's values by program order.
+    if (tid == 0) {
+        load_hdr(0, &hdr[0]);
+        if (total > 1) load_hdr(a.n > 1 ? 1 : 0, &hdr[1]);
+    }
     __syncthreads();
     copy_list(&hdr[0], 0);
-    // The rating's own rows pu[u], qi[i] and biases travel in registers / shared memory one rating ahead: they are
-    // fetched during the previous rating's history update, by the very thread that wrote them last, so a rating that
-    // repeats the user or the item reads its predecessor's values by program order.
-    double puf = 0.0, qif = 0.0;
+    double puf = 0.0, qif = 0.0, nbu = 0.0, nbi = 0.0;
     if (tid < D) {
         puf = a.pu[(size_t)hdr[0].u * D + tid];
         qif = a.qi[(size_t)hdr[0].i * D + tid];
     }
     if (tid == 0) {
-        nb[0] = a.bu[hdr[0].u];
-        nb[1] = a.bi[hdr[0].i];
+        nbu = a.bu[hdr[0].u];
+        nbi = a.bi[hdr[0].i];
     }
     __syncthreads();
 
-    double sse = 0.0;       // thread 0
-    long long t = 0;        // position inside the epoch
-    int epoch = 0;
+    double sse = 0.0;                       // thread 0
+    long long t = 0;                        // position of rating s inside its epoch
+    long long t2 = 2 % a.n;                 // ... of rating s + 2
+    int epoch = 0, c0 = 0;                  // c0 = s % 3
     for (long long s = 0; s < total; ++s) {
-        const int cur = (int)(s & 1);
-        const SpHdr *h = &hdr[cur];
+        const int c1 = c0 == 2 ? 0 : c0 + 1, c2 = c1 == 2 ? 0 : c1 + 1, lb = (int)(s & 1);
+        const SpHdr *h = &hdr[c0];
         const int u = h->u, i = h->i, nI = h->nI;
         const long long p0 = h->p0;
         const double r = h->r;
         const double sqrt_Iu = sqrt((double)nI);                                  // :241
-        const int *lst = list + cur * SP_CAP, *mls = mlist + cur * SP_CAP;
-        const double b_u = nb[2 * cur], b_i = nb[2 * cur + 1];
-        if (tid == T - 1 && s + 1 < total) load_hdr(t + 1 < a.n ? t + 1 : 0, &hdr[cur ^ 1]);
+        const int *lst = list + lb * SP_CAP, *mls = mlist + lb * SP_CAP;
+        if (tid == 0) {                     // fetched during the previous rating; read after the second barrier
+            nb[0] = nbu;
+            nb[1] = nbi;
+        }
+        const bool pf2 = tid == T - 1 && s + 2 < total;
+        int h2u = 0, h2i = 0;
+        double h2r = 0.0;
+        if (pf2) {                          // issued here, consumed after the second barrier
+            h2u = a.users[t2];
+            h2i = a.items[t2];
+            h2r = a.ratings[t2];
+        }
 
         // (1) implicit feedback: sum of the history rows (:243-246)
         double acc[M];
@@ -169,7 +185,6 @@ __global__ void __launch_bounds__(1024, 1) k_svdpp_seq(SpArgs a) {
             const int used = nI < W ? nI : W;
             for (int w2 = 0; w2 < used; ++w2) sum += red[(size_t)w2 * D + tid];
             ui = nI > 0 ? sum / sqrt_Iu : 0.0;
-            uimpl[tid] = ui;
             qold[tid] = qif;
             prod = qif * (puf + ui);
         }
@@ -178,11 +193,19 @@ __global__ void __launch_bounds__(1024, 1) k_svdpp_seq(SpArgs a) {
             if (lane == 0) wsum[w] = ws;
         }
         __syncthreads();
+        long long h2p0 = 0, h2p1 = 0;
+        if (pf2) {                          // second link of the header chain, consumed before the third barrier
+            h2p0 = a.ur_ptr[h2u];
+            h2p1 = a.ur_ptr[h2u + 1];
+        }
         double dot = 0.0;
         for (int w2 = 0; w2 < Dw; ++w2) dot += wsum[w2];
+        const double b_u = nb[0], b_i = nb[1];
         const double err = r - (prm.global_mean + b_u + b_i + dot);               // identical in every thread
 
         // (3) updates (:254-263)
+        const bool more = s + 1 < total;
+        const SpHdr *hn = &hdr[c1];         // the next rating (complete since the previous rating's third barrier)
         if (tid == 0) {
             sse += err * err;
             a.bu[u] = b_u + prm.lr_bu * (err - prm.reg_bu * b_u);
@@ -191,17 +214,17 @@ __global__ void __launch_bounds__(1024, 1) k_svdpp_seq(SpArgs a) {
                 if (a.sse_out) a.sse_out[epoch] = sse;
                 sse = 0.0;
             }
-            if (s + 1 < total) {            // after the two stores above, in program order
-                nb[2 * (cur ^ 1)] = a.bu[hdr[cur ^ 1].u];
-                nb[2 * (cur ^ 1) + 1] = a.bi[hdr[cur ^ 1].i];
+            if (more) {                     // after the two stores above, in program order
+                nbu = a.bu[hn->u];
+                nbi = a.bi[hn->i];
             }
         }
         if (tid < D) {
             a.pu[(size_t)u * D + tid] = puf + prm.lr_pu * (err * qif - prm.reg_pu * puf);
             a.qi[(size_t)i * D + tid] = qif + prm.lr_qi * (err * (puf + ui) - prm.reg_qi * qif);
-            if (s + 1 < total) {            // next rating's rows: issued now, consumed after the next two barriers
-                puf = a.pu[(size_t)hdr[cur ^ 1].u * D + tid];
-                qif = a.qi[(size_t)hdr[cur ^ 1].i * D + tid];
+            if (more) {                     // next rating's rows: issued now, consumed after the next two barriers
+                puf = a.pu[(size_t)hn->u * D + tid];
+                qif = a.qi[(size_t)hn->i * D + tid];
             }
         }
         double c[M];
@@ -225,12 +248,22 @@ __global__ void __launch_bounds__(1024, 1) k_svdpp_seq(SpArgs a) {
                 }
             }
         }
-        if (s + 1 < total) copy_list(&hdr[cur ^ 1], cur ^ 1);   // hdr[cur ^ 1] was completed before the first barrier
+        if (more) copy_list(hn, lb ^ 1);
+        if (pf2) {
+            SpHdr *hw = &hdr[c2];           // last read as the current header one rating ago
+            hw->u = h2u;
+            hw->i = h2i;
+            hw->r = h2r;
+            hw->p0 = h2p0;
+            hw->nI = (int)(h2p1 - h2p0);
+        }
         __syncthreads();
+        c0 = c1;
         if (++t == a.n) {
             t = 0;
             ++epoch;
         }
+        if (++t2 == a.n) t2 = 0;
     }
 }
 
@@ -252,12 +285,13 @@ __global__ void k_svdpp_user_factors(const double *pu, const double *yj, const i
 }
 
 static size_t sp_smem_bytes(int threads, int D) {
-    return ((size_t)(threads / 32) * D + 2 * (size_t)D + 32 + 4) * sizeof(double) + 2 * sizeof(SpHdr) +
+    return ((size_t)(threads / 32) * D + (size_t)D + 32 + 2) * sizeof(double) + 3 * sizeof(SpHdr) +
            4 * (size_t)SP_CAP * sizeof(int);
 }
 
 template <int M>
 static int sp_launch(daisy_ctx *h, const SpArgs &a, int threads, cudaStream_t s) {
+    if (M >= 8 && threads > 512) threads = 512;     // the kernel's launch bound for the wide instantiations
     const size_t smem = sp_smem_bytes(threads, a.D);
     DAISY_CUDA(cudaFuncSetAttribute(k_svdpp_seq<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_svdpp_seq<M><<<1, threads, smem, s>>>(a);
