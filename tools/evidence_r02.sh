@@ -29,6 +29,7 @@ if [ "$mode" = one ]; then
   tail -5 gpurun_out/r02_experimental_svdpp.log
   for w in bprfm_bn sgns neumf svdpp; do timeout 300 python bench.py --workload $w > gpurun_out/r02_bench_$w.json 2> gpurun_out/r02_bench_$w.err; cut -c1-220 gpurun_out/r02_bench_$w.json; done
   # SVD++: block size of the one-block kernel (barrier cost against rows in flight)
+  DAISY_SVDPP_HOT=0 timeout 300 python bench.py --workload svdpp --steps 1 > gpurun_out/r02_bench_svdpp_nohot.json 2>/dev/null; cut -c1-120 gpurun_out/r02_bench_svdpp_nohot.json
   for t in 128 256 512; do DAISY_SVDPP_THREADS=$t timeout 300 python bench.py --workload svdpp --steps 1 > gpurun_out/r02_bench_svdpp_t$t.json 2>/dev/null; cut -c1-120 gpurun_out/r02_bench_svdpp_t$t.json; done
 else
   N=${2:-8}
