@@ -91,6 +91,16 @@ def test_svdpp_against_c_oracle(U, I, D, n, E):
     assert np.isclose(a.sse_[E - 1], ref["sse"], rtol=1e-9)
     b = fit_from(SVDpp(U, I, n_factors=D, n_epochs=E, verbose=False), users, items, ratings, pu0, qi0, yj0)
     assert np.array_equal(a.yj, b.yj) and np.array_equal(a.pu, b.pu)      # run-to-run bit-reproducible
+    old = os.environ.get("DAISY_SVDPP_HOT")
+    os.environ["DAISY_SVDPP_HOT"] = "0"                                   # no yj rows resident in shared memory: same arithmetic
+    try:
+        c = fit_from(SVDpp(U, I, n_factors=D, n_epochs=E, verbose=False), users, items, ratings, pu0, qi0, yj0)
+    finally:
+        if old is None:
+            del os.environ["DAISY_SVDPP_HOT"]
+        else:
+            os.environ["DAISY_SVDPP_HOT"] = old
+    assert np.array_equal(a.yj, c.yj) and np.array_equal(a.qi, c.qi) and np.array_equal(a.bu, c.bu)
 
 
 def test_svdpp_bad_item_raises_and_leaves_no_partial_state():
