@@ -649,9 +649,9 @@ def test_neumf_gpu_tests_pass_over_the_emulated_kernels(golden, monkeypatch):
     _EmuProduct(monkeypatch, "neumf")
     monkeypatch.setattr(ncf_mlp.NeuMF, "_device", lambda self: self.embed_user_MLP.weight.device)
     cpu = torch.device("cpu")
-    G.test_neumf_golden_four_steps(golden, cpu, "mlp", "MLP")
+    G.test_neumf_against_oracle(cpu, "MLP", 50, 70, 8, 1, 33)
     if os.environ.get("DAISY_EMU_FULL") == "1":
-        G.test_neumf_against_oracle(cpu, "MLP", 50, 70, 8, 1, 33)
+        G.test_neumf_golden_four_steps(golden, cpu, "mlp", "MLP")
         G.test_neumf_golden_four_steps(golden, cpu, "neumf", "NeuMF-end")
         G.test_neumf_is_bit_reproducible_and_reports_bad_ids(cpu)
 
