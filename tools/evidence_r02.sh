@@ -1,5 +1,5 @@
 # Round 2, first GPU calls: what round 1 could not measure after its GPU budget ended.
-#   1 GPU :  gpurun --timeout 600 -- 'bash tools/evidence_r02.sh one'
+#   1 GPU :  gpurun --timeout 1500 -- 'bash tools/evidence_r02.sh one'   (after: bash tools/build_variants.sh)
 #   N GPUs:  gpurun --gpus 8 --timeout 400 -- 'bash tools/evidence_r02.sh many 8'     (then 4, 2)
 set -x
 mode=${1:-one}
