@@ -16,7 +16,8 @@ Race check: every emulated CUDA thread is an OS thread, so ThreadSanitizer sees 
 writing one location (validated on a kernel with its barrier removed: one report; with it: none) --
     DAISY_EMU_SANITIZE=thread LD_PRELOAD="$(gcc -print-file-name=libtsan.so)" TSAN_OPTIONS=report_signal_unsafe=0 \
         python -m pytest tests/test_kernel_emulation.py
-(12 passed, no data-race report; the SVD++ unit added later: its four kernel tests clean under both as well).
+(12 passed, no data-race report; the SVD++ unit added later: its four kernel tests clean under both as well, and the
+whole file -- 26 tests, the emulated GPU-test runs included -- passes under AddressSanitizer + UBSan without a report).
 
 The gated GPU test FILES of the experimental units also run here, over the emulated kernels (last section): a small
 parameter set by default, the rest with DAISY_EMU_FULL=1 (about a quarter of an hour on 8 host cores)."""
