@@ -220,14 +220,14 @@ def bpr_adam_step_closed_form(P, Q, mP, vP, mQ, vQ, triples, step, lr,
     np.add.at(gQ, j, s[:, None] * pu)
     bc1 = 1.0 - beta1 ** step
     bc2 = 1.0 - beta2 ** step
-    step_size = lr / bc1
+    step_size = lr * np.sqrt(bc2) / bc1          # torch/optim/_functional.py: sparse_adam
 
     def upd(W, m, v, g, rows):
         rows = np.unique(rows)
         W = W.copy()
-        m[rows] = beta1 * m[rows] + (1 - beta1) * g[rows]
-        v[rows] = beta2 * v[rows] + (1 - beta2) * g[rows] * g[rows]
-        denom = np.sqrt(v[rows]) / np.sqrt(bc2) + eps
+        m[rows] = m[rows] + (1 - beta1) * (g[rows] - m[rows])
+        v[rows] = v[rows] + (1 - beta2) * (g[rows] * g[rows] - v[rows])
+        denom = np.sqrt(v[rows]) + eps           # eps is not bias-corrected in SparseAdam (dense Adam divides it in)
         W[rows] = W[rows] - step_size * m[rows] / denom
         return W, m, v
 

@@ -52,7 +52,8 @@ class BPR(nn.Module):
 
     # -- library plumbing ---------------------------------------------------------------------
     def _tables(self):
-        P, Q = self.embed_user.weight, self.embed_item.weight
+        # straight from _modules: the attribute route (__getattr__ below) would fold the lazy decay in on every step
+        P, Q = self._modules["embed_user"].weight, self._modules["embed_item"].weight
         if not P.is_cuda:
             _lib.require_cuda()
             raise _lib.DaisyError("BPR tables are on the CPU: call model.cuda() first (no CPU fallback)")
@@ -124,10 +125,34 @@ class BPR(nn.Module):
         shape = torch.as_tensor(user).shape
         return pred_i.reshape(shape), pred_j.reshape(shape)
 
-    # state leaving the library's control must carry true weights
+    # State leaving the library's control must carry true weights.  Between two steps the tables hold W / c; every
+    # route by which reference-style code reaches them -- ``model.embed_user.weight``, ``parameters()``,
+    # ``state_dict()``, pickling, ``.cpu()`` -- folds c in first (one pass over the tables, and only when c != 1).
+    # A tensor obtained EARLIER and kept across later steps is the one thing this cannot cover: re-read it.
+    def __getattr__(self, name):
+        if name in ("embed_user", "embed_item"):
+            d = self.__dict__
+            h = d.get("_handle")
+            if h is not None and h.scale != 1.0:
+                self.materialize()
+        return super().__getattr__(name)
+
     def state_dict(self, *args, **kwargs):
         self.materialize()
         return super().state_dict(*args, **kwargs)
+
+    def named_parameters(self, *args, **kwargs):      # parameters() is built on this
+        self.materialize()
+        return super().named_parameters(*args, **kwargs)
+
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        """Loaded weights are TRUE weights: the pending decay scale of whatever the tables held is dropped (the
+        reference's restore-the-best-checkpoint pattern after some steps with weight_decay > 0)."""
+        out = super().load_state_dict(state_dict, *args, **kwargs)
+        if self._handle is not None:
+            self._handle.scale = 1.0
+        self._pending_scale = 1.0
+        return out
 
     def __getstate__(self):
         self.materialize()

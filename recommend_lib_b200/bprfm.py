@@ -30,11 +30,19 @@ class BPRFM(nn.Module):
     refreshed from that buffer whenever they are read through ``forward``, ``state_dict`` or ``sync()``.
     """
 
+    def __new__(cls, num_features=None, num_factors=None, batch_norm=False, drop_prob=(0.0, 0.0), *args, **kwargs):
+        # the reference has ONE class (BPRFMRecommender.py:29-55) and the script's defaults are batch_norm=True,
+        # drop_prob=[0.5, 0.2] (:116-125): that configuration is the batch-norm + dropout step of csrc/fmbn.cu
+        if cls is BPRFM and batch_norm:
+            from .bprfm_bn import BPRFMBN
+            return BPRFMBN(num_features, num_factors, True, drop_prob, *args, **kwargs)
+        return super().__new__(cls)
+
     def __init__(self, num_features, num_factors, batch_norm=False, drop_prob=(0.0, 0.0), user_num=None, max_batch=4096):
         super().__init__()
         if batch_norm or any(float(p) != 0.0 for p in drop_prob):
-            raise NotImplementedError("only batch_norm=False, drop_prob=[0, 0] is on this (GPU-verified) path; the batch-norm "
-                                      "+ dropout step is bprfm_bn.BPRFMBN / FMBNAdagrad (experimental: not yet run on a GPU)")
+            raise NotImplementedError("dropout without batch norm is not on an accelerated path (the script cannot select "
+                                      "it: --batch_norm is on by default and has no off switch, BPRFMRecommender.py:116-125)")
         if user_num is None or not (0 < int(user_num) < int(num_features)):
             raise ValueError("user_num (features [0, user_num) are users, the rest items) is required")
         if num_factors % 4:
@@ -153,6 +161,12 @@ class FMAdagrad:
     """``optim.Adagrad(model.parameters(), lr, initial_accumulator_value=1e-8)`` + the step of
     BPRFMRecommender.py:214-219, fused: ``step(features_i, feature_values_i, features_j, feature_values_j)``.
     Adagrad moves only elements with a gradient, so the fused sparse step equals the reference's dense one."""
+
+    def __new__(cls, model=None, *args, **kwargs):
+        from .bprfm_bn import BPRFMBN, FMBNAdagrad
+        if cls is FMAdagrad and isinstance(model, BPRFMBN):        # BPRFM(batch_norm=True) built a BPRFMBN
+            return FMBNAdagrad(model, *args, **kwargs)
+        return super().__new__(cls)
 
     def __init__(self, model: BPRFM, lr=0.05, initial_accumulator_value=1e-8, eps=1e-10):
         self.model, self.lr, self.eps = model, float(lr), float(eps)

@@ -1,9 +1,9 @@
 """BPR-FM at the reference script's DEFAULTS -- batch norm + dropout on the FM vector (BPRFMRecommender.py:45-80, 116-125)
 -- on the C-ABI library (``daisy_fmbn_step`` / ``daisy_fmbn_forward``, csrc/fmbn.cu).  SURVEY.md section 8f, row N3.
 
-EXPERIMENTAL: the kernels are compiled for sm_100a but have not run on a GPU yet (round 1 ended its GPU budget first);
-``bprfm.BPRFM(batch_norm=True)`` therefore still raises and points here, and tests/test_bprfm_bn_gpu.py runs only with
-``DAISY_EXPERIMENTAL=1``.  The checker is ``oracle/bprfm_oracle.py: BPRFMFull``, pinned to the unmodified reference.
+``bprfm.BPRFM(batch_norm=True, ...)`` builds this class (and ``FMAdagrad`` on it the optimiser below), so the reference's
+one constructor covers both configurations.  Parity: tests/test_bprfm_bn_gpu.py against the golden run of the unmodified
+reference class and ``oracle/bprfm_oracle.py: BPRFMFull``.
 
 Same module structure as the reference class, so ``state_dict()`` / ``torch.save(model)`` carry the same keys:
 ``embeddings``, ``biases``, ``bias_``, ``FM_layers = Sequential(BatchNorm1d(num_factors), Dropout(drop_prob[0]))``.

@@ -206,6 +206,7 @@ extern "C" int daisy_destroy(daisy_handle_t h) {
     }
     for (int i = 0; i < DAISY_MAX_BGRAPH; ++i)
         if (h->bgraph[i].exec) cudaGraphExecDestroy(h->bgraph[i].exec);
+    if (h->pool_state == 1) cudaMemPoolDestroy(h->pool);
     if (h->err_host) cudaFreeHost(h->err_host);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_call) cudaEventDestroy(h->ev_call);

@@ -55,12 +55,14 @@ struct SgdOpt {
 struct AdamOpt {
     static constexpr bool kNeedOldItem = true;
     float *P, *Q, *mP, *vP, *mQ, *vQ;
-    float b1, b2, step_size, inv_sqrt_bc2, eps;
+    float b1, b2, step_size, eps;   // step_size = lr * sqrt(1 - b2^t) / (1 - b1^t)
     int D4;
+    // torch/optim/_functional.py: sparse_adam -- old += (1 - b) * (new - old); denom = sqrt(v) + eps (eps is NOT
+    // divided by the bias correction, unlike dense Adam); param -= step_size * m / denom
     __device__ __forceinline__ float one(float w, float g, float &m, float &v) const {
-        m = fmaf(b1, m, (1.f - b1) * g);
-        v = fmaf(b2, v, (1.f - b2) * g * g);
-        return w - step_size * m / (sqrtf(v) * inv_sqrt_bc2 + eps);
+        m = fmaf(1.f - b1, g - m, m);
+        v = fmaf(1.f - b2, g * g - v, v);
+        return w - step_size * (m / (sqrtf(v) + eps));
     }
     __device__ __forceinline__ void apply(int tbl, size_t row, int e, float4 old, float4 d) const {
         const size_t idx = row * D4 + e;
@@ -195,8 +197,7 @@ extern "C" int daisy_bpr_adam_step(daisy_handle_t h, float *P, float *Q, float *
     opt.b2 = beta2;
     const double bc1 = 1.0 - pow((double)beta1, (double)step_no);
     const double bc2 = 1.0 - pow((double)beta2, (double)step_no);
-    opt.step_size = (float)((double)lr / bc1);
-    opt.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    opt.step_size = (float)((double)lr * sqrt(bc2) / bc1);
     opt.eps = eps;
     opt.D4 = h->D / 4;
     return run_step<AdamOpt>(h, P, Q, triples, B, opt, 1.0f, loss_accum, (cudaStream_t)stream, nullptr,

@@ -160,6 +160,12 @@ struct daisy_ctx {
     BookGraph bgraph[DAISY_MAX_BGRAPH];
     int n_bgraph, bgraph_next;
 
+    // stream-ordered scratch of the calls that size their workspace per call (sampler, full-catalogue top-K, funk-SVD,
+    // SVD++): a PRIVATE memory pool of this handle, created on first use, that keeps freed blocks cached between calls
+    // (release threshold = max) -- the device's default pool, which the rest of the process shares, is left alone
+    cudaMemPool_t pool;
+    int pool_state;  // 0 not created, 1 ready, -1 creation failed (cudaMallocAsync from the default pool, untuned)
+
     // --- instrumentation ---
     int64_t launches;
     int timing;                       // 0 off, 1 main kernel only (asynchronous event pool), 2 every phase (syncs per step)
@@ -209,6 +215,28 @@ void daisy_shard_free(daisy_ctx *h);  // shard.cu
     } while (0)
 
 static inline int daisy_ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// Stream-ordered allocation from the handle's private pool (see daisy_ctx::pool); freed with cudaFreeAsync.
+static inline cudaError_t daisy_scratch_alloc(daisy_ctx *h, void **p, size_t bytes, cudaStream_t s) {
+    if (h->pool_state == 0) {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = h->device;
+        if (cudaMemPoolCreate(&h->pool, &props) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            h->pool_state = 1;
+        } else {
+            (void)cudaGetLastError();
+            h->pool_state = -1;
+        }
+    }
+    if (h->pool_state == 1) return cudaMallocFromPoolAsync(p, bytes ? bytes : 1, h->pool, s);
+    return cudaMallocAsync(p, bytes ? bytes : 1, s);
+}
 
 // RAII-less device guard: the handle is bound to one device.
 struct DeviceGuard {

@@ -1,10 +1,8 @@
 // BPR-FM with two one-hot features at the reference script's DEFAULTS: batch norm + dropout on the FM vector
 // (BPRFMRecommender.py:45-80 model, :116-125 defaults, :214-219 step).
 //
-// STATUS: compiled for sm_100a, NOT YET RUN ON A GPU (written after the GPU budget of round 1 was spent); the GPU tests
-// (tests/test_bprfm_bn_gpu.py) are excluded from the default run until it has been (DAISY_EXPERIMENTAL=1 runs them).
-// Executed so far only under the host emulation of tests/emu (tests/test_kernel_emulation.py: golden run + oracle green).
-// The checker exists and is pinned to the unmodified reference: oracle/bprfm_oracle.py: BPRFMFull.
+// Parity: tests/test_bprfm_bn_gpu.py (golden run of the unmodified reference class + oracle/bprfm_oracle.py: BPRFMFull
+// on seeded shapes); the same translation unit also runs under the host emulation of tests/emu.
 //
 // With features = [user, user_num + item] and values 1 the bi-interaction vector is x = e_u (.) e_i.  BatchNorm1d in
 // training mode couples the samples of a batch through per-factor column statistics, so one step is a short chain of
@@ -29,7 +27,9 @@ namespace {
 constexpr int FM_MAX_F = 255;  // k_fm_apply keeps (F + 1) / 32 accumulators per lane in registers
 
 struct FmScratch {
-    float *X, *s, *lossp, *mu, *var, *inv, *A, *Bs, *c1, *c2, *contrib;
+    float *X, *s, *lossp, *mu, *var, *inv, *c1, *c2, *contrib;
+    double *A, *Bs;  // per (call, factor) sums of dz and dz * xhat: the two calls' sums nearly cancel in d beta, so they
+                     // stay double until they have been added (a float here costs 1e-4 of d beta at batch 333)
     uint32_t *kin, *kout, *vin, *vout;
     void *cub;
     size_t cub_bytes, total;
@@ -54,8 +54,8 @@ static void fm_carve(char *base, int64_t B, int F, FmScratch &w) {
     w.mu = (float *)take(2 * f * 4);
     w.var = (float *)take(2 * f * 4);
     w.inv = (float *)take(2 * f * 4);
-    w.A = (float *)take(2 * f * 4);
-    w.Bs = (float *)take(2 * f * 4);
+    w.A = (double *)take(2 * f * 8);
+    w.Bs = (double *)take(2 * f * 8);
     w.c1 = (float *)take(2 * f * 4);
     w.c2 = (float *)take(2 * f * 4);
     w.contrib = (float *)take(3 * b * (f + 1) * 4);
@@ -171,8 +171,8 @@ __global__ void __launch_bounds__(256) k_fm_score(const float *__restrict__ X, c
 __global__ void __launch_bounds__(256) k_fm_colsums(const float *__restrict__ X, const float *__restrict__ s, int B, int F,
                                                      const float *__restrict__ mu, const float *__restrict__ inv,
                                                      const float *__restrict__ gamma, const float *__restrict__ mask_i,
-                                                     const float *__restrict__ mask_j, float *__restrict__ A,
-                                                     float *__restrict__ Bs, float *__restrict__ c1,
+                                                     const float *__restrict__ mask_j, double *__restrict__ A,
+                                                     double *__restrict__ Bs, float *__restrict__ c1,
                                                      float *__restrict__ c2) {
     __shared__ double shA[8][33], shB[8][33];
     const int tx = threadIdx.x, ty = threadIdx.y, f = blockIdx.x * 32 + tx, c = blockIdx.y;
@@ -199,8 +199,8 @@ __global__ void __launch_bounds__(256) k_fm_colsums(const float *__restrict__ X,
             ta += shA[k][tx];
             tb += shB[k][tx];
         }
-        A[c * F + f] = (float)ta;
-        Bs[c * F + f] = (float)tb;
+        A[c * F + f] = ta;
+        Bs[c * F + f] = tb;
         c1[c * F + f] = (float)((double)gamma[f] * ta / (double)B);   // mean_b(d xhat)
         c2[c * F + f] = (float)((double)gamma[f] * tb / (double)B);   // mean_b(d xhat * xhat)
     }
@@ -296,13 +296,13 @@ __global__ void __launch_bounds__(256) k_fm_apply(const uint32_t *__restrict__ k
 
 // one block: Adagrad on gamma / beta, running statistics (two _out calls per step: positive, then negative), loss
 __global__ void __launch_bounds__(256) k_fm_bn_step(int B, int F, const float *__restrict__ mu, const float *__restrict__ var,
-                                                     const float *__restrict__ A, const float *__restrict__ Bs,
+                                                     const double *__restrict__ A, const double *__restrict__ Bs,
                                                      float *__restrict__ gamma, float *__restrict__ beta,
                                                      float *__restrict__ acc_gamma, float *__restrict__ acc_beta,
                                                      float *__restrict__ rmean, float *__restrict__ rvar, float lr, float eps,
                                                      float momentum, const float *__restrict__ lossp, double *loss_accum) {
     for (int f = threadIdx.x; f < F; f += blockDim.x) {
-        const float dg = Bs[f] + Bs[F + f], db = A[f] + A[F + f];
+        const float dg = (float)(Bs[f] + Bs[F + f]), db = (float)(A[f] + A[F + f]);
         float a = acc_gamma[f] + dg * dg;
         acc_gamma[f] = a;
         gamma[f] -= lr * dg / (sqrtf(a) + eps);

@@ -45,7 +45,37 @@ struct MfArgs {
     long long n;
     int epochs, D;
     daisy_mf_params prm;
-    unsigned spin_cap;
+    unsigned long long stall_ns;   // a waiter gives up when the whole grid made no progress for this long
+};
+
+__device__ __forceinline__ unsigned long long mf_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Stall detector of the two schedules' spin loops, called by the polling lane every 2^12 polls.  A wait may be
+// legitimately long (a light warp waiting for the hot item's warp to finish an epoch), so the test is not "how long
+// have I waited" but "how long has NOBODY moved": *progress is bumped by every warp as it works (the ticket counter
+// of the ticket schedule, a link counter of the item-owner schedule); if it stands still for stall_ns of wall time
+// (globaltimer), or another warp has already given up, the waiter raises the abort flag and leaves.
+struct StallWatch {
+    unsigned long long t_last = 0, prog_last = 0;
+    __device__ __forceinline__ bool stalled(const unsigned long long *progress, int *abort_flag, unsigned long long stall_ns) {
+        if (*(volatile int *)abort_flag) return true;
+        const unsigned long long now = mf_globaltimer();
+        const unsigned long long pr = *(volatile const unsigned long long *)progress;
+        if (t_last == 0 || pr != prog_last) {
+            t_last = now;
+            prog_last = pr;
+            return false;
+        }
+        if (now - t_last > stall_ns) {
+            atomicExch(abort_flag, 1);
+            return true;
+        }
+        return false;
+    }
 };
 
 __global__ void __launch_bounds__(128) k_mf_dataflow(MfArgs a) {
@@ -68,10 +98,10 @@ __global__ void __launch_bounds__(128) k_mf_dataflow(MfArgs a) {
         int bail = 0;
         if (lane == 0) {
             unsigned spins = 0;
+            StallWatch watch;
             while (ld_acquire_u32(&a.ver_u[u]) != want_u || ld_acquire_u32(&a.ver_i[i]) != want_i) {
                 __nanosleep(32);
-                if (++spins > a.spin_cap || *(volatile int *)a.abort_flag) {
-                    atomicExch(a.abort_flag, 1);
+                if ((++spins & 0xfffu) == 0 && watch.stalled(a.ticket, a.abort_flag, a.stall_ns)) {
                     bail = 1;
                     break;
                 }
@@ -158,10 +188,11 @@ struct OwnArgs {
     double *err2;
     int *abort_flag;
     unsigned long long *stats;  // optional (DAISY_MF_STATS=1): [0] links, [1] links that took the blocking path, [2] item switches
+    unsigned long long *progress;  // links done by all warps (bumped once per group): what the stall detector watches
     long long n;
     int epochs, D;
     daisy_mf_params prm;
-    unsigned spin_cap;
+    unsigned long long stall_ns;
 };
 
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
@@ -278,10 +309,10 @@ __global__ void __launch_bounds__(128) k_mf_owner(OwnArgs a) {
                 int bail = 0;
                 if (lane == 0) {
                     unsigned spins = 0;
+                    StallWatch watch;
                     while (ld_acquire_u32(&a.ver_u[u]) != want) {
                         __nanosleep(20);
-                        if (++spins > a.spin_cap || *(volatile int *)a.abort_flag) {
-                            atomicExch(a.abort_flag, 1);
+                        if ((++spins & 0xfffu) == 0 && watch.stalled(a.progress, a.abort_flag, a.stall_ns)) {
                             bail = 1;
                             break;
                         }
@@ -342,6 +373,7 @@ __global__ void __launch_bounds__(128) k_mf_owner(OwnArgs a) {
         __syncwarp();
         if (pend_u >= 0) st_relaxed_u32(&a.ver_u[pend_u], pend_v);
         pend_u = -1;
+        if (lane == 0) atomicAdd(a.progress, (unsigned long long)K);  // fire and forget: the stall detector's clock
         valid = __ballot_sync(FULL, u1 >= 0 && vnext == want1);
 #pragma unroll
         for (int j = 0; j < K; ++j) {
@@ -481,23 +513,18 @@ __global__ void k_mf_predict(const double *__restrict__ pu, const double *__rest
     }
 }
 
-// Stream-ordered scratch (cudaMallocAsync from the device's default pool, kept cached between fits): ~45 buffers per
-// fit cost microseconds instead of the ~100 ms of as many cudaMalloc / cudaFree pairs.  Freed on scope exit.
+// Stream-ordered scratch (the handle's private pool, kept cached between fits): ~45 buffers per fit cost
+// microseconds instead of the ~100 ms of as many cudaMalloc / cudaFree pairs.  Freed on scope exit.
 struct Scratch {
     void *p[64];
     int n = 0;
     cudaStream_t s;
-    explicit Scratch(cudaStream_t stream, int device) : s(stream) {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-    }
+    daisy_ctx *h;
+    explicit Scratch(cudaStream_t stream, daisy_ctx *ctx) : s(stream), h(ctx) {}
     template <class T>
     int get(T **out, size_t count) {
         *out = nullptr;
-        cudaError_t e = cudaMallocAsync((void **)out, (count ? count : 1) * sizeof(T), s);
+        cudaError_t e = daisy_scratch_alloc(h, (void **)out, (count ? count : 1) * sizeof(T), s);
         if (e != cudaSuccess) {
             daisy_set_error("cudaMallocAsync of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
             return DAISY_ENOMEM;
@@ -547,7 +574,7 @@ extern "C" int daisy_mf_fit(daisy_handle_t h, double *pu, double *qi, double *bu
     DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
     cudaStream_t s = (cudaStream_t)stream;
     const size_t N = (size_t)n;
-    Scratch ws(s, h->device);
+    Scratch ws(s, h);
     uint32_t *key, *key_s, *val, *val_s;
     int *start, *start_scan, *need_u, *need_i, *cnt_u, *cnt_i, *abort_flag;
     unsigned *ver_u, *ver_i;
@@ -590,7 +617,22 @@ extern "C" int daisy_mf_fit(daisy_handle_t h, double *pu, double *qi, double *bu
     }
     unsigned long long *dbg_stats = nullptr;
     const char *sched = getenv("DAISY_MF_SCHEDULE");
-    const bool owner = !(sched && strcmp(sched, "ticket") == 0) && h->D <= 512;
+    bool owner = !(sched && strcmp(sched, "ticket") == 0) && h->D <= 512;
+    // Copies of the four arrays as they came in: a fit that aborts (stall detector) hands the tables back untouched
+    // instead of partially trained.  Funk-SVD tables are small (config 2: 10 MB).
+    double *bk_pu, *bk_qi, *bk_bu, *bk_bi;
+    const size_t n_pu = (size_t)h->U * h->D, n_qi = (size_t)h->I * h->D;
+    rc = ws.get(&bk_pu, n_pu);
+    if (!rc) rc = ws.get(&bk_qi, n_qi);
+    if (!rc) rc = ws.get(&bk_bu, (size_t)h->U);
+    if (!rc) rc = ws.get(&bk_bi, (size_t)h->I);
+    if (rc) return rc;
+    DAISY_CUDA(cudaMemcpyAsync(bk_pu, pu, n_pu * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    DAISY_CUDA(cudaMemcpyAsync(bk_qi, qi, n_qi * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    DAISY_CUDA(cudaMemcpyAsync(bk_bu, bu, (size_t)h->U * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    DAISY_CUDA(cudaMemcpyAsync(bk_bi, bi, (size_t)h->I * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    const char *stall_env = getenv("DAISY_MF_STALL_MS");
+    const unsigned long long stall_ns = (unsigned long long)((stall_env && atof(stall_env) > 0 ? atof(stall_env) : 10000.0) * 1e6);
     if (owner) {
         int occ = 0;
         const int DVsel = h->D <= 32 ? 1 : h->D <= 64 ? 2 : h->D <= 128 ? 4 : h->D <= 256 ? 8 : 16;
@@ -640,7 +682,8 @@ extern "C" int daisy_mf_fit(daisy_handle_t h, double *pu, double *qi, double *bu
         o.lk_u = lk_u; o.lk_i = lk_i; o.lk_r = lk_r; o.lk_need = lk_need; o.lk_cnt = lk_cnt; o.lk_t = lk_t;
         o.wptr = wptr; o.ver_u = ver_u; o.err2 = err2; o.abort_flag = abort_flag;
         o.n = n; o.epochs = n_epochs; o.D = h->D; o.prm = *prm;
-        o.spin_cap = 1u << 26;
+        o.stall_ns = stall_ns;
+        o.progress = ticket;   // the ticket word is free under this schedule
         o.stats = nullptr;
         const char *st_env = getenv("DAISY_MF_STATS");
         if (st_env && atoi(st_env) > 0) {
@@ -649,23 +692,31 @@ extern "C" int daisy_mf_fit(daisy_handle_t h, double *pu, double *qi, double *bu
             DAISY_CUDA(cudaMemsetAsync(o.stats, 0, 8 * sizeof(unsigned long long), s));
             dbg_stats = o.stats;
         }
+        // The schedule is deadlock-free only if all W warps are resident at once (a resident warp may wait for a
+        // version owned by any other warp): a COOPERATIVE launch either gets the whole grid co-resident -- whatever
+        // else is running on the device -- or fails, in which case the fit falls back to the ticket schedule, whose
+        // earliest unprocessed rating is always held by a resident warp.
         const int grid = h->num_sms * per_sm;
-        switch (DVsel) {
-            case 1: k_mf_owner<1><<<grid, 128, 0, s>>>(o); break;
-            case 2: k_mf_owner<2><<<grid, 128, 0, s>>>(o); break;
-            case 4: k_mf_owner<4><<<grid, 128, 0, s>>>(o); break;
-            case 8: k_mf_owner<8><<<grid, 128, 0, s>>>(o); break;
-            default: k_mf_owner<16><<<grid, 128, 0, s>>>(o); break;
+        void *kargs[] = {(void *)&o};
+        const void *fn = DVsel == 1 ? (const void *)k_mf_owner<1> : DVsel == 2 ? (const void *)k_mf_owner<2>
+                       : DVsel == 4 ? (const void *)k_mf_owner<4> : DVsel == 8 ? (const void *)k_mf_owner<8>
+                                                                                  : (const void *)k_mf_owner<16>;
+        cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(128), kargs, 0, s);
+        if (le != cudaSuccess) {
+            (void)cudaGetLastError();
+            owner = false;
+        } else {
+            h->launches += 1;
         }
-        DAISY_LAUNCH_CHECK(h);
-    } else {
+    }
+    if (!owner) {
         MfArgs a;
         a.pu = pu; a.qi = qi; a.bu = bu; a.bi = bi;
         a.users = users; a.items = items; a.ratings = ratings;
         a.need_u = need_u; a.need_i = need_i; a.cnt_u = cnt_u; a.cnt_i = cnt_i;
         a.ver_u = ver_u; a.ver_i = ver_i; a.ticket = ticket; a.err2 = err2; a.abort_flag = abort_flag;
         a.n = n; a.epochs = n_epochs; a.D = h->D; a.prm = *prm;
-        a.spin_cap = 1u << 24;  // ~1 s of polling: a correct schedule never gets near it
+        a.stall_ns = stall_ns;
         int occ = 0;
         DAISY_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mf_dataflow, 128, 0));
         if (occ < 1) occ = 1;
@@ -688,7 +739,15 @@ extern "C" int daisy_mf_fit(daisy_handle_t h, double *pu, double *qi, double *bu
         fprintf(stderr, "[daisy_mf_fit] links %llu blocking %llu item-switches %llu | hottest warp: links %llu blocking %llu switches %llu\n",
                 hs[0], hs[1], hs[2], hs[3], hs[4], hs[5]);
     }
-    DAISY_REQUIRE(!aborted, DAISY_ECUDA, "daisy_mf_fit: dataflow schedule stalled (spin cap reached) -- tables are partial");
+    if (aborted) {  // hand the tables back as they came in
+        DAISY_CUDA(cudaMemcpyAsync(pu, bk_pu, n_pu * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        DAISY_CUDA(cudaMemcpyAsync(qi, bk_qi, n_qi * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        DAISY_CUDA(cudaMemcpyAsync(bu, bk_bu, (size_t)h->U * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        DAISY_CUDA(cudaMemcpyAsync(bi, bk_bi, (size_t)h->I * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        DAISY_CUDA(cudaStreamSynchronize(s));
+    }
+    DAISY_REQUIRE(!aborted, DAISY_ECUDA, "daisy_mf_fit: schedule stalled (no rating processed for %.0f ms) -- the tables "
+                  "were restored to their state before the call", (double)stall_ns * 1e-6);
     return DAISY_OK;
 }
 

@@ -103,7 +103,8 @@ extern "C" int daisy_sample_triples(daisy_handle_t h, const int32_t *pairs, int6
     DAISY_REQUIRE(h != nullptr, DAISY_EINVAL, "null handle");
     DAISY_REQUIRE(n_pairs >= 0 && num_ng >= 1 && n_keys >= 0, DAISY_EINVAL, "bad sizes");
     const long long n = (long long)n_pairs * num_ng;
-    DAISY_REQUIRE(n < (1LL << 32), DAISY_EUNSUPPORTED, "at most 2^32 - 1 triples per epoch");
+    // one CUB radix sort shuffles the epoch and its item count is an int
+    DAISY_REQUIRE(n < (1LL << 31), DAISY_EUNSUPPORTED, "at most 2^31 - 1 triples per call (%lld asked for)", n);
     if (n == 0) return DAISY_OK;
     DAISY_REQUIRE(pairs && triples_out && (pos_keys || n_keys == 0), DAISY_EINVAL, "null argument");
     DeviceGuard g(h->device);
@@ -118,23 +119,18 @@ extern "C" int daisy_sample_triples(daisy_handle_t h, const int32_t *pairs, int6
         DAISY_LAUNCH_CHECK(h);
         return DAISY_OK;
     }
-    // stream-ordered scratch (cached in the device's default pool between epochs)
+    // stream-ordered scratch (cached in the handle's private pool between epochs)
     int32_t *tmp_tri = nullptr;
     uint32_t *key = nullptr, *key_s = nullptr, *val = nullptr, *val_s = nullptr;
     void *cub_tmp = nullptr;
     size_t cub_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, key, key_s, val, val_s, (int)n, 0, 32, s);
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
-        unsigned long long keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    bool ok = cudaMallocAsync((void **)&tmp_tri, (size_t)n * 3 * sizeof(int32_t), s) == cudaSuccess;
-    ok = ok && cudaMallocAsync((void **)&key, (size_t)n * 4, s) == cudaSuccess;
-    ok = ok && cudaMallocAsync((void **)&key_s, (size_t)n * 4, s) == cudaSuccess;
-    ok = ok && cudaMallocAsync((void **)&val, (size_t)n * 4, s) == cudaSuccess;
-    ok = ok && cudaMallocAsync((void **)&val_s, (size_t)n * 4, s) == cudaSuccess;
-    ok = ok && cudaMallocAsync(&cub_tmp, cub_bytes + 256, s) == cudaSuccess;
+    bool ok = daisy_scratch_alloc(h, (void **)&tmp_tri, (size_t)n * 3 * sizeof(int32_t), s) == cudaSuccess;
+    ok = ok && daisy_scratch_alloc(h, (void **)&key, (size_t)n * 4, s) == cudaSuccess;
+    ok = ok && daisy_scratch_alloc(h, (void **)&key_s, (size_t)n * 4, s) == cudaSuccess;
+    ok = ok && daisy_scratch_alloc(h, (void **)&val, (size_t)n * 4, s) == cudaSuccess;
+    ok = ok && daisy_scratch_alloc(h, (void **)&val_s, (size_t)n * 4, s) == cudaSuccess;
+    ok = ok && daisy_scratch_alloc(h, &cub_tmp, cub_bytes + 256, s) == cudaSuccess;
     int rc = DAISY_OK;
     if (!ok) {
         cudaGetLastError();

@@ -592,6 +592,11 @@ static int shard_apply(daisy_ctx *h, float lr, float wd, cudaStream_t s) {
 static int shard_barrier(daisy_ctx *h, cudaStream_t s) {
     daisy_shard *sh = h->sh;
     if (sh->world == 1) return DAISY_OK;
+    // ranks emulated in ONE process share a device and a stream: a barrier kernel of rank r would spin on flags that
+    // only later launches of the same stream can set.  The caller orders the phases there (daisy_shard_compute /
+    // daisy_shard_apply), so a barrier -- and with it daisy_shard_step -- is a usage error, reported at once.
+    DAISY_REQUIRE(!sh->in_process, DAISY_EINVAL, "in-process sharding (daisy_shard_attach(.., in_process=1)) has no barrier: "
+                  "drive daisy_shard_compute / daisy_shard_apply of all ranks in lockstep instead of daisy_shard_step");
     DeviceGuard g(h->device);
     DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
     sh->epoch++;

@@ -403,7 +403,7 @@ extern "C" int daisy_svdpp_fit(daisy_handle_t h, double *pu, double *qi, double 
     a.slot = nullptr;
     int *hotbuf = nullptr;
     if (H > 0) {
-        DAISY_CUDA(cudaMallocAsync((void **)&hotbuf, 2 * (size_t)h->I * sizeof(int), s));
+        DAISY_CUDA(daisy_scratch_alloc(h, (void **)&hotbuf, 2 * (size_t)h->I * sizeof(int), s));
         DAISY_CUDA(cudaMemsetAsync(hotbuf, 0, 2 * (size_t)h->I * sizeof(int), s));
         k_svdpp_hot<<<1, 1024, 0, s>>>(ur_ptr, ur_idx, (long long)h->U, (int)h->I, (int)H, h->err, hotbuf, hotbuf + h->I);
         DAISY_LAUNCH_CHECK(h);

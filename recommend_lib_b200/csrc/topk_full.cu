@@ -432,19 +432,14 @@ extern "C" int daisy_topk_full(daisy_handle_t h, const float *P, const float *Q,
     int32_t *titem = nullptr;
     int *cnt = nullptr, *redo = nullptr;
     unsigned long long *cand = nullptr;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
-        unsigned long long keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    bool ok = cudaMallocAsync((void **)&Qs, (size_t)Ms * h->D * sizeof(float), s) == cudaSuccess;
-    ok = ok && cudaMallocAsync((void **)&Ss, (size_t)Tu * Ms * sizeof(float), s) == cudaSuccess;
-    ok = ok && cudaMallocAsync((void **)&tscore, (size_t)Tu * r * sizeof(float), s) == cudaSuccess;
-    ok = ok && cudaMallocAsync((void **)&titem, (size_t)Tu * r * sizeof(int32_t), s) == cudaSuccess;
-    ok = ok && cudaMallocAsync((void **)&thr, (size_t)Tu * sizeof(float), s) == cudaSuccess;
-    ok = ok && cudaMallocAsync((void **)&cnt, (size_t)Tu * sizeof(int), s) == cudaSuccess;
-    ok = ok && cudaMallocAsync((void **)&redo, (size_t)N * sizeof(int), s) == cudaSuccess;
-    ok = ok && cudaMallocAsync((void **)&cand, (size_t)Tu * cap * sizeof(unsigned long long), s) == cudaSuccess;
+    bool ok = daisy_scratch_alloc(h, (void **)&Qs, (size_t)Ms * h->D * sizeof(float), s) == cudaSuccess;
+    ok = ok && daisy_scratch_alloc(h, (void **)&Ss, (size_t)Tu * Ms * sizeof(float), s) == cudaSuccess;
+    ok = ok && daisy_scratch_alloc(h, (void **)&tscore, (size_t)Tu * r * sizeof(float), s) == cudaSuccess;
+    ok = ok && daisy_scratch_alloc(h, (void **)&titem, (size_t)Tu * r * sizeof(int32_t), s) == cudaSuccess;
+    ok = ok && daisy_scratch_alloc(h, (void **)&thr, (size_t)Tu * sizeof(float), s) == cudaSuccess;
+    ok = ok && daisy_scratch_alloc(h, (void **)&cnt, (size_t)Tu * sizeof(int), s) == cudaSuccess;
+    ok = ok && daisy_scratch_alloc(h, (void **)&redo, (size_t)N * sizeof(int), s) == cudaSuccess;
+    ok = ok && daisy_scratch_alloc(h, (void **)&cand, (size_t)Tu * cap * sizeof(unsigned long long), s) == cudaSuccess;
     int rc = DAISY_OK;
     int *redo_host = nullptr;
     if (!ok) {

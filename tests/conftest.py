@@ -14,12 +14,6 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-def pytest_collection_modifyitems(config, items):
-    """GPU tests never silently pass without a device: they are skipped unless -m gpu selected them,
-    and when selected without a device they FAIL (the product has no CPU fallback)."""
-    pass
-
-
 @pytest.fixture(scope="session")
 def golden():
     def load(name):

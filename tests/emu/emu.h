@@ -41,6 +41,11 @@ enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 typedef void *cudaMemPool_t;
 enum { cudaMemPoolAttrReleaseThreshold = 0 };
+enum { cudaMemAllocationTypePinned = 1, cudaMemHandleTypeNone = 0, cudaMemLocationTypeDevice = 1 };
+struct cudaMemPoolProps { int allocType, handleTypes; struct { int type, id; } location; };
+inline cudaError_t cudaMemPoolCreate(cudaMemPool_t *, const cudaMemPoolProps *) { return 1; }  // "no private pool": plain cudaMallocAsync
+inline cudaError_t cudaMemPoolDestroy(cudaMemPool_t) { return cudaSuccess; }
+inline cudaError_t cudaMallocFromPoolAsync(void **p, size_t n, cudaMemPool_t, cudaStream_t) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : 1; }
 inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t *, int) { return 1; }  // "no pool": the caller skips its tuning
 inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, int, void *) { return cudaSuccess; }
 

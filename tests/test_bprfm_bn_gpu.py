@@ -2,8 +2,7 @@
 daisy_fmbn_step / daisy_fmbn_forward through BPRFMBN + FMBNAdagrad against the golden run of the unmodified reference
 (recorded dropout masks) and the closed-form oracle (oracle/bprfm_oracle.py: BPRFMFull).
 
-EXPERIMENTAL PATH: csrc/fmbn.cu was written after round 1's GPU budget was spent and has not run on a GPU yet, so this
-file is NOT part of the default `-m gpu` run: it runs with DAISY_EXPERIMENTAL=1 (first thing next round).  Tolerances
+First run on a B200 in round 2 (profiles/r02a_*).  Tolerances
 are the ones of tests/test_bprfm_gpu.py: 1e-5 on well-conditioned quantities; with the script's Adagrad accumulator of
 1e-8 an element whose gradient nearly cancels is ill-conditioned (embeddings 1e-4, biases 2e-4, see
 test_oracle_golden.py::test_bprfm_full_oracle_matches_reference_with_batch_norm_and_dropout)."""
@@ -14,9 +13,7 @@ import pytest
 
 from conftest import rel_err
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DAISY_EXPERIMENTAL") != "1",
-                                 reason="csrc/fmbn.cu has not run on a GPU yet: set DAISY_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 

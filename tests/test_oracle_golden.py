@@ -38,6 +38,46 @@ def test_torch_port_is_bit_identical_to_reference_small(golden):
         assert loss == pytest.approx(float(g["losses"][k]), rel=1e-6)
 
 
+def test_sparse_adam_closed_form_is_pinned_to_torch_sparse_adam():
+    """Lazy sparse Adam has no Daisy counterpart (BPRMFRecommender.py:154 is optim.SGD): its stated oracle is
+    torch.optim.SparseAdam on nn.Embedding(sparse=True) under the reference's loss (BPRMFRecommender.py:172-176).
+    Four steps with repeated rows, rows that skip steps (their moments must stay put), float64 and float32."""
+    import torch
+    rng = np.random.default_rng(5)
+    U, I, D, B = 40, 30, 16, 200
+    P0 = (rng.standard_normal((U, D)) * 0.3)
+    Q0 = (rng.standard_normal((I, D)) * 0.3)
+    batches = []
+    for k in range(4):
+        t = np.stack([rng.integers(0, U - 5 * (k % 2), B), rng.integers(0, I // 2, B), rng.integers(0, I, B)], 1)
+        t[:40, 1] = 3                                     # a hot positive item
+        batches.append(t.astype(np.int32))
+    for dtype, tdtype, tol in ((np.float64, torch.float64, 1e-12), (np.float32, torch.float32, 1e-5)):
+        eu = torch.nn.Embedding(U, D, sparse=True, dtype=tdtype)
+        ei = torch.nn.Embedding(I, D, sparse=True, dtype=tdtype)
+        with torch.no_grad():
+            eu.weight.copy_(torch.from_numpy(P0))
+            ei.weight.copy_(torch.from_numpy(Q0))
+        opt = torch.optim.SparseAdam(list(eu.parameters()) + list(ei.parameters()), lr=0.01)
+        P, Q = P0.astype(dtype), Q0.astype(dtype)
+        st = [np.zeros_like(P), np.zeros_like(P), np.zeros_like(Q), np.zeros_like(Q)]
+        for k, b in enumerate(batches):
+            u, i, j = (torch.from_numpy(b[:, c].astype(np.int64)) for c in range(3))
+            opt.zero_grad()
+            pu = eu(u)
+            loss_t = -((pu * ei(i)).sum(-1) - (pu * ei(j)).sum(-1)).sigmoid().log().sum()
+            loss_t.backward()
+            opt.step()
+            P, Q, st[0], st[1], st[2], st[3], loss = bpr_oracle.bpr_adam_step_closed_form(P, Q, *st, b, k + 1, 0.01,
+                                                                                          dtype=dtype)
+            assert abs(loss - float(loss_t.detach())) / float(loss_t.detach()) < 1e-6
+            assert rel_err(P, eu.weight.detach().numpy()) <= tol, (dtype, k)
+            assert rel_err(Q, ei.weight.detach().numpy()) <= tol, (dtype, k)
+        sP, sQ = opt.state[eu.weight], opt.state[ei.weight]
+        assert rel_err(st[0], sP["exp_avg"].numpy()) <= tol and rel_err(st[1], sP["exp_avg_sq"].numpy()) <= tol
+        assert rel_err(st[2], sQ["exp_avg"].numpy()) <= tol and rel_err(st[3], sQ["exp_avg_sq"].numpy()) <= tol
+
+
 def test_forward_matches_reference(golden):
     g = golden("bpr_small.npz")
     b = g["batches"][0]

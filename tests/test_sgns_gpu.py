@@ -2,8 +2,7 @@
 Item2Vec + SGNS + SGNSAdam classes against the golden run of the unmodified reference (recorded negatives, both sampling
 branches) and the closed-form oracle (oracle/sgns_oracle.py).
 
-EXPERIMENTAL PATH: csrc/sgns.cu was written after round 1's GPU budget was spent and has not run on a GPU yet, so this
-file is NOT part of the default `-m gpu` run: it runs with DAISY_EXPERIMENTAL=1 (first thing next round).
+First run on a B200 in round 2 (profiles/r02a_*).
 Tolerance 1e-5 relative (max-abs-diff / max-abs) on both tables and on the loss."""
 import os
 
@@ -12,9 +11,7 @@ import pytest
 
 from conftest import rel_err
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DAISY_EXPERIMENTAL") != "1",
-                                 reason="csrc/sgns.cu has not run on a GPU yet: set DAISY_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 

@@ -2,8 +2,7 @@
 drop-in SVDpp class against the golden run of the reference's own compiled Cython class (tests/golden/svdpp_small.npz)
 and the C oracle (oracle/mf_oracle.c: mf_oracle_svdpp_fit, bit-identical to that class).
 
-EXPERIMENTAL PATH: csrc/svdpp.cu was written after round 1's GPU budget was spent and has not run on a GPU yet, so this
-file is NOT part of the default `-m gpu` run: it runs with DAISY_EXPERIMENTAL=1 (first thing next round).
+First run on a B200 in round 2 (profiles/r02a_*).
 float64 on both sides; two sums are re-associated on the device (history rows over warps, factors over lanes), so
 agreement is to rounding (1e-9 relative, as for funk-SVD), the sequential update ORDER is the reference's."""
 import os
@@ -11,9 +10,7 @@ import os
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DAISY_EXPERIMENTAL") != "1",
-                                 reason="csrc/svdpp.cu has not run on a GPU yet: set DAISY_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 pd = pytest.importorskip("pandas")
 
