@@ -188,6 +188,13 @@ def run_reference(args):
                              "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if args.gpus > 1:
+        # said in the line itself: this arm is NOT the b200 arm's configuration (one rank's 1/N shard of the tables, one
+        # rank's batch), so a ratio of the two values is not a like-for-like speed-up
+        line["same_config"] = False
+        line["config"]["note"] = (f"config 5 does not fit the reference's single-process CPU path (61 GB of tables + dense "
+                                  f"gradients): one rank's 1/{args.gpus} shard with one rank's batch, for scale only -- "
+                                  f"not comparable with the {args.gpus}-GPU line")
     print(json.dumps(line), flush=True)
 
 
@@ -217,10 +224,13 @@ def run_single(args):
     opt = BPRSGD(model, lr=cfg["lr"], weight_decay=cfg["wd"])
     h = model.handle(B)
     if args.l2_window:                          # north star: hot item rows pinned in L2 (access-policy window)
-        model.pin_hot_items(None, 1.0)
+        model.pin_hot_items(args.l2_window_rows or None, 1.0)
 
     nb = K + W
-    host = torch.from_numpy(synthetic_triples(nb * B, U, I, seed=2019, zipf=cfg["zipf"]).reshape(nb, B, 3)).pin_memory()
+    # --hot-prefix: item id = popularity rank (what a popularity-ordered catalogue, or a popularity remap, looks like):
+    # the Zipf head is a contiguous prefix of the item table, which is what an access-policy window can cover
+    host = torch.from_numpy(synthetic_triples(nb * B, U, I, seed=2019, zipf=cfg["zipf"],
+                                              permute_items=not args.hot_prefix).reshape(nb, B, 3)).pin_memory()
     devtri = host.to(dev)
     loss_dev = torch.zeros(nb, dtype=torch.float64, device=dev)
     loss_host = torch.zeros(nb, dtype=torch.float64).pin_memory()
@@ -324,11 +334,13 @@ def run_single(args):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["workload"], "user_num": U, "item_num": I, "dim": D, "batch": B,
-                       "lr": cfg["lr"], "wd": cfg["wd"], "item_popularity": "zipf(1.0), permuted",
+                       "lr": cfg["lr"], "wd": cfg["wd"], "item_popularity": "zipf(1.0), " + ("id = popularity rank" if args.hot_prefix else "permuted"),
                        "l2": ("inputs larger than L2 (6.1 GB of tables, ~3 GB touched per step vs 126 MB L2)"
                               if args.workload == "config4" else
                               "tables (85 MB) fit the 126 MB L2: L2-resident workload, the HBM roofline does not bound it"),
                        "l2_access_policy_window": bool(args.l2_window),
+                       "l2_window_rows": (args.l2_window_rows or I) if args.l2_window else 0,
+                       "hot_items_are_a_prefix": bool(args.hot_prefix),
                        "lazy_decay_materialized_in_timed_region": ("once, after the last timed step (as at an epoch end)" if not mat_every
                                                                    else f"every {mat_every} steps and after the last timed step"),
                        "api": ("BPRSGD.epoch -> daisy_bpr_epoch: ONE library call runs the K timed steps"
@@ -588,8 +600,7 @@ def run_bprfm(args):
 
 
 def run_experimental(args):
-    """Secondary lines of the two EXPERIMENTAL next-row paths (not yet run on a GPU when this was written; DESIGN.md
-    section 9): `--workload bprfm_bn` = BPR-FM at the script's defaults (batch norm + dropout 0.5, ml-100k shape,
+    """Secondary lines of three next-row paths: `--workload bprfm_bn` = BPR-FM at the script's defaults (batch norm + dropout 0.5, ml-100k shape,
     hidden_factor 64, batch 4 096, Adagrad) through FMBNAdagrad.step; `--workload sgns` = Item2Vec / SGNS at the script's
     defaults (window 5 -> 10 context items, 20 negatives, e_dim 300, batch 4 096, Adam; ml-100k vocabulary) through
     SGNSAdam.step.  Device-timed steps with resident inputs, then the same steps from pinned host inputs with the loss
@@ -621,6 +632,9 @@ def run_experimental(args):
         workload = ("BPR-FM training step at the script's defaults on the ml-100k shape (943 + 1682 features, hidden_factor "
                     "64, batch 4096, batch norm, dropout 0.5 drawn on the device, Adagrad lr 0.05)")
         h2d = B * 12
+        # per triple: 3 feature rows and their Adagrad accumulators read and written (embedding + bias) + the ids
+        alg_bytes = B * (3 * 2 * 2 * 4 * (F + 1) + 12)
+        alg_note = "3 rows x (value + Adagrad state) x (read + write) x 4 (F + 1) B + 12 B of ids per triple"
     elif args.workload == "neumf":
         from recommend_lib_b200.ncf_mlp import NeuMF, NeuMFAdam
         from oracle import neumf_oracle
@@ -646,6 +660,9 @@ def run_experimental(args):
         workload = ("NCF training step, model 'NeuMF-end' at the script's defaults on the ml-100k shape (943 x 1682, factor_num "
                     "32, 3 MLP layers, batch 256, dropout 0, Adam lr 0.001)")
         h2d = B * 12
+        n_param = sum(p.numel() for p in model.parameters())
+        alg_bytes = 8 * 4 * n_param + B * 12       # torch's dense Adam: param, grad, m, v read + written, whatever B is
+        alg_note = "dense Adam over every parameter (8 x 4 B per element per step, independent of the batch) + ids"
     else:
         from recommend_lib_b200.item2vec import Item2Vec, SGNS, SGNSAdam
         from oracle import sgns_oracle
@@ -668,6 +685,10 @@ def run_experimental(args):
         workload = ("Item2Vec / SGNS training step at the script's defaults (ml-100k vocabulary of 1683, e_dim 300, batch "
                     "4096, 10 context items, 20 negatives each drawn on the device from unigram^0.75, dense Adam)")
         h2d = B * 4 * (1 + C)
+        # per example: the centre row + C (1 + n_negs) output rows gathered; per step: dense Adam over both tables
+        alg_bytes = B * (1 + C * (1 + N)) * 4 * D + 2 * V * D * 8 * 4
+        alg_note = ("(1 + C (1 + n_negs)) rows x 4 e_dim B gathered per example + dense Adam over both tables "
+                    "(8 x 4 B per element per step)")
     devin = [tuple(t.to(dev) for t in x) for x in inputs]
     for s in range(W):
         opt.step(*devin[s])
@@ -699,11 +720,18 @@ def run_experimental(args):
     cpu_dt = time.time() - t0
     line = {"metric": metric, "value": units * K / (ms * 1e-3), "unit": unit, "n_gpus": 1, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": workload, "batch": B, "status": "experimental path, first version",
+            "data": "synthetic", "config": {"workload": workload, "batch": B, "status": "first version (GPU-verified in round 2)",
                                             "l2": "tables are L2-resident at this size"},
             "e2e": {"value": units * K / (ms2 * 1e-3), "unit": unit, "ms_per_step": ms2 / K, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 8},
-            "gpu_launches": int(launches), "roofline": None,
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms / K * 1e-3) / 1e9, "peak": measured_peaks()[0], "unit": "GB/s",
+                         "frac": alg_bytes / (ms / K * 1e-3) / 1e9 / measured_peaks()[0], "traffic": None,
+                         "algorithmic_bytes_per_step": alg_bytes, "kernel": "whole step (every launch of the step)",
+                         "peak_source": measured_peaks()[1],
+                         "note": alg_note + "; the tables are L2-resident at the script's sizes, so the step is bound by "
+                                 "launch latency and dependent passes, not by HBM: the fraction says how far from a "
+                                 "bandwidth-bound regime this shape is, not how good the kernels are"},
             "cpu_baseline": {"value": units * nc / cpu_dt, "unit": unit, "cores": 1, "kind": "port",
                              "sample": f"{nc} steps of the closed-form restatement (numpy, float64) of the reference loop"},
             "mean_loss_per_step": loss_dev}
@@ -905,7 +933,9 @@ def run_sampler(args):
 # ------------------------------------------------------------------------------------------------
 def run_eval(args):
     """users/s of daisy_topk_full: top-100 of all 2 M items for a seeded sample of 16 384 users (SURVEY 8d, config 4's
-    evaluation), fp32 scores on CUDA cores (ranking parity) + exact radix select."""
+    evaluation).  Default: candidates filtered on the tensor cores (k_filter_tc: tcgen05 BF16 MMA, TMEM accumulators, TMA
+    operand tiles) with an error-bounded threshold, re-scored in exact fp32 and selected -- bit-identical to the fp32
+    CUDA-core path (DAISY_TOPK_TC=0), which this line also times on a bounded sample of the users and compares."""
     import torch
     from recommend_lib_b200.bpr import BPR
     from recommend_lib_b200.metrics import topk_full
@@ -917,41 +947,82 @@ def run_eval(args):
     model.embed_user.weight = torch.nn.Parameter(torch.empty((U, D), device=dev).normal_(0, 0.01), requires_grad=False)
     model.embed_item.weight = torch.nn.Parameter(torch.empty((I, D), device=dev).normal_(0, 0.01), requires_grad=False)
     users = torch.from_numpy(np.random.default_rng(2019).choice(U, N, replace=False).astype(np.int32)).to(dev)
-    K_steps, W = max(1, min(args.steps, 3)), 1
-    for _ in range(W):
-        items, scores = topk_full(model, users[:2048], K)
+    use_tc = os.environ.get("DAISY_TOPK_TC", "1") != "0"
+    K_steps, W = max(1, min(args.steps, 5)), 3
+    for _ in range(W):                                 # full size: the workspace pool grows to its final size here
+        items, scores = topk_full(model, users, K)
     torch.cuda.synchronize()
+    h = model.handle()
+    h.set_timing(1)
+    h.topk_tc_ms()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    watch = ClockSampler(0)
+    watch.start()
     ev0.record()
     for _ in range(K_steps):
         items, scores = topk_full(model, users, K)
     ev1.record()
     torch.cuda.synchronize()
     model.check()
+    watch.stop()
+    clocks = watch.summary()
     ms = ev0.elapsed_time(ev1) / K_steps
+    f_ms, r_ms, n_tc = h.topk_tc_ms()
+    h.set_timing(0)
     flops = 2.0 * N * I * D
-    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    # the CUDA-core filter on a bounded sample of the same users: same answer bit for bit, and its time beside it
+    n_cmp = min(N, 2048)
+    os.environ["DAISY_TOPK_TC"] = "0"
+    topk_full(model, users[:256], K)
+    torch.cuda.synchronize()
+    ev0.record()
+    it_s, sc_s = topk_full(model, users[:n_cmp], K)
+    ev1.record()
+    torch.cuda.synchronize()
+    simt_ms = ev0.elapsed_time(ev1)
+    os.environ["DAISY_TOPK_TC"] = "1" if use_tc else "0"
+    same = bool(torch.equal(it_s, items[:n_cmp]) and torch.equal(sc_s, scores[:n_cmp]))
+    assert same, "tensor-core filtered top-K differs from the CUDA-core path"
     # bounded CPU sample: exact fp32 scores + argpartition for a few users (what a vectorised CPU ranking costs)
     from oracle import bpr_oracle
-    Pc = model.embed_user.weight[users[:8].long()].cpu().numpy()
-    Qc = model.embed_item.weight.cpu().numpy()
+    Pc = model._tables()[0][users[:8].long()].cpu().numpy()
+    Qc = model._tables()[1].cpu().numpy()
     t0 = time.time()
     ref_items, _ = bpr_oracle.full_topk(Pc, Qc, np.arange(8), K)
     cpu_dt = time.time() - t0
     agree = float((items[:8].cpu().numpy() == ref_items).mean())
+    peaks = measured_peaks()[2]
+    if use_tc and n_tc:
+        tc_peak = float(peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 2250.0)
+        ach = flops / (f_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "k_filter_tc", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s",
+                "frac": ach / tc_peak, "traffic": None, "kernel_ms": f_ms, "launches_timed": n_tc,
+                "algorithmic_flops_per_launch": flops,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, back to back)" if peaks else
+                               "nominal dense bf16 2250 TFLOP/s (MEASURED_PEAKS.json absent)",
+                "rescore_kernel_ms": r_ms, "whole_call_tflops": flops / (ms * 1e-3) / 1e12,
+                "note": "BF16 tcgen05 filter with an error-bounded threshold (candidate superset), then exact fp32 "
+                        "re-scoring + selection: results bit-identical to the fp32 CUDA-core path"}
+    else:
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        roof = {"bound": "fp32-fma", "kernel": "k_score_tile", "achieved": flops / (ms * 1e-3) / 1e12, "peak": fp32_peak,
+                "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / fp32_peak, "traffic": None,
+                "note": "CUDA-core fp32 filter (DAISY_TOPK_TC=0); peak = 148 SMs x 128 FMA/clk x 1.965 GHz (nominal)"}
     line = {"metric": "bpr_full_catalogue_topk_users_per_s", "value": N / (ms * 1e-3), "unit": "users/s", "n_gpus": 1,
             "steps": K_steps, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "bf16 filter + f32 ranking" if use_tc else "f32", "data": "synthetic",
             "config": {"workload": "full-catalogue top-100 for 16 384 users of config 4 (2 M items, dim 128)", "users": N,
-                       "item_num": I, "dim": D, "top_k": K, "step": "one evaluation of all sampled users"},
-            "roofline": {"bound": "fp32-fma", "achieved": flops / (ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": flops / (ms * 1e-3) / 1e12 / fp32_peak, "traffic": None,
-                         "note": "CUDA-core fp32 (scores must be fp32 sums of fp32 products for ranking parity); peak = "
-                                 "148 SMs x 128 FMA/clk x 1.965 GHz (nominal, not in MEASURED_PEAKS.json)"},
+                       "item_num": I, "dim": D, "top_k": K, "step": "one evaluation of all sampled users",
+                       "l2": "inputs larger than L2 (1 GB item table + 0.5 GB bf16 copy)"},
+            "roofline": roof,
+            "cuda_core_path": {"users": n_cmp, "ms": simt_ms, "users_per_s": n_cmp / (simt_ms * 1e-3),
+                               "identical_items_and_scores": same},
             "cpu_baseline": {"value": 8 / cpu_dt, "unit": "users/s", "cores": os.cpu_count(), "kind": "port",
                              "sample": "numpy fp32 scores + exact top-100 for 8 users (oracle full_topk), agreement "
                                        f"with the device's items {agree:.3f}"},
             "gpu_launches": int(model.handle().launches)}
+    if clocks:
+        line["clocks"] = clocks
     print(json.dumps(line), flush=True)
 
 
@@ -978,6 +1049,9 @@ def main():
     ap.add_argument("--epoch-api", action="store_true",
                     help="config3/config4: run the K timed steps through ONE daisy_bpr_epoch call (BPRSGD.epoch)")
     ap.add_argument("--l2-window", action="store_true", help="pin the item table in L2 (access-policy window)")
+    ap.add_argument("--l2-window-rows", type=int, default=0, help="rows of the item table the window covers (0 = all)")
+    ap.add_argument("--hot-prefix", action="store_true",
+                    help="experiment: item id = popularity rank (hot items are a prefix of the table)")
     ap.add_argument("--mapping", default="symm", choices=["symm", "ipc"],
                     help="N > 1, peer exchange: how the ranks map each other's arenas")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
@@ -989,7 +1063,7 @@ def main():
         return run_reference(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 or world > 1:
-        from recommend_lib_b200.sharded import bench_sharded
+        from bench_sharded import bench_sharded
         return bench_sharded(args, CFG5, METRIC, UNIT)
     if args.workload == "config1":
         return run_config1(args)

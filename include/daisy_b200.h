@@ -191,9 +191,10 @@ DAISY_API int daisy_shard_last_counts(daisy_handle_t h, uint32_t *owner_off_out,
 
 /* Lazy sparse Adam variant of the step (no Daisy counterpart -- BPR-MF uses SGD only; semantics =
  * torch.optim.SparseAdam: only rows present in the batch change, weights and moments alike).
- * mP,vP [user_num,dim], mQ,vQ [item_num,dim] fp32 moments owned by the caller; step_no is 1-based. */
+ * mP,vP [user_num,dim], mQ,vQ [item_num,dim] fp32 moments owned by the caller; step_no is 1-based.  The betas are
+ * doubles: torch forms 1 - beta in double before it meets the fp32 tensors (1.f - 0.999f is off by 1.3e-5). */
 DAISY_API int daisy_bpr_adam_step(daisy_handle_t h, float *P, float *Q, float *mP, float *vP, float *mQ, float *vQ,
-                        const int32_t *triples, int64_t B, float lr, float beta1, float beta2, float eps,
+                        const int32_t *triples, int64_t B, float lr, double beta1, double beta2, float eps,
                         int64_t step_no, double *loss_accum, daisy_stream_t stream);
 
 /* ---- BPR-FM with two one-hot features per example ------------------
@@ -266,6 +267,14 @@ DAISY_API int daisy_topk_full(daisy_handle_t h, const float *P, const float *Q, 
 DAISY_API int daisy_sample_triples(daisy_handle_t h, const int32_t *pairs, int64_t n_pairs, int num_ng,
                                    const int64_t *pos_keys, int64_t n_keys, uint64_t seed, uint32_t epoch, int shuffle,
                                    int32_t *triples_out, daisy_stream_t stream);
+
+/* Row-sharded training (no counterpart in the single-device reference): the share of rank
+ * [u0, u1) of a GLOBAL epoch.  triples int32 [n,3] (device; global ids, the same on every rank, already shuffled) ->
+ * out: the triples whose user lies in [u0, u1), order kept, user column made local; batch_off [ceil(n/batch)+1]
+ * (device, int64): where the rank's share of each global batch of `batch` triples starts in out.  Step k of every
+ * rank then runs on out[batch_off[k] .. batch_off[k+1]) and the sharded step equals daisy_bpr_step on global batch k. */
+DAISY_API int daisy_route_triples(daisy_handle_t h, const int32_t *triples, int64_t n, int64_t batch, int64_t u0,
+                                  int64_t u1, int32_t *out, int64_t *batch_off, daisy_stream_t stream);
 
 /* ---- funk-SVD / RSVD (util/matrix_factorization.pyx) ---------------------------------------------
  * variant: 0 = SVD (:132-151), 1 = RSVD version 1, 2 = RSVD version 2 (:41-61).
@@ -423,6 +432,10 @@ DAISY_API int daisy_last_step_timing(daisy_handle_t h, float *ms_main_kernel, fl
 /* Timing mode 1 (asynchronous, main fused kernel only): average device time of that kernel over the steps
  * issued since daisy_set_timing(h, 1), and how many launches were measured.  Synchronises on the events. */
 DAISY_API int daisy_main_kernel_ms(daisy_handle_t h, double *avg_ms, int64_t *count);
+/* daisy_topk_full with timing on (daisy_set_timing(h, 1)): device time of the tensor-core filter kernel (k_filter_tc)
+ * and of the whole call's filtered path, averaged over the calls since the last query; *count = filter launches
+ * measured (0: the tensor-core filter did not run).  Synchronises on the events; resets the averages. */
+DAISY_API int daisy_topk_tc_ms(daisy_handle_t h, double *filter_ms, double *rescore_ms, int64_t *count);
 /* Timing mode 2 (synchronises once per step): average device time of each phase of the step, in launch order:
  * prep, sort_i, refs, sort_u, sort_q, slots, main, seg_u, seg_q, heavy, loss (11 values). */
 #define DAISY_NUM_PHASES 11

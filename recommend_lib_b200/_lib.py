@@ -100,11 +100,12 @@ SIGNATURES = {
     "daisy_shard_peer_q": [c_vp, c_i32, ctypes.POINTER(c_vp)],
     "daisy_gather_rows": [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp],
     "daisy_shard_phase_ms": [c_vp, ctypes.POINTER(c_f64), ctypes.POINTER(c_i64)],
-    "daisy_bpr_adam_step": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32,
+    "daisy_bpr_adam_step": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f64, c_f64, c_f32,
                             c_i64, c_vp, c_vp],
     "daisy_topk_candidates": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp],
     "daisy_topk_full": [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp],
     "daisy_sample_triples": [c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, ctypes.c_uint64, ctypes.c_uint32, c_i32, c_vp, c_vp],
+    "daisy_route_triples": [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp],
     "daisy_mf_fit": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, ctypes.POINTER(MFParams),
                      c_vp, c_vp],
     "daisy_mf_predict": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_f64, c_vp, c_vp],
@@ -124,6 +125,7 @@ SIGNATURES = {
     "daisy_set_timing": [c_vp, c_i32],
     "daisy_last_step_timing": [c_vp, ctypes.POINTER(c_f32), ctypes.POINTER(c_f32)],
     "daisy_main_kernel_ms": [c_vp, ctypes.POINTER(c_f64), ctypes.POINTER(c_i64)],
+    "daisy_topk_tc_ms": [c_vp, ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), ctypes.POINTER(c_i64)],
     "daisy_phase_ms": [c_vp, ctypes.POINTER(c_f64), c_i32, ctypes.POINTER(c_i64)],
     "daisy_set_l2_window": [c_vp, c_vp, c_i64, c_f32, c_vp],
     "daisy_trace": [c_vp, c_i32, ctypes.POINTER(c_f64), c_i32, ctypes.POINTER(c_i32)],
@@ -271,6 +273,12 @@ class Handle:
         avg, cnt = c_f64(), c_i64()
         check(self.L.daisy_main_kernel_ms(self.ptr, ctypes.byref(avg), ctypes.byref(cnt)))
         return avg.value, cnt.value
+
+    def topk_tc_ms(self):
+        """(filter kernel ms, rescore kernel ms, launches measured) of daisy_topk_full's tensor-core filter since the last call."""
+        f, r, cnt = c_f64(), c_f64(), c_i64()
+        check(self.L.daisy_topk_tc_ms(self.ptr, ctypes.byref(f), ctypes.byref(r), ctypes.byref(cnt)))
+        return f.value, r.value, cnt.value
 
     def phase_ms(self):
         arr = (c_f64 * NUM_PHASES)()

@@ -206,6 +206,8 @@ extern "C" int daisy_destroy(daisy_handle_t h) {
     }
     for (int i = 0; i < DAISY_MAX_BGRAPH; ++i)
         if (h->bgraph[i].exec) cudaGraphExecDestroy(h->bgraph[i].exec);
+    for (int i = 0; i < 3; ++i)
+        if (h->tc_ev[i]) cudaEventDestroy(h->tc_ev[i]);
     if (h->pool_state == 1) cudaMemPoolDestroy(h->pool);
     if (h->err_host) cudaFreeHost(h->err_host);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
@@ -241,6 +243,10 @@ extern "C" int daisy_check(daisy_handle_t h, daisy_stream_t stream) {
         }
         if (bits & 32) {
             daisy_set_error("sharded step: a receive region overflowed");
+            return DAISY_ECUDA;
+        }
+        if (bits & 256) {
+            daisy_set_error("daisy_topk_full: the tensor-core filter pipeline timed out (an mbarrier never completed)");
             return DAISY_ECUDA;
         }
         daisy_set_error("index out of range in self (first offending position %d; user ids must be < %lld, item ids < %lld)",

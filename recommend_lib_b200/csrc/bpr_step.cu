@@ -55,13 +55,14 @@ struct SgdOpt {
 struct AdamOpt {
     static constexpr bool kNeedOldItem = true;
     float *P, *Q, *mP, *vP, *mQ, *vQ;
-    float b1, b2, step_size, eps;   // step_size = lr * sqrt(1 - b2^t) / (1 - b1^t)
+    float omb1, omb2, step_size, eps;   // 1 - beta1, 1 - beta2 (rounded from double: 1.f - 0.999f is off by 1.3e-5 of
+                                        // its value); step_size = lr * sqrt(1 - b2^t) / (1 - b1^t)
     int D4;
     // torch/optim/_functional.py: sparse_adam -- old += (1 - b) * (new - old); denom = sqrt(v) + eps (eps is NOT
     // divided by the bias correction, unlike dense Adam); param -= step_size * m / denom
     __device__ __forceinline__ float one(float w, float g, float &m, float &v) const {
-        m = fmaf(1.f - b1, g - m, m);
-        v = fmaf(1.f - b2, g * g - v, v);
+        m = fmaf(omb1, g - m, m);
+        v = fmaf(omb2, g * g - v, v);
         return w - step_size * (m / (sqrtf(v) + eps));
     }
     __device__ __forceinline__ void apply(int tbl, size_t row, int e, float4 old, float4 d) const {
@@ -181,7 +182,7 @@ extern "C" int daisy_bpr_epoch(daisy_handle_t h, float *P, float *Q, const int32
 }
 
 extern "C" int daisy_bpr_adam_step(daisy_handle_t h, float *P, float *Q, float *mP, float *vP, float *mQ, float *vQ,
-                                   const int32_t *triples, int64_t B, float lr, float beta1, float beta2, float eps,
+                                   const int32_t *triples, int64_t B, float lr, double beta1, double beta2, float eps,
                                    int64_t step_no, double *loss_accum, daisy_stream_t stream) {
     int rc = check_step_args(h, P, Q, triples, B);
     if (rc) return rc;
@@ -193,10 +194,10 @@ extern "C" int daisy_bpr_adam_step(daisy_handle_t h, float *P, float *Q, float *
     DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
     AdamOpt opt;
     opt.P = P; opt.Q = Q; opt.mP = mP; opt.vP = vP; opt.mQ = mQ; opt.vQ = vQ;
-    opt.b1 = beta1;
-    opt.b2 = beta2;
-    const double bc1 = 1.0 - pow((double)beta1, (double)step_no);
-    const double bc2 = 1.0 - pow((double)beta2, (double)step_no);
+    opt.omb1 = (float)(1.0 - beta1);
+    opt.omb2 = (float)(1.0 - beta2);
+    const double bc1 = 1.0 - pow(beta1, (double)step_no);
+    const double bc2 = 1.0 - pow(beta2, (double)step_no);
     opt.step_size = (float)((double)lr * sqrt(bc2) / bc1);
     opt.eps = eps;
     opt.D4 = h->D / 4;

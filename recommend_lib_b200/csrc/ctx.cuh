@@ -167,6 +167,10 @@ struct daisy_ctx {
     int pool_state;  // 0 not created, 1 ready, -1 creation failed (cudaMallocAsync from the default pool, untuned)
 
     // --- instrumentation ---
+    cudaEvent_t tc_ev[3];             // timing != 0: around k_filter_tc and k_rescore of the last daisy_tc_filter call
+    int tc_ev_pending;
+    double tc_filter_ms, tc_rescore_ms;
+    int64_t tc_count;
     int64_t launches;
     int timing;                       // 0 off, 1 main kernel only (asynchronous event pool), 2 every phase (syncs per step)
     cudaEvent_t ev[PH_COUNT + 1];     // timing == 2

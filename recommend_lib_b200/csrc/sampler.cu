@@ -15,6 +15,7 @@
 //           until u * item_num + j is not in the sorted positive-key list (binary search)
 //   shuffle: slots ordered by (philox(key = seed ^ (0, 0x9E3779B9), ctr = (s_lo, s_hi, epoch, 0xFFFFFFFF))[0], s)
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "ctx.cuh"
 
@@ -95,6 +96,30 @@ __global__ void k_permute_triples(const int32_t *__restrict__ in, const uint32_t
     out[3 * r + 2] = in[3 * s + 2];
 }
 
+// ---- owner routing of a global epoch (row-sharded training) -------------------------------------
+__global__ void k_route_flag(const int32_t *__restrict__ tri, long long n, uint32_t u0, uint32_t u1, uint32_t *__restrict__ flag) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint32_t u = (uint32_t)tri[3 * t];
+    flag[t] = (u >= u0 && u < u1) ? 1u : 0u;
+}
+// pos = exclusive prefix sum of flag: a kept triple lands at pos[t] (stable: the order inside a batch is the epoch's),
+// and the first triple of global batch b records where the rank's share of that batch starts
+__global__ void k_route_scatter(const int32_t *__restrict__ tri, long long n, long long batch, uint32_t u0,
+                                const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
+                                int32_t *__restrict__ out, int64_t *__restrict__ batch_off, long long n_batches) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint32_t p = pos[t];
+    if (t % batch == 0) batch_off[t / batch] = (int64_t)p;
+    if (t == n - 1) batch_off[n_batches] = (int64_t)p + flag[t];
+    if (flag[t]) {
+        out[3 * (size_t)p] = (int32_t)((uint32_t)tri[3 * t] - u0);
+        out[3 * (size_t)p + 1] = tri[3 * t + 1];
+        out[3 * (size_t)p + 2] = tri[3 * t + 2];
+    }
+}
+
 }  // namespace
 
 extern "C" int daisy_sample_triples(daisy_handle_t h, const int32_t *pairs, int64_t n_pairs, int num_ng,
@@ -151,6 +176,55 @@ extern "C" int daisy_sample_triples(daisy_handle_t h, const int32_t *pairs, int6
         }
     }
     for (void *p : {(void *)tmp_tri, (void *)key, (void *)key_s, (void *)val, (void *)val_s, cub_tmp})
+        if (p) cudaFreeAsync(p, s);
+    return rc;
+}
+
+// Row-sharded training (one process per GPU, users block-sharded): the rank's share of a GLOBAL epoch.  triples is the
+// epoch every rank holds identically (int32 [n, 3], global ids, already shuffled; device memory); the triples whose
+// user lies in [u0, u1) are compacted into out -- order kept, user column made local (u - u0) -- and batch_off
+// [ceil(n / batch) + 1] (device, int64) receives where the rank's share of every global batch of `batch` triples
+// starts, so that step k of every rank processes exactly its part of global batch k: the sharded step then equals
+// daisy_bpr_step on the global batch (tests/test_sharded_gpu.py).  No counterpart in the reference (single device).
+extern "C" int daisy_route_triples(daisy_handle_t h, const int32_t *triples, int64_t n, int64_t batch, int64_t u0, int64_t u1,
+                                   int32_t *out, int64_t *batch_off, daisy_stream_t stream) {
+    DAISY_REQUIRE(h != nullptr, DAISY_EINVAL, "null handle");
+    DAISY_REQUIRE(n >= 0 && n < (1LL << 31) && batch >= 1 && u0 >= 0 && u1 >= u0 && u1 < (1LL << 32), DAISY_EINVAL, "bad sizes");
+    DAISY_REQUIRE(batch_off != nullptr, DAISY_EINVAL, "null argument");
+    DeviceGuard g(h->device);
+    DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) {
+        DAISY_CUDA(cudaMemsetAsync(batch_off, 0, sizeof(int64_t), s));
+        return DAISY_OK;
+    }
+    DAISY_REQUIRE(triples && out, DAISY_EINVAL, "null argument");
+    const long long n_batches = (n + batch - 1) / batch;
+    uint32_t *flag = nullptr, *pos = nullptr;
+    void *tmp = nullptr;
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, flag, pos, (int)n, s);
+    bool ok = daisy_scratch_alloc(h, (void **)&flag, (size_t)n * 4, s) == cudaSuccess;
+    ok = ok && daisy_scratch_alloc(h, (void **)&pos, (size_t)n * 4, s) == cudaSuccess;
+    ok = ok && daisy_scratch_alloc(h, &tmp, tb + 256, s) == cudaSuccess;
+    int rc = DAISY_OK;
+    if (!ok) {
+        cudaGetLastError();
+        daisy_set_error("routing scratch allocation failed (%lld triples)", (long long)n);
+        rc = DAISY_ENOMEM;
+    } else {
+        const int T = 256, grid = daisy_ceil_div(n, T);
+        k_route_flag<<<grid, T, 0, s>>>(triples, n, (uint32_t)u0, (uint32_t)u1, flag);
+        size_t tb2 = tb + 256;
+        cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tb2, flag, pos, (int)n, s);
+        k_route_scatter<<<grid, T, 0, s>>>(triples, n, batch, (uint32_t)u0, flag, pos, out, batch_off, n_batches);
+        h->launches += 4;
+        if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+            daisy_set_error("routing launch failed: %s", cudaGetErrorString(e));
+            rc = DAISY_ECUDA;
+        }
+    }
+    for (void *p : {(void *)flag, (void *)pos, tmp})
         if (p) cudaFreeAsync(p, s);
     return rc;
 }

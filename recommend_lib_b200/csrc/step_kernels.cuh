@@ -1222,7 +1222,7 @@ __global__ void DAISY_SEG_BOUNDS k_seg_all(const float *__restrict__ P, const fl
                                                   float *__restrict__ stage2, int D4, Opt opt, int NS, int blocksU,
                                                   int blocksQ, int long_len, const uint32_t *__restrict__ longs,
                                                   int longs_cap, uint32_t *ticket, const float *__restrict__ loss_part,
-                                                  int n_part, double *loss_accum) {
+                                                  int n_part, double *loss_accum, int ilvQ) {
     const int b = blockIdx.x, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     if (b >= NS + blocksU + blocksQ) {  // fixed-order reduction of the per-warp loss partials (double accumulation)
@@ -1243,7 +1243,15 @@ __global__ void DAISY_SEG_BOUNDS k_seg_all(const float *__restrict__ P, const fl
     if (b >= NS) {
         const int wb = b - NS;
         const int tbl = wb < blocksU ? 0 : 1;
-        seg_window<V, Opt, WIN>((long long)(tbl ? wb - blocksU : wb) * 8 + wid, tbl, tbl ? Q : P, tbl ? qkey_s : ukey_s,
+        int w = tbl ? wb - blocksU : wb;
+        if (tbl && ilvQ > 1) {
+            // row-sharded step: the sorted item refs are grouped by owner, so blocks that start together would all
+            // push to the same owner (incast); deal the item blocks round-robin over ilvQ ranges of the order instead
+            // (blocksQ was rounded up to a multiple of ilvQ by the launcher; windows past the end find no refs)
+            const int per = blocksQ / ilvQ;
+            w = (w % ilvQ) * per + w / ilvQ;
+        }
+        seg_window<V, Opt, WIN>((long long)w * 8 + wid, tbl, tbl ? Q : P, tbl ? qkey_s : ukey_s,
                                 tbl ? nQ : B, tbl ? q_sentinel : 0xFFFFFFFFu, tbl ? stageQ : stageU, D4, opt, long_len);
         return;
     }
@@ -1744,21 +1752,24 @@ static int table_phase_v(daisy_ctx *h, const StepPlan &pl, const float *P, const
     {   // every multi-contribution row of both tables + the loss in one launch
         const int NS = (pl.small && B <= DAISY_SMALL_CAP) ? 64 : 2 * h->num_sms;
         int blocksU, blocksQ;
+        const int ilvQ = (pl.jsrc && pl.ilv > 1) ? pl.ilv : 0;   // row-sharded step: owner-interleaved item blocks
         if (pl.small) {
             blocksU = daisy_ceil_div(B, 8 * DAISY_SMALL_WIN), blocksQ = daisy_ceil_div(2 * B, 8 * DAISY_SMALL_WIN);
             k_seg_all<V, Opt, DAISY_SMALL_WIN, DAISY_SMALL_SLICE><<<NS + blocksU + blocksQ + (loss_accum ? 1 : 0), 256, 0, s>>>(
                 P, Q, k.ukey_s, k.qkey_s, B, 2 * B, 0xFFFFFFFFu, h->stageU, h->stageQ, h->stage2, D4, opt, NS, blocksU, blocksQ,
-                DAISY_SMALL_SLICE, k.longs, h->longs_cap, h->ticket, h->loss_part, warps, loss_accum);
+                DAISY_SMALL_SLICE, k.longs, h->longs_cap, h->ticket, h->loss_part, warps, loss_accum, 0);
         } else if (h->seg_win == 16) {  // DAISY_SEG_WIN: sorted refs per warp of the window blocks (general path)
             blocksU = daisy_ceil_div(B, 8 * 16), blocksQ = daisy_ceil_div(2 * (int64_t)B, 8 * 16);
+            if (ilvQ) blocksQ = daisy_ceil_div(blocksQ, ilvQ) * ilvQ;
             k_seg_all<V, Opt, 16, DAISY_SLICE><<<NS + blocksU + blocksQ + (loss_accum ? 1 : 0), 256, 0, s>>>(
                 P, Q, k.ukey_s, k.qkey_s, B, 2 * B, pl.I, h->stageU, h->stageQ, h->stage2, D4, opt, NS, blocksU, blocksQ,
-                h->heavy_len, k.longs, h->longs_cap, h->ticket, h->loss_part, warps, loss_accum);
+                h->heavy_len, k.longs, h->longs_cap, h->ticket, h->loss_part, warps, loss_accum, ilvQ);
         } else {
             blocksU = daisy_ceil_div(B, 8 * 32), blocksQ = daisy_ceil_div(2 * (int64_t)B, 8 * 32);
+            if (ilvQ) blocksQ = daisy_ceil_div(blocksQ, ilvQ) * ilvQ;
             k_seg_all<V, Opt, 32, DAISY_SLICE><<<NS + blocksU + blocksQ + (loss_accum ? 1 : 0), 256, 0, s>>>(
                 P, Q, k.ukey_s, k.qkey_s, B, 2 * B, pl.I, h->stageU, h->stageQ, h->stage2, D4, opt, NS, blocksU, blocksQ,
-                h->heavy_len, k.longs, h->longs_cap, h->ticket, h->loss_part, warps, loss_accum);
+                h->heavy_len, k.longs, h->longs_cap, h->ticket, h->loss_part, warps, loss_accum, ilvQ);
         }
         DAISY_LAUNCH_CHECK(h);
         for (int ph = PH_SEG_U; ph <= PH_LOSS; ++ph) phase_mark(h, ph, s);

@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include "ctx.cuh"
+#include "topk_tc.cuh"
 
 namespace {
 
@@ -427,7 +428,13 @@ extern "C" int daisy_topk_full(daisy_handle_t h, const float *P, const float *Q,
     if (r < 8) r = 8;
     if (r > 128) return exact_range(users, N, 0);
     const int cap = 4 * E;  // 8192 at K <= 128: 64 KB of keys in shared memory for the final sort
-    const int64_t Tu = N < 4096 ? N : 4096;
+    // step 2 on the tensor cores (topk_tc.cu: BF16 tcgen05 filter with an error-bounded threshold, then the exact fp32
+    // re-scoring of the candidates) unless DAISY_TOPK_TC=0 or the shape is outside its range (dim > 128)
+    const char *tc_env = getenv("DAISY_TOPK_TC");
+    const bool use_tc = !(tc_env && atoi(tc_env) == 0) && daisy_tc_supported(h);
+    const int64_t Tu_max = use_tc ? 16384 : 4096;
+    const int64_t Tu = N < Tu_max ? N : Tu_max;
+    TcItems tci = {nullptr, nullptr, 0};
     float *Qs = nullptr, *Ss = nullptr, *tscore = nullptr, *thr = nullptr;
     int32_t *titem = nullptr;
     int *cnt = nullptr, *redo = nullptr;
@@ -451,24 +458,31 @@ extern "C" int daisy_topk_full(daisy_handle_t h, const float *P, const float *Q,
         k_sample_rows<<<daisy_ceil_div(Ms, 8), 256, 0, s>>>(Q, stride, Ms, h->D / 4, Qs);
         h->launches++;
         cudaFuncSetAttribute(k_select_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * (int)sizeof(unsigned long long));
-        for (int64_t first = 0; first < N; first += Tu) {
+        if (use_tc) rc = daisy_tc_prepare_items(h, Q, &tci, s);
+        for (int64_t first = 0; first < N && !rc; first += Tu) {
             const int nu = (int)((N - first < Tu) ? (N - first) : Tu);
             dim3 gs((unsigned)((Ms + BN - 1) / BN), (unsigned)((nu + BM - 1) / BM));
             k_score_tile<false><<<gs, 256, 0, s>>>(P, Qs, users + first, nu, (uint32_t)h->U, Ms, h->D, c2, Ss, h->err, nullptr,
                                                    nullptr, nullptr, 0);
             k_select_topk<<<nu, SEL_THREADS, 0, s>>>(Ss, Ms, r, 0, titem, tscore);
             k_thr_from_topk<<<daisy_ceil_div(nu, 256), 256, 0, s>>>(tscore, r, nu, thr, cnt);
-            dim3 gf((unsigned)((I + BN - 1) / BN), (unsigned)((nu + BM - 1) / BM));
-            k_score_tile<true><<<gf, 256, 0, s>>>(P, Q, users + first, nu, (uint32_t)h->U, I, h->D, c2, nullptr, h->err, thr, cnt,
-                                                  cand, cap);
+            if (use_tc) {
+                rc = daisy_tc_filter(h, P, Q, &tci, users + first, nu, c2, thr, cnt, cand, cap, (int)((int64_t)r * I / Ms), s);
+                if (rc) break;
+            } else {
+                dim3 gf((unsigned)((I + BN - 1) / BN), (unsigned)((nu + BM - 1) / BM));
+                k_score_tile<true><<<gf, 256, 0, s>>>(P, Q, users + first, nu, (uint32_t)h->U, I, h->D, c2, nullptr, h->err, thr,
+                                                      cnt, cand, cap);
+            }
             k_select_cand<<<nu, 1024, cap * sizeof(unsigned long long), s>>>(cand, cnt, cap, K, first, excl_ptr, excl_idx,
                                                                              out_item, out_score, redo + first);
             h->launches += 5;
         }
-        if (cudaGetLastError() != cudaSuccess) {
+        if (!rc && cudaGetLastError() != cudaSuccess) {
             daisy_set_error("top-K launch failed");
             rc = DAISY_ECUDA;
         }
+        daisy_tc_free_items(&tci, s);
         redo_host = (int *)malloc((size_t)N * sizeof(int));
         if (!rc && (!redo_host || cudaMemcpyAsync(redo_host, redo, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
                     cudaStreamSynchronize(s) != cudaSuccess)) {

@@ -442,190 +442,190 @@ class PeerShardedBPR:
             out.append(torch.cat(parts))
         return out[0][:self.layout.user_num], out[1][:self.layout.item_num]
 
+    # ---- owner routing ----------------------------------------------------------------------------------------------
+    def route(self, triples, batch):
+        """The rank's share of a GLOBAL epoch (``daisy_route_triples``): ``triples`` int32 [n, 3] on the device with global
+        ids, identical on every rank and already shuffled.  Returns (local triples [m, 3] with the user column made local,
+        offsets: a list of ceil(n / batch) + 1 ints) -- step k of this rank runs on ``local[off[k]:off[k + 1]]``, its part
+        of global batch k, so the sharded step equals the single-device step on that batch."""
+        vp = self._lib.c_vp
+        t = triples
+        if not (t.is_cuda and t.dtype == torch.int32 and t.dim() == 2 and t.shape[1] == 3 and t.is_contiguous()):
+            raise ValueError("triples must be a contiguous int32 [n, 3] device tensor")
+        n, batch = int(t.shape[0]), int(batch)
+        nb = (n + batch - 1) // batch
+        out = torch.empty((max(n, 1), 3), dtype=torch.int32, device=self.device)
+        off = torch.zeros(nb + 1, dtype=torch.int64, device=self.device)
+        u0, u1 = self.layout.user_range(self.rank)
+        self._lib.check(self.h.L.daisy_route_triples(self.h.ptr, vp(t.data_ptr()), n, batch, u0, u1, vp(out.data_ptr()),
+                                                     vp(off.data_ptr()), self._s()))
+        off = off.cpu().tolist()                          # synchronises: the step loop slices on the host
+        return out[:off[-1]], off
+
+    # ---- evaluation over the sharded item table (users partitioned: every rank ranks its own users, no merge across
+    #      ranks; SURVEY.md section 8e) --------------------------------------------------------------------------------
+    def _peer_q(self, owner):
+        """The item shard of ``owner`` as mapped into this process: a [rows, D] tensor view on peer memory."""
+        q = self._lib.c_vp()
+        self._lib.check(self.h.L.daisy_shard_peer_q(self.h.ptr, int(owner), ctypes.byref(q)))
+        i0, i1 = self.layout.item_range(owner)
+        with torch.cuda.device(self.device):
+            return torch.as_tensor(_DeviceView(q.value, max(i1 - i0, 1), self.dim), device=self.device)[:i1 - i0], q.value
+
+    def _eval_handle(self, rows):
+        """A light handle (no step workspace) over (local users x `rows` item rows) for the evaluation kernels."""
+        key = int(rows)
+        hs = self.__dict__.setdefault("_eval_handles", {})
+        if key not in hs:
+            hs[key] = self._lib.Handle(self.device.index, max(self.P.shape[0], 1), max(key, 1), self.dim, 0)
+        return hs[key]
+
+    def gather_item_rows(self, items_global):
+        """Rows of the GLOBAL item table for sorted, duplicate-free ids (int64 / int32 device tensor): every owner's part
+        is read straight from that owner's memory (``daisy_gather_rows`` on the peer mapping).  Call after
+        ``materialize()`` (true weights; the call ends with the barrier that makes the peers' shards final)."""
+        vp = self._lib.c_vp
+        ids = items_global.to(device=self.device, dtype=torch.int64)
+        out = torch.empty((ids.shape[0], self.dim), dtype=torch.float32, device=self.device)
+        bounds = torch.searchsorted(ids, self.layout.item_bounds(self.device)).tolist()
+        for o in range(self.world):
+            a, b = bounds[o], bounds[o + 1]
+            if b > a:
+                _, qptr = self._peer_q(o)
+                idx = (ids[a:b] - self.layout.item_range(o)[0]).to(torch.int32).contiguous()
+                self._lib.check(self.h.L.daisy_gather_rows(self.h.ptr, vp(qptr), vp(idx.data_ptr()), b - a,
+                                                           vp(out[a:b].data_ptr()), self._s()))
+        return out
+
+    def topk_candidates(self, users_local, cands_global, top_k):
+        """``metric_eval`` semantics (util/metrics.py:46-66) for THIS rank's users: users_local [N] (local indices),
+        cands_global [N, C] (global item ids, ground truth first) -> candidate positions [N, K] in rank order.  The
+        candidates' rows are fetched once from their owners; scores and the (score desc, position asc) order are those of
+        ``daisy_topk_candidates`` on the unsharded tables."""
+        vp = self._lib.c_vp
+        users = torch.as_tensor(np.asarray(users_local)).to(self.device, torch.int32).contiguous()
+        cands = torch.as_tensor(np.asarray(cands_global)).to(self.device, torch.int64)
+        N, C = cands.shape
+        pos = torch.empty((N, top_k), dtype=torch.int32, device=self.device)
+        if N == 0:
+            return pos
+        uniq, inv = torch.unique(cands.reshape(-1), return_inverse=True)
+        cache = self.gather_item_rows(uniq)
+        cidx = inv.reshape(N, C).to(torch.int32).contiguous()
+        h = self._eval_handle(uniq.shape[0])
+        items = torch.empty((N, top_k), dtype=torch.int32, device=self.device)
+        scores = torch.empty((N, top_k), dtype=torch.float32, device=self.device)
+        self._lib.check(h.L.daisy_topk_candidates(h.ptr, vp(self._P_ptr), vp(cache.data_ptr()), vp(users.data_ptr()),
+                                                  vp(cidx.data_ptr()), N, C, int(top_k), vp(pos.data_ptr()),
+                                                  vp(items.data_ptr()), vp(scores.data_ptr()), self._s()))
+        self._lib.check(h.L.daisy_check(h.ptr, self._s()))
+        return pos
+
+    def metric_eval(self, eval_users, eval_cands, top_k, group=None):
+        """(HR@K, NDCG@K) over ALL evaluated users (global ids; every rank passes the same arrays): each rank ranks the
+        users it owns, the per-user hits / gains are summed over the ranks."""
+        eu = np.asarray(eval_users).reshape(-1)
+        u0, u1 = self.layout.user_range(self.rank)
+        mine = np.nonzero((eu >= u0) & (eu < u1))[0]
+        self.materialize()
+        pos = self.topk_candidates(eu[mine] - u0, np.asarray(eval_cands)[mine], top_k).cpu().numpy()
+        hit = pos == 0
+        hr = hit.any(axis=1)
+        ndcg = np.where(hr, 1.0 / np.log2(hit.argmax(axis=1) + 2.0), 0.0)
+        t = torch.tensor([hr.sum(), ndcg.sum(), float(len(mine))], dtype=torch.float64, device=self.device)
+        if self.world > 1 and self.mapping != "local":
+            dist.all_reduce(t, group=group if group is not None else self.group)
+        t = t.cpu().numpy()
+        return float(t[0] / max(t[2], 1.0)), float(t[1] / max(t[2], 1.0))
+
+    def topk_full(self, users_local, k, exclude=None):
+        """Full-catalogue top-k for THIS rank's users over the sharded item table: the shards are streamed one owner at a
+        time into a local buffer (one NVLink copy per shard), ``daisy_topk_full`` ranks the users against each, and the
+        per-shard winners are merged -- scores are the exact fp32 scores and the order is (score desc, global item asc),
+        so the result equals ``daisy_topk_full`` on the unsharded table.  Returns (items [N, k] int64 global ids,
+        scores [N, k])."""
+        vp = self._lib.c_vp
+        users = torch.as_tensor(np.asarray(users_local)).to(self.device, torch.int32).contiguous()
+        N = users.shape[0]
+        self.materialize()
+        all_items, all_scores = [], []
+        buf = None
+        for o in range(self.world):
+            i0, i1 = self.layout.item_range(o)
+            rows = i1 - i0
+            if rows <= 0:
+                continue
+            kk = min(int(k), rows)
+            view, qptr = self._peer_q(o)
+            if o == self.rank:
+                q_local_ptr = qptr
+            else:
+                if buf is None:
+                    buf = torch.empty((self.layout.i_per, self.dim), dtype=torch.float32, device=self.device)
+                buf[:rows].copy_(view)                     # the shard crosses NVLink once
+                q_local_ptr = buf.data_ptr()
+            h = self._eval_handle(rows)
+            items = torch.empty((N, kk), dtype=torch.int32, device=self.device)
+            scores = torch.empty((N, kk), dtype=torch.float32, device=self.device)
+            ptr_t = idx_t = None
+            if exclude is not None:
+                ex = [np.asarray(e, dtype=np.int64) for e in exclude]
+                ex = [(e[(e >= i0) & (e < i1)] - i0).astype(np.int32) for e in ex]
+                ptr = np.zeros(N + 1, dtype=np.int64)
+                np.cumsum([len(e) for e in ex], out=ptr[1:])
+                idx = np.concatenate(ex) if ptr[-1] else np.zeros(0, np.int32)
+                ptr_t, idx_t = torch.from_numpy(ptr).to(self.device), torch.from_numpy(idx).to(self.device)
+            self._lib.check(h.L.daisy_topk_full(h.ptr, vp(self._P_ptr), vp(q_local_ptr), vp(users.data_ptr()), N, kk,
+                                                vp(ptr_t.data_ptr()) if ptr_t is not None else None,
+                                                vp(idx_t.data_ptr()) if idx_t is not None and idx_t.numel() else None,
+                                                vp(items.data_ptr()), vp(scores.data_ptr()), self._s()))
+            self._lib.check(h.L.daisy_check(h.ptr, self._s()))
+            all_items.append(items.to(torch.int64) + i0)
+            all_scores.append(scores)
+        items, scores = torch.cat(all_items, 1), torch.cat(all_scores, 1)
+        # (score desc, item asc): stable sort by item, then stable sort by score
+        o1 = torch.argsort(items, dim=1, stable=True)
+        items, scores = items.gather(1, o1), scores.gather(1, o1)
+        o2 = torch.argsort(scores, dim=1, descending=True, stable=True)
+        kk = min(int(k), items.shape[1])
+        if self.world > 1 and self.mapping != "local":
+            dist.barrier(self.group)                      # nobody steps (and rewrites its shard) while a peer still reads it
+        return items.gather(1, o2)[:, :kk], scores.gather(1, o2)[:, :kk]
+
+    # ---- the training loop --------------------------------------------------------------------------------------------
+    def fit(self, train_pairs, epochs, batch_size, num_ng=4, seed=2019, eval_users=None, eval_cands=None, topk=10,
+            verbose=False):
+        """The epoch loop of BPRMFRecommender.py:157-181 over the row-sharded model: every rank draws the SAME epoch from
+        the deterministic host sampler (``sampler.TripleSampler``: global ids, global shuffle), keeps the triples of the
+        users it owns (``route``), and step k of every rank is its part of global batch k -- so losses and metrics are
+        those of the single-device ``BPRMFRecommender.fit`` on the same triples, up to the fp32 summation order of row
+        sums that arrive from several ranks.  ``batch_size`` is the GLOBAL batch; the handle must have been created
+        with ``max_batch`` >= the largest local share (``max_batch=batch_size`` is always enough).
+        Returns ``history`` = [{epoch, loss, hr, ndcg}]."""
+        from .sampler import TripleSampler
+        sampler = TripleSampler(train_pairs, self.layout.item_num, num_ng=num_ng, seed=seed)
+        n = len(sampler)
+        pinned = torch.empty((n, 3), dtype=torch.int32).pin_memory()
+        history = []
+        for ep in range(int(epochs)):
+            pinned.numpy()[:] = sampler.sample_epoch(ep)
+            local, off = self.route(pinned.to(self.device, non_blocking=True), batch_size)
+            for k in range(len(off) - 1):
+                self.step(local[off[k]:off[k + 1]])
+            self.materialize()
+            rec = dict(epoch=ep + 1, loss=self.loss_sum(reduce=True))
+            self.check()
+            if eval_users is not None:
+                rec["hr"], rec["ndcg"] = self.metric_eval(eval_users, eval_cands, topk)
+            history.append(rec)
+            if verbose and self.rank == 0:
+                print(rec, flush=True)
+        return history
+
     def close(self):
         torch.cuda.synchronize(self.device)
         self.Q = None
+        for h in self.__dict__.get("_eval_handles", {}).values():
+            h.close()
         self.h.close()
         self._symm_hdl = self._symm_buf = None
-
-
-# ----------------------------------------------------------------------------------------------------------------
-# bench.py --gpus N  (launched by torchrun, one rank per GPU)
-# ----------------------------------------------------------------------------------------------------------------
-def bench_sharded(args, cfg, metric, unit):
-    import json
-    from .sampler import _rng, zipf_items
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", str(rank)))
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
-    U, I, D, B = cfg["user_num"], cfg["item_num"], cfg["dim"], cfg["batch"]
-    if args.scale != 1.0:
-        U, I = int(U * args.scale), int(I * args.scale)
-    if args.batch:
-        B = args.batch
-    K, W = args.steps, max(args.warmup, 3)
-    peer = args.exchange == "peer"
-    if peer:
-        model = PeerShardedBPR(U, I, D, lr=cfg["lr"], wd=cfg["wd"], max_batch=B, rank=rank, world=world, device=dev,
-                               seed=2019, mapping=args.mapping).connect()
-        handle, loss_dev, check = model.h, model.loss, model.check
-    else:
-        model = ShardedBPR(U, I, D, lr=cfg["lr"], wd=cfg["wd"], max_batch=B, rank=rank, world=world, device=dev,
-                           comm=DistComm(), seed=2019)
-        handle, loss_dev, check = model.backend.h, model.backend.loss, model.backend.check
-    u0, u1 = model.layout.user_range(rank)
-    nb = K + W
-    g = _rng(2019, 40, rank)
-    host = np.empty((nb * B, 3), dtype=np.int32)
-    host[:, 0] = g.integers(0, u1 - u0, size=nb * B)                       # local user index: routed by owner
-    host[:, 1] = zipf_items(g, nb * B, I, cfg["zipf"], perm_seed=2019)     # global ids, Zipf over a permuted catalogue
-    host[:, 2] = g.integers(0, I, size=nb * B)
-    host = torch.from_numpy(host.reshape(nb, B, 3)).pin_memory()
-    devtri = host.to(dev)
-    if peer:
-        handle.set_inputs_ready(True)      # device triples are uploaded and synchronised before they are used
-
-    def run(first, count, src):
-        for s in range(first, first + count):
-            if peer:
-                model.step(src[s])
-            else:
-                model.step(src[s] if src is devtri else src[s].to(dev, non_blocking=True))
-
-    run(0, W, devtri)
-    model.materialize()                             # warm the lazy-decay pass too (first launch loads its code)
-    check()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if not peer:
-        model.wire_rows = 0
-    launches0 = handle.launches
-    clocks = None
-    try:                                            # every rank samples its own GPU (rank 0's goes into `clocks`)
-        import bench as _bench
-        clocks = _bench.ClockSampler(local)         # NVML initialisation takes tens of ms: before the barrier
-    except Exception:
-        clocks = None
-    torch.cuda.synchronize()
-    dist.barrier()                                  # all ranks enter the timed region together
-    if clocks is not None:
-        clocks.start()
-    if os.environ.get("DAISY_TRACE_TIMED") and peer:
-        handle.trace_start()
-    ev0.record()
-    run(W, K, devtri)
-    model.materialize()
-    ev1.record()
-    torch.cuda.synchronize()
-    if clocks is not None:
-        clocks.stop()
-    if os.environ.get("DAISY_TRACE_TIMED") and peer:
-        rows = [[round(x, 2) for x in row] for row in handle.trace_dump()]
-        print(f"rank {rank} timed-region trace:", rows, flush=True)
-    dist.barrier()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    launches = handle.launches - launches0
-    if peer:
-        cnt = model.last_counts()
-        remote = sum(cnt) - cnt[rank]
-        wire_rows = 2 * remote * K         # fetched rows in + pushed sums out, per rank (last step's count, every step alike)
-    else:
-        wire_rows = model.wire_rows
-    # e2e: host triples, per-step loss read-back
-    loss_host = torch.zeros(nb, dtype=torch.float64).pin_memory()
-    run(0, W, host)
-    torch.cuda.synchronize()
-    dist.barrier()
-    ev0.record()
-    for s in range(W, W + K):
-        if peer:
-            model.step(host[s])
-        else:
-            model.step(host[s].to(dev, non_blocking=True))
-        loss_host[s:s + 1].copy_(loss_dev, non_blocking=True)
-    model.materialize()
-    ev1.record()
-    torch.cuda.synchronize()
-    dist.barrier()
-    ms2 = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-    dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    check()
-    phases = None
-    # the fused peer path always adds its per-rank phase profile (10 serialised steps AFTER both timed regions): it is
-    # what says which rank the others wait for at the barrier; --no-phases drops it
-    want_phases = args.phases or (peer and not getattr(args, "no_phases", False))
-    if args.phases and not peer:
-        model.profile = []
-        run(0, min(nb, 10), devtri)
-        phases = model.profile_summary()
-        model.profile = None
-    elif want_phases:
-        handle.set_timing(2)
-        run(0, min(nb, 10), devtri)
-        phases, _ = model.phase_ms()
-        inner, _ = handle.phase_ms()
-        phases["compute_push_detail"] = {k: round(v, 4) for k, v in inner.items()}
-        handle.set_timing(0)
-    if args.trace and peer:
-        torch.cuda.synchronize()
-        dist.barrier()
-        handle.trace_start()
-        run(0, min(nb, 12), devtri)
-        rows = [[round(x, 3) for x in row] for row in handle.trace_dump()]
-        for r in range(world):
-            if r == rank:
-                print(f"rank {rank} trace_ms(book_begin, book_end, kernels_begin, compute_end):", rows, flush=True)
-            dist.barrier()
-    by_rank = None
-    if want_phases and peer:                        # which rank waits for which: the phases of every rank, side by side
-        mine = {"rank": rank, "sm_mhz": (clocks.summary()["sm_mhz"] if clocks is not None else None)}
-        mine.update({k: round(v, 4) for k, v in phases.items() if k != "compute_push_detail"})
-        mine["main"] = phases["compute_push_detail"].get("main")
-        by_rank = [None] * world
-        dist.all_gather_object(by_rank, mine)
-    if rank == 0:
-        ms_total, ms_e2e = float(ms), float(ms2)
-        value = B * world * K / (ms_total * 1e-3)
-        # NVLink bytes per step and direction at one GPU: it RECEIVES the rows it fetches and SERVES the rows its peers
-        # fetch from it (egress), and it PUSHES its row sums (egress) and receives its peers' (ingress); by symmetry
-        # every direction carries (remote rows) x 4D bytes twice.  wire_rows = 2 x remote rows of this rank.
-        each_way = wire_rows / K * 4 * D
-        peak_nvl = 770.0
-        step_s = ms_total / K * 1e-3
-        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": {"workload": cfg["workload"], "user_num": U, "item_num": I, "dim": D,
-                           "batch_per_gpu": B, "global_batch": B * world, "lr": cfg["lr"], "wd": cfg["wd"],
-                           "sharding": ("block rows, triples routed to the user's owner; item rows read from / row "
-                                        "sums stored to the owners' memory by the step kernels over NVLink (peer "
-                                        "pointers), flag barriers, deterministic owner-side merge") if peer else
-                                       ("block rows, triples routed to the user's owner, item rows + row gradients "
-                                        "exchanged by NCCL all-to-all"),
-                           "exchange": args.exchange, "peer_mapping": args.mapping if peer else None,
-                           "main_schedule": (f"chunks dealt round-robin over "
-                                             f"{os.environ.get('DAISY_SHARD_INTERLEAVE') or world} owner ranges "
-                                             f"(DAISY_SHARD_INTERLEAVE; 0 = sorted order)") if peer else None,
-                           "l2": "inputs larger than L2", "lazy_decay_materialized_in_timed_region": True},
-                "clocks": clocks.summary() if clocks is not None else None,
-                "e2e": {"value": B * world * K / (ms_e2e * 1e-3), "unit": unit, "ms_per_step": ms_e2e / K,
-                        "h2d_bytes_per_step": B * 12 * world, "d2h_bytes_per_step": 8 * world},
-                "gpu_launches": int(launches),
-                "roofline": {"bound": "nvlink", "achieved": each_way / step_s / 1e9, "peak": peak_nvl,
-                             "unit": "GB/s per direction per GPU", "frac": each_way / step_s / 1e9 / peak_nvl,
-                             "traffic": None, "peak_source": "measured peer copy (B200_PROFILING.md)",
-                             "remote_rows_per_step_per_gpu": wire_rows / K / 2,
-                             "nvlink_bytes_per_step_per_gpu_each_way": each_way,
-                             "note": "whole step (compute + barriers + owner merge), not the fused kernel alone",
-                             "hbm_whole_step_frac": (B * (24 * D + 12) / step_s / 1e9) / 6461.8}}
-        if phases:
-            line["phase_ms(device,host)"] = phases
-        if by_rank:
-            line["phase_ms_by_rank"] = by_rank
-        print(json.dumps(line), flush=True)
-    dist.destroy_process_group()

@@ -18,4 +18,13 @@ struct DeviceRadixSort {
         return cudaSuccess;
     }
 };
+struct DeviceScan {
+    template <class In, class Out>
+    static cudaError_t ExclusiveSum(void *tmp, size_t &tmp_bytes, const In *in, Out *out, int n, cudaStream_t = nullptr) {
+        if (!tmp) { tmp_bytes = 1; return cudaSuccess; }
+        Out acc = 0;
+        for (int i = 0; i < n; ++i) { const Out v = (Out)in[i]; out[i] = acc; acc += v; }
+        return cudaSuccess;
+    }
+};
 }  // namespace cub

@@ -82,9 +82,15 @@ def test_bprfm_against_oracle(dev, U, I, F, B, steps):
 
 
 def test_bprfm_rejects_what_is_not_accelerated(dev):
-    from recommend_lib_b200.bprfm import BPRFM
+    from recommend_lib_b200.bprfm import BPRFM, FMAdagrad
+    from recommend_lib_b200.bprfm_bn import BPRFMBN, FMBNAdagrad
+    # the script's defaults (batch norm + dropout, BPRFMRecommender.py:116-125) build the batch-norm model ...
+    bn = BPRFM(10, 8, True, [0.5, 0.2], user_num=4)
+    assert isinstance(bn, BPRFMBN) and bn.drop_prob == [0.5, 0.2] and "FM_layers.0.weight" in bn.state_dict()
+    assert isinstance(FMAdagrad(bn, lr=0.05), FMBNAdagrad)
+    # ... dropout WITHOUT batch norm (not selectable from the script's command line) is on no accelerated path
     with pytest.raises(NotImplementedError):
-        BPRFM(10, 8, True, [0.5, 0.2], user_num=4)
+        BPRFM(10, 8, False, [0.5, 0.0], user_num=4)
     with pytest.raises(ValueError):
         BPRFM(10, 8, False, [0.0, 0.0])
     m = BPRFM(10, 8, False, [0.0, 0.0], user_num=4).to(dev)

@@ -3,7 +3,7 @@ N3): daisy_neumf_step / daisy_neumf_forward through the drop-in NeuMF + NeuMFAda
 unmodified reference and the closed-form oracle (oracle/neumf_oracle.py).
 
 First run on a B200 in round 2 (profiles/r02a_*).
-Tolerance 1e-5 relative (max-abs-diff / max-abs) on every parameter and on the loss (2e-5 on the tower weights)."""
+Tolerance 1e-5 relative (max-abs-diff / max-abs) on every parameter and on the loss (tower weights: plus 1 % of one Adam step, see the test)."""
 import os
 
 import numpy as np
@@ -94,11 +94,14 @@ def test_neumf_against_oracle(dev, name, U, I, F, L, B):
         ref.update({f"W{l}": ora.Ws[l] for l in range(L)})
         ref.update({f"b{l}": ora.bs[l] for l in range(L)})
         for key, r in ref.items():
-            # Adam's first steps divide by sqrt(v) ~ |g|: an element whose gradient is a near-cancelling sum over the
-            # batch turns fp32 rounding of g into a visible fraction of the lr-sized update; the tower weights hold such
-            # elements (measured on the B200: 1.1e-5 on W0 at step 0, every other tensor <= 1e-5)
-            tol = 2e-5 if key.startswith("W") else 1e-5
-            assert rel_err(st[key], r) <= tol, (s, key, rel_err(st[key], r))
+            # Adam's first steps move an element by lr * g / (|g| + eps): an element of the tower weights whose gradient
+            # is a near-cancelling sum over the batch (|g| within a few orders of eps = 1e-8) turns fp32 rounding of g
+            # into a fraction of the lr-sized step, whatever the implementation (measured on the B200: 0.24 % of one
+            # step on W0 of the widest tower).  Tower weights: 1e-5 relative plus 1 % of a step; everything else 1e-5.
+            if key.startswith("W"):
+                assert np.abs(st[key] - r).max() <= 1e-5 * np.abs(r).max() + 0.01 * opt.lr, (s, key, rel_err(st[key], r))
+            else:
+                assert rel_err(st[key], r) <= 1e-5, (s, key, rel_err(st[key], r))
     m.check()
     assert np.allclose(m(torch.from_numpy(u), torch.from_numpy(i)).cpu().numpy(), ora.forward(u, i), rtol=1e-4, atol=1e-5)
 
