@@ -122,8 +122,8 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
 #define A(ptr, n) if (!rc) rc = dalloc(&h->ptr, (n))
     A(err, 2);
     if (B > 0) {
-        A(triples, 2 * 3 * B);
-        for (int i = 0; i < 2; ++i) {
+        A(triples, DAISY_NSETS * 3 * B);
+        for (int i = 0; i < DAISY_NSETS; ++i) {
             A(book[i].st, 3 * B);
             A(book[i].ukey_s, B); A(book[i].qkey_s, 2 * B);
             A(book[i].uslot, B); A(book[i].jslot, B); A(book[i].islot, B);
@@ -157,7 +157,7 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
     }
     if (!rc) {
         if (B > 0) {
-            for (int i = 0; i < 2; ++i) cudaMemset(h->book[i].islot, 0xFF, B * sizeof(uint32_t));
+            for (int i = 0; i < DAISY_NSETS; ++i) cudaMemset(h->book[i].islot, 0xFF, B * sizeof(uint32_t));
             cudaMemset(h->ticket, 0, (size_t)h->longs_cap * sizeof(uint32_t));
         }
         k_err_reset<<<1, 1>>>(h->err);
@@ -168,7 +168,7 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
         cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, prio_hi);
         cudaEventCreateWithFlags(&h->ev_call, cudaEventDisableTiming);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < DAISY_NSETS; ++i) {
             cudaEventCreateWithFlags(&h->book[i].ready, cudaEventDisableTiming);
             cudaEventCreateWithFlags(&h->book[i].freed, cudaEventDisableTiming);
         }
@@ -196,7 +196,7 @@ extern "C" int daisy_destroy(daisy_handle_t h) {
                     h->own_tmp};
     for (void *p : ptrs)
         if (p) cudaFree(p);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < DAISY_NSETS; ++i) {
         void *bp[] = {h->book[i].st, h->book[i].ukey_s, h->book[i].qkey_s, h->book[i].uslot, h->book[i].jslot,
                       h->book[i].islot, h->book[i].longs};
         for (void *p : bp)

@@ -14,6 +14,11 @@
 #define DAISY_SLICE 64     // contributions per level-1 slice of a very hot row
 #define DAISY_TRACE_STEPS 48
 #define DAISY_SMALL_CAP 8192  // largest batch of the small-batch path: 2B item refs are sorted by ONE thread block
+// Bookkeeping sets (sorted triples, sorted ref keys, slots) in flight.  With 2, the bookkeeping of step n+1 can only start
+// once the table kernels of step n-1 are done -- i.e. together with the kernels of step n -- and, sharing the device with
+// them, its 0.33 ms stretch to the whole 0.66 ms period: every step's kernels then wait for their own bookkeeping
+// (profiles/r02e_bench_trace.json).  A third set lets the side stream run a full step ahead.
+#define DAISY_NSETS 3
 #define DAISY_EVPOOL 2048  // main-kernel event pairs kept between two daisy_main_kernel_ms() calls
 
 // Phases of one BPR step, in launch order (daisy_last_step_phases).
@@ -77,7 +82,7 @@ struct daisy_shard {
     int attached;
     int in_process;  // peers live in this process (lockstep emulation): the caller orders the phases, no barrier kernels
     ShardPeers peers;
-    ShardSet set[2];
+    ShardSet set[DAISY_NSETS];
     uint32_t *cidx;   // [2*maxB] scan scratch (bookkeeping stream only)
     float *cache;     // [2*maxB, D] fetched pre-step item rows of the current batch
     uint32_t epoch;   // barrier epoch (same sequence on every rank)
@@ -94,7 +99,7 @@ struct BookGraph {
     int set, B, launches;
     uint32_t U, I;
 };
-#define DAISY_MAX_BGRAPH 6
+#define DAISY_MAX_BGRAPH 9
 
 struct daisy_ctx {
     int device;
@@ -105,10 +110,10 @@ struct daisy_ctx {
     double scale;  // lazy L2 decay factor c: true tables = c * stored tables
 
     // --- workspace (device) ---
-    int32_t *triples;       // [2][maxB,3]  H2D landing zones of daisy_bpr_step_host (one per bookkeeping set)
+    int32_t *triples;       // [DAISY_NSETS][maxB,3]  H2D landing zones of daisy_bpr_step_host (one per bookkeeping set)
     // Bookkeeping products the table-touching kernels read; double-buffered so that the bookkeeping of step n+1
     // (side stream) overlaps the kernels of step n (caller's stream).
-    BookSet book[2];
+    BookSet book[DAISY_NSETS];
     int book_idx;
     cudaStream_t side_stream;
     cudaEvent_t ev_call;

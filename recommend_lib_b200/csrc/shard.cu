@@ -614,7 +614,7 @@ void daisy_shard_free(daisy_ctx *h) {
         if (sh->pev[i]) cudaEventDestroy(sh->pev[i]);
     for (int r = 0; r < sh->world; ++r)
         if (sh->ipc_opened[r] && sh->peer_arena[r]) cudaIpcCloseMemHandle(sh->peer_arena[r]);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < DAISY_NSETS; ++i) {
         void *ptrs[] = {sh->set[i].uniq_gid, (void *)sh->set[i].src, (void *)sh->set[i].dst, sh->set[i].owner_off,
                         sh->set[i].multi, (void *)sh->set[i].jsrc, (void *)sh->set[i].isrc};
         for (void *p : ptrs)
@@ -682,7 +682,7 @@ extern "C" int daisy_shard_init(daisy_handle_t h, int rank, int world, int64_t i
     }
     ok = ok && cudaMalloc((void **)&sh->cidx, cap * sizeof(uint32_t)) == cudaSuccess;
     ok = ok && cudaMalloc((void **)&sh->cache, cap * D * sizeof(float)) == cudaSuccess;
-    for (int i = 0; i < 2 && ok; ++i) {
+    for (int i = 0; i < DAISY_NSETS && ok; ++i) {
         ok = ok && cudaMalloc((void **)&sh->set[i].uniq_gid, cap * sizeof(uint32_t)) == cudaSuccess;
         ok = ok && cudaMalloc((void **)&sh->set[i].src, cap * sizeof(float *)) == cudaSuccess;
         ok = ok && cudaMalloc((void **)&sh->set[i].dst, cap * sizeof(float *)) == cudaSuccess;
@@ -834,7 +834,7 @@ extern "C" int daisy_shard_last_counts(daisy_handle_t h, uint32_t *owner_off_out
     DeviceGuard g(h->device);
     DAISY_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     DAISY_CUDA(cudaStreamSynchronize(h->side_stream));
-    const ShardSet &ss = h->sh->set[h->book_idx ^ 1];  // the set the most recent step used
+    const ShardSet &ss = h->sh->set[(h->book_idx + DAISY_NSETS - 1) % DAISY_NSETS];  // the set the most recent step used
     DAISY_CUDA(cudaMemcpy(owner_off_out, ss.owner_off, (h->sh->world + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return DAISY_OK;
 }

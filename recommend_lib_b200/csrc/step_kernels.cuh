@@ -1588,7 +1588,7 @@ static int book_phase(daisy_ctx *h, StepPlan &pl, const int32_t *triples, int64_
     pl.ilv = sh ? sh->ilv : 0;
     BookSet &k = h->book[h->book_idx];
     pl.k = &k;
-    h->book_idx ^= 1;
+    h->book_idx = (h->book_idx + 1) % DAISY_NSETS;
     if (h->timing == 2) {
         if (h->ev_pending) {  // fold the previous step's phase times in
             cudaEventSynchronize(h->ev[PH_COUNT]);
