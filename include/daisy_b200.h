@@ -152,6 +152,12 @@ DAISY_API int daisy_owner_apply(daisy_handle_t h, float *Q_local, const int32_t 
  *                       Every rank must call it the same number of times (B may be 0).  Asynchronous, no host sync.
  *   daisy_shard_compute / _barrier / _apply   the phases of daisy_shard_step, for callers that drive several ranks
  *                       from one process in lockstep (all computes, then all applies; no barrier kernels).
+ *   daisy_shard_prepare / _classify   the same lockstep protocol with the EXCLUSIVE-ROW BYPASS of daisy_shard_step
+ *                       (DAISY_SHARD_BYPASS): all prepares (bookkeeping + id lists into the owners), all classifies
+ *                       (every owner tells every sender which of its rows no other rank references this step), all
+ *                       computes (same B; a sender stores the UPDATED row of an exclusive row straight into its
+ *                       owner's shard instead of a sum the owner would have to add), all applies (shared rows only).
+ *                       Results are bit-identical with and without the bypass.
  *   daisy_shard_materialize   daisy_materialize on (P_local, q_local) + barrier (peers read q_local).
  * Semantics = daisy_bpr_step on the global batch (gradients at the pre-step tables, repeated rows accumulate);
  * contributions to a row are added in sender-rank order, so results are bit-reproducible. */
@@ -167,6 +173,8 @@ DAISY_API int daisy_shard_step_host(daisy_handle_t h, float *P_local, const int3
                                     float wd, double *loss_accum, daisy_stream_t stream);
 DAISY_API int daisy_shard_compute(daisy_handle_t h, float *P_local, const int32_t *triples, int64_t B, float lr, float wd,
                                   double *loss_accum, daisy_stream_t stream);
+DAISY_API int daisy_shard_prepare(daisy_handle_t h, float *P_local, const int32_t *triples, int64_t B, daisy_stream_t stream);
+DAISY_API int daisy_shard_classify(daisy_handle_t h, daisy_stream_t stream);
 DAISY_API int daisy_shard_barrier(daisy_handle_t h, daisy_stream_t stream);
 DAISY_API int daisy_shard_apply(daisy_handle_t h, float lr, float wd, daisy_stream_t stream);
 DAISY_API int daisy_shard_materialize(daisy_handle_t h, float *P_local, daisy_stream_t stream);

@@ -92,6 +92,8 @@ SIGNATURES = {
     "daisy_shard_step": [c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp],
     "daisy_shard_step_host": [c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp],
     "daisy_shard_compute": [c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp],
+    "daisy_shard_prepare": [c_vp, c_vp, c_vp, c_i64, c_vp],
+    "daisy_shard_classify": [c_vp, c_vp],
     "daisy_shard_barrier": [c_vp, c_vp],
     "daisy_shard_apply": [c_vp, c_f32, c_f32, c_vp],
     "daisy_shard_materialize": [c_vp, c_vp, c_vp],

@@ -113,6 +113,8 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
     if (h->mid_max > h->mid_cap) h->mid_max = h->mid_cap;
     h->graph_max_b = env_int("DAISY_GRAPH_MAX_B", 262144);
     if (h->graph_max_b < 0) h->graph_max_b = 0;
+    h->merged_sort = env_int("DAISY_MERGED_SORT", -1);
+    h->main_max_blocks = env_int("DAISY_MAIN_MAX_BLOCKS", 0);
     h->small_max = env_int("DAISY_SMALL_MAX", DAISY_SMALL_CAP);
     if (h->small_max < 0) h->small_max = 0;
     if (h->small_max > DAISY_SMALL_CAP) h->small_max = DAISY_SMALL_CAP;
@@ -129,7 +131,7 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
             A(book[i].uslot, B); A(book[i].jslot, B); A(book[i].islot, B);
             A(book[i].longs, 2 + 5 * (size_t)h->longs_cap);
         }
-        A(key_in, 2 * B); A(val_in, 2 * B); A(val_out, 2 * B);
+        A(key_in, 3 * B); A(val_in, 3 * B); A(val_out, 3 * B); A(key_out, 3 * B);
         A(ukey_in, B); A(uval_in, B); A(uval_out, B);
         A(ikey_in, B); A(ikey_out, B); A(ival_in, B); A(ival_out, B);
         A(stageU, B * dim);
@@ -143,7 +145,7 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
     if (!rc && B > 0) {
         size_t need = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, need, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
-                                        (uint32_t *)nullptr, (int)(2 * B), 0, 32, (cudaStream_t)0);
+                                        (uint32_t *)nullptr, (int)(3 * B), 0, 32, (cudaStream_t)0);
         size_t need_scan = 0;  // the sharded bookkeeping also scans 2B flags (step_kernels.cuh)
         cub::DeviceScan::InclusiveSum(nullptr, need_scan, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)(2 * B),
                                       (cudaStream_t)0);
@@ -167,6 +169,16 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
         cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, prio_hi);
+        // DAISY_BOOK_SMS = n > 0: the bookkeeping stream gets n SMs of its own and the table kernels the rest
+        // (partition.cu); a driver that cannot partition leaves the shared-SM pipeline in place
+        if (B > 0 && h->pipeline && env_int("DAISY_BOOK_SMS", 0) > 0) {
+            if (daisy_partition_create(h, env_int("DAISY_BOOK_SMS", 0)) == DAISY_OK && h->part_ok) {
+                cudaStreamDestroy(h->side_stream);
+                h->side_stream = h->part_book_stream;
+            } else if (env_int("DAISY_BOOK_SMS_REQUIRED", 0)) {
+                rc = DAISY_EUNSUPPORTED;
+            }
+        }
         cudaEventCreateWithFlags(&h->ev_call, cudaEventDisableTiming);
         for (int i = 0; i < DAISY_NSETS; ++i) {
             cudaEventCreateWithFlags(&h->book[i].ready, cudaEventDisableTiming);
@@ -191,7 +203,7 @@ extern "C" int daisy_destroy(daisy_handle_t h) {
     cudaDeviceSynchronize();
     daisy_shard_free(h);
     void *ptrs[] = {h->triples, h->key_in, h->val_in, h->val_out, h->ukey_in, h->uval_in, h->uval_out, h->ikey_in,
-                    h->ikey_out, h->ival_in, h->ival_out, h->stageU, h->stageQ, h->stage2, h->loss_part,
+                    h->ikey_out, h->ival_in, h->ival_out, h->stageU, h->stageQ, h->stage2, h->loss_part, h->key_out,
                     h->err, h->cub_tmp, h->ticket, h->mid_buf, h->gradP, h->gradQ, h->wpart, h->scores, h->sel_hist, h->own_key, h->own_key_s, h->own_val, h->own_val_s,
                     h->own_tmp};
     for (void *p : ptrs)
@@ -210,6 +222,10 @@ extern "C" int daisy_destroy(daisy_handle_t h) {
         if (h->tc_ev[i]) cudaEventDestroy(h->tc_ev[i]);
     if (h->pool_state == 1) cudaMemPoolDestroy(h->pool);
     if (h->err_host) cudaFreeHost(h->err_host);
+    if (h->part_ok) {
+        h->side_stream = nullptr;  // it is the partition's bookkeeping stream
+        daisy_partition_destroy(h);
+    }
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_call) cudaEventDestroy(h->ev_call);
     for (int i = 0; i <= PH_COUNT; ++i)

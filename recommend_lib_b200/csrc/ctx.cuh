@@ -53,12 +53,15 @@ struct BookSet {
 //   recv_ids [G][cap]        int32  the LOCAL row ids those sums belong to (ascending, duplicate-free per sender)
 //   recv_cnt [G]             uint32 how many entries sender s pushed this step
 //   flags    [G]             uint32 barrier arrivals (epoch numbers), written by the peers
+//   excl     [G][cap]        uint8  written by owner o into region o: 1 = the row of this rank's k-th entry for owner o is
+//                                   referenced by no other rank this step (exclusive-row bypass, shard.cu)
 struct ShardPeers {  // the same regions of every rank's arena, as mapped into THIS process; passed to kernels by value
     float *q[DAISY_MAX_RANKS];
     float *recv_g[DAISY_MAX_RANKS];
     int32_t *recv_ids[DAISY_MAX_RANKS];
     uint32_t *recv_cnt[DAISY_MAX_RANKS];
     uint32_t *flags[DAISY_MAX_RANKS];
+    uint8_t *excl[DAISY_MAX_RANKS];
 };
 
 struct ShardSet {         // per bookkeeping set (double-buffered like BookSet)
@@ -76,7 +79,7 @@ struct daisy_shard {
     int64_t I_global, i_per, cap;  // cap = entries per sender region = 2 * maxB (a batch references at most 2B item rows)
     char *arena;
     int arena_owned;  // 1: cudaMalloc'ed by daisy_shard_init (legacy CUDA IPC export), 0: provided by the caller
-    size_t arena_bytes, off_q, off_g, off_ids, off_cnt, off_flags;
+    size_t arena_bytes, off_q, off_g, off_ids, off_cnt, off_flags, off_excl;
     char *peer_arena[DAISY_MAX_RANKS];
     int ipc_opened[DAISY_MAX_RANKS];
     int attached;
@@ -86,6 +89,15 @@ struct daisy_shard {
     uint32_t *cidx;   // [2*maxB] scan scratch (bookkeeping stream only)
     float *cache;     // [2*maxB, D] fetched pre-step item rows of the current batch
     uint32_t epoch;   // barrier epoch (same sequence on every rank)
+    // exclusive-row bypass: owner-side bitmaps over the local item rows (referenced by >= 1 / >= 2 ranks this step)
+    uint32_t *bm_seen, *bm_multi;
+    size_t bm_words;
+    int bypass;       // DAISY_SHARD_BYPASS (default 1)
+    int classified;   // this step's entries have been classified (daisy_shard_classify ran): bypass is live
+    int prepared;     // daisy_shard_prepare ran for the step daisy_shard_compute is about to finish
+    int prepared_set; // ... into this bookkeeping set
+    int64_t prepared_B;
+    void *plan;       // StepPlan of the prepared step (step_kernels.cuh), owned by shard.cu
     int ilv;          // chunk interleave of the main kernel = world (DAISY_SHARD_INTERLEAVE; 0 / 1 = sorted order)
     // phase profile (daisy_set_timing(h, 2)): bookkeeping, fetch, compute+push, barrier, apply, barrier
     cudaEvent_t pev[7];
@@ -120,7 +132,9 @@ struct daisy_ctx {
     int pipeline;           // 1: bookkeeping on the side stream (default), 0: everything on the caller's stream
     int inputs_ready;       // 1: device triples passed to daisy_bpr_step are complete at call time (no stream dependency)
     // bookkeeping scratch, used on the bookkeeping stream only
-    uint32_t *key_in, *val_in, *val_out;    // [2*maxB] item refs (negatives + run heads): unsorted keys/values, sorted values
+    uint32_t *key_in, *val_in, *val_out;    // [3*maxB] item refs (negatives + run heads) [2*maxB]: unsorted keys/values, sorted
+                                            // values; the merged sort (step_kernels.cuh) appends the user refs [maxB]
+    uint32_t *key_out;                      // [3*maxB] merged sort: sorted keys before k_slots_merged splits them
     uint32_t *ukey_in, *uval_in, *uval_out; // [maxB]   user refs
     uint32_t *ikey_in, *ikey_out, *ival_in, *ival_out;  // [maxB]   (positive item, triple id), unsorted / sorted
     void *cub_tmp;
@@ -154,6 +168,13 @@ struct daisy_ctx {
     int pairs_mode;  // set by csrc/gmf.cu around book_phase: the batch holds (user, item, label) samples
     float *gradP, *gradQ;  // [U, D], [I, D] dense gradient buffers of the GMF step (allocated on first use, kept zero between steps)
     float *wpart;    // [maxB, D + 1] per-sample contributions to the predict layer's gradient (GMF step)
+    int merged_sort; // general path: ONE radix sort for user + item refs: 1 always, 0 never, -1 (default) when it costs no extra passes
+    int main_max_blocks;  // experiment (DAISY_MAIN_MAX_BLOCKS): resident blocks per SM of the TMA main kernel capped through its shared-memory request
+    // SM partitioning (partition.cu): bookkeeping stream on part_book_sms SMs, table kernels on the rest
+    int part_ok, part_book_sms, part_main_sms;
+    void *part_green[2];
+    cudaStream_t part_book_stream, part_main_stream;
+    cudaEvent_t part_ev_in, part_ev_out;
     int seg_win;     // sorted refs per warp of k_seg_all's window blocks in the general path: 32 (default) or 16
     int small_max;   // batches up to this many triples take the 3-launch small-batch path (0 = never; <= DAISY_SMALL_CAP)
     int64_t mid_max; // ... and up to this many the same path with k_mid_book (0 = never; <= mid_cap)
@@ -195,6 +216,8 @@ struct daisy_ctx {
 
 void daisy_set_error(const char *fmt, ...);
 void daisy_shard_free(daisy_ctx *h);  // shard.cu
+int daisy_partition_create(daisy_ctx *h, int book_sms);  // partition.cu
+void daisy_partition_destroy(daisy_ctx *h);
 
 #define DAISY_CUDA(call)                                                                     \
     do {                                                                                     \

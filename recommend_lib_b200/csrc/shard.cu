@@ -197,14 +197,22 @@ extern "C" int daisy_owner_apply(daisy_handle_t h, float *Q_local, const int32_t
 namespace {
 
 struct PushOpt {
-    static constexpr bool kNeedOldItem = false;
+    static constexpr bool kNeedOldItem = true;
     float *P;
-    float *const *dst;  // per cache row: where its descent sum goes (peer or local address)
+    float *const *dst;  // per cache row: where its descent sum goes (peer or local address).  Bit 0 set (exclusive-row
+                        // bypass): no other rank references the row this step, the address is the row itself in its
+                        // owner's q and what is stored is the UPDATED ROW -- the same fmaf the owner's pass would do
     float alpha;
     int D4;
     __device__ __forceinline__ void apply(int tbl, size_t row, int e, float4 old, float4 d) const {
         if (tbl) {
-            reinterpret_cast<float4 *>(dst[row])[e] = d;
+            const uintptr_t a = reinterpret_cast<uintptr_t>(dst[row]);
+            float4 *p = reinterpret_cast<float4 *>(a & ~(uintptr_t)1);
+            if (a & 1)
+                p[e] = make_float4(fmaf(alpha, d.x, old.x), fmaf(alpha, d.y, old.y), fmaf(alpha, d.z, old.z),
+                                   fmaf(alpha, d.w, old.w));
+            else
+                p[e] = d;
         } else {
             st_row(P, row * D4 + e,
                    make_float4(fmaf(alpha, d.x, old.x), fmaf(alpha, d.y, old.y), fmaf(alpha, d.z, old.z),
@@ -290,6 +298,54 @@ __global__ void __launch_bounds__(256) k_shard_fetch(const float *const *__restr
 // A rank without triples this step pushes nothing: tell every owner so.
 __global__ void k_shard_push_none(int G, int me, ShardPeers peers) {
     if (threadIdx.x < G) peers.recv_cnt[threadIdx.x][me] = 0u;
+}
+
+// Exclusive-row bypass, owner side.  After every rank's id list has arrived (barrier), the owner marks which of its rows
+// are referenced by ONE rank only this step: two bitmaps over the local rows (seen by >= 1 rank, by >= 2 ranks; a
+// sender's list is duplicate-free, so a second hit is a second rank) ...
+__global__ void k_owner_count(const int32_t *__restrict__ recv_ids, const uint32_t *__restrict__ recv_cnt, size_t cap,
+                              uint32_t rows_local, uint32_t *__restrict__ seen, uint32_t *__restrict__ multi) {
+    const int snd = blockIdx.y;
+    uint32_t n = recv_cnt[snd];
+    if (n > cap) n = (uint32_t)cap;
+    const int32_t *ids = recv_ids + (size_t)snd * cap;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)ids[k];
+        if (r >= rows_local) continue;
+        const uint32_t bit = 1u << (r & 31);
+        const uint32_t old = atomicOr(&seen[r >> 5], bit);
+        if (old & bit) atomicOr(&multi[r >> 5], bit);
+    }
+}
+
+// ... and tells every sender, entry by entry, whether the row is its alone (1-byte peer stores into region `me` of the
+// sender's excl array).  The sender then stores the updated row straight into the owner's q instead of pushing a sum
+// the owner would have to read, add and write back (k_owner_add skips those entries).
+__global__ void k_owner_classify(const int32_t *__restrict__ recv_ids, const uint32_t *__restrict__ recv_cnt, size_t cap,
+                                 uint32_t rows_local, const uint32_t *__restrict__ multi, int me, ShardPeers peers) {
+    const int snd = blockIdx.y;
+    uint32_t n = recv_cnt[snd];
+    if (n > cap) n = (uint32_t)cap;
+    const int32_t *ids = recv_ids + (size_t)snd * cap;
+    uint8_t *out = peers.excl[snd] + (size_t)me * cap;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)ids[k];
+        out[k] = (r < rows_local && !((multi[r >> 5] >> (r & 31)) & 1u)) ? 1 : 0;
+    }
+}
+
+// Sender side, after the owners' verdicts have arrived (barrier): the destination of an exclusive cache row becomes
+// the row itself in its owner's q, tagged in bit 0 (PushOpt::apply).
+__global__ void k_shard_tag_dst(const uint32_t *__restrict__ owner_off, int G, const uint32_t *__restrict__ uniq_gid,
+                                uint32_t i_per, size_t cap, int D, const uint8_t *__restrict__ excl, ShardPeers peers,
+                                float **__restrict__ dst) {
+    const uint32_t nuniq = owner_off[G];
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nuniq; c += gridDim.x * blockDim.x) {
+        const uint32_t g = uniq_gid[c];
+        const uint32_t o = g / i_per;
+        if (excl[(size_t)o * cap + (c - owner_off[o])])
+            dst[c] = reinterpret_cast<float *>(reinterpret_cast<uintptr_t>(peers.q[o] + (size_t)(g - o * i_per) * D) | 1u);
+    }
 }
 
 // Cross-GPU barrier on the stream: everything this rank wrote to peer memory in earlier kernels of the stream is
@@ -421,6 +477,7 @@ static void shard_layout(daisy_shard *sh, int dim, int64_t max_batch, int world,
     sh->off_ids = off;    off = align_up(off + G * cap * sizeof(int32_t), 256);
     sh->off_cnt = off;    off = align_up(off + DAISY_MAX_RANKS * sizeof(uint32_t), 256);
     sh->off_flags = off;  off = align_up(off + DAISY_MAX_RANKS * sizeof(uint32_t), 256);
+    sh->off_excl = off;   off = align_up(off + G * cap, 256);
     sh->arena_bytes = off;
 }
 
@@ -431,6 +488,7 @@ static void shard_set_peers(daisy_shard *sh, int r, char *base) {
     sh->peers.recv_ids[r] = (int32_t *)(base + sh->off_ids);
     sh->peers.recv_cnt[r] = (uint32_t *)(base + sh->off_cnt);
     sh->peers.flags[r] = (uint32_t *)(base + sh->off_flags);
+    sh->peers.excl[r] = (uint8_t *)(base + sh->off_excl);
 }
 
 static int shard_ready(daisy_ctx *h) {
@@ -443,9 +501,6 @@ static int shard_ready(daisy_ctx *h) {
 template <int V>
 static void launch_fetch(daisy_ctx *h, const ShardSet &ss, cudaStream_t s) {
     daisy_shard *sh = h->sh;
-    k_shard_push_ids<<<h->num_sms * 2, 256, 0, s>>>(ss.owner_off, sh->world, ss.uniq_gid, (uint32_t)sh->i_per, sh->rank,
-                                                    (size_t)sh->cap, sh->peers);
-    h->launches++;
     k_shard_fetch<V, 4><<<h->num_sms * 4, 256, 0, s>>>(ss.src, ss.multi, ss.owner_off, sh->world, sh->cache, h->D / 4, sh->ilv);
 }
 
@@ -459,7 +514,9 @@ template <int V, int R>
 __global__ void __launch_bounds__(256) k_owner_add(float *__restrict__ Q, const float *__restrict__ recv_g,
                                                     const int32_t *__restrict__ recv_ids,
                                                     const uint32_t *__restrict__ recv_cnt_s, size_t cap, int D4, float alpha,
-                                                    uint32_t rows_local, int *err) {
+                                                    uint32_t rows_local, int *err, const uint32_t *__restrict__ multi) {
+    // multi != null (exclusive-row bypass live this step): an entry whose row no other rank referenced has already been
+    // written, updated, by its sender -- only rows shared between ranks are added here
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
     const uint32_t nwarps = (uint32_t)((gridDim.x * (size_t)blockDim.x) >> 5);
@@ -481,6 +538,8 @@ __global__ void __launch_bounds__(256) k_owner_add(float *__restrict__ Q, const 
                 row[jj] = (uint32_t)recv_ids[k0 + jj];
                 if (row[jj] >= rows_local) {
                     if (lane == 0) atomicOr(&err[0], 1);
+                    row[jj] = 0xFFFFFFFFu;
+                } else if (multi && !((multi[row[jj] >> 5] >> (row[jj] & 31)) & 1u)) {
                     row[jj] = 0xFFFFFFFFu;
                 }
             }
@@ -525,25 +584,25 @@ static void launch_merge(daisy_ctx *h, float alpha, cudaStream_t s) {
         k_owner_add<V, R><<<h->num_sms * 8, 256, 0, s>>>(sh->peers.q[me], sh->peers.recv_g[me] + (size_t)snd * cap * h->D,
                                                          sh->peers.recv_ids[me] + (size_t)snd * cap,
                                                          sh->peers.recv_cnt[me] + snd, cap, h->D / 4, alpha, (uint32_t)h->I,
-                                                         h->err);
+                                                         h->err, sh->classified ? sh->bm_multi : nullptr);
         if (snd + 1 < sh->world) h->launches++;
     }
 }
 
-static int shard_compute(daisy_ctx *h, float *P_local, const int32_t *triples_dev, const int32_t *host_src, int64_t B,
-                         float lr, float wd, double *loss_accum, cudaStream_t s) {
+// First part of a step: this rank's bookkeeping, and the id list / counts of what it will push stored into the owners.
+static int shard_prepare(daisy_ctx *h, const int32_t *triples_dev, const int32_t *host_src, int64_t B, cudaStream_t s) {
     daisy_shard *sh = h->sh;
-    const double shrink = 1.0 - (double)lr * (double)wd;
-    DAISY_REQUIRE(shrink > 0.0, DAISY_EINVAL, "lr*wd = %g >= 1: the L2 shrink factor is not positive", (double)lr * wd);
     DeviceGuard g(h->device);
     DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
-    if (B == 0) {  // no triples here this step: the rank's rows still decay, and the owners must see empty regions
+    sh->prepared = 1;
+    sh->prepared_B = B;
+    sh->classified = 0;
+    if (B == 0) {  // no triples here this step: the owners must see empty regions
         k_shard_push_none<<<1, 32, 0, s>>>(sh->world, sh->rank, sh->peers);
         DAISY_LAUNCH_CHECK(h);
-        h->scale *= shrink;
         return DAISY_OK;
     }
-    StepPlan pl;
+    StepPlan &pl = *(StepPlan *)sh->plan;
     const bool prof = h->timing == 2;
     if (prof) {
         if (!sh->pev[0])
@@ -554,8 +613,56 @@ static int shard_compute(daisy_ctx *h, float *P_local, const int32_t *triples_de
                         host_src != nullptr || h->inputs_ready, sh);
     if (rc) return rc;
     if (prof) cudaEventRecord(sh->pev[1], s);
+    sh->prepared_set = pl.set;
+    const ShardSet &ss = sh->set[pl.set];
+    k_shard_push_ids<<<h->num_sms * 2, 256, 0, s>>>(ss.owner_off, sh->world, ss.uniq_gid, (uint32_t)sh->i_per, sh->rank,
+                                                    (size_t)sh->cap, sh->peers);
+    DAISY_LAUNCH_CHECK(h);
+    return DAISY_OK;
+}
+
+// Exclusive-row bypass, owner side (every rank's id list has arrived): which entries name a row no other rank references.
+static int shard_classify(daisy_ctx *h, cudaStream_t s) {
+    daisy_shard *sh = h->sh;
+    DeviceGuard g(h->device);
+    DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
+    DAISY_CUDA(cudaMemsetAsync(sh->bm_seen, 0, sh->bm_words * sizeof(uint32_t), s));
+    DAISY_CUDA(cudaMemsetAsync(sh->bm_multi, 0, sh->bm_words * sizeof(uint32_t), s));
+    const dim3 grid((unsigned)(h->num_sms * 2), (unsigned)sh->world);
+    const int me = sh->rank;
+    k_owner_count<<<grid, 256, 0, s>>>(sh->peers.recv_ids[me], sh->peers.recv_cnt[me], (size_t)sh->cap, (uint32_t)h->I,
+                                       sh->bm_seen, sh->bm_multi);
+    DAISY_LAUNCH_CHECK(h);
+    k_owner_classify<<<grid, 256, 0, s>>>(sh->peers.recv_ids[me], sh->peers.recv_cnt[me], (size_t)sh->cap, (uint32_t)h->I,
+                                          sh->bm_multi, me, sh->peers);
+    DAISY_LAUNCH_CHECK(h);
+    h->launches += 3;
+    sh->classified = 1;
+    return DAISY_OK;
+}
+
+// Rest of the step on this rank: fetch of the repeated rows + the fused compute / push kernels.
+static int shard_finish(daisy_ctx *h, float *P_local, float lr, float wd, double *loss_accum, cudaStream_t s) {
+    daisy_shard *sh = h->sh;
+    const double shrink = 1.0 - (double)lr * (double)wd;
+    DAISY_REQUIRE(shrink > 0.0, DAISY_EINVAL, "lr*wd = %g >= 1: the L2 shrink factor is not positive", (double)lr * wd);
+    DAISY_REQUIRE(sh->prepared, DAISY_EINVAL, "no prepared step");
+    DeviceGuard g(h->device);
+    DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
+    sh->prepared = 0;
+    if (sh->prepared_B == 0) {  // the rank's rows still decay
+        h->scale *= shrink;
+        return DAISY_OK;
+    }
+    const StepPlan &pl = *(const StepPlan *)sh->plan;
+    const bool prof = h->timing == 2;
     const ShardSet &ss = sh->set[pl.set];
     const int D4 = h->D / 4;
+    if (sh->classified) {
+        k_shard_tag_dst<<<h->num_sms * 2, 256, 0, s>>>(ss.owner_off, sh->world, ss.uniq_gid, (uint32_t)sh->i_per,
+                                                       (size_t)sh->cap, h->D, sh->peers.excl[sh->rank], sh->peers, ss.dst);
+        DAISY_LAUNCH_CHECK(h);
+    }
     if (D4 <= 32) launch_fetch<1>(h, ss, s);
     else if (D4 <= 64) launch_fetch<2>(h, ss, s);
     else if (D4 <= 96) launch_fetch<3>(h, ss, s);
@@ -567,7 +674,7 @@ static int shard_compute(daisy_ctx *h, float *P_local, const int32_t *triples_de
     opt.dst = ss.dst;
     opt.alpha = (float)((double)lr / shrink);
     opt.D4 = D4;
-    rc = table_phase<PushOpt>(h, pl, P_local, sh->cache, opt, (float)(h->scale * h->scale), loss_accum);
+    int rc = table_phase<PushOpt>(h, pl, P_local, sh->cache, opt, (float)(h->scale * h->scale), loss_accum);
     if (rc) return rc;
     if (prof) cudaEventRecord(sh->pev[3], s);
     h->scale *= shrink;
@@ -614,6 +721,9 @@ void daisy_shard_free(daisy_ctx *h) {
         if (sh->pev[i]) cudaEventDestroy(sh->pev[i]);
     for (int r = 0; r < sh->world; ++r)
         if (sh->ipc_opened[r] && sh->peer_arena[r]) cudaIpcCloseMemHandle(sh->peer_arena[r]);
+    if (sh->bm_seen) cudaFree(sh->bm_seen);
+    if (sh->bm_multi) cudaFree(sh->bm_multi);
+    if (sh->plan) delete (StepPlan *)sh->plan;
     for (int i = 0; i < DAISY_NSETS; ++i) {
         void *ptrs[] = {sh->set[i].uniq_gid, (void *)sh->set[i].src, (void *)sh->set[i].dst, sh->set[i].owner_off,
                         sh->set[i].multi, (void *)sh->set[i].jsrc, (void *)sh->set[i].isrc};
@@ -682,6 +792,15 @@ extern "C" int daisy_shard_init(daisy_handle_t h, int rank, int world, int64_t i
     }
     ok = ok && cudaMalloc((void **)&sh->cidx, cap * sizeof(uint32_t)) == cudaSuccess;
     ok = ok && cudaMalloc((void **)&sh->cache, cap * D * sizeof(float)) == cudaSuccess;
+    sh->bm_words = ((size_t)sh->i_per + 31) / 32 + 1;
+    ok = ok && cudaMalloc((void **)&sh->bm_seen, sh->bm_words * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMalloc((void **)&sh->bm_multi, sh->bm_words * sizeof(uint32_t)) == cudaSuccess;
+    sh->plan = new StepPlan();
+    {   // exclusive-row bypass (on by default; the single-pass owner merge does not know about it)
+        const char *v = getenv("DAISY_SHARD_BYPASS");
+        const char *m = getenv("DAISY_OWNER_MERGE");
+        sh->bypass = ((v && *v) ? atoi(v) != 0 : 0) && !(m && atoi(m) == 1);
+    }
     for (int i = 0; i < DAISY_NSETS && ok; ++i) {
         ok = ok && cudaMalloc((void **)&sh->set[i].uniq_gid, cap * sizeof(uint32_t)) == cudaSuccess;
         ok = ok && cudaMalloc((void **)&sh->set[i].src, cap * sizeof(float *)) == cudaSuccess;
@@ -757,7 +876,32 @@ extern "C" int daisy_shard_compute(daisy_handle_t h, float *P_local, const int32
     if (rc) return rc;
     rc = check_step_args(h, P_local, h->sh->cache, triples, B);
     if (rc) return rc;
-    return shard_compute(h, P_local, triples, nullptr, B, lr, wd, loss_accum, (cudaStream_t)stream);
+    if (!h->sh->prepared) {  // one-call form: no classification => every sum goes through the owner's pass
+        rc = shard_prepare(h, triples, nullptr, B, (cudaStream_t)stream);
+        if (rc) return rc;
+    } else {
+        DAISY_REQUIRE(B == h->sh->prepared_B, DAISY_EINVAL, "daisy_shard_compute: %lld triples, but %lld were prepared",
+                      (long long)B, (long long)h->sh->prepared_B);
+    }
+    return shard_finish(h, P_local, lr, wd, loss_accum, (cudaStream_t)stream);
+}
+
+extern "C" int daisy_shard_prepare(daisy_handle_t h, float *P_local, const int32_t *triples, int64_t B,
+                                   daisy_stream_t stream) {
+    int rc = shard_ready(h);
+    if (rc) return rc;
+    rc = check_step_args(h, P_local, h->sh->cache, triples, B);
+    if (rc) return rc;
+    DAISY_REQUIRE(!h->sh->prepared, DAISY_EINVAL, "a prepared step is pending: call daisy_shard_compute first");
+    return shard_prepare(h, triples, nullptr, B, (cudaStream_t)stream);
+}
+
+extern "C" int daisy_shard_classify(daisy_handle_t h, daisy_stream_t stream) {
+    int rc = shard_ready(h);
+    if (rc) return rc;
+    DAISY_REQUIRE(h->sh->prepared, DAISY_EINVAL, "daisy_shard_classify follows daisy_shard_prepare of every rank");
+    if (!h->sh->bypass) return DAISY_OK;
+    return shard_classify(h, (cudaStream_t)stream);
 }
 
 extern "C" int daisy_shard_apply(daisy_handle_t h, float lr, float wd, daisy_stream_t stream) {
@@ -777,7 +921,13 @@ static int shard_step_impl(daisy_handle_t h, float *P_local, const int32_t *trip
     cudaStream_t s = (cudaStream_t)stream;
     daisy_shard *sh = h->sh;
     const bool prof = h->timing == 2 && B > 0;
-    int rc = shard_compute(h, P_local, triples_dev, host_src, B, lr, wd, loss_accum, s);
+    int rc = shard_prepare(h, triples_dev, host_src, B, s);
+    if (!rc && sh->bypass && sh->world > 1) {  // ids are in the owners' memory -> verdicts are in the senders' memory
+        rc = shard_barrier(h, s);
+        if (!rc) rc = shard_classify(h, s);
+        if (!rc) rc = shard_barrier(h, s);
+    }
+    if (!rc) rc = shard_finish(h, P_local, lr, wd, loss_accum, s);
     if (!rc) rc = shard_barrier(h, s);
     if (!rc && prof) cudaEventRecord(sh->pev[4], s);
     if (!rc) rc = shard_apply(h, lr, wd, s);

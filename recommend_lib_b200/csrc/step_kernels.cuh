@@ -51,8 +51,10 @@ __global__ void k_prep(const int32_t *__restrict__ triples, int B, uint32_t U, u
 __global__ void k_refs(const int32_t *__restrict__ triples, const uint32_t *__restrict__ order,
                        const uint32_t *__restrict__ sorted_i, int B, uint32_t U, uint32_t I, int C,
                        int32_t *__restrict__ st, uint32_t *__restrict__ ukey, uint32_t *__restrict__ uval,
-                       uint32_t *__restrict__ qkey, uint32_t *__restrict__ qval, uint32_t *__restrict__ islot) {
+                       uint32_t *__restrict__ qkey, uint32_t *__restrict__ qval, uint32_t *__restrict__ islot,
+                       uint32_t ukey_off, uint32_t *__restrict__ longs_hdr) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0 && longs_hdr) longs_hdr[0] = longs_hdr[1] = 0u;  // merged sort: the list is filled by k_slots_merged
     if (k >= B) return;
     uint32_t u, i, j;
     bool bad;
@@ -60,7 +62,7 @@ __global__ void k_refs(const int32_t *__restrict__ triples, const uint32_t *__re
     st[3 * (size_t)k] = (int32_t)u;
     st[3 * (size_t)k + 1] = (int32_t)i;
     st[3 * (size_t)k + 2] = (int32_t)j;
-    ukey[k] = u;
+    ukey[k] = u + ukey_off;  // merged sort (book_kernels): user keys follow the item keys and the sentinel
     uval[k] = (uint32_t)k;
     qkey[k] = j;  // negative-item ref of sorted triple k
     qval[k] = (uint32_t)k;
@@ -103,6 +105,60 @@ __global__ void k_slots_item(const uint32_t *__restrict__ key, const uint32_t *_
     else
         islot[v - B] = slot;
     if (first && longs) list_long_row(key, n, p, r, 1, long_len, DAISY_SLICE, longs, longs_cap);
+}
+
+// One sort for all 3B refs (book_kernels: merged sort).  Keys: item rows [0, I), the sentinel I of the non-head positive
+// refs, user rows as I + 1 + u -- so the sorted array is [item refs | sentinels | user refs] and the user part starts at
+// position 2B exactly.  Same slots and lists as k_slots_item + k_slots_user; also splits the sorted keys into the set's
+// qkey_s [2B] and ukey_s [B] (user keys back to row ids), which is what the table kernels read.
+__global__ void k_slots_merged(const uint32_t *__restrict__ key, const uint32_t *__restrict__ val, int B, uint32_t I,
+                               uint32_t *__restrict__ qkey_s, uint32_t *__restrict__ ukey_s,
+                               uint32_t *__restrict__ uslot, uint32_t *__restrict__ jslot, uint32_t *__restrict__ islot,
+                               uint32_t *longs, int longs_cap, int long_len) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n2 = 2 * (long long)B, n3 = 3 * (long long)B;
+    if (p >= n3) return;
+    const uint32_t r = key[p];
+    if (p < n2) {
+        qkey_s[p] = r;
+        if (r == I) return;
+        const bool first = (p == 0) || (key[p - 1] != r);
+        const bool last = (p == n2 - 1) || (key[p + 1] != r);
+        const uint32_t slot = (first && last) ? DAISY_DIRECT : (uint32_t)p;
+        const uint32_t v = val[p];
+        if (v < (uint32_t)B)
+            jslot[v] = slot;
+        else
+            islot[v - B] = slot;
+        if (first && longs) list_long_row(key, (int)n2, (int)p, r, 1, long_len, DAISY_SLICE, longs, longs_cap);
+    } else {
+        const int q = (int)(p - n2);
+        const uint32_t *ukey = key + n2;
+        ukey_s[q] = r - (I + 1u);
+        const bool first = (q == 0) || (ukey[q - 1] != r);
+        const bool last = (q == B - 1) || (ukey[q + 1] != r);
+        uslot[val[p]] = (first && last) ? DAISY_DIRECT : (uint32_t)q;
+        if (first && longs) {  // the list holds row ids: search the run in the offset keys, record the row itself
+            if (q + long_len < B && ukey[q + long_len] == r) {
+                int lo = q + long_len, hi = B - 1;
+                while (lo < hi) {
+                    const int mid = (int)(((long long)lo + hi + 1) >> 1);
+                    if (ukey[mid] == r) lo = mid; else hi = mid - 1;
+                }
+                const uint32_t len = (uint32_t)(lo - q + 1);
+                const uint32_t rr = atomicAdd(&longs[0], 1u);
+                const uint32_t sl0 = atomicAdd(&longs[1], (len + DAISY_SLICE - 1) / DAISY_SLICE);
+                if ((int)rr < longs_cap) {
+                    uint32_t *rec = longs + 2 + 5 * (size_t)rr;
+                    rec[0] = 0u;
+                    rec[1] = r - (I + 1u);
+                    rec[2] = (uint32_t)q;
+                    rec[3] = len;
+                    rec[4] = sl0;
+                }
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1382,6 +1438,16 @@ static int bits_for(uint64_t max_value) {  // number of low bits needed to repre
     return b;
 }
 
+// merged sort of the 3B refs (book_kernels): worth it when it costs no more element-passes than the two separate sorts
+// (it always saves the fixed cost of one sort: histogram + scan launches and one wave per pass)
+static bool use_merged_sort(const daisy_ctx *h, uint32_t U, uint32_t I) {
+    if (h->merged_sort == 0) return false;
+    if ((uint64_t)U + I > 0xFFFFFFF0ull || 3 * h->maxB >= (1ll << 31)) return false;
+    if (h->merged_sort == 1) return true;
+    const int pu = (bits_for(U - 1) + 7) / 8, pq = (bits_for(I) + 7) / 8, pm = (bits_for((uint64_t)I + U) + 7) / 8;
+    return 3 * pm <= pu + 2 * pq;
+}
+
 static int auto_chunk(const daisy_ctx *h, int64_t B) {
     if (h->chunk > 0) return h->chunk;
     // keep >= ~4 waves of 32 resident warps per SM before growing the chunk
@@ -1512,8 +1578,27 @@ static int book_kernels(daisy_ctx *h, BookSet &k, const StepPlan &pl, const int3
     h->launches += 4;
     phase_mark(h, PH_SORT_I, s);
     // refs
+    // One sort for all 3B refs when the table is not sharded and the combined key space costs no extra radix passes
+    // (config 4: 10 M users + 2 M items = 24 bits = 3 passes over 3 M pairs, instead of 3 over 1 M + 3 over 2 M, and
+    // 7 launches instead of 14): bit-identical products, the sort is stable and the refs enter it in the same order.
+    if (!sh && use_merged_sort(h, U, I)) {
+        k_refs<<<daisy_ceil_div(B, T), T, 0, bs>>>(triples, h->ival_out, h->ikey_out, B, U, I, C, k.st, h->key_in + 2 * (size_t)B,
+                                                   h->val_in + 2 * (size_t)B, h->key_in, h->val_in, k.islot, I + 1u, k.longs);
+        DAISY_LAUNCH_CHECK(h);
+        phase_mark(h, PH_REFS, s);
+        tmp = h->cub_tmp_bytes;
+        DAISY_CUDA(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->key_in, h->key_out, h->val_in, h->val_out, 3 * B, 0,
+                                                   bits_for((uint64_t)I + U), bs));
+        h->launches += 4;
+        phase_mark(h, PH_SORT_U, s);
+        phase_mark(h, PH_SORT_Q, s);
+        k_slots_merged<<<daisy_ceil_div(3 * (int64_t)B, T), T, 0, bs>>>(h->key_out, h->val_out, B, I, k.qkey_s, k.ukey_s, k.uslot,
+                                                                        k.jslot, k.islot, k.longs, h->longs_cap, h->heavy_len);
+        DAISY_LAUNCH_CHECK(h);
+        return DAISY_OK;
+    }
     k_refs<<<daisy_ceil_div(B, T), T, 0, bs>>>(triples, h->ival_out, h->ikey_out, B, U, I, C, k.st, h->ukey_in,
-                                               h->uval_in, h->key_in, h->val_in, k.islot);
+                                               h->uval_in, h->key_in, h->val_in, k.islot, 0u, nullptr);
     DAISY_LAUNCH_CHECK(h);
     phase_mark(h, PH_REFS, s);
     tmp = h->cub_tmp_bytes;
@@ -1725,7 +1810,11 @@ static int table_phase_v(daisy_ctx *h, const StepPlan &pl, const float *P, const
     if ((size_t)S * stage_bytes > (size_t)56 * 1024) S = (int)((size_t)56 * 1024 / stage_bytes);
     if (pl.small) S = 0;  // one triple per warp: nothing to pipeline
     if (S >= 2) {
-        const size_t smem = S * stage_bytes + (size_t)8 * S * 8;
+        size_t smem = S * stage_bytes + (size_t)8 * S * 8;
+        if (h->main_max_blocks > 0) {  // experiment: leave room on every SM for the bookkeeping stream's blocks
+            const size_t floor_b = ((size_t)233472 / (size_t)(h->main_max_blocks + 1) + 1023) / 1024 * 1024;
+            if (floor_b > smem && floor_b <= (size_t)227 * 1024) smem = floor_b;
+        }
         static size_t granted_tab[2][64];  // per instantiation (V, Opt): shared memory already granted, by PTR and device
         size_t &granted = granted_tab[pl.jsrc ? 1 : 0][h->device & 63];
         if (pl.jsrc) {
@@ -1803,9 +1892,24 @@ static int run_step(daisy_ctx *h, const float *P, const float *Q, const int32_t 
     // local item shard
     const uint32_t U = (uint32_t)h->U, I = (uint32_t)(h->item_rows_override ? h->item_rows_override : h->I);
     StepPlan pl;
-    int rc = book_phase(h, pl, triples, B, U, I, s, host_src, inputs_ready, nullptr);
+    // SM partitioning (partition.cu): the table kernels run on the partition that excludes the bookkeeping stream's SMs,
+    // ordered after the caller's earlier work and before its later work by two events
+    const bool part = h->part_ok && h->pipeline && h->timing != 2;
+    cudaStream_t ks = s;
+    if (part) {
+        DAISY_CUDA(cudaEventRecord(h->part_ev_in, s));
+        DAISY_CUDA(cudaStreamWaitEvent(h->part_main_stream, h->part_ev_in, 0));
+        ks = h->part_main_stream;
+    }
+    int rc = book_phase(h, pl, triples, B, U, I, ks, host_src, inputs_ready, nullptr);
     if (rc) return rc;
-    return table_phase<Opt>(h, pl, P, Q, opt, c2, loss_accum);
+    rc = table_phase<Opt>(h, pl, P, Q, opt, c2, loss_accum);
+    if (rc) return rc;
+    if (part) {
+        DAISY_CUDA(cudaEventRecord(h->part_ev_out, ks));
+        DAISY_CUDA(cudaStreamWaitEvent(s, h->part_ev_out, 0));
+    }
+    return DAISY_OK;
 }
 
 static int check_step_args(daisy_ctx *h, const void *P, const void *Q, const void *triples, int64_t B) {

@@ -399,6 +399,17 @@ class PeerShardedBPR:
         self._lib.check(self.h.L.daisy_shard_compute(self.h.ptr, vp(self._P_ptr), vp(triples.data_ptr() if B else 0), B,
                                                      self.lr, self.wd, vp(self.loss.data_ptr()), self._s()))
 
+    def prepare(self, triples):
+        """Lockstep protocol with the exclusive-row bypass: prepare (all ranks) -> classify (all) -> compute (all, the
+        same triples) -> apply (all)."""
+        vp = self._lib.c_vp
+        B = int(triples.shape[0])
+        self._lib.check(self.h.L.daisy_shard_prepare(self.h.ptr, vp(self._P_ptr), vp(triples.data_ptr() if B else 0), B,
+                                                     self._s()))
+
+    def classify(self):
+        self._lib.check(self.h.L.daisy_shard_classify(self.h.ptr, self._s()))
+
     def apply(self):
         self._lib.check(self.h.L.daisy_shard_apply(self.h.ptr, self.lr, self.wd, self._s()))
 

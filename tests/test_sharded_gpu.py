@@ -93,6 +93,18 @@ def _peer_lockstep(shards, batches_per_rank):
         s.apply()
 
 
+def _peer_lockstep_bypass(shards, batches_per_rank):
+    """The same step with the exclusive-row bypass: ids to the owners, verdicts back, then compute and apply."""
+    for s, b in zip(shards, batches_per_rank):
+        s.prepare(b)
+    for s in shards:
+        s.classify()
+    for s, b in zip(shards, batches_per_rank):
+        s.compute(b)
+    for s in shards:
+        s.apply()
+
+
 def _make_peer_shards(G, U, I, D, B, P0, Q0, lr=0.05, wd=0.01):
     from recommend_lib_b200.sharded import PeerShardedBPR
     dev = torch.device("cuda:0")
@@ -137,6 +149,38 @@ def test_peer_sharded_lockstep_matches_oracle_and_unsharded(G, U, I, D, B):
     assert rel_err(Q, m.embed_item.weight.detach().cpu().numpy()) <= 1e-5
     for s in shards:
         s.close()
+
+
+@pytest.mark.parametrize("G,U,I,D,B", [(2, 400, 300, 64, 6000), (3, 1000, 70001, 128, 20000), (4, 64, 50, 32, 37),
+                                       (8, 5000, 300001, 128, 40000), (2, 500, 4000, 256, 3000)])
+def test_peer_sharded_exclusive_row_bypass_is_bit_identical(G, U, I, D, B, monkeypatch):
+    """DAISY_SHARD_BYPASS: a row that only ONE rank references in a step is written back, updated, by that rank (same
+    fmaf on the same operands as the owner's pass) and skipped by the owner: tables and losses must equal the run
+    without the bypass bit for bit -- with catalogues small enough that most rows are shared (the owner's pass keeps
+    its sender-rank order) and large enough that most are exclusive."""
+    from sharded_testing import route
+    dev = torch.device("cuda:0")
+    lr, wd, steps = 0.05, 0.01, 3
+    P0, Q0, batches = _problem(U, I, D, B, steps, seed=G + 20)
+    batches[1][:, 0] = batches[1][:, 0] % max(1, U // G)       # second step: only rank 0 has triples
+    outs = []
+    for bypass in ("0", "1"):
+        monkeypatch.setenv("DAISY_SHARD_BYPASS", bypass)
+        shards = _make_peer_shards(G, U, I, D, B, P0, Q0, lr, wd)
+        for b in batches:
+            per_rank = [torch.from_numpy(route(b, s.layout, s.rank)).to(dev) for s in shards]
+            (_peer_lockstep_bypass if bypass == "1" else _peer_lockstep)(shards, per_rank)
+        for s in shards:
+            s.check()
+            s.materialize()
+        outs.append((torch.cat([s.P for s in shards]).clone(), torch.cat([s.Q for s in shards]).clone(),
+                     [s.loss_sum() for s in shards]))
+        for s in shards:
+            s.close()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2]
+    from oracle import bpr_oracle
+    Pr, Qr, _ = bpr_oracle.bpr_run_closed_form(P0, Q0, batches, lr, wd, np.float64)
+    assert rel_err(outs[1][0].cpu().numpy(), Pr) <= 1e-5 and rel_err(outs[1][1].cpu().numpy(), Qr) <= 1e-5
 
 
 def test_peer_sharded_is_deterministic_and_handles_empty_ranks():

@@ -8,7 +8,7 @@ tail -6 gpurun_out/r02m_tests_n$N.log
 run() {  # $1 = tag, rest = environment
   tag=$1; shift
   env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
-    bench.py --gpus $N --steps 50 --warmup 5 > gpurun_out/r02m_bench_n${N}_${tag}.json 2> gpurun_out/r02m_bench_n${N}_${tag}.err
+    bench.py --gpus $N --steps 50 --warmup 5 2> gpurun_out/r02m_bench_n${N}_${tag}.err | grep "^{" > gpurun_out/r02m_bench_n${N}_${tag}.json
   python - <<PY
 import json
 try:
