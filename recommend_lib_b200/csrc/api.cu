@@ -168,7 +168,8 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
         // bandwidth-bound kernels of step n are still dispatching blocks
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-        cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, prio_hi);
+        cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking,
+                                     env_int("DAISY_BOOK_LOW_PRIORITY", 0) ? prio_lo : prio_hi);
         // DAISY_BOOK_SMS = n > 0: the bookkeeping stream gets n SMs of its own and the table kernels the rest
         // (partition.cu); a driver that cannot partition leaves the shared-SM pipeline in place
         if (B > 0 && h->pipeline && env_int("DAISY_BOOK_SMS", 0) > 0) {

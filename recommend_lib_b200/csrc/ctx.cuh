@@ -91,6 +91,9 @@ struct daisy_shard {
     uint32_t epoch;   // barrier epoch (same sequence on every rank)
     // exclusive-row bypass: owner-side bitmaps over the local item rows (referenced by >= 1 / >= 2 ranks this step)
     uint32_t *bm_seen, *bm_multi;
+    cudaStream_t aux_stream;  // daisy_shard_step: the id exchange runs here, next to the fetch on the caller's stream
+    cudaEvent_t aux_ev[2];
+    uint32_t *shared_idx, *shared_cnt;  // [G][cap], [G]: per sender, the entries whose row is shared between ranks
     size_t bm_words;
     int bypass;       // DAISY_SHARD_BYPASS (default 1)
     int classified;   // this step's entries have been classified (daisy_shard_classify ran): bypass is live

@@ -322,15 +322,34 @@ __global__ void k_owner_count(const int32_t *__restrict__ recv_ids, const uint32
 // sender's excl array).  The sender then stores the updated row straight into the owner's q instead of pushing a sum
 // the owner would have to read, add and write back (k_owner_add skips those entries).
 __global__ void k_owner_classify(const int32_t *__restrict__ recv_ids, const uint32_t *__restrict__ recv_cnt, size_t cap,
-                                 uint32_t rows_local, const uint32_t *__restrict__ multi, int me, ShardPeers peers) {
+                                 uint32_t rows_local, const uint32_t *__restrict__ multi, int me, ShardPeers peers,
+                                 uint32_t *__restrict__ shared_idx, uint32_t *__restrict__ shared_cnt) {
+    // The entries that stay with the owner (rows shared between ranks, and bad ids for the error flag) are also listed
+    // per sender, so that the owner's passes walk those few entries instead of scanning every id.  The order inside
+    // a list is arbitrary (atomics) and does not matter: the entries of one sender name distinct rows.
     const int snd = blockIdx.y;
     uint32_t n = recv_cnt[snd];
     if (n > cap) n = (uint32_t)cap;
     const int32_t *ids = recv_ids + (size_t)snd * cap;
     uint8_t *out = peers.excl[snd] + (size_t)me * cap;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const uint32_t r = (uint32_t)ids[k];
-        out[k] = (r < rows_local && !((multi[r >> 5] >> (r & 31)) & 1u)) ? 1 : 0;
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t n_up = (n + 31u) & ~31u;  // whole warps iterate together (ballot below)
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_up; k += stride) {
+        bool keep = false;
+        if (k < n) {
+            const uint32_t r = (uint32_t)ids[k];
+            const bool excl = r < rows_local && !((multi[r >> 5] >> (r & 31)) & 1u);
+            out[k] = excl ? 1 : 0;
+            keep = !excl;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&shared_cnt[snd], (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) shared_idx[(size_t)snd * cap + base + __popc(m & ((1u << lane) - 1u))] = k;
+        }
     }
 }
 
@@ -514,13 +533,14 @@ template <int V, int R>
 __global__ void __launch_bounds__(256) k_owner_add(float *__restrict__ Q, const float *__restrict__ recv_g,
                                                     const int32_t *__restrict__ recv_ids,
                                                     const uint32_t *__restrict__ recv_cnt_s, size_t cap, int D4, float alpha,
-                                                    uint32_t rows_local, int *err, const uint32_t *__restrict__ multi) {
-    // multi != null (exclusive-row bypass live this step): an entry whose row no other rank referenced has already been
-    // written, updated, by its sender -- only rows shared between ranks are added here
+                                                    uint32_t rows_local, int *err, const uint32_t *__restrict__ list,
+                                                    const uint32_t *__restrict__ list_cnt) {
+    // list != null (exclusive-row bypass live this step): an entry whose row no other rank referenced has already been
+    // written, updated, by its sender -- only the listed entries (rows shared between ranks) are added here
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
     const uint32_t nwarps = (uint32_t)((gridDim.x * (size_t)blockDim.x) >> 5);
-    uint32_t n = *recv_cnt_s;
+    uint32_t n = list ? *list_cnt : *recv_cnt_s;
     if (n > cap) {  // cannot happen (a sender has at most 2*maxB = cap distinct rows); never read out of bounds
         if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(&err[0], 32);
         n = (uint32_t)cap;
@@ -530,16 +550,16 @@ __global__ void __launch_bounds__(256) k_owner_add(float *__restrict__ Q, const 
     for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
     for (uint32_t k0 = warp * R; k0 < n; k0 += nwarps * R) {
         float4 g[R][V], old[R][V];
-        uint32_t row[R];
+        uint32_t row[R], ent[R];
 #pragma unroll
         for (int jj = 0; jj < R; ++jj) {
             row[jj] = 0xFFFFFFFFu;
+            ent[jj] = 0;
             if (k0 + jj < n) {
-                row[jj] = (uint32_t)recv_ids[k0 + jj];
+                ent[jj] = list ? list[k0 + jj] : k0 + jj;
+                row[jj] = (uint32_t)recv_ids[ent[jj]];
                 if (row[jj] >= rows_local) {
                     if (lane == 0) atomicOr(&err[0], 1);
-                    row[jj] = 0xFFFFFFFFu;
-                } else if (multi && !((multi[row[jj] >> 5] >> (row[jj] & 31)) & 1u)) {
                     row[jj] = 0xFFFFFFFFu;
                 }
             }
@@ -550,7 +570,7 @@ __global__ void __launch_bounds__(256) k_owner_add(float *__restrict__ Q, const 
 #pragma unroll
                 for (int v = 0; v < V; ++v)
                     if (act[v]) {
-                        g[jj][v] = ld_stream(recv_g, (size_t)(k0 + jj) * D4 + lane + 32 * v);
+                        g[jj][v] = ld_stream(recv_g, (size_t)ent[jj] * D4 + lane + 32 * v);
                         old[jj][v] = ld_row(Q, (size_t)row[jj] * D4 + lane + 32 * v);
                     }
             }
@@ -584,13 +604,18 @@ static void launch_merge(daisy_ctx *h, float alpha, cudaStream_t s) {
         k_owner_add<V, R><<<h->num_sms * 8, 256, 0, s>>>(sh->peers.q[me], sh->peers.recv_g[me] + (size_t)snd * cap * h->D,
                                                          sh->peers.recv_ids[me] + (size_t)snd * cap,
                                                          sh->peers.recv_cnt[me] + snd, cap, h->D / 4, alpha, (uint32_t)h->I,
-                                                         h->err, sh->classified ? sh->bm_multi : nullptr);
+                                                         h->err, sh->classified ? sh->shared_idx + (size_t)snd * cap : nullptr,
+                                                         sh->shared_cnt + snd);
         if (snd + 1 < sh->world) h->launches++;
     }
 }
 
 // First part of a step: this rank's bookkeeping, and the id list / counts of what it will push stored into the owners.
-static int shard_prepare(daisy_ctx *h, const int32_t *triples_dev, const int32_t *host_src, int64_t B, cudaStream_t s) {
+// xs: the stream the id exchange runs on.  daisy_shard_step passes the handle's auxiliary stream so that the chain
+// ids -> barrier -> verdicts -> barrier -> tagged destinations runs NEXT TO the fetch of the repeated rows (both only
+// need the bookkeeping and the previous step); everything else passes xs = s.
+static int shard_prepare(daisy_ctx *h, const int32_t *triples_dev, const int32_t *host_src, int64_t B, cudaStream_t s,
+                         cudaStream_t xs) {
     daisy_shard *sh = h->sh;
     DeviceGuard g(h->device);
     DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
@@ -598,7 +623,11 @@ static int shard_prepare(daisy_ctx *h, const int32_t *triples_dev, const int32_t
     sh->prepared_B = B;
     sh->classified = 0;
     if (B == 0) {  // no triples here this step: the owners must see empty regions
-        k_shard_push_none<<<1, 32, 0, s>>>(sh->world, sh->rank, sh->peers);
+        if (xs != s) {
+            DAISY_CUDA(cudaEventRecord(sh->aux_ev[0], s));
+            DAISY_CUDA(cudaStreamWaitEvent(xs, sh->aux_ev[0], 0));
+        }
+        k_shard_push_none<<<1, 32, 0, xs>>>(sh->world, sh->rank, sh->peers);
         DAISY_LAUNCH_CHECK(h);
         return DAISY_OK;
     }
@@ -615,7 +644,11 @@ static int shard_prepare(daisy_ctx *h, const int32_t *triples_dev, const int32_t
     if (prof) cudaEventRecord(sh->pev[1], s);
     sh->prepared_set = pl.set;
     const ShardSet &ss = sh->set[pl.set];
-    k_shard_push_ids<<<h->num_sms * 2, 256, 0, s>>>(ss.owner_off, sh->world, ss.uniq_gid, (uint32_t)sh->i_per, sh->rank,
+    if (xs != s) {  // s has just been ordered behind the bookkeeping (book_phase) and carries the previous step
+        DAISY_CUDA(cudaEventRecord(sh->aux_ev[0], s));
+        DAISY_CUDA(cudaStreamWaitEvent(xs, sh->aux_ev[0], 0));
+    }
+    k_shard_push_ids<<<h->num_sms * 2, 256, 0, xs>>>(ss.owner_off, sh->world, ss.uniq_gid, (uint32_t)sh->i_per, sh->rank,
                                                     (size_t)sh->cap, sh->peers);
     DAISY_LAUNCH_CHECK(h);
     return DAISY_OK;
@@ -628,13 +661,14 @@ static int shard_classify(daisy_ctx *h, cudaStream_t s) {
     DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
     DAISY_CUDA(cudaMemsetAsync(sh->bm_seen, 0, sh->bm_words * sizeof(uint32_t), s));
     DAISY_CUDA(cudaMemsetAsync(sh->bm_multi, 0, sh->bm_words * sizeof(uint32_t), s));
+    DAISY_CUDA(cudaMemsetAsync(sh->shared_cnt, 0, DAISY_MAX_RANKS * sizeof(uint32_t), s));
     const dim3 grid((unsigned)(h->num_sms * 2), (unsigned)sh->world);
     const int me = sh->rank;
     k_owner_count<<<grid, 256, 0, s>>>(sh->peers.recv_ids[me], sh->peers.recv_cnt[me], (size_t)sh->cap, (uint32_t)h->I,
                                        sh->bm_seen, sh->bm_multi);
     DAISY_LAUNCH_CHECK(h);
     k_owner_classify<<<grid, 256, 0, s>>>(sh->peers.recv_ids[me], sh->peers.recv_cnt[me], (size_t)sh->cap, (uint32_t)h->I,
-                                          sh->bm_multi, me, sh->peers);
+                                          sh->bm_multi, me, sh->peers, sh->shared_idx, sh->shared_cnt);
     DAISY_LAUNCH_CHECK(h);
     h->launches += 3;
     sh->classified = 1;
@@ -642,7 +676,8 @@ static int shard_classify(daisy_ctx *h, cudaStream_t s) {
 }
 
 // Rest of the step on this rank: fetch of the repeated rows + the fused compute / push kernels.
-static int shard_finish(daisy_ctx *h, float *P_local, float lr, float wd, double *loss_accum, cudaStream_t s) {
+static int shard_finish(daisy_ctx *h, float *P_local, float lr, float wd, double *loss_accum, cudaStream_t s,
+                        cudaStream_t xs) {
     daisy_shard *sh = h->sh;
     const double shrink = 1.0 - (double)lr * (double)wd;
     DAISY_REQUIRE(shrink > 0.0, DAISY_EINVAL, "lr*wd = %g >= 1: the L2 shrink factor is not positive", (double)lr * wd);
@@ -651,6 +686,10 @@ static int shard_finish(daisy_ctx *h, float *P_local, float lr, float wd, double
     DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
     sh->prepared = 0;
     if (sh->prepared_B == 0) {  // the rank's rows still decay
+        if (xs != s) {
+            DAISY_CUDA(cudaEventRecord(sh->aux_ev[1], xs));
+            DAISY_CUDA(cudaStreamWaitEvent(s, sh->aux_ev[1], 0));
+        }
         h->scale *= shrink;
         return DAISY_OK;
     }
@@ -659,15 +698,17 @@ static int shard_finish(daisy_ctx *h, float *P_local, float lr, float wd, double
     const ShardSet &ss = sh->set[pl.set];
     const int D4 = h->D / 4;
     if (sh->classified) {
-        k_shard_tag_dst<<<h->num_sms * 2, 256, 0, s>>>(ss.owner_off, sh->world, ss.uniq_gid, (uint32_t)sh->i_per,
-                                                       (size_t)sh->cap, h->D, sh->peers.excl[sh->rank], sh->peers, ss.dst);
+        k_shard_tag_dst<<<h->num_sms * 2, 256, 0, xs>>>(ss.owner_off, sh->world, ss.uniq_gid, (uint32_t)sh->i_per,
+                                                        (size_t)sh->cap, h->D, sh->peers.excl[sh->rank], sh->peers, ss.dst);
         DAISY_LAUNCH_CHECK(h);
     }
+    if (xs != s) DAISY_CUDA(cudaEventRecord(sh->aux_ev[1], xs));
     if (D4 <= 32) launch_fetch<1>(h, ss, s);
     else if (D4 <= 64) launch_fetch<2>(h, ss, s);
     else if (D4 <= 96) launch_fetch<3>(h, ss, s);
     else launch_fetch<4>(h, ss, s);
     DAISY_LAUNCH_CHECK(h);
+    if (xs != s) DAISY_CUDA(cudaStreamWaitEvent(s, sh->aux_ev[1], 0));
     if (prof) cudaEventRecord(sh->pev[2], s);
     PushOpt opt;
     opt.P = P_local;
@@ -723,6 +764,11 @@ void daisy_shard_free(daisy_ctx *h) {
         if (sh->ipc_opened[r] && sh->peer_arena[r]) cudaIpcCloseMemHandle(sh->peer_arena[r]);
     if (sh->bm_seen) cudaFree(sh->bm_seen);
     if (sh->bm_multi) cudaFree(sh->bm_multi);
+    if (sh->shared_idx) cudaFree(sh->shared_idx);
+    if (sh->shared_cnt) cudaFree(sh->shared_cnt);
+    if (sh->aux_stream) cudaStreamDestroy(sh->aux_stream);
+    for (int i = 0; i < 2; ++i)
+        if (sh->aux_ev[i]) cudaEventDestroy(sh->aux_ev[i]);
     if (sh->plan) delete (StepPlan *)sh->plan;
     for (int i = 0; i < DAISY_NSETS; ++i) {
         void *ptrs[] = {sh->set[i].uniq_gid, (void *)sh->set[i].src, (void *)sh->set[i].dst, sh->set[i].owner_off,
@@ -795,11 +841,19 @@ extern "C" int daisy_shard_init(daisy_handle_t h, int rank, int world, int64_t i
     sh->bm_words = ((size_t)sh->i_per + 31) / 32 + 1;
     ok = ok && cudaMalloc((void **)&sh->bm_seen, sh->bm_words * sizeof(uint32_t)) == cudaSuccess;
     ok = ok && cudaMalloc((void **)&sh->bm_multi, sh->bm_words * sizeof(uint32_t)) == cudaSuccess;
+    {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        ok = ok && cudaStreamCreateWithPriority(&sh->aux_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+        for (int i = 0; i < 2 && ok; ++i) ok = cudaEventCreateWithFlags(&sh->aux_ev[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    ok = ok && cudaMalloc((void **)&sh->shared_idx, (size_t)world * cap * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMalloc((void **)&sh->shared_cnt, DAISY_MAX_RANKS * sizeof(uint32_t)) == cudaSuccess;
     sh->plan = new StepPlan();
     {   // exclusive-row bypass (on by default; the single-pass owner merge does not know about it)
         const char *v = getenv("DAISY_SHARD_BYPASS");
         const char *m = getenv("DAISY_OWNER_MERGE");
-        sh->bypass = ((v && *v) ? atoi(v) != 0 : 0) && !(m && atoi(m) == 1);
+        sh->bypass = ((v && *v) ? atoi(v) != 0 : 1) && !(m && atoi(m) == 1);
     }
     for (int i = 0; i < DAISY_NSETS && ok; ++i) {
         ok = ok && cudaMalloc((void **)&sh->set[i].uniq_gid, cap * sizeof(uint32_t)) == cudaSuccess;
@@ -877,13 +931,13 @@ extern "C" int daisy_shard_compute(daisy_handle_t h, float *P_local, const int32
     rc = check_step_args(h, P_local, h->sh->cache, triples, B);
     if (rc) return rc;
     if (!h->sh->prepared) {  // one-call form: no classification => every sum goes through the owner's pass
-        rc = shard_prepare(h, triples, nullptr, B, (cudaStream_t)stream);
+        rc = shard_prepare(h, triples, nullptr, B, (cudaStream_t)stream, (cudaStream_t)stream);
         if (rc) return rc;
     } else {
         DAISY_REQUIRE(B == h->sh->prepared_B, DAISY_EINVAL, "daisy_shard_compute: %lld triples, but %lld were prepared",
                       (long long)B, (long long)h->sh->prepared_B);
     }
-    return shard_finish(h, P_local, lr, wd, loss_accum, (cudaStream_t)stream);
+    return shard_finish(h, P_local, lr, wd, loss_accum, (cudaStream_t)stream, (cudaStream_t)stream);
 }
 
 extern "C" int daisy_shard_prepare(daisy_handle_t h, float *P_local, const int32_t *triples, int64_t B,
@@ -893,7 +947,7 @@ extern "C" int daisy_shard_prepare(daisy_handle_t h, float *P_local, const int32
     rc = check_step_args(h, P_local, h->sh->cache, triples, B);
     if (rc) return rc;
     DAISY_REQUIRE(!h->sh->prepared, DAISY_EINVAL, "a prepared step is pending: call daisy_shard_compute first");
-    return shard_prepare(h, triples, nullptr, B, (cudaStream_t)stream);
+    return shard_prepare(h, triples, nullptr, B, (cudaStream_t)stream, (cudaStream_t)stream);
 }
 
 extern "C" int daisy_shard_classify(daisy_handle_t h, daisy_stream_t stream) {
@@ -921,13 +975,15 @@ static int shard_step_impl(daisy_handle_t h, float *P_local, const int32_t *trip
     cudaStream_t s = (cudaStream_t)stream;
     daisy_shard *sh = h->sh;
     const bool prof = h->timing == 2 && B > 0;
-    int rc = shard_prepare(h, triples_dev, host_src, B, s);
-    if (!rc && sh->bypass && sh->world > 1) {  // ids are in the owners' memory -> verdicts are in the senders' memory
-        rc = shard_barrier(h, s);
-        if (!rc) rc = shard_classify(h, s);
-        if (!rc) rc = shard_barrier(h, s);
+    const bool live = sh->bypass && sh->world > 1;
+    cudaStream_t xs = (live && sh->aux_stream && h->timing != 2) ? sh->aux_stream : s;
+    int rc = shard_prepare(h, triples_dev, host_src, B, s, xs);
+    if (!rc && live) {  // ids are in the owners' memory -> verdicts are in the senders' memory
+        rc = shard_barrier(h, xs);
+        if (!rc) rc = shard_classify(h, xs);
+        if (!rc) rc = shard_barrier(h, xs);
     }
-    if (!rc) rc = shard_finish(h, P_local, lr, wd, loss_accum, s);
+    if (!rc) rc = shard_finish(h, P_local, lr, wd, loss_accum, s, xs);
     if (!rc) rc = shard_barrier(h, s);
     if (!rc && prof) cudaEventRecord(sh->pev[4], s);
     if (!rc) rc = shard_apply(h, lr, wd, s);
