@@ -13,7 +13,7 @@ One step = one pass of the hot path (daisy_bpr_step) over one batch of synthetic
   value : whole-job triples/s with the triples already resident in HBM (CUDA events, max over ranks)
   e2e   : the same through the public API (BPRSGD.step on pinned HOST triples -> daisy_bpr_step_host), with
           the H2D copy of every step's triples and a D2H read of every step's loss inside the timed region
-  roofline : dominant kernel (k_bpr_main) -- algorithmic bytes (24*D+12 per triple) / its mean launch time,
+  roofline : dominant kernel (k_bpr_main_tma) -- algorithmic bytes (24*D+12 per triple) / its mean launch time,
           measured live with CUDA events on the launching stream, against MEASURED_PEAKS.json
   cpu_baseline : the reference's CPU path (oracle TorchPort: nn.Embedding-equivalent tables + autograd +
           optim.SGD, the calls of BPRMFRecommender.py:172-176) timed on this box's host cores, bounded sample
@@ -352,8 +352,10 @@ def run_single(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": B * 12,
                     "d2h_bytes_per_step": 8 / K if args.epoch_api else 8},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_bpr_main", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": traffic,
+            "roofline": {"bound": "hbm", "kernel": "k_bpr_main_tma<1, SgdOpt, false>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "traffic_source": "ncu --set full capture of this kernel on this workload (profiles/main_kernel_traffic.json)",
+                         "frac_on_dram_traffic": (traffic / (main_ms * 1e-3) / 1e9 / peak) if (traffic and main_ms > 0 and peak) else None,
                          "algorithmic_bytes_per_launch": abytes, "kernel_ms": main_ms, "launches_timed": int(main_n),
                          "peak_source": peak_src,
                          "whole_step_frac": (abytes / (ms_total / K * 1e-3) / 1e9) / peak},

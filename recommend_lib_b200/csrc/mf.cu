@@ -193,6 +193,8 @@ struct OwnArgs {
     int epochs, D;
     daisy_mf_params prm;
     unsigned long long stall_ns;
+    int batch;                     // DAISY_MF_BATCH (default 1): batched groups (k_mf_owner)
+    unsigned poll_ns;              // DAISY_MF_POLL_NS (default 20): back-off between two polls of a version
 };
 
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
@@ -241,7 +243,12 @@ __global__ void __launch_bounds__(128) k_mf_owner(OwnArgs a) {
     unsigned want0 = 0, want1 = 0, t0 = 0, t1 = 0, e0 = 0, e1 = 0;
     // (epoch, offset) of the link x the next load_meta call starts at; advanced by K per call (no 64-bit divisions)
     unsigned meta_e = 0, meta_off = 0;
-    auto load_meta = [&](unsigned long long x, int &mu, int &mi, double &mr, unsigned &mw, unsigned &mt, unsigned &me) {
+    // The expected version of a link is e * (#ratings of its user) + (rank among them).  The two factors are kept as
+    // loaded (cnt1, need1) and only combined where want1 is first needed, a whole group later: an in-order warp stalls
+    // at the first USE of a load, and combining them here exposed one global round trip per group (~1000 cycles
+    // of the hottest warp's ~10 000 per group, DAISY_MF_STATS).
+    unsigned cnt1 = 0, need1 = 0;
+    auto load_meta = [&](unsigned long long x, int &mu, int &mi, double &mr, unsigned &mc, unsigned &mn, unsigned &mt, unsigned &me) {
         mu = -1;
         unsigned e = meta_e, off = meta_off + (unsigned)lane;
         while (off >= len) { off -= len; ++e; }
@@ -252,13 +259,15 @@ __global__ void __launch_bounds__(128) k_mf_owner(OwnArgs a) {
             mu = a.lk_u[k];
             mi = a.lk_i[k];
             mr = a.lk_r[k];
-            mw = e * a.lk_cnt[k] + a.lk_need[k];
+            mc = a.lk_cnt[k];
+            mn = a.lk_need[k];
             mt = a.lk_t[k];
             me = e;
         }
     };
-    load_meta(0, u0, i0, r0, want0, t0, e0);
-    load_meta(K, u1, i1, r1, want1, t1, e1);
+    load_meta(0, u0, i0, r0, cnt1, need1, t0, e0);
+    want0 = e0 * cnt1 + need1;
+    load_meta(K, u1, i1, r1, cnt1, need1, t1, e1);
 
     double R[K][DV], Bu[K];  // prefetched user rows / biases of the current group (valid where `valid` has the bit)
 #pragma unroll
@@ -268,11 +277,224 @@ __global__ void __launch_bounds__(128) k_mf_owner(OwnArgs a) {
         for (int v = 0; v < DV; ++v) R[j][v] = 0.0;
     }
     unsigned valid = 0;
-    unsigned long long n_slow = 0, n_switch = 0;
+    unsigned long long n_slow = 0, n_switch = 0, n_batch = 0;
+    long long tm[6] = {0, 0, 0, 0, 0, 0};  // DAISY_MF_STATS: cycles of the hottest warp by segment (see daisy_mf_fit)
+    const bool timed = a.stats != nullptr && w == 0;
+    long long tc = timed ? clock64() : 0;
+#define DAISY_MF_TICK(slot)                       \
+    if (timed) {                                  \
+        const long long now_ = clock64();         \
+        tm[slot] += now_ - tc;                    \
+        tc = now_;                                \
+    }
     int pend_u = -1;         // lane j: user whose version update from link j of the current group is not published yet
     unsigned pend_v = 0;
 
     for (unsigned long long x0 = 0; x0 < L; x0 += K) {
+        // ---- batched group (K == 8): see mf_batched_group below the loop body ------------------------------------
+        bool batched = false;
+        if (K == 8 && a.batch) {
+            const int i_first = __shfl_sync(FULL, i0, 0);
+            const unsigned same = __match_any_sync(FULL, lane < K ? u0 : -2 - lane);
+            batched = __all_sync(FULL, lane >= K || (u0 >= 0 && i0 == i_first && same == (1u << lane)));
+        }
+        if (batched) {
+            // A full group on ONE item with pairwise distinct users -- decided from the link list alone, never from
+            // timing, so a fit takes the same arithmetic path on every run (bit-reproducible).  The K dot products
+            // q_k . p_k form a chain through the item row: q_{k+1} = al q_k + be_k p_k, al = 1 - lr_qi reg_qi,
+            // be_k = lr_qi err_k, so  q_k . p_k = al^k (q_0 . p_k) + sum_{l<k} al^(k-1-l) be_l (p_l . p_k).
+            // The K + K(K-1)/2 = 36 vector dot products on the right do not depend on each other: they are formed
+            // first (independent FMAs, ONE transposing reduction for 32 of them), and the chain shrinks to a scalar
+            // recurrence (~k FMAs per link) -- instead of a 5-round warp reduction per link.  The row updates then
+            // follow the reference's formulas element by element with those errors.
+            ++n_batch;
+            const int i = __shfl_sync(FULL, i0, 0);
+            if (i != cur_item) {
+                ++n_switch;
+                if (cur_item >= 0) {
+#pragma unroll
+                    for (int v = 0; v < DV; ++v)
+                        if (act[v]) __stcg(a.qi + (size_t)cur_item * D + lane + 32 * v, q[v]);
+                    if (lane == 0) __stcg(a.bi + cur_item, b_i);
+                }
+#pragma unroll
+                for (int v = 0; v < DV; ++v) q[v] = act[v] ? __ldcg(a.qi + (size_t)i * D + lane + 32 * v) : 0.0;
+                b_i = __ldcg(a.bi + i);
+                cur_item = i;
+            }
+            const double al = 1.0 - prm.lr_qi * prm.reg_qi;
+            double a0 = 1.0, cf[8], bi_run = b_i;
+            // one link of the scalar recurrence: dot = a0 * dk + sum_l cf[l] * g(l, k) has been formed by the caller
+#define DAISY_MF_SCALAR_STEP(k, dot, err_out, nbu_out)                                                       \
+            {                                                                                                \
+                const double r_ = __shfl_sync(FULL, r0, (k));                                                \
+                const double bu_ = Bu[(k)];                                                                  \
+                double err_, nbu_ = bu_, nbi_ = bi_run;                                                      \
+                if (prm.variant == 0) {                                                                      \
+                    err_ = r_ - (prm.global_mean + bu_ + bi_run + (dot));                                    \
+                    if (prm.biased) {                                                                        \
+                        nbu_ = bu_ + prm.lr_bu * (err_ - prm.reg_bu * bu_);                                  \
+                        nbi_ = bi_run + prm.lr_bi * (err_ - prm.reg_bi * bi_run);                            \
+                    }                                                                                        \
+                } else {                                                                                     \
+                    err_ = r_ - (bu_ + bi_run + (dot));                                                      \
+                    if (prm.variant == 2) {                                                                  \
+                        const double inc_ = prm.lr_bu * (err_ - prm.reg2 * (bu_ + bi_run - prm.global_mean)); \
+                        nbu_ = bu_ + inc_;                                                                   \
+                        nbi_ = bi_run + inc_;                                                                \
+                    }                                                                                        \
+                }                                                                                            \
+                (err_out) = err_;                                                                            \
+                (nbu_out) = nbu_;                                                                            \
+                bi_run = nbi_;                                                                               \
+                _Pragma("unroll") for (int l_ = 0; l_ < (k); ++l_) cf[l_] *= al;                             \
+                cf[(k)] = prm.lr_qi * err_;                                                                  \
+                a0 *= al;                                                                                    \
+            }
+            // the row update of link k with its error: the reference's formulas, element by element
+#define DAISY_MF_ROW_UPDATE(k, err, nbu_k)                                                                   \
+            {                                                                                                \
+                const int u_ = __shfl_sync(FULL, u0, (k));                                                   \
+                _Pragma("unroll") for (int v = 0; v < DV; ++v)                                               \
+                    if (act[v]) {                                                                            \
+                        const double puf = R[(k)][v], qif = q[v];                                            \
+                        __stcg(a.pu + (size_t)u_ * D + lane + 32 * v, puf + prm.lr_pu * ((err) * qif - prm.reg_pu * puf)); \
+                        q[v] = qif + prm.lr_qi * ((err) * puf - prm.reg_qi * qif);                           \
+                    }                                                                                        \
+                if (lane == 0 && (nbu_k) != Bu[(k)]) __stcg(a.bu + u_, (nbu_k));                             \
+                if (a.err2) {                                                                                \
+                    const unsigned t_ = __shfl_sync(FULL, t0, (k)), e_ = __shfl_sync(FULL, e0, (k));         \
+                    if (lane == 0) a.err2[(size_t)e_ * a.n + t_] = (err) * (err);                            \
+                }                                                                                            \
+            }
+            if (valid == (1u << K) - 1u) {
+                // ---- every row of the group was ready when it was prefetched: all dot products at once ------------
+                // (1) per-lane partial sums of the 36 dot products: s[0..7] = q . p_j, then p_l . p_j for l < j
+                double sa[32], sb[4];
+                {
+                    int idx = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        double t = 0.0;
+#pragma unroll
+                        for (int v = 0; v < DV; ++v) t = fma(q[v], R[j][v], t);   // inactive slices hold zeros
+                        sa[idx++] = t;
+                    }
+#pragma unroll
+                    for (int l = 0; l < 8; ++l)
+#pragma unroll
+                        for (int j = l + 1; j < 8; ++j) {
+                            double t = 0.0;
+#pragma unroll
+                            for (int v = 0; v < DV; ++v) t = fma(R[l][v], R[j][v], t);
+                            if (idx < 32) sa[idx] = t; else sb[idx - 32] = t;
+                            ++idx;
+                        }
+                }
+                // (2) transposing reduction: after the five rounds lane L holds the warp total of value L in sa[0].  Every
+                // total is formed by the same additions as warp_sum_d's butterfly (offsets 16, 8, 4, 2, 1), which is
+                // what the one-link-at-a-time variant below uses: the two variants agree bit for bit.
+#define DAISY_RS_ROUND(H)                                                            \
+                {                                                                    \
+                    const bool up = (lane & (H)) != 0;                               \
+                    _Pragma("unroll") for (int ii = 0; ii < (H); ++ii) {             \
+                        const double send = up ? sa[ii] : sa[ii + (H)];              \
+                        const double keep = up ? sa[ii + (H)] : sa[ii];              \
+                        sa[ii] = keep + __shfl_xor_sync(FULL, send, (H));            \
+                    }                                                                \
+                }
+                DAISY_RS_ROUND(16) DAISY_RS_ROUND(8) DAISY_RS_ROUND(4) DAISY_RS_ROUND(2) DAISY_RS_ROUND(1)
+#undef DAISY_RS_ROUND
+                const double tot = sa[0];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) sb[x] = warp_sum_d(sb[x]);
+                DAISY_MF_TICK(0)
+                // value index of p_l . p_j (l < j) in the order they were formed
+#define DAISY_GIDX(l, j) (8 + (l) * 7 - ((l) * ((l) - 1)) / 2 + ((j) - (l) - 1))
+                // (3) the scalar recurrence, computed redundantly by every lane
+                double errs[8], nbu[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    double dot = a0 * __shfl_sync(FULL, tot, k);
+#pragma unroll
+                    for (int l = 0; l < k; ++l) {
+                        const int gi = DAISY_GIDX(l, k);
+                        const double g = gi < 32 ? __shfl_sync(FULL, tot, gi & 31) : sb[(gi - 32) & 3];
+                        dot = fma(cf[l], g, dot);
+                    }
+                    DAISY_MF_SCALAR_STEP(k, dot, errs[k], nbu[k])
+                }
+#undef DAISY_GIDX
+                DAISY_MF_TICK(1)
+                // (4) the row updates in the reference's order
+#pragma unroll
+                for (int k = 0; k < 8; ++k) DAISY_MF_ROW_UPDATE(k, errs[k], nbu[k])
+                DAISY_MF_TICK(2)
+                if (lane < K) {  // version updates of the group: published with the group's fence below
+                    pend_u = u0;
+                    pend_v = want0 + 1;
+                }
+            } else {
+                // ---- some rows were not ready: one link at a time, SAME arithmetic (dot products against the group's
+                // initial item row q_0 and the earlier rows of the group, each reduced by warp_sum_d), so the result does
+                // not depend on which variant ran.  Before blocking on a row, everything this warp holds back is
+                // published -- an earlier link of the group may be what the row's producer is waiting for.
+                double q_0[DV];
+#pragma unroll
+                for (int v = 0; v < DV; ++v) q_0[v] = q[v];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (!(valid & (1u << k))) {  // warp-uniform
+                        ++n_slow;
+                        const int u = __shfl_sync(FULL, u0, k);
+                        const unsigned want = __shfl_sync(FULL, want0, k);
+                        fence_acq_rel_gpu();
+                        __syncwarp();
+                        if (pend_u >= 0) st_relaxed_u32(&a.ver_u[pend_u], pend_v);
+                        pend_u = -1;
+                        int bail = 0;
+                        if (lane == 0) {
+                            unsigned spins = 0;
+                            StallWatch watch;
+                            while (ld_acquire_u32(&a.ver_u[u]) != want) {
+                                __nanosleep(a.poll_ns);
+                                if ((++spins & 0xfffu) == 0 && watch.stalled(a.progress, a.abort_flag, a.stall_ns)) {
+                                    bail = 1;
+                                    break;
+                                }
+                            }
+                        }
+                        bail = __shfl_sync(FULL, bail, 0);
+                        if (bail) return;
+                        if (ld_acquire_u32(&a.ver_u[u]) != want) atomicExch(a.abort_flag, 2);
+#pragma unroll
+                        for (int v = 0; v < DV; ++v) R[k][v] = act[v] ? __ldcg(a.pu + (size_t)u * D + lane + 32 * v) : 0.0;
+                        Bu[k] = __ldcg(a.bu + u);
+                    }
+                    double t = 0.0;
+#pragma unroll
+                    for (int v = 0; v < DV; ++v) t = fma(q_0[v], R[k][v], t);
+                    double dot = a0 * warp_sum_d(t);
+#pragma unroll
+                    for (int l = 0; l < k; ++l) {
+                        double g = 0.0;
+#pragma unroll
+                        for (int v = 0; v < DV; ++v) g = fma(R[l][v], R[k][v], g);
+                        dot = fma(cf[l], warp_sum_d(g), dot);
+                    }
+                    double err_k, nbu_k;
+                    DAISY_MF_SCALAR_STEP(k, dot, err_k, nbu_k)
+                    DAISY_MF_ROW_UPDATE(k, err_k, nbu_k)
+                    if (lane == k) {
+                        pend_u = u0;
+                        pend_v = want0 + 1;
+                    }
+                }
+            }
+#undef DAISY_MF_SCALAR_STEP
+#undef DAISY_MF_ROW_UPDATE
+            b_i = bi_run;
+        } else
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const int u = __shfl_sync(FULL, u0, j);
@@ -311,7 +533,7 @@ __global__ void __launch_bounds__(128) k_mf_owner(OwnArgs a) {
                     unsigned spins = 0;
                     StallWatch watch;
                     while (ld_acquire_u32(&a.ver_u[u]) != want) {
-                        __nanosleep(20);
+                        __nanosleep(a.poll_ns);
                         if ((++spins & 0xfffu) == 0 && watch.stalled(a.progress, a.abort_flag, a.stall_ns)) {
                             bail = 1;
                             break;
@@ -367,6 +589,7 @@ __global__ void __launch_bounds__(128) k_mf_owner(OwnArgs a) {
             }
         }
         // ---- one fence for the group: publish its versions, pick up the next group's user rows ----------------
+        DAISY_MF_TICK(5)   // (everything of the group that is not one of the batched segments)
         unsigned vnext = 0;
         if (u1 >= 0) vnext = ld_relaxed_u32(&a.ver_u[u1]);
         fence_acq_rel_gpu();
@@ -374,7 +597,9 @@ __global__ void __launch_bounds__(128) k_mf_owner(OwnArgs a) {
         if (pend_u >= 0) st_relaxed_u32(&a.ver_u[pend_u], pend_v);
         pend_u = -1;
         if (lane == 0) atomicAdd(a.progress, (unsigned long long)K);  // fire and forget: the stall detector's clock
+        want1 = e1 * cnt1 + need1;
         valid = __ballot_sync(FULL, u1 >= 0 && vnext == want1);
+        DAISY_MF_TICK(3)
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             if (valid & (1u << j)) {  // warp-uniform
@@ -385,14 +610,18 @@ __global__ void __launch_bounds__(128) k_mf_owner(OwnArgs a) {
             }
         }
         u0 = u1; i0 = i1; r0 = r1; want0 = want1; t0 = t1; e0 = e1;
-        load_meta(x0 + 2 * K, u1, i1, r1, want1, t1, e1);
+        load_meta(x0 + 2 * K, u1, i1, r1, cnt1, need1, t1, e1);
+        DAISY_MF_TICK(4)
     }
     // (the loop's last iteration published every pending version)
     if (a.stats && lane == 0) {
         atomicAdd(&a.stats[0], L);
         atomicAdd(&a.stats[1], n_slow);
         atomicAdd(&a.stats[2], n_switch);
-        if (w == 0) {  // the hottest item's warp
+        atomicAdd(&a.stats[6], n_batch);
+        if (w == 0) {
+            a.stats[7] = n_batch;
+            for (int x = 0; x < 6; ++x) a.stats[8 + x] = (unsigned long long)tm[x];  // the hottest item's warp
             a.stats[3] = L;
             a.stats[4] = n_slow;
             a.stats[5] = n_switch;
@@ -641,6 +870,10 @@ extern "C" int daisy_mf_fit(daisy_handle_t h, double *pu, double *qi, double *bu
 #undef OCC_
         if (occ < 1) occ = 1;
         int per_sm = occ < 8 ? occ : 8;
+        {
+            const char *env = getenv("DAISY_MF_BLOCKS_PER_SM");
+            if (env && atoi(env) > 0 && atoi(env) < per_sm) per_sm = atoi(env);
+        }
         const unsigned W = (unsigned)(h->num_sms * per_sm * 4);
         uint32_t *hkey, *hkey_s, *hval, *hval_s, *rank;
         int *lk_u, *lk_i;
@@ -683,13 +916,19 @@ extern "C" int daisy_mf_fit(daisy_handle_t h, double *pu, double *qi, double *bu
         o.wptr = wptr; o.ver_u = ver_u; o.err2 = err2; o.abort_flag = abort_flag;
         o.n = n; o.epochs = n_epochs; o.D = h->D; o.prm = *prm;
         o.stall_ns = stall_ns;
+        {
+            const char *be = getenv("DAISY_MF_BATCH");
+            o.batch = (be && *be) ? (atoi(be) != 0) : 1;
+            const char *pe = getenv("DAISY_MF_POLL_NS");
+            o.poll_ns = (pe && atoi(pe) > 0) ? (unsigned)atoi(pe) : 20u;
+        }
         o.progress = ticket;   // the ticket word is free under this schedule
         o.stats = nullptr;
         const char *st_env = getenv("DAISY_MF_STATS");
         if (st_env && atoi(st_env) > 0) {
-            rc = ws.get(&o.stats, 8);
+            rc = ws.get(&o.stats, 16);
             if (rc) return rc;
-            DAISY_CUDA(cudaMemsetAsync(o.stats, 0, 8 * sizeof(unsigned long long), s));
+            DAISY_CUDA(cudaMemsetAsync(o.stats, 0, 16 * sizeof(unsigned long long), s));
             dbg_stats = o.stats;
         }
         // The schedule is deadlock-free only if all W warps are resident at once (a resident warp may wait for a
@@ -734,10 +973,14 @@ extern "C" int daisy_mf_fit(daisy_handle_t h, double *pu, double *qi, double *bu
     DAISY_CUDA(cudaMemcpyAsync(&aborted, abort_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
     DAISY_CUDA(cudaStreamSynchronize(s));
     if (dbg_stats) {
-        unsigned long long hs[8];
+        unsigned long long hs[16];
         DAISY_CUDA(cudaMemcpy(hs, dbg_stats, sizeof(hs), cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[daisy_mf_fit] links %llu blocking %llu item-switches %llu | hottest warp: links %llu blocking %llu switches %llu\n",
-                hs[0], hs[1], hs[2], hs[3], hs[4], hs[5]);
+        fprintf(stderr, "[daisy_mf_fit] hottest warp, cycles: batched dots + reduction %llu, recurrence %llu, row updates %llu | "
+                        "version reads + fence + publish %llu, row prefetch issue + next metadata %llu, rest of the groups %llu\n",
+                hs[8], hs[9], hs[10], hs[11], hs[12], hs[13]);
+        fprintf(stderr, "[daisy_mf_fit] links %llu blocking %llu item-switches %llu batched groups %llu | hottest warp: links %llu "
+                        "blocking %llu switches %llu batched groups %llu\n",
+                hs[0], hs[1], hs[2], hs[6], hs[3], hs[4], hs[5], hs[7]);
     }
     if (aborted) {  // hand the tables back as they came in
         DAISY_CUDA(cudaMemcpyAsync(pu, bk_pu, n_pu * sizeof(double), cudaMemcpyDeviceToDevice, s));

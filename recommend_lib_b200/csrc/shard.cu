@@ -587,6 +587,84 @@ __global__ void __launch_bounds__(256) k_owner_add(float *__restrict__ Q, const 
     }
 }
 
+// Owner side with the exclusive-row bypass live: what is left are the rows SHARED between ranks (a few per cent of the
+// entries), listed per sender by k_owner_classify.  One launch instead of one pass per sender: a warp per listed entry
+// finds the row in the other senders' id lists (ascending => binary search, one sender per lane, all searches at once);
+// the warp of the row's lowest-ranked sender then adds the senders' sums IN RANK ORDER, one fmaf each -- exactly what
+// the passes of k_owner_add do one after the other, so the result is bit-identical -- the others leave.
+template <int V>
+__global__ void __launch_bounds__(256) k_owner_add_shared(float *__restrict__ Q, const float *__restrict__ recv_g,
+                                                           const int32_t *__restrict__ recv_ids,
+                                                           const uint32_t *__restrict__ recv_cnt,
+                                                           const uint32_t *__restrict__ shared_idx,
+                                                           const uint32_t *__restrict__ shared_cnt, int G, size_t cap, int D4,
+                                                           float alpha, uint32_t rows_local, int *err) {
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t NONE = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const uint32_t nwarps = (uint32_t)((gridDim.x * (size_t)blockDim.x) >> 5);
+    uint32_t n_l = 0, c_l = 0;       // lane sp < G: entries / listed entries of sender sp
+    if (lane < G) {
+        n_l = recv_cnt[lane];
+        if (n_l > cap) n_l = (uint32_t)cap;
+        c_l = shared_cnt[lane];
+        if (c_l > n_l) c_l = n_l;
+    }
+    uint32_t end_l = c_l;            // inclusive prefix sum of the list lengths
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, end_l, o);
+        if (lane >= o) end_l += t;
+    }
+    const uint32_t total = __shfl_sync(FULL, end_l, 31);
+    bool act[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
+    for (uint32_t task = warp; task < total; task += nwarps) {
+        const int s = __popc(__ballot_sync(FULL, lane < G && task >= end_l));   // the sender whose list holds the task
+        const uint32_t first = __shfl_sync(FULL, end_l - c_l, s);
+        const uint32_t ent = shared_idx[(size_t)s * cap + (task - first)];
+        const uint32_t row = (uint32_t)recv_ids[(size_t)s * cap + ent];
+        if (row >= rows_local) {     // warp-uniform
+            if (lane == 0) atomicOr(&err[0], 1);
+            continue;
+        }
+        uint32_t pos = NONE;
+        if (lane == s) {
+            pos = ent;
+        } else if (lane < G) {
+            const int32_t *ids = recv_ids + (size_t)lane * cap;
+            uint32_t lo = 0, hi = n_l;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if ((uint32_t)ids[mid] < row) lo = mid + 1; else hi = mid;
+            }
+            if (lo < n_l && (uint32_t)ids[lo] == row) pos = lo;
+        }
+        unsigned has = __ballot_sync(FULL, pos != NONE);
+        if (has & ((1u << s) - 1u)) continue;   // a lower-ranked sender's warp owns this row
+        float4 q[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) q[v] = act[v] ? ld_row(Q, (size_t)row * D4 + lane + 32 * v) : f4_zero();
+        while (has) {
+            const int sp = __ffs(has) - 1;
+            has &= has - 1;
+            const size_t at = ((size_t)sp * cap + __shfl_sync(FULL, pos, sp)) * D4;
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if (act[v]) {
+                    const float4 g = ld_stream(recv_g, at + lane + 32 * v);
+                    q[v] = make_float4(fmaf(alpha, g.x, q[v].x), fmaf(alpha, g.y, q[v].y), fmaf(alpha, g.z, q[v].z),
+                                       fmaf(alpha, g.w, q[v].w));
+                }
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+            if (act[v]) st_row(Q, (size_t)row * D4 + lane + 32 * v, q[v]);
+    }
+}
+
 template <int V>
 static void launch_merge(daisy_ctx *h, float alpha, cudaStream_t s) {
     daisy_shard *sh = h->sh;
@@ -600,6 +678,13 @@ static void launch_merge(daisy_ctx *h, float alpha, cudaStream_t s) {
     }
     constexpr int R = V == 1 ? 4 : 2;
     const size_t cap = (size_t)sh->cap;
+    static const int shared_passes = getenv("DAISY_OWNER_SHARED_PASSES") && atoi(getenv("DAISY_OWNER_SHARED_PASSES")) == 1;
+    if (sh->classified && !shared_passes) {
+        k_owner_add_shared<V><<<h->num_sms * 8, 256, 0, s>>>(sh->peers.q[me], sh->peers.recv_g[me], sh->peers.recv_ids[me],
+                                                             sh->peers.recv_cnt[me], sh->shared_idx, sh->shared_cnt, sh->world,
+                                                             cap, h->D / 4, alpha, (uint32_t)h->I, h->err);
+        return;
+    }
     for (int snd = 0; snd < sh->world; ++snd) {
         k_owner_add<V, R><<<h->num_sms * 8, 256, 0, s>>>(sh->peers.q[me], sh->peers.recv_g[me] + (size_t)snd * cap * h->D,
                                                          sh->peers.recv_ids[me] + (size_t)snd * cap,

@@ -147,6 +147,44 @@ def test_single_hot_row_chain_and_determinism():
     assert rel_err(outs[0][0], o["pu"]) <= 1e-9 and rel_err(outs[0][1], o["qi"]) <= 1e-9
 
 
+def test_batched_groups_match_the_link_by_link_schedule_and_are_reproducible(monkeypatch, _schedule):
+    """k_mf_owner takes a full group of 8 links on one item with distinct users through the batched form (all dot
+    products at once, scalar recurrence for the chain).  Which groups are batched follows from the rating list alone,
+    and the batched arithmetic is the same whether or not every row was ready -- so two runs agree bit for bit even
+    with warps racing each other -- and the result agrees with the link-by-link schedule (DAISY_MF_BATCH=0) and the C
+    oracle to rounding.  Hot items (Zipf) and all three bias variants."""
+    if _schedule != "owner":
+        pytest.skip("item-owner schedule only")
+    from oracle import mf_oracle
+    from recommend_lib_b200.mf import SVD, RSVD
+    from recommend_lib_b200.sampler import synthetic_ratings
+    U, I, D, N, E = 2000, 300, 128, 120_000, 3
+    users, items, ratings = synthetic_ratings(N, U, I, seed=77)
+    df = pd.DataFrame({"user": users, "item": items, "rating": ratings})
+    for make, names, ofit in ((lambda: SVD(U, I, n_factors=D, n_epochs=E, verbose=False), ("pu", "qi", "bu", "bi"),
+                               lambda p0, q0: mf_oracle.svd_fit(users, items, ratings, p0, q0, n_epochs=E)),
+                              (lambda: RSVD(U, I, n_factors=D, n_epochs=E, version=1, verbose=False), ("ui", "vj", "ci", "dj"),
+                               lambda p0, q0: mf_oracle.rsvd_fit(users, items, ratings, p0, q0, n_epochs=E, version=1)),
+                              (lambda: RSVD(U, I, n_factors=D, n_epochs=E, version=2, verbose=False), ("ui", "vj", "ci", "dj"),
+                               lambda p0, q0: mf_oracle.rsvd_fit(users, items, ratings, p0, q0, n_epochs=E, version=2))):
+        runs = {}
+        for tag, env in (("b1", "1"), ("b2", "1"), ("seq", "0")):
+            monkeypatch.setenv("DAISY_MF_BATCH", env)
+            np.random.seed(11)
+            a = make()
+            a.fit(df)
+            runs[tag] = [np.array(getattr(a, k)).copy() for k in names]
+        for x, y in zip(runs["b1"], runs["b2"]):
+            assert np.array_equal(x, y)
+        for x, y in zip(runs["b1"], runs["seq"]):
+            assert rel_err(x, y) <= 1e-10
+        np.random.seed(11)
+        p0, q0 = mf_oracle.draw_init(U, I, D)
+        o = ofit(p0, q0)
+        for x, k in zip(runs["b1"], names):
+            assert rel_err(x, o[k]) <= TOL, k
+
+
 def test_live_reference_extension_when_present():
     from oracle.build_ref import load_ref
     from recommend_lib_b200.mf import RSVD
