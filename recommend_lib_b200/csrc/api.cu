@@ -184,7 +184,9 @@ extern "C" int daisy_create(daisy_handle_t *out, int device, int64_t user_num, i
         for (int i = 0; i < DAISY_NSETS; ++i) {
             cudaEventCreateWithFlags(&h->book[i].ready, cudaEventDisableTiming);
             cudaEventCreateWithFlags(&h->book[i].freed, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&h->book[i].copied, cudaEventDisableTiming);
         }
+        if (B > 0 && env_int("DAISY_COPY_STREAM", 1)) cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
         if (cudaDeviceSynchronize() != cudaSuccess) {
             daisy_set_error("workspace initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
             rc = DAISY_ECUDA;
@@ -216,6 +218,7 @@ extern "C" int daisy_destroy(daisy_handle_t h) {
             if (p) cudaFree(p);
         if (h->book[i].ready) cudaEventDestroy(h->book[i].ready);
         if (h->book[i].freed) cudaEventDestroy(h->book[i].freed);
+        if (h->book[i].copied) cudaEventDestroy(h->book[i].copied);
     }
     for (int i = 0; i < DAISY_MAX_BGRAPH; ++i)
         if (h->bgraph[i].exec) cudaGraphExecDestroy(h->bgraph[i].exec);
@@ -223,6 +226,7 @@ extern "C" int daisy_destroy(daisy_handle_t h) {
         if (h->tc_ev[i]) cudaEventDestroy(h->tc_ev[i]);
     if (h->pool_state == 1) cudaMemPoolDestroy(h->pool);
     if (h->err_host) cudaFreeHost(h->err_host);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->part_ok) {
         h->side_stream = nullptr;  // it is the partition's bookkeeping stream
         daisy_partition_destroy(h);

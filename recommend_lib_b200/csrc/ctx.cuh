@@ -43,7 +43,7 @@ struct BookSet {
     uint32_t *uslot, *jslot, *islot;  // [maxB]  per sorted triple: DAISY_DIRECT or staging slot
     uint32_t *longs;                // rows too long for one warp (k_seg_all): [0] = #rows, [1] = #slices, then 5 words per
                                     // row (table, row, first sorted position, length, first slice), like `heavy`
-    cudaEvent_t ready, freed;
+    cudaEvent_t ready, freed, copied;  // bookkeeping done / table kernels done / host triples landed (copy stream)
 };
 
 // ---- row-sharded tables over peer memory (shard.cu) ----------------------------------------------------------------
@@ -131,6 +131,7 @@ struct daisy_ctx {
     BookSet book[DAISY_NSETS];
     int book_idx;
     cudaStream_t side_stream;
+    cudaStream_t copy_stream;  // H2D of *_step_host triples (DAISY_COPY_STREAM=0: on the bookkeeping stream)
     cudaEvent_t ev_call;
     int pipeline;           // 1: bookkeeping on the side stream (default), 0: everything on the caller's stream
     int inputs_ready;       // 1: device triples passed to daisy_bpr_step are complete at call time (no stream dependency)

@@ -18,13 +18,16 @@
 // scores with the exact path's arithmetic and k_select_cand (topk_full.cu) orders them, so the result is bit-identical
 // to the exact path -- tests/test_bpr_gpu.py::test_topk_full_*.
 //
-// Kernel k_filter_tc (persistent, one CTA per SM, 384 threads):
+// Kernel k_filter_tc (persistent, one CTA per SM, 640 threads):
 //   warp 0      TMA producer: the unit's user tile A [256 users x Dp] once, then item tiles B [128 items x Dp] through a
 //               3-stage ring (mbarrier full / empty pairs)
 //   warp 1      MMA issuer (one elected lane): per item tile 2 x (Dp / 16) tcgen05.mma 128x128x16 into one of two
 //               256-column accumulator buffers; tcgen05.commit frees the smem stage and publishes the accumulator
 //   warp 2      TMEM allocation (all 512 columns) / deallocation
-//   warps 4..11 epilogue (two per TMEM lane quarter, each half of the columns): tcgen05.ld 32 lanes x 32 columns, max tree
+//   warps 4..19 epilogue (four per TMEM lane quarter, each a quarter of the columns: with 8 warps the kernel took 19.8 ms
+//               for 16 384 x 2 M x 128, with 16 it takes 16.8 -- the scan is latency-bound, issue slots 23 % busy; issuing
+//               the next TMEM load before scanning the current one was tried and is SLOWER, profiles/r02o_*):
+//               tcgen05.ld 32 lanes x 32 columns, max tree
 //               of the 32 scores against the row's tau, rare append into slots reserved in blocks
 // Work unit = (group of 256 users, chunk of item tiles); units are dealt round-robin so that the CTAs running at the
 // same time stream the same few chunks of Q~ (they stay in L2: every item tile is read from HBM about once and from L2
@@ -45,7 +48,7 @@ constexpr int KATOM = 64;    // bf16 elements per 128-byte swizzle row
 constexpr int STAGES = 3;
 constexpr int ATOM_BYTES = 128 * 128;  // 128 rows x 128 bytes: one TMA box, 16 KB
 #ifndef DAISY_TC_EPI_WARPS
-#define DAISY_TC_EPI_WARPS 8
+#define DAISY_TC_EPI_WARPS 16
 #endif
 constexpr int EPI_WARPS = DAISY_TC_EPI_WARPS;  // epilogue warps (4, 8 or 16): EPI_WARPS / 4 per TMEM lane quarter, each takes an
                                                // equal share of a tile's columns
