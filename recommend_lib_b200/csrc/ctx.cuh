@@ -94,6 +94,10 @@ struct daisy_shard {
     cudaStream_t aux_stream;  // daisy_shard_step: the id exchange runs here, next to the fetch on the caller's stream
     cudaEvent_t aux_ev[2];
     uint32_t *shared_idx, *shared_cnt;  // [G][cap], [G]: per sender, the entries whose row is shared between ranks
+    // one SLOT per shared row: slot_of_row [i_per], slot_row [max_slots], pairs [max_slots][G] = the entry of every sender
+    // naming the row (or 0xFFFFFFFF), slot_n = slots claimed this step (lives behind shared_cnt), bm_claim = claim bitmap
+    uint32_t *bm_claim, *slot_of_row, *slot_row, *pairs, *slot_n;
+    uint32_t max_slots;
     size_t bm_words;
     int bypass;       // DAISY_SHARD_BYPASS (default 1)
     int classified;   // this step's entries have been classified (daisy_shard_classify ran): bypass is live

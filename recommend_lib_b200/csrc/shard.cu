@@ -320,13 +320,16 @@ __global__ void k_owner_count(const int32_t *__restrict__ recv_ids, const uint32
 
 // ... and tells every sender, entry by entry, whether the row is its alone (1-byte peer stores into region `me` of the
 // sender's excl array).  The sender then stores the updated row straight into the owner's q instead of pushing a sum
-// the owner would have to read, add and write back (k_owner_add skips those entries).
+// the owner would have to read, add and write back.  What stays with the owner are the rows SHARED between ranks: every
+// such row gets a SLOT (claimed once through a third bitmap) with one cell per sender, filled by k_owner_pairs, so that
+// the owner's kernel can walk the shared rows directly; the shared entries are also listed per sender for the
+// pass-per-sender variant (order inside a list is arbitrary and does not matter: a sender's entries name distinct rows).
 __global__ void k_owner_classify(const int32_t *__restrict__ recv_ids, const uint32_t *__restrict__ recv_cnt, size_t cap,
                                  uint32_t rows_local, const uint32_t *__restrict__ multi, int me, ShardPeers peers,
-                                 uint32_t *__restrict__ shared_idx, uint32_t *__restrict__ shared_cnt) {
-    // The entries that stay with the owner (rows shared between ranks, and bad ids for the error flag) are also listed
-    // per sender, so that the owner's passes walk those few entries instead of scanning every id.  The order inside
-    // a list is arbitrary (atomics) and does not matter: the entries of one sender name distinct rows.
+                                 uint32_t *__restrict__ shared_idx, uint32_t *__restrict__ shared_cnt,
+                                 uint32_t *__restrict__ claim, uint32_t *__restrict__ slot_of_row,
+                                 uint32_t *__restrict__ slot_row, uint32_t *__restrict__ pairs, uint32_t *__restrict__ slot_n,
+                                 uint32_t max_slots, int G, int *err) {
     const int snd = blockIdx.y;
     uint32_t n = recv_cnt[snd];
     if (n > cap) n = (uint32_t)cap;
@@ -339,9 +342,23 @@ __global__ void k_owner_classify(const int32_t *__restrict__ recv_ids, const uin
         bool keep = false;
         if (k < n) {
             const uint32_t r = (uint32_t)ids[k];
-            const bool excl = r < rows_local && !((multi[r >> 5] >> (r & 31)) & 1u);
-            out[k] = excl ? 1 : 0;
-            keep = !excl;
+            if (r >= rows_local) {  // cannot happen (senders park bad ids on row 0 and flag them); never index with it
+                atomicOr(&err[0], 1);
+                out[k] = 0;
+            } else {
+                const uint32_t bit = 1u << (r & 31);
+                const bool excl = !(multi[r >> 5] & bit);
+                out[k] = excl ? 1 : 0;
+                keep = !excl;
+                if (keep && !(atomicOr(&claim[r >> 5], bit) & bit)) {  // first entry of this row seen by the kernel
+                    const uint32_t sl = atomicAdd(slot_n, 1u);
+                    slot_of_row[r] = sl;
+                    if (sl < max_slots) {
+                        slot_row[sl] = r;
+                        for (int sp = 0; sp < G; ++sp) pairs[(size_t)sl * G + sp] = 0xFFFFFFFFu;
+                    }
+                }
+            }
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         if (m) {
@@ -350,6 +367,19 @@ __global__ void k_owner_classify(const int32_t *__restrict__ recv_ids, const uin
             base = __shfl_sync(0xffffffffu, base, 0);
             if (keep) shared_idx[(size_t)snd * cap + base + __popc(m & ((1u << lane) - 1u))] = k;
         }
+    }
+}
+
+// Every listed entry enters its row's slot: pairs[slot][sender] = entry index in the sender's region.
+__global__ void k_owner_pairs(const int32_t *__restrict__ recv_ids, const uint32_t *__restrict__ shared_idx,
+                              const uint32_t *__restrict__ shared_cnt, size_t cap, const uint32_t *__restrict__ slot_of_row,
+                              uint32_t *__restrict__ pairs, uint32_t max_slots, int G) {
+    const int snd = blockIdx.y;
+    const uint32_t n = shared_cnt[snd];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const uint32_t k = shared_idx[(size_t)snd * cap + t];
+        const uint32_t sl = slot_of_row[(uint32_t)recv_ids[(size_t)snd * cap + k]];
+        if (sl < max_slots) pairs[(size_t)sl * G + snd] = k;
     }
 }
 
@@ -588,69 +618,37 @@ __global__ void __launch_bounds__(256) k_owner_add(float *__restrict__ Q, const 
 }
 
 // Owner side with the exclusive-row bypass live: what is left are the rows SHARED between ranks (a few per cent of the
-// entries), listed per sender by k_owner_classify.  One launch instead of one pass per sender: a warp per listed entry
-// finds the row in the other senders' id lists (ascending => binary search, one sender per lane, all searches at once);
-// the warp of the row's lowest-ranked sender then adds the senders' sums IN RANK ORDER, one fmaf each -- exactly what
-// the passes of k_owner_add do one after the other, so the result is bit-identical -- the others leave.
+// entries).  One launch instead of one pass per sender: a warp per shared row (its slot names the row and, per sender,
+// the entry holding that sender's sum) adds the senders' sums IN RANK ORDER, one fmaf each -- exactly what the passes
+// of k_owner_add do one after the other, so the result is bit-identical -- and updates the row once.  (A first version
+// found a row's senders by binary searches in the id lists: 17 dependent loads per entry, slower than the passes at
+// 2 GPUs -- profiles/r02p_bench_n2_*.)
 template <int V>
-__global__ void __launch_bounds__(256) k_owner_add_shared(float *__restrict__ Q, const float *__restrict__ recv_g,
-                                                           const int32_t *__restrict__ recv_ids,
-                                                           const uint32_t *__restrict__ recv_cnt,
-                                                           const uint32_t *__restrict__ shared_idx,
-                                                           const uint32_t *__restrict__ shared_cnt, int G, size_t cap, int D4,
-                                                           float alpha, uint32_t rows_local, int *err) {
+__global__ void __launch_bounds__(256) k_owner_add_slots(float *__restrict__ Q, const float *__restrict__ recv_g,
+                                                          const uint32_t *__restrict__ slot_row,
+                                                          const uint32_t *__restrict__ pairs,
+                                                          const uint32_t *__restrict__ slot_n, uint32_t max_slots, int G,
+                                                          size_t cap, int D4, float alpha) {
     const unsigned FULL = 0xffffffffu;
-    const uint32_t NONE = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
     const uint32_t nwarps = (uint32_t)((gridDim.x * (size_t)blockDim.x) >> 5);
-    uint32_t n_l = 0, c_l = 0;       // lane sp < G: entries / listed entries of sender sp
-    if (lane < G) {
-        n_l = recv_cnt[lane];
-        if (n_l > cap) n_l = (uint32_t)cap;
-        c_l = shared_cnt[lane];
-        if (c_l > n_l) c_l = n_l;
-    }
-    uint32_t end_l = c_l;            // inclusive prefix sum of the list lengths
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(FULL, end_l, o);
-        if (lane >= o) end_l += t;
-    }
-    const uint32_t total = __shfl_sync(FULL, end_l, 31);
+    uint32_t n = *slot_n;
+    if (n > max_slots) n = max_slots;
     bool act[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) act[v] = (lane + 32 * v) < D4;
-    for (uint32_t task = warp; task < total; task += nwarps) {
-        const int s = __popc(__ballot_sync(FULL, lane < G && task >= end_l));   // the sender whose list holds the task
-        const uint32_t first = __shfl_sync(FULL, end_l - c_l, s);
-        const uint32_t ent = shared_idx[(size_t)s * cap + (task - first)];
-        const uint32_t row = (uint32_t)recv_ids[(size_t)s * cap + ent];
-        if (row >= rows_local) {     // warp-uniform
-            if (lane == 0) atomicOr(&err[0], 1);
-            continue;
-        }
-        uint32_t pos = NONE;
-        if (lane == s) {
-            pos = ent;
-        } else if (lane < G) {
-            const int32_t *ids = recv_ids + (size_t)lane * cap;
-            uint32_t lo = 0, hi = n_l;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if ((uint32_t)ids[mid] < row) lo = mid + 1; else hi = mid;
-            }
-            if (lo < n_l && (uint32_t)ids[lo] == row) pos = lo;
-        }
-        unsigned has = __ballot_sync(FULL, pos != NONE);
-        if (has & ((1u << s) - 1u)) continue;   // a lower-ranked sender's warp owns this row
+    for (uint32_t sl = warp; sl < n; sl += nwarps) {
+        const uint32_t row = slot_row[sl];
+        const uint32_t ent = lane < G ? pairs[(size_t)sl * G + lane] : 0xFFFFFFFFu;
+        unsigned has = __ballot_sync(FULL, ent != 0xFFFFFFFFu);
         float4 q[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) q[v] = act[v] ? ld_row(Q, (size_t)row * D4 + lane + 32 * v) : f4_zero();
         while (has) {
             const int sp = __ffs(has) - 1;
             has &= has - 1;
-            const size_t at = ((size_t)sp * cap + __shfl_sync(FULL, pos, sp)) * D4;
+            const size_t at = ((size_t)sp * cap + __shfl_sync(FULL, ent, sp)) * D4;
 #pragma unroll
             for (int v = 0; v < V; ++v)
                 if (act[v]) {
@@ -680,9 +678,8 @@ static void launch_merge(daisy_ctx *h, float alpha, cudaStream_t s) {
     const size_t cap = (size_t)sh->cap;
     static const int shared_passes = getenv("DAISY_OWNER_SHARED_PASSES") && atoi(getenv("DAISY_OWNER_SHARED_PASSES")) == 1;
     if (sh->classified && !shared_passes) {
-        k_owner_add_shared<V><<<h->num_sms * 8, 256, 0, s>>>(sh->peers.q[me], sh->peers.recv_g[me], sh->peers.recv_ids[me],
-                                                             sh->peers.recv_cnt[me], sh->shared_idx, sh->shared_cnt, sh->world,
-                                                             cap, h->D / 4, alpha, (uint32_t)h->I, h->err);
+        k_owner_add_slots<V><<<h->num_sms * 8, 256, 0, s>>>(sh->peers.q[me], sh->peers.recv_g[me], sh->slot_row, sh->pairs,
+                                                            sh->slot_n, sh->max_slots, sh->world, cap, h->D / 4, alpha);
         return;
     }
     for (int snd = 0; snd < sh->world; ++snd) {
@@ -746,16 +743,21 @@ static int shard_classify(daisy_ctx *h, cudaStream_t s) {
     DAISY_REQUIRE(g.ok, DAISY_ECUDA, "cannot select device %d", h->device);
     DAISY_CUDA(cudaMemsetAsync(sh->bm_seen, 0, sh->bm_words * sizeof(uint32_t), s));
     DAISY_CUDA(cudaMemsetAsync(sh->bm_multi, 0, sh->bm_words * sizeof(uint32_t), s));
-    DAISY_CUDA(cudaMemsetAsync(sh->shared_cnt, 0, DAISY_MAX_RANKS * sizeof(uint32_t), s));
+    DAISY_CUDA(cudaMemsetAsync(sh->bm_claim, 0, sh->bm_words * sizeof(uint32_t), s));
+    DAISY_CUDA(cudaMemsetAsync(sh->shared_cnt, 0, (DAISY_MAX_RANKS + 1) * sizeof(uint32_t), s));
     const dim3 grid((unsigned)(h->num_sms * 2), (unsigned)sh->world);
     const int me = sh->rank;
     k_owner_count<<<grid, 256, 0, s>>>(sh->peers.recv_ids[me], sh->peers.recv_cnt[me], (size_t)sh->cap, (uint32_t)h->I,
                                        sh->bm_seen, sh->bm_multi);
     DAISY_LAUNCH_CHECK(h);
     k_owner_classify<<<grid, 256, 0, s>>>(sh->peers.recv_ids[me], sh->peers.recv_cnt[me], (size_t)sh->cap, (uint32_t)h->I,
-                                          sh->bm_multi, me, sh->peers, sh->shared_idx, sh->shared_cnt);
+                                          sh->bm_multi, me, sh->peers, sh->shared_idx, sh->shared_cnt, sh->bm_claim,
+                                          sh->slot_of_row, sh->slot_row, sh->pairs, sh->slot_n, sh->max_slots, sh->world, h->err);
     DAISY_LAUNCH_CHECK(h);
-    h->launches += 3;
+    k_owner_pairs<<<grid, 256, 0, s>>>(sh->peers.recv_ids[me], sh->shared_idx, sh->shared_cnt, (size_t)sh->cap,
+                                       sh->slot_of_row, sh->pairs, sh->max_slots, sh->world);
+    DAISY_LAUNCH_CHECK(h);
+    h->launches += 4;
     sh->classified = 1;
     return DAISY_OK;
 }
@@ -851,6 +853,8 @@ void daisy_shard_free(daisy_ctx *h) {
     if (sh->bm_multi) cudaFree(sh->bm_multi);
     if (sh->shared_idx) cudaFree(sh->shared_idx);
     if (sh->shared_cnt) cudaFree(sh->shared_cnt);
+    for (void *p : {(void *)sh->bm_claim, (void *)sh->slot_of_row, (void *)sh->slot_row, (void *)sh->pairs})
+        if (p) cudaFree(p);
     if (sh->aux_stream) cudaStreamDestroy(sh->aux_stream);
     for (int i = 0; i < 2; ++i)
         if (sh->aux_ev[i]) cudaEventDestroy(sh->aux_ev[i]);
@@ -933,7 +937,16 @@ extern "C" int daisy_shard_init(daisy_handle_t h, int rank, int world, int64_t i
         for (int i = 0; i < 2 && ok; ++i) ok = cudaEventCreateWithFlags(&sh->aux_ev[i], cudaEventDisableTiming) == cudaSuccess;
     }
     ok = ok && cudaMalloc((void **)&sh->shared_idx, (size_t)world * cap * sizeof(uint32_t)) == cudaSuccess;
-    ok = ok && cudaMalloc((void **)&sh->shared_cnt, DAISY_MAX_RANKS * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMalloc((void **)&sh->shared_cnt, (DAISY_MAX_RANKS + 1) * sizeof(uint32_t)) == cudaSuccess;
+    sh->slot_n = sh->shared_cnt ? sh->shared_cnt + DAISY_MAX_RANKS : nullptr;
+    {   // a shared row is named by >= 2 senders: at most half of all entries, and at most every local row
+        const size_t half = (size_t)world * cap / 2 + 1, rows = (size_t)sh->i_per + 1;
+        sh->max_slots = (uint32_t)(half < rows ? half : rows);
+    }
+    ok = ok && cudaMalloc((void **)&sh->bm_claim, sh->bm_words * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMalloc((void **)&sh->slot_of_row, ((size_t)sh->i_per + 1) * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMalloc((void **)&sh->slot_row, (size_t)sh->max_slots * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMalloc((void **)&sh->pairs, (size_t)sh->max_slots * world * sizeof(uint32_t)) == cudaSuccess;
     sh->plan = new StepPlan();
     {   // exclusive-row bypass (on by default; the single-pass owner merge does not know about it)
         const char *v = getenv("DAISY_SHARD_BYPASS");
