@@ -370,8 +370,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  : "memory");
 }
 
+// DAISY_MAIN_MIN_BLOCKS (build-time experiment, tools/build_variants.sh): minimum resident blocks per SM the compiler must
+// allow -- 5 caps the kernel at 51 registers (default build: 62 registers at V = 1, 4 blocks per SM by registers).
+#ifndef DAISY_MAIN_MIN_BLOCKS
+#define DAISY_MAIN_BOUNDS __launch_bounds__(256)
+#else
+#define DAISY_MAIN_BOUNDS __launch_bounds__(256, (V == 1 ? DAISY_MAIN_MIN_BLOCKS : 1))
+#endif
 template <int V, class Opt, bool PTR>
-__global__ void __launch_bounds__(256) k_bpr_main_tma(MainArgs a, Opt opt, int S) {
+__global__ void DAISY_MAIN_BOUNDS k_bpr_main_tma(MainArgs a, Opt opt, int S) {
     extern __shared__ __align__(128) unsigned char dsm[];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
