@@ -819,7 +819,7 @@ def run_mf(args):
 
 
 # ------------------------------------------------------------------------------------------------
-# SVD++ (secondary line of an experimental path)
+# SVD++ (secondary line)
 # ------------------------------------------------------------------------------------------------
 def run_svdpp(args):
     """ratings/s of SVDpp.fit (daisy_svdpp_fit: one thread block walking the ratings in order, float64) on the
@@ -873,7 +873,7 @@ def run_svdpp(args):
             "warmup": 1, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"SVD++ (SVDpp.fit) on ml-1m-shaped synthetic ratings (config 2's set), n_factors {D}",
-                       "status": "experimental path, first version", "user_num": U, "item_num": I, "ratings": N, "dim": D,
+                       "status": "first version (one block walks the sequential loop)", "user_num": U, "item_num": I, "ratings": N, "dim": D,
                        "history_rows_per_rating": rows,
                        "step": "one epoch (a pass over the ratings in the given order, strictly sequential semantics)",
                        "l2": "tables are L2-resident; one thread block: the bound is one SM's L2 bandwidth and the barrier chain"},

@@ -313,7 +313,7 @@ DAISY_API int daisy_mf_predict(daisy_handle_t h, const double *pu, const double 
                      double *est, daisy_stream_t stream);
 
 /* ---- SVD++: SVDpp.fit / SVDpp.predict, util/matrix_factorization.pyx:193-288 -----------
- * EXPERIMENTAL: compiled for sm_100a, not yet run on a GPU (csrc/svdpp.cu has the status and the plan).
+ * GPU-verified in round 2 (tests/test_svdpp_gpu.py); csrc/svdpp.cu has the measured state and the plan.
  * daisy_svdpp_fit runs `n_epochs` passes over the n ratings IN THE GIVEN ORDER with the reference's strictly sequential
  * semantics (loop body :238-263): every rating of user u updates bu[u], bi[i], pu[u], qi[i] and the implicit-feedback
  * row yj[j] of EVERY item j in the user's history.  Tables are float64 like the reference's (pu [U,dim], qi [I,dim],
@@ -342,8 +342,7 @@ DAISY_API int daisy_svdpp_user_factors(daisy_handle_t h, const double *pu, const
                              const int32_t *ur_idx, double *z_out, daisy_stream_t stream);
 
 /* ---- BPR-FM at the reference script's defaults: batch norm + dropout ---------------------
- * EXPERIMENTAL: compiled for sm_100a, not yet run on a GPU (csrc/fmbn.cu has the status); the verified BPR-FM path is
- * daisy_bprfm_adagrad_step (batch_norm off, dropout 0).
+ * GPU-verified in round 2 (tests/test_bprfm_bn_gpu.py); batch_norm off + dropout 0 is daisy_bprfm_adagrad_step.
  * Replaces, for features = [user, user_num + item] with values 1 (util/data_loader.py:159-172, 595-614):
  *   BPRFM._out with nn.BatchNorm1d(num_factors) + nn.Dropout(drop_prob[0])   BPRFMRecommender.py:45-80
  *   the training step + optim.Adagrad over every parameter                    BPRFMRecommender.py:191-193, 214-219
@@ -377,7 +376,7 @@ DAISY_API int daisy_fmbn_forward(daisy_handle_t h, const daisy_fmbn_params *p, c
                        float *pred_i, float *pred_j, daisy_stream_t stream);
 
 /* ---- Item2Vec / skip-gram with negative sampling ---------------------------------------
- * EXPERIMENTAL: compiled for sm_100a, not yet run on a GPU (csrc/sgns.cu has the status).
+ * GPU-verified in round 2 (tests/test_sgns_gpu.py).
  * Replaces Item2Vec.forward_i / forward_o + SGNS.forward (Item2VecRecommender.py:60-97) with the negatives given, and
  * loss.backward() + optim.Adam(sgns.parameters()).step() (:266, 274-277; torch's Adam is dense: every row of both
  * tables is stepped).  Device pointers owned by the caller, fp32, contiguous. */
@@ -399,8 +398,7 @@ DAISY_API int daisy_sgns_step(daisy_handle_t h, const daisy_sgns_params *p, cons
                     int64_t scratch_bytes, double *loss_accum, daisy_stream_t stream);
 
 /* ---- NCF with an MLP tower: model 'MLP' and the script's default 'NeuMF-end'  ----------
- * EXPERIMENTAL: compiled for sm_100a, not yet run on a GPU (csrc/neumf.cu has the status); the verified NCF path is the
- * GMF variant (daisy_gmf_step).
+ * GPU-verified in round 2 (tests/test_neumf_gpu.py); the GMF variant is daisy_gmf_step.
  * Replaces NCF.forward (NCFRecommender.py:105-125) with dropout 0 and the training step :283-287 with
  * nn.BCEWithLogitsLoss() (:255) and optim.Adam(model.parameters(), lr) (:260).  Device pointers owned by the caller (the
  * module's parameter tensors and the optimizer's exp_avg / exp_avg_sq), fp32, contiguous; torch's Linear layout

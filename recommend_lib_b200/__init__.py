@@ -8,14 +8,12 @@ Public surface (mirrors the reference):
 * ``SVD`` / ``RSVD`` (ctor kwargs, ``fit``, ``predict``)  -- util/matrix_factorization.pyx:5-167
 * ``NCF(..., model='GMF')`` + ``GMFAdam``           -- NCFRecommender.py:28-125, 255-287 (next row)
 * ``BPRFM(..., batch_norm=False, drop_prob=[0, 0])`` + ``FMAdagrad``  -- BPRFMRecommender.py:29-80, 191-219 (N3)
-* ``BPRFMBN(..., batch_norm=True, drop_prob)`` + ``FMBNAdagrad``     -- the same script at its defaults; EXPERIMENTAL,
-  compiled but not yet run on a GPU (bprfm_bn.py)
+* ``BPRFMBN(..., batch_norm=True, drop_prob)`` + ``FMBNAdagrad``     -- the same script at its defaults
+  (bprfm_bn.py; ``BPRFM(batch_norm=True)`` builds it)
 * ``NeuMF(..., model in ('MLP', 'NeuMF-end'))`` + ``NeuMFAdam``  -- NCFRecommender.py:28-125, 255-287 with the MLP tower
-  (the script's default model); EXPERIMENTAL, compiled but not yet run on a GPU (ncf_mlp.py)
-* ``Item2Vec`` / ``SGNS`` + ``SGNSAdam``                        -- Item2VecRecommender.py:37-97, 266-277 (N4); EXPERIMENTAL,
-  compiled but not yet run on a GPU (item2vec.py)
-* ``SVDpp`` (ctor kwargs, ``fit``, ``predict``)                -- util/matrix_factorization.pyx:169-288 (N4); EXPERIMENTAL,
-  compiled but not yet run on a GPU (svdpp.py)
+  (the script's default model; ncf_mlp.py -- outside the scope table, kept because it exists)
+* ``Item2Vec`` / ``SGNS`` + ``SGNSAdam``                        -- Item2VecRecommender.py:37-97, 266-277 (N4; item2vec.py)
+* ``SVDpp`` (ctor kwargs, ``fit``, ``predict``)                -- util/matrix_factorization.pyx:169-288 (N4; svdpp.py)
 
 All compute goes through the C-ABI library ``libdaisy_b200.so`` (``include/daisy_b200.h``);
 there is no CPU fallback: using any of the above without the built library or without

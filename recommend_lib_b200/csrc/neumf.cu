@@ -2,9 +2,9 @@
 // dropout 0 (the script's default), BCEWithLogitsLoss (mean) and dense torch Adam (:255-260, 283-287).
 // SURVEY.md section 8f, row N3; the GMF variant is csrc/gmf.cu.
 //
-// STATUS: compiled for sm_100a, NOT YET RUN ON A GPU (written after the GPU budget of round 1 was spent); the GPU tests
-// (tests/test_neumf_gpu.py) are excluded from the default run until it has been (DAISY_EXPERIMENTAL=1 runs them).
-// Executed so far only under the host emulation of tests/emu (tests/test_kernel_emulation.py: golden run + oracle green).
+// STATUS: GPU-verified in round 2 (tests/test_neumf_gpu.py passes on a B200 and runs in the default -m gpu suite; bench line under
+// profiles/r02a_bench_neumf.json).  Before that it had run under the host emulation of tests/emu
+// (tests/test_kernel_emulation.py: golden run + oracle green), which still covers it on CPU.
 // The checker is pinned to the unmodified reference: the NeuMF checker under oracle/.
 //
 // First version, plain kernels, every reduction in a fixed order (bit-reproducible):

@@ -1,9 +1,9 @@
 // Item2Vec / skip-gram with negative sampling: the training step of
 // Item2VecRecommender.py:60-97 (Item2Vec.forward_i / forward_o, SGNS.forward) + :266, 274-277 (dense torch Adam).
 //
-// STATUS: compiled for sm_100a, NOT YET RUN ON A GPU (written after the GPU budget of round 1 was spent); the GPU tests
-// (tests/test_sgns_gpu.py) are excluded from the default run until it has been (DAISY_EXPERIMENTAL=1 runs them).
-// Executed so far only under the host emulation of tests/emu (tests/test_kernel_emulation.py: golden run + oracle green).
+// STATUS: GPU-verified in round 2 (tests/test_sgns_gpu.py passes on a B200 and runs in the default -m gpu suite; bench line under
+// profiles/r02a_bench_sgns.json).  Before that it had run under the host emulation of tests/emu
+// (tests/test_kernel_emulation.py: golden run + oracle green), which still covers it on CPU.
 // The checker exists and is pinned to the unmodified reference: oracle/sgns_oracle.py.
 //
 // Per example b: one centre row i_b = ivectors[iword_b], C context rows and C * n_negs negative rows of ovectors

@@ -1,8 +1,8 @@
 // SVD++: SVDpp.fit / SVDpp.predict of util/matrix_factorization.pyx:169-288.
 //
-// STATUS: compiled for sm_100a, NOT YET RUN ON A GPU (written after the GPU budget of round 1 was spent); the GPU tests
-// (tests/test_svdpp_gpu.py) are excluded from the default run until it has been (DAISY_EXPERIMENTAL=1 runs them).
-// Executed so far only under the host emulation of tests/emu (tests/test_kernel_emulation.py: golden run + oracle green).
+// STATUS: GPU-verified in round 2 (tests/test_svdpp_gpu.py passes on a B200 and runs in the default -m gpu suite; bench line under
+// profiles/r02a_bench_svdpp.json).  Before that it had run under the host emulation of tests/emu
+// (tests/test_kernel_emulation.py: golden run + oracle green), which still covers it on CPU.
 // The checker (the C restatement of the loop under oracle/) is bit-identical to the reference's own compiled class.
 //
 // The reference loop (:236-263) is strictly sequential, and unlike funk-SVD (csrc/mf.cu) it has no dataflow
@@ -32,7 +32,8 @@
 // Arithmetic: float64 throughout; the result is the sequential result up to the rounding of the two re-associated sums
 // (rows over warps, factors over lanes); the element-wise updates are the reference's expressions.  The tables of the
 // reference script's sizes are L2-resident (ml-1m, D = 128: 3 x 3.8 MB + 6 MB), so the bound is one SM's L2 bandwidth:
-// 2 x |Iu| x 8D bytes per rating.  Second version (next round, once this one is measured): the factors are independent
+// 2 x |Iu| x 8D bytes per rating.  Measured (ml-1m shape, n_factors 20): 5 us per rating = 0.19-0.20 M ratings/s, the barrier
+// chain (3 block barriers + one L2 round trip per rating), barely ahead of one host core.  Second version (not built): the factors are independent
 // given err, so a thread-block cluster can own D / 16 factors per block -- its slice of yj in shared memory --
 // and exchange one partial dot product per rating through distributed shared memory.
 #include "ctx.cuh"
@@ -392,11 +393,14 @@ extern "C" int daisy_svdpp_fit(daisy_handle_t h, double *pu, double *qi, double 
     a.D = D;
     a.I = (int)h->I;
     a.prm = *prm;
-    // resident rows: what is left of the 227 KB of shared memory holds the yj rows of the most frequent items
-    // (DAISY_SVDPP_HOT=<rows> overrides, 0 disables)
+    // resident rows: what is left of the 227 KB of shared memory can hold the yj rows of the most frequent items.
+    // OFF by default since it was measured (profiles/r02a_bench_svdpp*.json, n_factors 20: 203 k ratings/s without,
+    // 189 k with: a 160-byte row comes from L2 as fast as the slot indirection costs); DAISY_SVDPP_HOT=<rows> enables it
+    // (results are bit-identical either way, tests/test_svdpp_gpu.py).
     const size_t budget = 224 * 1024, base = sp_smem_bytes(threads, D);
     long long H = base < budget ? (long long)((budget - base) / ((size_t)D * sizeof(double))) : 0;
     if (const char *e = getenv("DAISY_SVDPP_HOT")) H = atoll(e) < H ? atoll(e) : H;
+    else H = 0;
     if (H > h->I) H = h->I;
     if (H < 0 || h->I > 0x7fffffffLL) H = 0;
     a.H = (int)H;

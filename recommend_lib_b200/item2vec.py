@@ -1,9 +1,8 @@
 """Drop-ins for ``class Item2Vec`` and ``class SGNS`` of the reference (Item2VecRecommender.py:37-97) and for the training
 step of its script (:266, 274-277), on the C-ABI library (``daisy_sgns_step``, csrc/sgns.cu).  SURVEY.md section 8f, N4.
 
-EXPERIMENTAL: the kernels are compiled for sm_100a but have not run on a GPU yet (round 1 ended its GPU budget first);
-tests/test_sgns_gpu.py runs only with ``DAISY_EXPERIMENTAL=1``.  The checker is ``oracle/sgns_oracle.py``, pinned to
-the unmodified reference classes.  No CPU fallback.
+GPU-verified in round 2 (tests/test_sgns_gpu.py, part of the default ``-m gpu`` suite).  The checker is
+``oracle/sgns_oracle.py``, pinned to the unmodified reference classes.  No CPU fallback.
 """
 from __future__ import annotations
 

@@ -42,7 +42,7 @@ class NCF(nn.Module):
         super().__init__()
         if model != "GMF":
             raise NotImplementedError("only model='GMF' is on this (GPU-verified) path; 'MLP' / 'NeuMF-end' are "
-                                      "ncf_mlp.NeuMF / NeuMFAdam (experimental: not yet run on a GPU)")
+                                      "ncf_mlp.NeuMF / NeuMFAdam")
         if factor_num % 4:
             raise ValueError("factor_num must be a multiple of 4 (rows move as 128-bit vectors)")
         self.dropout, self.model = dropout, model

@@ -3,9 +3,9 @@
 (:255-260, 283-287), on the C-ABI library (``daisy_neumf_forward`` / ``daisy_neumf_step``, csrc/neumf.cu).
 SURVEY.md section 8f, row N3.  The GMF variant is ``ncf.NCF`` / ``GMFAdam``.
 
-EXPERIMENTAL: the kernels are compiled for sm_100a but have not run on a GPU yet (round 1 ended its GPU budget first);
-tests/test_neumf_gpu.py runs only with ``DAISY_EXPERIMENTAL=1``.  The checker is the NeuMF checker under ``oracle/``, pinned to
-the unmodified reference class; the same translation unit passes it under the host emulation of tests/emu.
+GPU-verified in round 2 (tests/test_neumf_gpu.py, part of the default ``-m gpu`` suite); outside the scope table
+(SURVEY 2 #13), kept because it exists.  The checker is the NeuMF checker under ``oracle/``, pinned to the unmodified
+reference class; the same translation unit passes it under the host emulation of tests/emu.
 
 Same module structure as the reference (all four embedding tables, ``MLP_layers = Sequential(Dropout, Linear, ReLU, ...)``,
 ``predict_layer``), so ``state_dict()`` / ``torch.save(model)`` carry the same keys.  No CPU fallback.

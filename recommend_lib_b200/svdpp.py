@@ -1,7 +1,7 @@
 """SVD++ behind Daisy's Cython class, computed by libdaisy_b200.so on a B200.
 
-EXPERIMENTAL: csrc/svdpp.cu is compiled for sm_100a and reproduces the reference's golden run under the host emulation
-of tests/emu, but has not run on a GPU yet (tests/test_svdpp_gpu.py, DAISY_EXPERIMENTAL=1).
+GPU-verified in round 2 (tests/test_svdpp_gpu.py, part of the default ``-m gpu`` suite); csrc/svdpp.cu also reproduces
+the reference's golden run under the host emulation of tests/emu.
 
 Drop-in for ``util.matrix_factorization.SVDpp`` (util/matrix_factorization.pyx:169-288; call site
 SVDppRecommender.py:142): same constructor keywords, ``fit(train_set)`` on a DataFrame with ``user, item, rating``
