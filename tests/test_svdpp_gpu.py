@@ -89,7 +89,8 @@ def test_svdpp_against_c_oracle(U, I, D, n, E):
     b = fit_from(SVDpp(U, I, n_factors=D, n_epochs=E, verbose=False), users, items, ratings, pu0, qi0, yj0)
     assert np.array_equal(a.yj, b.yj) and np.array_equal(a.pu, b.pu)      # run-to-run bit-reproducible
     old = os.environ.get("DAISY_SVDPP_HOT")
-    os.environ["DAISY_SVDPP_HOT"] = "0"                                   # no yj rows resident in shared memory: same arithmetic
+    os.environ["DAISY_SVDPP_HOT"] = "100000"                              # the most frequent yj rows resident in shared memory
+                                                                          # (as many as fit; off by default): same arithmetic
     try:
         c = fit_from(SVDpp(U, I, n_factors=D, n_epochs=E, verbose=False), users, items, ratings, pu0, qi0, yj0)
     finally:
