@@ -527,6 +527,37 @@ def test_sampler_kernels_emulated_match_the_oracle_bit_for_bit(shuffle):
     assert L.emu_err_flag(h) == 0
 
 
+@pytest.mark.parametrize("world,n,batch", [(2, 1000, 256), (3, 777, 100), (4, 37, 8), (2, 5, 100)])
+def test_route_triples_emulated_is_the_rank_share_of_every_global_batch(world, n, batch):
+    """daisy_route_triples (csrc/sampler.cu; the e2e region of the N > 1 bench and PeerShardedBPR.fit route with it):
+    every rank's share of a global epoch -- users in [u0, u1), order kept, user column made local, per-batch offsets --
+    against the numpy routing of tests/sharded_testing.py."""
+    from recommend_lib_b200.sharded import ShardLayout
+    from sharded_testing import route
+    L = _load("sampler")
+    U, I = 203, 77
+    rng = np.random.default_rng(n)
+    tri = np.stack([rng.integers(0, U, n), rng.integers(0, I, n), rng.integers(0, I, n)], 1).astype(np.int32)
+    layout = ShardLayout(U, I, world)
+    h = _dims_handle(L, U, I, 4)
+    L.daisy_route_triples.argtypes = [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]
+    nb = (n + batch - 1) // batch
+    total = 0
+    for rank in range(world):
+        u0, u1 = layout.user_range(rank)
+        out = np.full((n, 3), -1, np.int32)
+        off = np.full(nb + 1, -1, np.int64)
+        rc = L.daisy_route_triples(h, _p(tri), n, batch, u0, u1, _p(out), _p(off), None)
+        assert rc == 0, L.emu_last_error()
+        assert off[0] == 0 and np.all(np.diff(off) >= 0)
+        for k in range(nb):
+            want = route(tri[k * batch:(k + 1) * batch], layout, rank)
+            assert np.array_equal(out[off[k]:off[k + 1]], want), (rank, k)
+        total += int(off[-1])
+    assert total == n
+    assert L.emu_err_flag(h) == 0
+
+
 @pytest.mark.parametrize("I,D,N,K,paths", [(300, 16, 5, 10, ("exact",)), (33000, 8, 3, 10, ("exact", "filter"))])
 def test_full_catalogue_topk_emulated(monkeypatch, I, D, N, K, paths):
     """csrc/topk_full.cu (row A9, GPU-verified): both selection strategies under the emulation; the filtered path must
