@@ -257,3 +257,31 @@ def test_neumf_module_is_a_drop_in_and_has_no_cpu_path():
             m(z, z)
         with pytest.raises(_lib.DaisyError):
             NeuMFAdam(m).step(z, z, torch.zeros(2))
+
+
+def test_committed_bench_lines_carry_every_contract_key():
+    """The JSON lines bench.py printed on a B200 at the end of round 2 (N = 1 at the default and at the driver's flags,
+    N = 8 under torchrun) hold every key the bench contract names -- so a change to bench.py that drops one shows up here
+    when the lines are regenerated."""
+    import json
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles")
+    base = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+            "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"}
+    for name, n in (("r02s_bench_n1_default.json", 1), ("r02s_bench_n1_driver_flags.json", 1), ("r02r_bench_n8_default.json", 8)):
+        d = json.load(open(os.path.join(root, name)))
+        assert base <= set(d), (name, base - set(d))
+        assert d["metric"] == "bpr_mf_train_triples_per_s" and d["unit"] == "triples/s" and d["n_gpus"] == n
+        assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["dtype"] == "f32"
+        assert "workload" in d["config"] and "model" not in d["config"]
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] != d["value"]
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+        assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+        assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"]) and d["gpu_launches"] > 0
+        assert abs(d["value"] - d["config"].get("batch", d["config"].get("global_batch")) / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
+    d = json.load(open(os.path.join(root, "r02s_bench_n1_default.json")))
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] in ("port", "reference")
+    assert d["config"]["lazy_decay_materialized_in_timed_region"] is False and d["materialize_ms"] > 0
+    n8 = json.load(open(os.path.join(root, "r02r_bench_n8_default.json")))
+    chk = n8["config"]["parity_selfcheck"]
+    assert chk["ranks"] == 8 and all(v <= chk["tolerance"] for k, v in chk.items() if k.startswith("vs_"))
