@@ -9,12 +9,14 @@
 // passes over the gathered rows (the tables are L2-resident at the script's sizes; this first version is written for
 // clarity: every pass is a plain kernel, every reduction has a fixed order => bit-reproducible):
 //   k_fm_x        x_i = e_u (.) e_i, x_j = e_u (.) e_j                                   -> X [2][B][F]
-//   k_fm_stats    per (call, factor): mean and biased variance over the batch (double)     -> mu, var, inv
+//   k_fm_stats_sum / _var / _finish   per (call, factor): mean and biased variance over the batch (double; the batch
+//                 is cut into FM_Z slices, one block each, partials added in slice order)   -> mu, var, inv
 //   k_fm_score    xhat, z = gamma xhat + beta, dropout mask, pred_i - pred_j, s_b, loss    -> s [B], loss partials
-//   k_fm_colsums  per (call, factor): sum_b dz, sum_b dz xhat (double)                     -> c1, c2, d gamma, d beta
+//   k_fm_colsums_part / _finish   per (call, factor): sum_b dz, sum_b dz xhat (double, same slicing)  -> c1, c2, d gamma, d beta
 //   k_fm_grad     dx = inv (gamma dz - c1 - xhat c2); row-gradient contributions           -> contrib [3B][F+1], keys
 //   cub sort      contributions grouped by feature row (stable: ascending triple order inside a row)
-//   k_fm_apply    one warp per row: fixed-order sum of its contributions + Adagrad on the row and its bias
+//   k_fm_apply_slices / k_fm_apply   a row's contributions summed in slices of FM_SLICE (one warp each), then one warp
+//                 per row adds its slices in order + Adagrad on the row and its bias
 //   k_fm_bn_step  Adagrad on gamma / beta, running statistics (positive call first, then negative), loss
 // The user bias and bias_ cancel in pred_i - pred_j: their gradient is exactly zero here (the reference's is -s + s,
 // zero up to rounding).
@@ -25,9 +27,13 @@
 namespace {
 
 constexpr int FM_MAX_F = 255;  // k_fm_apply keeps (F + 1) / 32 accumulators per lane in registers
+constexpr int FM_Z = 64;       // batch slices of the column reductions (one block per slice and 32 factors)
+constexpr int FM_SLICE = 32;   // sorted contributions per slice of k_fm_apply_slices
 
 struct FmScratch {
     float *X, *s, *lossp, *mu, *var, *inv, *c1, *c2, *contrib;
+    double *part;    // [FM_Z][2 calls][F][2] partial column sums of the batch slices (k_fm_stats_*, k_fm_colsums_*)
+    float *spart;    // [3B][F + 1] slice sums of k_fm_apply_slices (indexed by the slice's first sorted position)
     double *A, *Bs;  // per (call, factor) sums of dz and dz * xhat: the two calls' sums nearly cancel in d beta, so they
                      // stay double until they have been added (a float here costs 1e-4 of d beta at batch 333)
     uint32_t *kin, *kout, *vin, *vout;
@@ -59,6 +65,8 @@ static void fm_carve(char *base, int64_t B, int F, FmScratch &w) {
     w.c1 = (float *)take(2 * f * 4);
     w.c2 = (float *)take(2 * f * 4);
     w.contrib = (float *)take(3 * b * (f + 1) * 4);
+    w.part = (double *)take((size_t)FM_Z * 2 * f * 2 * 8);
+    w.spart = (float *)take(3 * b * (f + 1) * 4);
     w.kin = (uint32_t *)take(3 * b * 4);
     w.kout = (uint32_t *)take(3 * b * 4);
     w.vin = (uint32_t *)take(3 * b * 4);
@@ -103,38 +111,73 @@ __global__ void __launch_bounds__(256) k_fm_x(const float *__restrict__ E, const
     }
 }
 
-// grid (ceil(F / 32), 2 calls), block (32 factors, 8 row groups): two-pass mean / variance in double, fixed order
-__global__ void __launch_bounds__(256) k_fm_stats(const float *__restrict__ X, int B, int F, float bn_eps,
-                                                   float *__restrict__ mu, float *__restrict__ var,
-                                                   float *__restrict__ inv) {
+// Column statistics of the batch (two-pass mean / variance in double, every sum in a fixed order).  The first version
+// walked the whole batch in ONE block per 32 factors -- 4 blocks on the GPU, 65 us at batch 4 096, and the same shape
+// cost k_fm_colsums 283 us (profiles/r02u_launches_bprfm_bn_summary.md).  Now: grid (ceil(F / 32), 2 calls, FM_Z batch
+// slices), block (32 factors, 8 row groups); a slice block leaves its partial sum in `part`, and whoever needs the
+// total adds the FM_Z partials in slice order (identical in every block).
+__device__ __forceinline__ void fm_slice(int B, int z, int &b0, int &b1) {
+    const int per = (B + FM_Z - 1) / FM_Z;
+    b0 = z * per;
+    b1 = min(B, b0 + per);
+}
+__device__ __forceinline__ double fm_total(const double *__restrict__ part, int c, int f, int F, int which) {
+    double t = 0.0;
+    for (int z = 0; z < FM_Z; ++z) t += part[(((size_t)z * 2 + c) * F + f) * 2 + which];
+    return t;
+}
+
+__global__ void __launch_bounds__(256) k_fm_stats_sum(const float *__restrict__ X, int B, int F, double *__restrict__ part) {
     __shared__ double sh[8][33];
-    const int tx = threadIdx.x, ty = threadIdx.y, f = blockIdx.x * 32 + tx, c = blockIdx.y;
+    const int tx = threadIdx.x, ty = threadIdx.y, f = blockIdx.x * 32 + tx, c = blockIdx.y, z = blockIdx.z;
     const float *x = X + (size_t)c * B * F;
+    int b0, b1;
+    fm_slice(B, z, b0, b1);
     double a = 0.0;
     if (f < F)
-        for (int b = ty; b < B; b += 8) a += (double)x[(size_t)b * F + f];
+        for (int b = b0 + ty; b < b1; b += 8) a += (double)x[(size_t)b * F + f];
     sh[ty][tx] = a;
     __syncthreads();
-    double m = 0.0;
-    for (int k = 0; k < 8; ++k) m += sh[k][tx];
-    m /= (double)B;
-    __syncthreads();
+    if (ty == 0 && f < F) {
+        double m = 0.0;
+        for (int k = 0; k < 8; ++k) m += sh[k][tx];
+        part[(((size_t)z * 2 + c) * F + f) * 2 + 0] = m;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fm_stats_var(const float *__restrict__ X, int B, int F, double *__restrict__ part) {
+    __shared__ double sh[8][33];
+    const int tx = threadIdx.x, ty = threadIdx.y, f = blockIdx.x * 32 + tx, c = blockIdx.y, z = blockIdx.z;
+    const float *x = X + (size_t)c * B * F;
+    int b0, b1;
+    fm_slice(B, z, b0, b1);
     double v = 0.0;
-    if (f < F)
-        for (int b = ty; b < B; b += 8) {
+    if (f < F) {
+        const double m = fm_total(part, c, f, F, 0) / (double)B;
+        for (int b = b0 + ty; b < b1; b += 8) {
             const double d = (double)x[(size_t)b * F + f] - m;
             v += d * d;
         }
+    }
     sh[ty][tx] = v;
     __syncthreads();
     if (ty == 0 && f < F) {
-        double s = 0.0;
-        for (int k = 0; k < 8; ++k) s += sh[k][tx];
-        s /= (double)B;  // biased variance normalises (nn.BatchNorm1d, training mode)
-        mu[c * F + f] = (float)m;
-        var[c * F + f] = (float)s;
-        inv[c * F + f] = (float)(1.0 / sqrt(s + (double)bn_eps));
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += sh[k][tx];
+        part[(((size_t)z * 2 + c) * F + f) * 2 + 1] = t;
     }
+}
+
+__global__ void k_fm_stats_finish(const double *__restrict__ part, int B, int F, float bn_eps, float *__restrict__ mu,
+                                  float *__restrict__ var, float *__restrict__ inv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * F) return;
+    const int c = i / F, f = i - c * F;
+    const double m = fm_total(part, c, f, F, 0) / (double)B;
+    const double sv = fm_total(part, c, f, F, 1) / (double)B;  // biased variance normalises (nn.BatchNorm1d, training mode)
+    mu[i] = (float)m;
+    var[i] = (float)sv;
+    inv[i] = (float)(1.0 / sqrt(sv + (double)bn_eps));
 }
 
 // one warp per triple: prediction difference, s_b = sigmoid(-(pred_i - pred_j)), loss
@@ -168,21 +211,21 @@ __global__ void __launch_bounds__(256) k_fm_score(const float *__restrict__ X, c
 }
 
 // grid (ceil(F / 32), 2 calls), block (32, 8): column sums of dz and dz * xhat in double, fixed order
-__global__ void __launch_bounds__(256) k_fm_colsums(const float *__restrict__ X, const float *__restrict__ s, int B, int F,
-                                                     const float *__restrict__ mu, const float *__restrict__ inv,
-                                                     const float *__restrict__ gamma, const float *__restrict__ mask_i,
-                                                     const float *__restrict__ mask_j, double *__restrict__ A,
-                                                     double *__restrict__ Bs, float *__restrict__ c1,
-                                                     float *__restrict__ c2) {
+__global__ void __launch_bounds__(256) k_fm_colsums_part(const float *__restrict__ X, const float *__restrict__ s, int B, int F,
+                                                          const float *__restrict__ mu, const float *__restrict__ inv,
+                                                          const float *__restrict__ mask_i, const float *__restrict__ mask_j,
+                                                          double *__restrict__ part) {
     __shared__ double shA[8][33], shB[8][33];
-    const int tx = threadIdx.x, ty = threadIdx.y, f = blockIdx.x * 32 + tx, c = blockIdx.y;
+    const int tx = threadIdx.x, ty = threadIdx.y, f = blockIdx.x * 32 + tx, c = blockIdx.y, z = blockIdx.z;
     const float *x = X + (size_t)c * B * F;
     const float *mask = c ? mask_j : mask_i;
     const float sign = c ? 1.f : -1.f;  // d loss / d pred_i = -s, d loss / d pred_j = +s
+    int b0, b1;
+    fm_slice(B, z, b0, b1);
     double a = 0.0, bs = 0.0;
     if (f < F) {
         const float m = mu[c * F + f], iv = inv[c * F + f];
-        for (int b = ty; b < B; b += 8) {
+        for (int b = b0 + ty; b < b1; b += 8) {
             float dz = sign * s[b];
             if (mask) dz *= mask[(size_t)b * F + f];
             const float xh = (x[(size_t)b * F + f] - m) * iv;
@@ -199,11 +242,22 @@ __global__ void __launch_bounds__(256) k_fm_colsums(const float *__restrict__ X,
             ta += shA[k][tx];
             tb += shB[k][tx];
         }
-        A[c * F + f] = ta;
-        Bs[c * F + f] = tb;
-        c1[c * F + f] = (float)((double)gamma[f] * ta / (double)B);   // mean_b(d xhat)
-        c2[c * F + f] = (float)((double)gamma[f] * tb / (double)B);   // mean_b(d xhat * xhat)
+        part[(((size_t)z * 2 + c) * F + f) * 2 + 0] = ta;
+        part[(((size_t)z * 2 + c) * F + f) * 2 + 1] = tb;
     }
+}
+
+__global__ void k_fm_colsums_finish(const double *__restrict__ part, int B, int F, const float *__restrict__ gamma,
+                                    double *__restrict__ A, double *__restrict__ Bs, float *__restrict__ c1,
+                                    float *__restrict__ c2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * F) return;
+    const int c = i / F, f = i - c * F;
+    const double ta = fm_total(part, c, f, F, 0), tb = fm_total(part, c, f, F, 1);
+    A[i] = ta;
+    Bs[i] = tb;
+    c1[i] = (float)((double)gamma[f] * ta / (double)B);   // mean_b(d xhat)
+    c2[i] = (float)((double)gamma[f] * tb / (double)B);   // mean_b(d xhat * xhat)
 }
 
 // one warp per triple: BN backward per element, contributions of the triple to its three feature rows
@@ -252,11 +306,44 @@ __global__ void __launch_bounds__(256) k_fm_grad(const float *__restrict__ E, co
     }
 }
 
-// one warp per sorted contribution; the warp at the FIRST contribution of a row sums them all in sorted (= triple) order
-// and applies Adagrad: state_sum += g^2, w -= lr g / (sqrt(state_sum) + eps)  (torch.optim.Adagrad, lr_decay 0)
-__global__ void __launch_bounds__(256) k_fm_apply(const uint32_t *__restrict__ kout, const uint32_t *__restrict__ vout, int n,
-                                                   const float *__restrict__ contrib, int F, float *__restrict__ E,
-                                                   float *__restrict__ bias, float *__restrict__ accE,
+// A row's contributions are consecutive in the sorted list; they are summed in slices so that a hot row (a Zipf item takes
+// hundreds of a batch's 3B contributions) is not one warp's serial walk (292 us at batch 4 096, first version).  A slice
+// starts at every row head and at every sorted position that is a multiple of FM_SLICE, and ends where the next one starts.
+// k_fm_apply_slices: one warp per sorted position; the warp at a slice start sums the slice in sorted (= triple) order.
+__global__ void __launch_bounds__(256) k_fm_apply_slices(const uint32_t *__restrict__ kout, const uint32_t *__restrict__ vout,
+                                                          int n, const float *__restrict__ contrib, int F,
+                                                          float *__restrict__ spart) {
+    const int lane = threadIdx.x & 31;
+    const int p = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    if (p >= n) return;
+    const uint32_t row = kout[p];
+    if (p % FM_SLICE != 0 && kout[p - 1] == row) return;  // warp-uniform: inside a slice
+    const size_t W = (size_t)F + 1;
+    const int stop = min(n, (p / FM_SLICE + 1) * FM_SLICE);
+    float acc[(FM_MAX_F + 1 + 31) / 32];
+#pragma unroll
+    for (int k = 0; k < (FM_MAX_F + 1 + 31) / 32; ++k) acc[k] = 0.f;
+#pragma unroll 4  // independent index -> row chains: let the scheduler put several rows in flight
+    for (int q = p; q < stop && kout[q] == row; ++q) {
+        const float *g = contrib + (size_t)vout[q] * W;
+#pragma unroll
+        for (int k = 0; k < (FM_MAX_F + 1 + 31) / 32; ++k) {
+            const int f = lane + 32 * k;
+            if (f <= F) acc[k] += g[f];
+        }
+    }
+    float *dst = spart + (size_t)p * W;
+#pragma unroll
+    for (int k = 0; k < (FM_MAX_F + 1 + 31) / 32; ++k) {
+        const int f = lane + 32 * k;
+        if (f <= F) dst[f] = acc[k];
+    }
+}
+
+// k_fm_apply: the warp at the FIRST contribution of a row adds the row's slice sums in slice order and applies Adagrad:
+// state_sum += g^2, w -= lr g / (sqrt(state_sum) + eps)  (torch.optim.Adagrad, lr_decay 0)
+__global__ void __launch_bounds__(256) k_fm_apply(const uint32_t *__restrict__ kout, int n, const float *__restrict__ spart, int F,
+                                                   float *__restrict__ E, float *__restrict__ bias, float *__restrict__ accE,
                                                    float *__restrict__ accb, float lr, float eps) {
     const int lane = threadIdx.x & 31;
     const int p = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
@@ -267,9 +354,8 @@ __global__ void __launch_bounds__(256) k_fm_apply(const uint32_t *__restrict__ k
     float acc[(FM_MAX_F + 1 + 31) / 32];
 #pragma unroll
     for (int k = 0; k < (FM_MAX_F + 1 + 31) / 32; ++k) acc[k] = 0.f;
-#pragma unroll 4  // independent index -> row chains: let the scheduler put several rows in flight
-    for (int q = p; q < n && kout[q] == row; ++q) {
-        const float *g = contrib + (size_t)vout[q] * W;
+    for (int q = p; q < n && kout[q] == row; q = (q / FM_SLICE + 1) * FM_SLICE) {  // the row's slice starts
+        const float *g = spart + (size_t)q * W;
 #pragma unroll
         for (int k = 0; k < (FM_MAX_F + 1 + 31) / 32; ++k) {
             const int f = lane + 32 * k;
@@ -406,16 +492,25 @@ extern "C" int daisy_fmbn_step(daisy_handle_t h, const daisy_fmbn_params *p, con
     const int Bi = (int)B, F = p->F, n = 3 * Bi;
     const uint32_t U = (uint32_t)p->user_num, I = (uint32_t)(p->num_features - p->user_num);
     const int wblocks = daisy_ceil_div(B, 8);
-    const dim3 cgrid(daisy_ceil_div(F, 32), 2), cblock(32, 8);
+    const dim3 cgrid(daisy_ceil_div(F, 32), 2, FM_Z), cblock(32, 8);
+    const int fgrid = daisy_ceil_div(2 * F, 256);
     k_fm_x<<<wblocks, 256, 0, s>>>(p->E, triples, Bi, F, U, I, w.X, h->err);
     DAISY_LAUNCH_CHECK(h);
-    k_fm_stats<<<cgrid, cblock, 0, s>>>(w.X, Bi, F, p->bn_eps, w.mu, w.var, w.inv);
+    k_fm_stats_sum<<<cgrid, cblock, 0, s>>>(w.X, Bi, F, w.part);
     DAISY_LAUNCH_CHECK(h);
+    k_fm_stats_var<<<cgrid, cblock, 0, s>>>(w.X, Bi, F, w.part);
+    DAISY_LAUNCH_CHECK(h);
+    k_fm_stats_finish<<<fgrid, 256, 0, s>>>(w.part, Bi, F, p->bn_eps, w.mu, w.var, w.inv);
+    DAISY_LAUNCH_CHECK(h);
+    h->launches += 2;
     k_fm_score<<<wblocks, 256, 0, s>>>(w.X, p->bias, triples, Bi, F, U, I, w.mu, w.inv, p->gamma, p->beta, mask_i, mask_j, w.s,
                                        w.lossp);
     DAISY_LAUNCH_CHECK(h);
-    k_fm_colsums<<<cgrid, cblock, 0, s>>>(w.X, w.s, Bi, F, w.mu, w.inv, p->gamma, mask_i, mask_j, w.A, w.Bs, w.c1, w.c2);
+    k_fm_colsums_part<<<cgrid, cblock, 0, s>>>(w.X, w.s, Bi, F, w.mu, w.inv, mask_i, mask_j, w.part);
     DAISY_LAUNCH_CHECK(h);
+    k_fm_colsums_finish<<<fgrid, 256, 0, s>>>(w.part, Bi, F, p->gamma, w.A, w.Bs, w.c1, w.c2);
+    DAISY_LAUNCH_CHECK(h);
+    h->launches += 1;
     k_fm_grad<<<wblocks, 256, 0, s>>>(p->E, w.X, w.s, triples, Bi, F, U, I, w.mu, w.inv, p->gamma, w.c1, w.c2, mask_i, mask_j,
                                       w.contrib, w.kin, w.vin);
     DAISY_LAUNCH_CHECK(h);
@@ -424,9 +519,11 @@ extern "C" int daisy_fmbn_step(daisy_handle_t h, const daisy_fmbn_params *p, con
     size_t cub_bytes = w.cub_bytes;
     DAISY_CUDA(cub::DeviceRadixSort::SortPairs(w.cub, cub_bytes, w.kin, w.kout, w.vin, w.vout, n, 0, bits, s));
     h->launches += 3;
-    k_fm_apply<<<daisy_ceil_div(n, 8), 256, 0, s>>>(w.kout, w.vout, n, w.contrib, F, p->E, p->bias, p->accE, p->accb, p->lr,
-                                                    p->eps);
+    k_fm_apply_slices<<<daisy_ceil_div(n, 8), 256, 0, s>>>(w.kout, w.vout, n, w.contrib, F, w.spart);
     DAISY_LAUNCH_CHECK(h);
+    k_fm_apply<<<daisy_ceil_div(n, 8), 256, 0, s>>>(w.kout, n, w.spart, F, p->E, p->bias, p->accE, p->accb, p->lr, p->eps);
+    DAISY_LAUNCH_CHECK(h);
+    h->launches += 1;
     k_fm_bn_step<<<1, 256, 0, s>>>(Bi, F, w.mu, w.var, w.A, w.Bs, p->gamma, p->beta, p->acc_gamma, p->acc_beta, p->running_mean,
                                    p->running_var, p->lr, p->eps, p->momentum, w.lossp, loss_accum);
     DAISY_LAUNCH_CHECK(h);

@@ -13,9 +13,13 @@
 // coefficient of every ref is stored (4 bytes instead of a D-float row):
 //   k_sgns_main     one warp per example: i_b in registers, R rows streamed, coefficients, centre-row gradient, loss
 //   cub sort x 2    (output row, ref) and (centre row, example), stable
-//   k_sgns_rows     one block per vocabulary row and table: its segment of the sorted list is cut into 8 fixed slices
-//                   (one per warp), the slice sums are added in slice order -> dense gradient rows, fixed order
-//                   => bit-reproducible; the padding row (nn.Embedding(padding_idx=0), :40-41) gets a zero gradient
+//   k_sgns_seg / k_sgns_scan / k_sgns_slices / k_sgns_combine   every row's segment of the sorted list is cut into slices
+//                   of SG_SLICE refs -- as many slices as the row is long -- one warp per slice, partial sums to scratch,
+//                   then one warp per row adds its slices in slice order -> dense gradient rows, fixed order =>
+//                   bit-reproducible.  (The first version cut EVERY row into 8 slices inside one block: under a
+//                   unigram^0.75 sampler the hottest rows hold 20-40 k of the 860 k refs, and their blocks made the
+//                   kernel 1.93 ms of a 2.36 ms step, profiles/r02u_launches_sgns_summary.md.)  The padding row
+//                   (nn.Embedding(padding_idx=0), :40-41) gets a zero gradient and is not summed at all
 //   k_sgns_adam     torch.optim.Adam is dense: every element of both tables is stepped
 #include <cub/cub.cuh>
 
@@ -29,9 +33,17 @@ constexpr int SG_K = SG_MAX_D / 32;
 struct SgScratch {
     float *coef, *ci, *lossp, *gI, *gO;
     uint32_t *kin, *kout, *vin, *vout, *ikin, *ikout, *ivin, *ivout;
+    uint32_t *seg_lo, *seg_len, *soff;   // [2V], [2V], [2V + 1]: per (table, row) first ref, refs, first slice
+    float *partial;                      // [max slices][D] slice sums
     void *cub;
     size_t cub_bytes, total;
 };
+
+constexpr int SG_SLICE = 128;            // refs per slice of a row's segment (one warp per slice)
+// a row of len refs has ceil(len / SG_SLICE) slices: at most (refs / SG_SLICE + 1) per row over both tables
+static size_t sg_max_slices(int64_t n, int64_t B, int64_t V) {
+    return (size_t)(n / SG_SLICE + B / SG_SLICE + 2 * V + 2);
+}
 
 // bound on cub::DeviceRadixSort::SortPairs temporary storage for n (uint32, uint32) pairs (see csrc/fmbn.cu)
 static size_t sg_sort_bytes(int64_t n) { return (size_t)n * 16 + ((size_t)1 << 20); }
@@ -57,6 +69,10 @@ static void sg_carve(char *base, int64_t B, int64_t R, int64_t V, int D, SgScrat
     w.ikout = (uint32_t *)take(b * 4);
     w.ivin = (uint32_t *)take(b * 4);
     w.ivout = (uint32_t *)take(b * 4);
+    w.seg_lo = (uint32_t *)take(2 * (size_t)V * 4);
+    w.seg_len = (uint32_t *)take(2 * (size_t)V * 4);
+    w.soff = (uint32_t *)take((2 * (size_t)V + 1) * 4);
+    w.partial = (float *)take(sg_max_slices((int64_t)n, B, V) * (size_t)D * 4);
     w.cub_bytes = sg_sort_bytes((int64_t)n);
     w.cub = take(w.cub_bytes);
     w.total = off;
@@ -154,63 +170,128 @@ __device__ __forceinline__ int sg_lower_bound(const uint32_t *__restrict__ a, in
     return lo;
 }
 
-// grid (V, 2): blockIdx.y = 0: gradient of ovectors[row] = sum over its refs of coef * ivectors[iword_b] (pre-step);
-//              blockIdx.y = 1: gradient of ivectors[row] = sum over the examples centred on it of their ci rows.
-template <int K>
-__global__ void __launch_bounds__(256) k_sgns_rows(const uint32_t *__restrict__ kout, const uint32_t *__restrict__ vout, int n,
-                                                    const uint32_t *__restrict__ ikout, const uint32_t *__restrict__ ivout, int B,
-                                                    int R, const float *__restrict__ coef, const float *__restrict__ ci,
-                                                    const float *__restrict__ iv, const uint32_t *__restrict__ ikin, int D,
-                                                    int padding_idx, float *__restrict__ gO, float *__restrict__ gI) {
-    __shared__ float part[8][32 * K];
-    __shared__ int seg[2];
-    const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
-    const uint32_t row = blockIdx.x;
-    const bool otab = blockIdx.y == 0;
+// idx = table * V + row, table 0: gradient of ovectors[row] = sum over its refs of coef * ivectors[iword_b] (pre-step);
+//                         table 1: gradient of ivectors[row] = sum over the examples centred on it of their ci rows.
+__global__ void k_sgns_seg(const uint32_t *__restrict__ kout, int n, const uint32_t *__restrict__ ikout, int B, uint32_t V,
+                           int padding_idx, uint32_t *__restrict__ seg_lo, uint32_t *__restrict__ seg_len,
+                           uint32_t *__restrict__ nsl) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 2u * V) return;
+    const bool otab = idx < V;
+    const uint32_t row = otab ? idx : idx - V;
     const uint32_t *keys = otab ? kout : ikout;
     const int len_all = otab ? n : B;
-    if (threadIdx.x == 0) seg[0] = sg_lower_bound(keys, len_all, row);
-    if (threadIdx.x == 32) seg[1] = sg_lower_bound(keys, len_all, row + 1u);
+    const int lo = sg_lower_bound(keys, len_all, row), hi = sg_lower_bound(keys, len_all, row + 1u);
+    seg_lo[idx] = (uint32_t)lo;
+    seg_len[idx] = (uint32_t)(hi - lo);
+    nsl[idx] = ((int)row == padding_idx) ? 0u : (uint32_t)((hi - lo + SG_SLICE - 1) / SG_SLICE);
+}
+
+// exclusive scan of the 2V slice counts, in place, plus the total behind them (one block; 2V is a few thousand)
+__global__ void __launch_bounds__(1024) k_sgns_scan(uint32_t *__restrict__ soff, uint32_t count) {
+    __shared__ uint32_t part[1024];
+    const uint32_t per = (count + 1023u) / 1024u, t = threadIdx.x;
+    const uint32_t b = t * per, e = min(count, b + per);
+    uint32_t sum = 0;
+    for (uint32_t i = b; i < e; ++i) sum += soff[i];
+    part[t] = sum;
     __syncthreads();
-    const int lo = seg[0], hi = seg[1], len = hi - lo;
-    const int per = (len + 7) / 8;
-    const int q0 = lo + wv * per, q1 = min(hi, q0 + per);
+    for (uint32_t o = 1; o < 1024u; o <<= 1) {
+        const uint32_t v = t >= o ? part[t - o] : 0u;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = part[t] - sum;  // exclusive prefix of this thread's chunk
+    for (uint32_t i = b; i < e; ++i) {
+        const uint32_t c = soff[i];
+        soff[i] = run;
+        run += c;
+    }
+    if (t == 1023u) soff[count] = part[1023];
+}
+
+// one warp per slice (grid-stride): the slice's refs summed in list order -> partial[slice]
+template <int K>
+__global__ void __launch_bounds__(256) k_sgns_slices(const uint32_t *__restrict__ vout, const uint32_t *__restrict__ ivout,
+                                                      int R, const float *__restrict__ coef, const float *__restrict__ ci,
+                                                      const float *__restrict__ iv, const uint32_t *__restrict__ ikin, int D,
+                                                      uint32_t V, const uint32_t *__restrict__ seg_lo,
+                                                      const uint32_t *__restrict__ seg_len, const uint32_t *__restrict__ soff,
+                                                      float *__restrict__ partial) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const uint32_t nwarps = (uint32_t)((gridDim.x * (size_t)blockDim.x) >> 5);
+    const uint32_t total = soff[2u * V];
+    for (uint32_t t = warp; t < total; t += nwarps) {
+        uint32_t lo = 0, hi = 2u * V;  // last idx with soff[idx] <= t (rows without slices share their successor's offset)
+        while (hi - lo > 1u) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (soff[mid] <= t) lo = mid; else hi = mid;
+        }
+        const uint32_t idx = lo;
+        const bool otab = idx < V;
+        const uint32_t j = t - soff[idx];
+        const uint32_t q0 = seg_lo[idx] + j * SG_SLICE;
+        const uint32_t q1 = min(seg_lo[idx] + seg_len[idx], q0 + SG_SLICE);
+        float acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = 0.f;
+#pragma unroll 4  // independent index -> row chains: let the scheduler put several rows in flight
+        for (uint32_t q = q0; q < q1; ++q) {
+            if (otab) {
+                const uint32_t p = vout[q];
+                const float c = coef[p];
+                const float *src = iv + (size_t)ikin[p / (uint32_t)R] * D;  // ikin[b] = validated centre row of example b
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int f = lane + 32 * k;
+                    if (f < D) acc[k] += c * src[f];
+                }
+            } else {
+                const float *src = ci + (size_t)ivout[q] * D;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int f = lane + 32 * k;
+                    if (f < D) acc[k] += src[f];
+                }
+            }
+        }
+        float *dst = partial + (size_t)t * D;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int f = lane + 32 * k;
+            if (f < D) dst[f] = acc[k];
+        }
+    }
+}
+
+// one warp per (table, row): its slices added in slice order -> dense gradient row (zero for the padding row and for
+// rows without refs)
+template <int K>
+__global__ void __launch_bounds__(256) k_sgns_combine(const uint32_t *__restrict__ soff, uint32_t V, int D,
+                                                       const float *__restrict__ partial, float *__restrict__ gO,
+                                                       float *__restrict__ gI) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t idx = (uint32_t)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    if (idx >= 2u * V) return;
+    const uint32_t s0 = soff[idx], s1 = soff[idx + 1];
     float acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = 0.f;
-#pragma unroll 4  // independent index -> row chains: let the scheduler put several rows in flight
-    for (int q = q0; q < q1; ++q) {
-        if (otab) {
-            const uint32_t p = vout[q];
-            const float c = coef[p];
-            const float *src = iv + (size_t)ikin[p / (uint32_t)R] * D;  // ikin[b] = validated centre row of example b
+    for (uint32_t sl = s0; sl < s1; ++sl) {
+        const float *src = partial + (size_t)sl * D;
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const int f = lane + 32 * k;
-                if (f < D) acc[k] += c * src[f];
-            }
-        } else {
-            const float *src = ci + (size_t)ivout[q] * D;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const int f = lane + 32 * k;
-                if (f < D) acc[k] += src[f];
-            }
+        for (int k = 0; k < K; ++k) {
+            const int f = lane + 32 * k;
+            if (f < D) acc[k] += src[f];
         }
     }
+    float *g = (idx < V ? gO + (size_t)idx * D : gI + (size_t)(idx - V) * D);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int f = lane + 32 * k;
-        if (f < D) part[wv][f] = acc[k];
-    }
-    __syncthreads();
-    float *g = (otab ? gO : gI) + (size_t)row * D;
-    const bool pad = (int)row == padding_idx;
-    for (int f = threadIdx.x; f < D; f += 256) {
-        float t = 0.f;
-#pragma unroll
-        for (int s = 0; s < 8; ++s) t += part[s][f];  // slice order
-        g[f] = pad ? 0.f : t;
+        if (f < D) g[f] = acc[k];
     }
 }
 
@@ -308,16 +389,28 @@ extern "C" int daisy_sgns_step(daisy_handle_t h, const daisy_sgns_params *p, con
         cub_bytes = w.cub_bytes;
         DAISY_CUDA(cub::DeviceRadixSort::SortPairs(w.cub, cub_bytes, w.ikin, w.ikout, w.ivin, w.ivout, Bi, 0, bits, s));
         h->launches += 6;
-        if (D <= 128)
-            k_sgns_rows<4><<<dim3(V, 2), 256, 0, s>>>(w.kout, w.vout, n, w.ikout, w.ivout, Bi, (int)R, w.coef, w.ci, p->iv, w.ikin,
-                                                      D, p->padding_idx, w.gO, w.gI);
-        else if (D <= 320)
-            k_sgns_rows<10><<<dim3(V, 2), 256, 0, s>>>(w.kout, w.vout, n, w.ikout, w.ivout, Bi, (int)R, w.coef, w.ci, p->iv, w.ikin,
-                                                       D, p->padding_idx, w.gO, w.gI);
-        else
-            k_sgns_rows<SG_K><<<dim3(V, 2), 256, 0, s>>>(w.kout, w.vout, n, w.ikout, w.ivout, Bi, (int)R, w.coef, w.ci, p->iv,
-                                                         w.ikin, D, p->padding_idx, w.gO, w.gI);
+        const int T = 256;
+        k_sgns_seg<<<daisy_ceil_div(2 * (int64_t)V, T), T, 0, s>>>(w.kout, n, w.ikout, Bi, V, p->padding_idx, w.seg_lo, w.seg_len,
+                                                                   w.soff);
         DAISY_LAUNCH_CHECK(h);
+        k_sgns_scan<<<1, 1024, 0, s>>>(w.soff, 2u * V);
+        DAISY_LAUNCH_CHECK(h);
+        const int sgrid = h->num_sms > 0 ? h->num_sms * 8 : 8, cgrid = daisy_ceil_div(2 * (int64_t)V, 8);
+        if (D <= 128) {
+            k_sgns_slices<4><<<sgrid, 256, 0, s>>>(w.vout, w.ivout, (int)R, w.coef, w.ci, p->iv, w.ikin, D, V, w.seg_lo, w.seg_len,
+                                                   w.soff, w.partial);
+            k_sgns_combine<4><<<cgrid, 256, 0, s>>>(w.soff, V, D, w.partial, w.gO, w.gI);
+        } else if (D <= 320) {
+            k_sgns_slices<10><<<sgrid, 256, 0, s>>>(w.vout, w.ivout, (int)R, w.coef, w.ci, p->iv, w.ikin, D, V, w.seg_lo, w.seg_len,
+                                                    w.soff, w.partial);
+            k_sgns_combine<10><<<cgrid, 256, 0, s>>>(w.soff, V, D, w.partial, w.gO, w.gI);
+        } else {
+            k_sgns_slices<SG_K><<<sgrid, 256, 0, s>>>(w.vout, w.ivout, (int)R, w.coef, w.ci, p->iv, w.ikin, D, V, w.seg_lo,
+                                                      w.seg_len, w.soff, w.partial);
+            k_sgns_combine<SG_K><<<cgrid, 256, 0, s>>>(w.soff, V, D, w.partial, w.gO, w.gI);
+        }
+        DAISY_LAUNCH_CHECK(h);
+        h->launches += 3;
     } else {  // optimizer.step() on an empty batch: zero gradients, the moments still decay
         DAISY_CUDA(cudaMemsetAsync(w.gI, 0, nvd * sizeof(float), s));
         DAISY_CUDA(cudaMemsetAsync(w.gO, 0, nvd * sizeof(float), s));
