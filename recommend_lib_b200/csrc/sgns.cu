@@ -115,22 +115,46 @@ __global__ void __launch_bounds__(256) k_sgns_main(const float *__restrict__ iv,
     }
     float loss = 0.f;
     const int NR = R - C;  // negatives per example
-    uint32_t ids = 0;  // lane l holds the (validated) row of ref r0 + l of the current group of 32 refs
-    for (int r = 0; r < R; ++r) {
-        if ((r & 31) == 0) {  // one coalesced id load per 32 refs instead of a dependent scalar load per ref
-            const int rr = r + lane;
-            ids = rr < R ? sg_row(rr < C ? owords[(size_t)b * C + rr] : nwords[(size_t)b * NR + (rr - C)], V, b, err) : 0u;
-        }
-        const uint32_t row = __shfl_sync(0xffffffffu, ids, r & 31);
-        const float *o = ov + (size_t)row * D;
-        float orow[K];
-        float dot = 0.f;
+    // Ids: lane l holds the (validated) row of ref r0 + l of the current group of 32 refs (one coalesced load per group,
+    // the next group's ids fetched a group ahead).  Rows: the row of ref r + 1 is loaded before ref r is consumed, so two
+    // rows of a warp are in flight (the first version loaded and consumed one row at a time: ~1 us per ref, 226 us for
+    // the kernel at the script's defaults, profiles/r02u_launches_sgns_summary.md).  Same arithmetic in the same order.
+    auto load_ids = [&](int r0) -> uint32_t {
+        const int rr = r0 + lane;
+        return rr < R ? sg_row(rr < C ? owords[(size_t)b * C + rr] : nwords[(size_t)b * NR + (rr - C)], V, b, err) : 0u;
+    };
+    uint32_t ids = load_ids(0), ids_next = load_ids(32);
+    float nrow[K];
+    uint32_t row_next = __shfl_sync(0xffffffffu, ids, 0);
+    {
+        const float *o = ov + (size_t)row_next * D;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int f = lane + 32 * k;
-            orow[k] = f < D ? o[f] : 0.f;
-            dot += ir[k] * orow[k];
+            nrow[k] = f < D ? o[f] : 0.f;
         }
+    }
+    for (int r = 0; r < R; ++r) {
+        const uint32_t row = row_next;
+        float orow[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) orow[k] = nrow[k];
+        if (r + 1 < R) {  // warp-uniform
+            if (((r + 1) & 31) == 0) {
+                ids = ids_next;
+                ids_next = load_ids(r + 1 + 32);
+            }
+            row_next = __shfl_sync(0xffffffffu, ids, (r + 1) & 31);
+            const float *o = ov + (size_t)row_next * D;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int f = lane + 32 * k;
+                nrow[k] = f < D ? o[f] : 0.f;
+            }
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) dot += ir[k] * orow[k];
         dot = warp_sum(dot);
         float c;
         if (r < C) {  // context row: -log sigmoid(x)
