@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(1024) k_svdpp_hot(const int64_t *ur_ptr, const
 template <int M>
 __global__ void __launch_bounds__(M >= 8 ? 512 : 1024, 1) k_svdpp_seq(SpArgs a) {   // D > 128: 512 threads, 128 registers
     extern __shared__ double sp_smem[];
+    constexpr int KEEP = M == 1 ? 6 : (M == 2 ? 3 : 0);   // history rows per warp held in registers between phases (1) and (3)
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, W = blockDim.x >> 5, T = blockDim.x;
     const int D = a.D;
     double *red = sp_smem;                  // [W][D]  per-warp partial sums of the history rows
@@ -210,10 +211,30 @@ __global__ void __launch_bounds__(M >= 8 ? 512 : 1024, 1) k_svdpp_seq(SpArgs a) 
         }
 
         // (1) implicit feedback: sum of the history rows (:243-246)
-        double acc[M];
+        // The first KEEP rows of every warp (histories of up to KEEP * W rows: all of them at the script's sizes) are
+        // loaded back to back into registers -- KEEP independent L2 round trips in flight instead of a load -> add chain
+        // per row -- and stay there for phase (3), which used to read every row a second time.  Same additions in the
+        // same order: bit-identical to the row-by-row walk.
+        double acc[M], keep[KEEP > 0 ? KEEP : 1][M];
 #pragma unroll
         for (int m = 0; m < M; ++m) acc[m] = 0.0;
-        for (int k = w; k < nI; k += W) {
+#pragma unroll
+        for (int j = 0; j < KEEP; ++j) {
+            const int k = w + j * W;
+            const bool on = k < nI;         // warp-uniform
+            const double *row = on ? row_of(k < SP_CAP ? lst[k] : enc(a.ur_idx[p0 + k])) : nullptr;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const int f = lane + 32 * m;
+                keep[j][m] = (on && f < D) ? row[f] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < KEEP; ++j)
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+                if (w + j * W < nI) acc[m] += keep[j][m];
+        for (int k = w + KEEP * W; k < nI; k += W) {
             const double *row = row_of(k < SP_CAP ? lst[k] : enc(a.ur_idx[p0 + k]));
 #pragma unroll
             for (int m = 0; m < M; ++m) {
@@ -232,8 +253,11 @@ __global__ void __launch_bounds__(M >= 8 ? 512 : 1024, 1) k_svdpp_seq(SpArgs a) 
         double ui = 0.0, prod = 0.0;
         if (tid < D) {
             double sum = 0.0;
-            const int used = nI < W ? nI : W;
-            for (int w2 = 0; w2 < used; ++w2) sum += red[(size_t)w2 * D + tid];
+            // every warp has written its partial (zeros where it had no row), so the loop runs over all W of them with a
+            // fixed trip count the compiler can unroll: the shared-memory loads go out together instead of one per add
+            // (adding the trailing zeros changes nothing)
+#pragma unroll 8
+            for (int w2 = 0; w2 < W; ++w2) sum += red[(size_t)w2 * D + tid];
             ui = nI > 0 ? sum / sqrt_Iu : 0.0;
             qold[tid] = qif;
             prod = qif * (puf + ui);
@@ -283,7 +307,24 @@ __global__ void __launch_bounds__(M >= 8 ? 512 : 1024, 1) k_svdpp_seq(SpArgs a) 
             const int f = lane + 32 * m;
             c[m] = f < D ? err * qold[f] / sqrt_Iu : 0.0;
         }
-        for (int k = w; k < nI; k += W) {
+#pragma unroll
+        for (int j = 0; j < KEEP; ++j) {    // the rows still in registers
+            const int k = w + j * W;
+            if (k >= nI) break;             // warp-uniform
+            const int mult = k < SP_CAP ? mls[k] : (a.ur_mult ? a.ur_mult[p0 + k] : 1);
+            if (mult == 0) continue;        // a later occurrence of an item: its first occurrence applies both
+            double *row = row_of(k < SP_CAP ? lst[k] : enc(a.ur_idx[p0 + k]));
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const int f = lane + 32 * m;
+                if (f < D) {
+                    double y = keep[j][m];
+                    for (int rep = 0; rep < mult; ++rep) y += prm.lr_yj * (c[m] - prm.reg_yj * y);
+                    row[f] = y;
+                }
+            }
+        }
+        for (int k = w + KEEP * W; k < nI; k += W) {
             const int mult = k < SP_CAP ? mls[k] : (a.ur_mult ? a.ur_mult[p0 + k] : 1);
             if (mult == 0) continue;        // a later occurrence of an item: its first occurrence applies both
             double *row = row_of(k < SP_CAP ? lst[k] : enc(a.ur_idx[p0 + k]));
